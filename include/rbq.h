@@ -1,0 +1,140 @@
+/* rbq.h -- C ABI of the B200-native IVF+RaBitQ search engine (librbq.so).
+ *
+ * Drop-in boundary for the search path of lqhl/rabitq-rs v0.7.0.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo).  Plain pointers and
+ * sizes only; no exceptions cross the boundary; all functions return an rbq_status.
+ *
+ * Threading: a handle may be shared between host threads; calls that launch work on one handle
+ * are serialised by an internal mutex (the reference's `&self` search is re-entrant; here the
+ * device workspace is per handle).
+ */
+#ifndef RBQ_H_
+#define RBQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors RabitqError (src/lib.rs:39-57). */
+typedef enum rbq_status {
+    RBQ_OK = 0,
+    RBQ_DIMENSION_MISMATCH = 1,  /* RabitqError::DimensionMismatch{expected,got} */
+    RBQ_INVALID_CONFIG = 2,      /* RabitqError::InvalidConfig(&str) */
+    RBQ_EMPTY_INDEX = 3,         /* RabitqError::EmptyIndex */
+    RBQ_IO = 4,                  /* RabitqError::Io */
+    RBQ_INVALID_PERSISTENCE = 5, /* RabitqError::InvalidPersistence(&str) */
+    RBQ_CUDA_ERROR = 6           /* no reference counterpart: device/driver failure */
+} rbq_status;
+
+/* Metric (src/lib.rs:31-37) and RotatorType (src/rotation.rs:8-15) tags = the on-disk tags. */
+enum { RBQ_METRIC_L2 = 0, RBQ_METRIC_INNER_PRODUCT = 1 };
+enum { RBQ_ROTATOR_MATRIX = 0, RBQ_ROTATOR_FHT_KAC = 1 };
+
+typedef struct rbq_index rbq_index; /* IvfRabitqIndex (src/ivf.rs:935-946), device resident */
+
+/* Thread-local message of the last failing call on this thread (Display of RabitqError). */
+const char* rbq_last_error(void);
+
+/* ---- persistence: IvfRabitqIndex::load_from_path / load_from_reader (src/ivf.rs:1477-1702) ----
+ * Parses the "RBQ1" v3 stream (same validation and error strings), uploads it to `device`.
+ * shard_rank/shard_count: inverted lists are assigned size-balanced to `shard_count` shards and only
+ * the lists of `shard_rank` are kept on this device (centroids and rotator replicated).  Use 0/1 for
+ * a complete index. */
+int rbq_index_load(const char* path, int device, int shard_rank, int shard_count, rbq_index** out);
+int rbq_index_load_mem(const uint8_t* bytes, size_t len, int device, int shard_rank, int shard_count,
+                       rbq_index** out);
+/* IvfRabitqIndex::save_to_path / save_to_writer (src/ivf.rs:1310-1474); complete (unsharded) handles only.
+ * rbq_index_save_mem: pass out==NULL to query the size. */
+int rbq_index_save(const rbq_index* ix, const char* path);
+int rbq_index_save_mem(const rbq_index* ix, uint8_t* out, size_t cap, size_t* written);
+void rbq_index_free(rbq_index* ix);
+
+/* ---- build: IvfRabitqIndex::train_with_clusters (src/ivf.rs:1025-1103) on the GPU ----
+ * data: n x dim row-major, centroids: nlist x dim, assignments: n cluster ids.  total_bits 1..9.
+ * rotator_type/seed as the reference; the rotator state is drawn from a seeded splitmix64 stream (the
+ * reference's ChaCha12 stream is not reproduced; the state is stored in the index file either way).
+ * faster_config != 0 uses a constant rescale factor (RabitqConfig::faster, src/quantizer.rs:33-45).
+ * rotator_state (optional, may be NULL): explicit flip bytes (4*padded/8) or matrix (padded^2 f32). */
+int rbq_index_build(const float* data, size_t n, size_t dim, const float* centroids, size_t nlist,
+                    const uint32_t* assignments, int total_bits, int metric, int rotator_type,
+                    uint64_t seed, int faster_config, const uint8_t* rotator_state, int device,
+                    rbq_index** out);
+
+/* ---- accessors: len / cluster_count (src/ivf.rs:1218-1230) and index fields ---- */
+size_t rbq_index_len(const rbq_index* ix);           /* all vectors of the index (all shards) */
+size_t rbq_index_local_len(const rbq_index* ix);     /* vectors resident in this shard */
+size_t rbq_index_dim(const rbq_index* ix);
+size_t rbq_index_padded_dim(const rbq_index* ix);
+size_t rbq_index_cluster_count(const rbq_index* ix);
+int rbq_index_metric(const rbq_index* ix);
+int rbq_index_ex_bits(const rbq_index* ix);
+int rbq_index_rotator_type(const rbq_index* ix);
+int rbq_index_device(const rbq_index* ix);
+
+/* ---- search: IvfRabitqIndex::batch_search / search / search_filtered (src/ivf.rs:1705-1752) ----
+ * queries: nq x dim row-major HOST memory.  Outputs (host): ids[nq*top_k], scores[nq*top_k] (L2:
+ * estimated squared distance ascending; IP: score descending = -distance), counts[nq] = results per
+ * query (<= top_k).  Unused slots: id = UINT64_MAX, score = 0.
+ * nprobe is clamped to [1, cluster_count]; top_k == 0 yields counts == 0 (src/ivf.rs:1791-1794).
+ * filter_bits (optional): dense bitset over u32 ids standing in for RoaringBitmap::contains
+ * (src/ivf.rs:2017-2022); bit i of word i/64. */
+int rbq_search_batch(const rbq_index* ix, const float* queries, size_t nq, size_t dim, size_t top_k,
+                     size_t nprobe, uint64_t* ids, float* scores, uint32_t* counts);
+int rbq_search_batch_filtered(const rbq_index* ix, const float* queries, size_t nq, size_t dim,
+                              size_t top_k, size_t nprobe, const uint64_t* filter_bits,
+                              size_t filter_nbits, uint64_t* ids, float* scores, uint32_t* counts);
+/* Same, all buffers DEVICE pointers on the index's device; enqueued on `stream` (cudaStream_t cast
+ * to void*, NULL = default stream); returns after enqueue (no host sync). d_dist (optional) receives
+ * the raw distances (used by the multi-GPU merge). */
+int rbq_search_batch_device(const rbq_index* ix, const float* d_queries, size_t nq, size_t dim,
+                            size_t top_k, size_t nprobe, const uint64_t* d_filter_bits,
+                            size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts,
+                            void* stream);
+
+/* ---- multi-GPU merge: k-way merge of per-shard top-k lists (no reference counterpart; the
+ * reference is single-process).  in_*: [nshards][nq][top_k] device arrays gathered from all shards
+ * (e.g. ncclAllGather); out_*: [nq][top_k].  Comparator = the reference's result order. */
+int rbq_merge_topk_device(const rbq_index* ix, int nshards, size_t nq, size_t top_k,
+                          const uint64_t* in_ids, const float* in_scores, const uint32_t* in_counts,
+                          uint64_t* out_ids, float* out_scores, uint32_t* out_counts, void* stream);
+
+/* ---- diagnostics (SearchDiagnostics, src/ivf.rs:151-155, plus roofline accounting) ---- */
+typedef struct rbq_search_stats {
+    uint64_t queries;           /* queries in the last search call on this handle */
+    uint64_t blocks_scanned;    /* 32-vector FastScan blocks streamed */
+    uint64_t bytes_scanned;     /* blocks_scanned * (4*padded_dim + 384): algorithmic scan bytes */
+    uint64_t candidates;        /* vectors whose lower bound was evaluated */
+    uint64_t refined;           /* ex-code dot products evaluated on device (>= reference's extended_evaluations) */
+    uint64_t admitted;          /* candidates that passed lb < distk in reference order (== estimated + non-finite) */
+    uint64_t kernel_launches;   /* CUDA kernels launched by the call */
+    float ms_prep, ms_coarse, ms_select, ms_scan; /* CUDA-event times of the last *profiled* call */
+} rbq_search_stats;
+int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
+/* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */
+int rbq_set_profiling(rbq_index* ix, int on);
+/* Coarse-stage implementation: 0 = exact FP32 scoring of every centroid (CUDA cores),
+ * 1 = tensor-core candidate GEMM + exact FP32 re-score (default when available). */
+int rbq_set_coarse_mode(rbq_index* ix, int mode);
+
+/* ---- stage probes (parity tests call each device stage in isolation; host buffers) ----
+ * rotated[nq*D], lut[nq*4D], scalars[nq*8] = delta,sum_vl,k1x,kbx,qnorm,sum_q,binary_scale,0
+ * (FhtKacRotator::rotate_into src/rotation.rs:350-401, QueryLut::new src/ivf.rs:798-845,
+ * QueryPrecomputed::new src/ivf.rs:862-878). */
+int rbq_debug_query_prep(const rbq_index* ix, const float* queries, size_t nq, size_t dim,
+                         float* rotated, uint8_t* lut, float* scalars);
+/* probe_cids[nq*nprobe], probe_consts[nq*nprobe*3] = g_add,g_error,dot_qc in visit order
+ * (src/ivf.rs:1782-1857). */
+int rbq_debug_probe(const rbq_index* ix, const float* queries, size_t nq, size_t dim, size_t nprobe,
+                    uint32_t* probe_cids, float* probe_consts);
+/* FastScan over one list for one query: accu[nb*32] (u16 semantics), ip/est/lb[nb*32]
+ * (simd::accumulate_batch_avx2 src/simd.rs:972, compute_batch_distances_u16 :1932). */
+int rbq_debug_scan_list(const rbq_index* ix, const float* query, size_t dim, size_t cluster,
+                        uint32_t* accu, float* ip, float* est, float* lb, size_t cap_vectors);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBQ_H_ */

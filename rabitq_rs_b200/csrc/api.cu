@@ -1,0 +1,538 @@
+// api.cu -- C entry points of librbq.so: handle lifetime, upload, the batched search pipeline.
+// Interfaces replaced: IvfRabitqIndex::{load_from_path, load_from_reader, save_to_path, search,
+// search_filtered, batch_search, len, cluster_count} (reference src/ivf.rs:1218-1230, 1310-1752).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "rbq_internal.h"
+
+using namespace rbq;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class T>
+int upload(rbq_index* h, const T* src, size_t count, const T** dst, size_t pad_bytes = 0) {
+    void* d = nullptr;
+    size_t bytes = count * sizeof(T);
+    RBQ_CUDA(cudaMalloc(&d, std::max<size_t>(bytes + pad_bytes, 16)));
+    h->allocations.push_back(d);
+    if (bytes) RBQ_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    if (pad_bytes) RBQ_CUDA(cudaMemset((char*)d + bytes, 0, pad_bytes));
+    *dst = reinterpret_cast<const T*>(d);
+    return RBQ_OK;
+}
+
+int validate_geometry(const HostIndex& hi) {
+    if (hi.D % 16 != 0)
+        return fail(RBQ_INVALID_CONFIG, "padded_dim must be a multiple of 16 (FastScan requirement, reference src/simd.rs:978-981)");
+    if (hi.D > 2048)
+        return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
+    if (hi.ex_bits > 8) return fail(RBQ_INVALID_CONFIG, "ex_bits > 8 is not supported");
+    return RBQ_OK;
+}
+
+void fill_geometry(rbq_index* h) {
+    const HostIndex& hi = h->host;
+    DevIndex& d = h->dev;
+    d.dim = (int)hi.dim;
+    d.D = (int)hi.D;
+    d.metric = hi.metric;
+    d.ex_bits = hi.ex_bits;
+    d.rot_type = hi.rot_type;
+    int lg = 0;
+    while ((2u << lg) <= hi.dim) ++lg;  // floor(log2(dim)), reference src/rotation.rs:263-266
+    d.trunc = 1 << lg;
+    d.fac = 1.0f / std::sqrt((float)d.trunc);
+    d.nlist = (uint32_t)hi.nlist;
+    d.block_stride = (uint32_t)hi.block_stride();
+    d.ex_stride = (uint32_t)hi.ex_stride();
+}
+
+// Move the host image to the device; bulk host arrays are released afterwards.
+int upload_index(rbq_index* h) {
+    HostIndex& hi = h->host;
+    int rc = validate_geometry(hi);
+    if (rc) return rc;
+    fill_geometry(h);
+    DevIndex& d = h->dev;
+    d.flip = nullptr;
+    d.matrix_t = nullptr;
+    if (hi.rot_type == RBQ_ROTATOR_FHT_KAC) {
+        if ((rc = upload(h, hi.rot_bytes.data(), hi.rot_bytes.size(), &d.flip))) return rc;
+    } else {
+        size_t D = hi.D;
+        std::vector<float> mt(D * D);
+        const float* m = reinterpret_cast<const float*>(hi.rot_bytes.data());
+        for (size_t r = 0; r < D; ++r)
+            for (size_t k = 0; k < D; ++k) mt[k * D + r] = m[r * D + k];
+        if ((rc = upload(h, mt.data(), mt.size(), &d.matrix_t))) return rc;
+    }
+    if ((rc = upload(h, hi.centroids.data(), hi.centroids.size(), &d.centroids))) return rc;
+    if ((rc = upload(h, hi.list_n.data(), hi.list_n.size(), &d.list_n))) return rc;
+    if ((rc = upload(h, hi.blk_off.data(), hi.blk_off.size(), &d.blk_off))) return rc;
+    if ((rc = upload(h, hi.vec_off.data(), hi.vec_off.size(), &d.vec_off))) return rc;
+    if ((rc = upload(h, hi.blocks.data(), hi.blocks.size(), &d.blocks))) return rc;
+    if ((rc = upload(h, hi.ids.data(), hi.ids.size(), &d.ids))) return rc;
+    if ((rc = upload(h, hi.ex.data(), hi.ex.size(), &d.ex, 16))) return rc;
+    if ((rc = upload(h, hi.f_add_ex.data(), hi.f_add_ex.size(), &d.f_add_ex))) return rc;
+    if ((rc = upload(h, hi.f_rescale_ex.data(), hi.f_rescale_ex.size(), &d.f_rescale_ex))) return rc;
+    std::vector<uint8_t>().swap(hi.blocks);
+    std::vector<uint64_t>().swap(hi.ids);
+    std::vector<uint8_t>().swap(hi.ex);
+    std::vector<float>().swap(hi.f_add_ex);
+    std::vector<float>().swap(hi.f_rescale_ex);
+    void* st = nullptr;
+    RBQ_CUDA(cudaMalloc(&st, sizeof(DevStats)));
+    RBQ_CUDA(cudaMemset(st, 0, sizeof(DevStats)));
+    h->allocations.push_back(st);
+    h->d_stats = reinterpret_cast<DevStats*>(st);
+    return RBQ_OK;
+}
+
+int ensure_ws(const rbq_index* h, size_t bytes) {
+    if (h->ws_bytes >= bytes) return RBQ_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    RBQ_CUDA(cudaMalloc(&h->ws, bytes));
+    h->ws_bytes = bytes;
+    return RBQ_OK;
+}
+
+struct Carver {
+    char* p;
+    size_t off = 0;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = reinterpret_cast<T*>(p + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+size_t tile_queries(const rbq_index* h, size_t nq) {
+    size_t per_q = (size_t)h->dev.nlist * 4;
+    size_t cap = std::max<size_t>(1, ((size_t)1 << 30) / std::max<size_t>(per_q, 1));
+    return std::min<size_t>({nq, (size_t)32768, cap});
+}
+
+size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_t dim, bool host_io, size_t filter_words) {
+    const size_t D = h->dev.D;
+    size_t n = 4096;
+    n += qt * D * 4 + 256;                 // rotated
+    n += qt * D * 4 + 256;                 // lut
+    n += qt * sizeof(QueryScalars) + 256;
+    n += qt * (size_t)h->dev.nlist * 4 + 256;  // scores
+    n += qt * nprobe * sizeof(Probe) + 256;
+    if (host_io) {
+        n += qt * dim * 4 + 256;
+        n += qt * top_k * 12 + qt * 4 + 768;
+        n += filter_words * 8 + 256;
+    }
+    return n;
+}
+
+// The pipeline on device buffers for one call (tiles internally).  d_filter may be null.
+int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t top_k, size_t nprobe,
+                  const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts,
+                  char* ws_base, size_t qt, cudaStream_t st, uint64_t* launches) {
+    const DevIndex& ix = h->dev;
+    const size_t D = ix.D;
+    Carver cv{ws_base};
+    float* d_rot = cv.take<float>(qt * D);
+    uint8_t* d_lut = cv.take<uint8_t>(qt * D * 4);
+    QueryScalars* d_qs = cv.take<QueryScalars>(qt);
+    float* d_sc = cv.take<float>(qt * (size_t)ix.nlist);
+    Probe* d_pr = cv.take<Probe>(qt * nprobe);
+    float ms[4] = {0, 0, 0, 0};
+    for (size_t q0 = 0; q0 < nq; q0 += qt) {
+        const size_t n = std::min(qt, nq - q0);
+        int rc;
+        if (h->profiling) cudaEventRecord(h->ev[0], st);
+        if ((rc = launch_query_prep(ix, d_queries + q0 * ix.dim, n, d_rot, d_lut, d_qs, st))) return rc;
+        if (h->profiling) cudaEventRecord(h->ev[1], st);
+        if ((rc = launch_coarse_exact(ix, d_rot, n, d_sc, st))) return rc;
+        if (h->profiling) cudaEventRecord(h->ev[2], st);
+        if ((rc = launch_probe_select(ix, d_rot, d_sc, n, nprobe, d_pr, st))) return rc;
+        if (h->profiling) cudaEventRecord(h->ev[3], st);
+        if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                              d_scores + q0 * top_k, d_counts + q0, h->d_stats, st)))
+            return rc;
+        *launches += 4;
+        if (h->profiling) {
+            cudaEventRecord(h->ev[4], st);
+            RBQ_CUDA(cudaEventSynchronize(h->ev[4]));
+            for (int i = 0; i < 4; ++i) {
+                float t = 0;
+                cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
+                ms[i] += t;
+            }
+        }
+    }
+    if (h->profiling) {
+        h->last_stats.ms_prep = ms[0];
+        h->last_stats.ms_coarse = ms[1];
+        h->last_stats.ms_select = ms[2];
+        h->last_stats.ms_scan = ms[3];
+    }
+    return RBQ_OK;
+}
+
+int check_search_args(const rbq_index* ix, size_t dim, size_t top_k, size_t* nprobe) {
+    if (!ix) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (ix->host.nvec_total == 0) return fail(RBQ_EMPTY_INDEX, "index is empty; call `train` first");
+    if (dim != ix->host.dim)
+        return fail(RBQ_DIMENSION_MISMATCH, "expected " + std::to_string(ix->host.dim) + ", got " + std::to_string(dim));
+    *nprobe = std::min(std::max<size_t>(*nprobe, 1), ix->host.nlist);  // reference src/ivf.rs:1791
+    if (top_k > scan_max_topk()) return fail(RBQ_INVALID_CONFIG, "top_k exceeds the device limit (1024)");
+    if (*nprobe > probe_select_max_nprobe())
+        return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
+    return RBQ_OK;
+}
+
+int finish_load(rbq_index* h, int device, rbq_index** out) {
+    h->device = device;
+    DeviceGuard g(device);
+    int rc = upload_index(h);
+    if (rc) {
+        rbq_index_free(h);
+        return rc;
+    }
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    *out = h;
+    return RBQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbq_index_load_mem(const uint8_t* bytes, size_t len, int device, int shard_rank, int shard_count, rbq_index** out) {
+    if (!bytes || !out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    *out = nullptr;
+    rbq_index* h = new rbq_index();
+    int rc = parse_rbq1(bytes, len, shard_rank, shard_count, h->host);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    return finish_load(h, device, out);
+}
+
+int rbq_index_load(const char* path, int device, int shard_rank, int shard_count, rbq_index** out) {
+    if (!path || !out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(RBQ_IO, std::string(strerror(errno)) + ": " + path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        close(fd);
+        return fail(RBQ_IO, std::string(strerror(errno)) + ": " + path);
+    }
+    size_t len = (size_t)sb.st_size;
+    void* map = len ? mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (len && map == MAP_FAILED) return fail(RBQ_IO, std::string("mmap failed: ") + path);
+    static const uint8_t empty = 0;
+    int rc = rbq_index_load_mem(len ? (const uint8_t*)map : &empty, len, device, shard_rank, shard_count, out);
+    if (len) munmap(map, len);
+    return rc;
+}
+
+void rbq_index_free(rbq_index* h) {
+    if (!h) return;
+    {
+        DeviceGuard g(h->device);
+        for (void* p : h->allocations) cudaFree(p);
+        if (h->ws) cudaFree(h->ws);
+        for (auto& e : h->ev)
+            if (e) cudaEventDestroy(e);
+    }
+    delete h;
+}
+
+int rbq_index_save_mem(const rbq_index* h, uint8_t* out, size_t cap, size_t* written) {
+    if (!h || !written) return fail(RBQ_INVALID_CONFIG, "null argument");
+    if (h->host.shard_count != 1) return fail(RBQ_INVALID_CONFIG, "only a complete (unsharded) index can be saved");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    HostIndex tmp = h->host;  // metadata + centroids/delta/vl; bulk arrays come back from the device
+    const size_t nb = tmp.blk_off[tmp.nlist], nv = tmp.vec_off[tmp.nlist];
+    tmp.blocks.resize(nb * tmp.block_stride());
+    tmp.ids.resize(nv);
+    tmp.ex.resize(nv * tmp.ex_stride());
+    tmp.f_add_ex.resize(nv);
+    tmp.f_rescale_ex.resize(nv);
+    if (!tmp.blocks.empty()) RBQ_CUDA(cudaMemcpy(tmp.blocks.data(), h->dev.blocks, tmp.blocks.size(), cudaMemcpyDeviceToHost));
+    if (nv) {
+        RBQ_CUDA(cudaMemcpy(tmp.ids.data(), h->dev.ids, nv * 8, cudaMemcpyDeviceToHost));
+        if (!tmp.ex.empty()) RBQ_CUDA(cudaMemcpy(tmp.ex.data(), h->dev.ex, tmp.ex.size(), cudaMemcpyDeviceToHost));
+        RBQ_CUDA(cudaMemcpy(tmp.f_add_ex.data(), h->dev.f_add_ex, nv * 4, cudaMemcpyDeviceToHost));
+        RBQ_CUDA(cudaMemcpy(tmp.f_rescale_ex.data(), h->dev.f_rescale_ex, nv * 4, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint8_t> buf;
+    write_rbq1(tmp, buf);
+    *written = buf.size();
+    if (out) {
+        if (cap < buf.size()) return fail(RBQ_IO, "output buffer too small");
+        std::memcpy(out, buf.data(), buf.size());
+    }
+    return RBQ_OK;
+}
+
+int rbq_index_save(const rbq_index* h, const char* path) {
+    if (!h || !path) return fail(RBQ_INVALID_CONFIG, "null argument");
+    size_t n = 0;
+    int rc = rbq_index_save_mem(h, nullptr, 0, &n);
+    if (rc) return rc;
+    std::vector<uint8_t> buf(n);
+    if ((rc = rbq_index_save_mem(h, buf.data(), n, &n))) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RBQ_IO, std::string(strerror(errno)) + ": " + path);
+    size_t w = fwrite(buf.data(), 1, n, f);
+    if (fclose(f) != 0 || w != n) return fail(RBQ_IO, std::string("short write: ") + path);
+    return RBQ_OK;
+}
+
+size_t rbq_index_len(const rbq_index* h) { return h ? (size_t)h->host.nvec_total : 0; }
+size_t rbq_index_local_len(const rbq_index* h) { return h ? (size_t)h->host.vec_off[h->host.nlist] : 0; }
+size_t rbq_index_dim(const rbq_index* h) { return h ? h->host.dim : 0; }
+size_t rbq_index_padded_dim(const rbq_index* h) { return h ? h->host.D : 0; }
+size_t rbq_index_cluster_count(const rbq_index* h) { return h ? h->host.nlist : 0; }
+int rbq_index_metric(const rbq_index* h) { return h ? h->host.metric : -1; }
+int rbq_index_ex_bits(const rbq_index* h) { return h ? h->host.ex_bits : -1; }
+int rbq_index_rotator_type(const rbq_index* h) { return h ? h->host.rot_type : -1; }
+int rbq_index_device(const rbq_index* h) { return h ? h->device : -1; }
+
+int rbq_set_profiling(rbq_index* h, int on) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    h->profiling = on != 0;
+    return RBQ_OK;
+}
+int rbq_set_coarse_mode(rbq_index* h, int mode) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (mode != 0) return fail(RBQ_INVALID_CONFIG, "coarse mode not available in this build");
+    h->coarse_mode = mode;
+    return RBQ_OK;
+}
+
+int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
+    if (!h || !out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DevStats ds;
+    RBQ_CUDA(cudaMemcpy(&ds, h->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
+    h->last_stats.blocks_scanned = ds.blocks;
+    h->last_stats.bytes_scanned = ds.blocks * (uint64_t)h->dev.block_stride;
+    h->last_stats.candidates = ds.candidates;
+    h->last_stats.refined = ds.refined;
+    h->last_stats.admitted = ds.admitted;
+    *out = h->last_stats;
+    return RBQ_OK;
+}
+
+int rbq_search_batch_device(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k,
+                            size_t nprobe, const uint64_t* d_filter_bits, size_t filter_nbits, uint64_t* d_ids,
+                            float* d_scores, uint32_t* d_counts, void* stream) {
+    int rc = check_search_args(h, dim, top_k, &nprobe);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    h->last_stats = rbq_search_stats{};
+    h->last_stats.queries = nq;
+    if (nq == 0) return RBQ_OK;
+    if (top_k == 0) {  // reference src/ivf.rs:1792-1794
+        RBQ_CUDA(cudaMemsetAsync(d_counts, 0, nq * 4, st));
+        return RBQ_OK;
+    }
+    const size_t qt = tile_queries(h, nq);
+    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, false, 0)))) return rc;
+    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), st));
+    uint64_t launches = 0;
+    rc = search_device(h, d_queries, nq, top_k, nprobe, d_filter_bits, filter_nbits, d_ids, d_scores, d_counts,
+                       (char*)h->ws, qt, st, &launches);
+    h->last_stats.kernel_launches = launches;
+    return rc;
+}
+
+int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t nq, size_t dim, size_t top_k,
+                              size_t nprobe, const uint64_t* filter_bits, size_t filter_nbits, uint64_t* ids,
+                              float* scores, uint32_t* counts) {
+    int rc = check_search_args(h, dim, top_k, &nprobe);
+    if (rc) return rc;
+    if (nq && (!queries || !counts || (top_k && (!ids || !scores)))) return fail(RBQ_INVALID_CONFIG, "null buffer");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->last_stats = rbq_search_stats{};
+    h->last_stats.queries = nq;
+    if (nq == 0) return RBQ_OK;
+    if (top_k == 0) {
+        std::memset(counts, 0, nq * 4);
+        return RBQ_OK;
+    }
+    const size_t qt = tile_queries(h, nq);
+    const size_t fwords = filter_bits ? (filter_nbits + 63) / 64 : 0;
+    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, true, fwords)))) return rc;
+    // host-io buffers live behind the pipeline buffers
+    Carver cv{(char*)h->ws};
+    cv.off = ws_need(h, qt, nprobe, top_k, dim, false, 0);
+    float* d_q = cv.take<float>(qt * dim);
+    uint64_t* d_ids = cv.take<uint64_t>(qt * top_k);
+    float* d_sc = cv.take<float>(qt * top_k);
+    uint32_t* d_cn = cv.take<uint32_t>(qt);
+    uint64_t* d_f = fwords ? cv.take<uint64_t>(fwords) : nullptr;
+    cudaStream_t st = nullptr;
+    if (d_f) RBQ_CUDA(cudaMemcpyAsync(d_f, filter_bits, fwords * 8, cudaMemcpyHostToDevice, st));
+    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), st));
+    uint64_t launches = 0;
+    for (size_t q0 = 0; q0 < nq; q0 += qt) {
+        const size_t n = std::min(qt, nq - q0);
+        RBQ_CUDA(cudaMemcpyAsync(d_q, queries + q0 * dim, n * dim * 4, cudaMemcpyHostToDevice, st));
+        rc = search_device(h, d_q, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, qt, st, &launches);
+        if (rc) return rc;
+        RBQ_CUDA(cudaMemcpyAsync(ids + q0 * top_k, d_ids, n * top_k * 8, cudaMemcpyDeviceToHost, st));
+        RBQ_CUDA(cudaMemcpyAsync(scores + q0 * top_k, d_sc, n * top_k * 4, cudaMemcpyDeviceToHost, st));
+        RBQ_CUDA(cudaMemcpyAsync(counts + q0, d_cn, n * 4, cudaMemcpyDeviceToHost, st));
+        RBQ_CUDA(cudaStreamSynchronize(st));
+    }
+    h->last_stats.kernel_launches = launches;
+    return RBQ_OK;
+}
+
+int rbq_search_batch(const rbq_index* h, const float* queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
+                     uint64_t* ids, float* scores, uint32_t* counts) {
+    return rbq_search_batch_filtered(h, queries, nq, dim, top_k, nprobe, nullptr, 0, ids, scores, counts);
+}
+
+int rbq_merge_topk_device(const rbq_index* h, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids,
+                          const float* in_scores, const uint32_t* in_counts, uint64_t* out_ids, float* out_scores,
+                          uint32_t* out_counts, void* stream) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    DeviceGuard g(h->device);
+    return launch_merge(h->host.metric, nshards, nq, top_k, in_ids, in_scores, in_counts, out_ids, out_scores,
+                        out_counts, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- stage probes ------------------------------------------------------------------------------
+int rbq_debug_query_prep(const rbq_index* h, const float* queries, size_t nq, size_t dim, float* rotated, uint8_t* lut,
+                         float* scalars) {
+    size_t np = 1;
+    int rc = check_search_args(h, dim, 1, &np);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t D = h->dev.D;
+    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32) + 4096))) return rc;
+    Carver cv{(char*)h->ws};
+    float* d_q = cv.take<float>(nq * dim);
+    float* d_rot = cv.take<float>(nq * D);
+    uint8_t* d_lut = cv.take<uint8_t>(nq * D * 4);
+    QueryScalars* d_qs = cv.take<QueryScalars>(nq);
+    RBQ_CUDA(cudaMemcpy(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice));
+    if ((rc = launch_query_prep(h->dev, d_q, nq, d_rot, d_lut, d_qs, nullptr))) return rc;
+    if (rotated) RBQ_CUDA(cudaMemcpy(rotated, d_rot, nq * D * 4, cudaMemcpyDeviceToHost));
+    if (lut) RBQ_CUDA(cudaMemcpy(lut, d_lut, nq * D * 4, cudaMemcpyDeviceToHost));
+    if (scalars) RBQ_CUDA(cudaMemcpy(scalars, d_qs, nq * sizeof(QueryScalars), cudaMemcpyDeviceToHost));
+    RBQ_CUDA(cudaDeviceSynchronize());
+    return RBQ_OK;
+}
+
+int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t dim, size_t nprobe, uint32_t* probe_cids,
+                    float* probe_consts) {
+    int rc = check_search_args(h, dim, 1, &nprobe);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t D = h->dev.D, nl = h->dev.nlist;
+    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * 16) + 8192))) return rc;
+    Carver cv{(char*)h->ws};
+    float* d_q = cv.take<float>(nq * dim);
+    float* d_rot = cv.take<float>(nq * D);
+    uint8_t* d_lut = cv.take<uint8_t>(nq * D * 4);
+    QueryScalars* d_qs = cv.take<QueryScalars>(nq);
+    float* d_sc = cv.take<float>(nq * nl);
+    Probe* d_pr = cv.take<Probe>(nq * nprobe);
+    RBQ_CUDA(cudaMemcpy(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice));
+    if ((rc = launch_query_prep(h->dev, d_q, nq, d_rot, d_lut, d_qs, nullptr))) return rc;
+    if ((rc = launch_coarse_exact(h->dev, d_rot, nq, d_sc, nullptr))) return rc;
+    if ((rc = launch_probe_select(h->dev, d_rot, d_sc, nq, nprobe, d_pr, nullptr))) return rc;
+    std::vector<Probe> pr(nq * nprobe);
+    RBQ_CUDA(cudaMemcpy(pr.data(), d_pr, pr.size() * sizeof(Probe), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < pr.size(); ++i) {
+        probe_cids[i] = pr[i].cid;
+        probe_consts[3 * i] = pr[i].g_add;
+        probe_consts[3 * i + 1] = pr[i].g_error;
+        probe_consts[3 * i + 2] = pr[i].dot_qc;
+    }
+    return RBQ_OK;
+}
+
+int rbq_debug_scan_list(const rbq_index* h, const float* query, size_t dim, size_t cluster, uint32_t* accu, float* ip,
+                        float* est, float* lb, size_t cap_vectors) {
+    size_t np = 1;
+    int rc = check_search_args(h, dim, 1, &np);
+    if (rc) return rc;
+    if (cluster >= h->host.nlist) return fail(RBQ_INVALID_CONFIG, "cluster out of range");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t D = h->dev.D, nl = h->dev.nlist;
+    const size_t nv = h->host.list_n[cluster], nb = (nv + kBatch - 1) / kBatch, slots = nb * kBatch;
+    if (cap_vectors < slots) return fail(RBQ_INVALID_CONFIG, "output buffers too small");
+    if ((rc = ensure_ws(h, dim * 4 + D * 8 + 64 + nl * 4 + 64 + slots * 16 + 8192))) return rc;
+    Carver cv{(char*)h->ws};
+    float* d_q = cv.take<float>(dim);
+    float* d_rot = cv.take<float>(D);
+    uint8_t* d_lut = cv.take<uint8_t>(D * 4);
+    QueryScalars* d_qs = cv.take<QueryScalars>(1);
+    float* d_sc = cv.take<float>(nl);
+    Probe* d_pr = cv.take<Probe>(nl);
+    uint32_t* d_accu = cv.take<uint32_t>(slots + 1);
+    float* d_ip = cv.take<float>(slots + 1);
+    float* d_est = cv.take<float>(slots + 1);
+    float* d_lb = cv.take<float>(slots + 1);
+    RBQ_CUDA(cudaMemcpy(d_q, query, dim * 4, cudaMemcpyHostToDevice));
+    if ((rc = launch_query_prep(h->dev, d_q, 1, d_rot, d_lut, d_qs, nullptr))) return rc;
+    // constants of this list in the reference's float order: reuse the probe kernel over all lists
+    if (nl > probe_select_max_nprobe()) return fail(RBQ_INVALID_CONFIG, "debug probe needs nlist <= 4096");
+    if ((rc = launch_coarse_exact(h->dev, d_rot, 1, d_sc, nullptr))) return rc;
+    if ((rc = launch_probe_select(h->dev, d_rot, d_sc, 1, nl, d_pr, nullptr))) return rc;
+    std::vector<Probe> pr(nl);
+    RBQ_CUDA(cudaMemcpy(pr.data(), d_pr, nl * sizeof(Probe), cudaMemcpyDeviceToHost));
+    float g_add = 0, g_error = 0;
+    for (auto& p : pr)
+        if (p.cid == cluster) {
+            g_add = p.g_add;
+            g_error = p.g_error;
+        }
+    if (slots == 0) return RBQ_OK;
+    if ((rc = launch_scan_debug(h->dev, d_lut, d_qs, (uint32_t)cluster, g_add, g_error, d_accu, d_ip, d_est, d_lb, nullptr)))
+        return rc;
+    RBQ_CUDA(cudaMemcpy(accu, d_accu, slots * 4, cudaMemcpyDeviceToHost));
+    RBQ_CUDA(cudaMemcpy(ip, d_ip, slots * 4, cudaMemcpyDeviceToHost));
+    RBQ_CUDA(cudaMemcpy(est, d_est, slots * 4, cudaMemcpyDeviceToHost));
+    RBQ_CUDA(cudaMemcpy(lb, d_lb, slots * 4, cudaMemcpyDeviceToHost));
+    return RBQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// rbq_internal.h -- shared host/device declarations of librbq (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rbq.h"
+
+namespace rbq {
+
+constexpr int kBatch = 32;  // FASTSCAN_BATCH_SIZE (reference src/simd.rs:768)
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+#define RBQ_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return ::rbq::fail(RBQ_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e_) + \
+                                                   " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+// ---- host image of an index (what the RBQ1 v3 stream holds, lists concatenated) -------------
+struct HostIndex {
+    uint32_t dim = 0, D = 0;
+    int metric = 0, rot_type = 1, ex_bits = 0;
+    std::vector<uint8_t> rot_bytes;  // FHT: 4*D/8 flip bytes; Matrix: D*D f32 row-major
+    size_t nlist = 0;
+    uint64_t nvec_total = 0;         // vectors in the whole index (all shards)
+    int shard_rank = 0, shard_count = 1;
+    std::vector<float> centroids;    // nlist*D (rotated space)
+    std::vector<uint32_t> list_n_all;  // size of every list (owned or not)
+    std::vector<uint32_t> list_n;      // size of every list on this shard (0 if not owned)
+    std::vector<uint32_t> blk_off;     // nlist+1, in 32-vector blocks, owned lists only
+    std::vector<uint64_t> vec_off;     // nlist+1
+    std::vector<uint8_t> blocks;       // owned blocks, each 4D+384 bytes
+    std::vector<uint64_t> ids;
+    std::vector<uint8_t> ex;           // owned vectors * (D*ex_bits/8)
+    std::vector<float> f_add_ex, f_rescale_ex, delta, vl;
+    size_t block_stride() const { return (size_t)D * 4 + 384; }
+    size_t ex_stride() const { return ex_bits > 0 ? (size_t)D * ex_bits / 8 : 0; }
+};
+
+// format.cc
+uint32_t crc32_ieee(uint32_t crc, const uint8_t* p, size_t n);
+int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, HostIndex& out);
+void write_rbq1(const HostIndex& ix, std::vector<uint8_t>& out);
+void assign_shards(const std::vector<uint64_t>& list_bytes, int shard_count, std::vector<int>& owner);
+
+// ---- device view passed by value to kernels ---------------------------------------------------
+struct DevIndex {
+    int dim, D, metric, ex_bits, rot_type;
+    int trunc;        // FHT window (largest power of two <= dim)
+    float fac;        // 1/sqrt(trunc)
+    uint32_t nlist;
+    uint32_t block_stride;  // 4D+384
+    uint32_t ex_stride;     // D*ex_bits/8
+    const uint8_t* flip;    // 4*D/8
+    const float* matrix_t;  // Matrix rotator, TRANSPOSED (k-major) for coalesced reads
+    const float* centroids; // nlist*D
+    const uint32_t* list_n; // nlist
+    const uint32_t* blk_off;
+    const uint64_t* vec_off;
+    const uint8_t* blocks;
+    const uint64_t* ids;
+    const uint8_t* ex;
+    const float* f_add_ex;
+    const float* f_rescale_ex;
+};
+
+struct QueryScalars {  // one per query, written by the prep kernel
+    float delta, sum_vl, k1x, kbx, qnorm, sum_q, bscale, pad;
+};
+struct Probe {  // one per (query, probe rank), written by the probe kernel
+    uint32_t cid;
+    float g_add, g_error, dot_qc;
+};
+struct DevStats {
+    unsigned long long blocks, candidates, refined, admitted;
+};
+
+// kernels (each .cu exposes a launcher)
+int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
+                      QueryScalars* d_qs, cudaStream_t st);
+int launch_coarse_exact(const DevIndex& ix, const float* d_rot, size_t nq, float* d_scores, cudaStream_t st);
+int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_scores, size_t nq, size_t nprobe,
+                        Probe* d_probes, cudaStream_t st);
+int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
+                const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter,
+                size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
+                cudaStream_t st);
+int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, uint32_t cluster,
+                      float g_add, float g_error, uint32_t* d_accu, float* d_ip, float* d_est, float* d_lb,
+                      cudaStream_t st);
+int launch_merge(int metric, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids, const float* in_scores,
+                 const uint32_t* in_counts, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                 cudaStream_t st);
+size_t probe_select_max_nprobe();
+size_t scan_max_topk();
+
+// build.cu: quantise n vectors (already grouped by list) on the device.
+struct BuildOut {  // device arrays, one entry per vector in list-concatenated order
+    uint8_t* bin_rows;  // n * D/8, MSB-first row-major sign codes
+    uint8_t* ex;        // n * ex_stride
+    float *f_add, *f_rescale, *f_error, *f_add_ex, *f_rescale_ex, *delta, *vl;
+};
+int launch_build_quantize(const DevIndex& ix, const float* d_rot, const uint32_t* d_list_of, size_t n,
+                          const float* d_cents, float t_const, const double* d_t_per_vec, BuildOut out,
+                          cudaStream_t st);
+int launch_rotate_only(const DevIndex& ix, const float* d_in, size_t n, float* d_out, cudaStream_t st);
+double best_rescale_factor_host(const float* o_abs, size_t dim, int ex_bits);
+float const_scaling_factor_host(size_t D, int ex_bits, uint64_t seed);
+
+}  // namespace rbq
+
+// the opaque handle
+struct rbq_index {
+    rbq::HostIndex host;  // metadata + (small) host-side arrays; bulk arrays are released after upload
+    rbq::DevIndex dev{};
+    int device = 0;
+    std::vector<void*> allocations;  // device allocations owned by the handle
+    // workspace (grown on demand, guarded by mu)
+    mutable std::mutex mu;
+    mutable void* ws = nullptr;
+    mutable size_t ws_bytes = 0;
+    mutable rbq::DevStats* d_stats = nullptr;
+    mutable rbq_search_stats last_stats{};
+    mutable cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false;
+    int coarse_mode = 0;
+};

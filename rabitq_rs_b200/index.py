@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's public search API over the C ABI.
+
+`IvfRabitqIndex` follows the pyo3 class of the reference (src/python_bindings.rs:338-720:
+constructor(dimension, metric), fit, fit_with_clusters, query, batch_query, save, load, __len__,
+cluster_count) and adds the typed entry points the Rust API has (`search`, `batch_search`,
+`search_filtered` with `SearchParams`, src/ivf.rs:1705-1752) returning u64 ids (the pyo3 class
+squeezes ids through f32 and loses precision above 2^24).
+
+Everything here is plumbing around librbq.so; there is no Python or CPU implementation of the
+search path in this package.
+"""
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+
+
+class Metric(enum.IntEnum):  # reference src/lib.rs:31-37
+    L2 = 0
+    InnerProduct = 1
+
+
+class RotatorType(enum.IntEnum):  # reference src/rotation.rs:8-15
+    MatrixRotator = 0
+    FhtKacRotator = 1
+
+
+@dataclass(frozen=True)
+class SearchParams:  # reference src/ivf.rs:22-26
+    top_k: int
+    nprobe: int
+
+
+class RabitqError(Exception):  # reference src/lib.rs:39-57
+    code = -1
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        if code is not None:
+            self.code = code
+
+
+class DimensionMismatch(RabitqError):
+    code = _ffi.DIMENSION_MISMATCH
+
+
+class InvalidConfig(RabitqError):
+    code = _ffi.INVALID_CONFIG
+
+
+class EmptyIndex(RabitqError):
+    code = _ffi.EMPTY_INDEX
+
+
+class IoError(RabitqError):
+    code = _ffi.IO
+
+
+class InvalidPersistence(RabitqError):
+    code = _ffi.INVALID_PERSISTENCE
+
+
+class CudaError(RabitqError):
+    code = _ffi.CUDA_ERROR
+
+
+_ERRORS = {c.code: c for c in (DimensionMismatch, InvalidConfig, EmptyIndex, IoError, InvalidPersistence, CudaError)}
+
+
+def _check(rc):
+    if rc != 0:
+        raise _ERRORS.get(rc, RabitqError)(_ffi.last_error(), rc)
+
+
+def _metric_from_str(metric):
+    if isinstance(metric, (Metric, int)):
+        return Metric(int(metric))
+    if metric in ("euclidean", "l2"):
+        return Metric.L2
+    if metric in ("angular", "ip", "inner_product"):
+        return Metric.InnerProduct
+    raise ValueError(f"Invalid metric: {metric}. Use 'euclidean' or 'angular'")
+
+
+def _rotator_from_str(rt):
+    if isinstance(rt, (RotatorType, int)):
+        return RotatorType(int(rt))
+    if rt in ("fht", "random"):
+        return RotatorType.FhtKacRotator
+    if rt in ("matrix", "identity"):
+        return RotatorType.MatrixRotator
+    raise ValueError(f"Invalid rotator_type: {rt}. Use 'fht', 'random', 'matrix', or 'identity'")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class IvfRabitqIndex:
+    """Device-resident IVF+RaBitQ index (one GPU, or one shard of a list-sharded index)."""
+
+    def __init__(self, dimension=None, metric="euclidean", device=0):
+        self._h = None
+        self.dimension = dimension
+        self.metric = _metric_from_str(metric)
+        self.device = int(device)
+
+    # ---- lifetime -------------------------------------------------------------------------
+    def _adopt(self, handle):
+        self.close()
+        self._h = handle
+        L = _ffi.lib()
+        self.dimension = int(L.rbq_index_dim(handle))
+        self.metric = Metric(L.rbq_index_metric(handle))
+
+    def close(self):
+        if self._h is not None:
+            _ffi.lib().rbq_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _need(self):
+        if self._h is None:
+            raise RuntimeError("Index not built yet. Call fit() first.")
+        return self._h
+
+    # ---- persistence (load_from_path / save_to_path) -----------------------------------------
+    @classmethod
+    def load_from_path(cls, path, device=0, shard_rank=0, shard_count=1):
+        self = cls(device=device)
+        self.load(path, shard_rank, shard_count)
+        return self
+
+    @classmethod
+    def load_from_bytes(cls, blob, device=0, shard_rank=0, shard_count=1):
+        self = cls(device=device)
+        buf = np.frombuffer(bytes(blob), np.uint8)
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_index_load_mem(_ptr(buf), buf.size, self.device, shard_rank, shard_count, C.byref(h)))
+        self._adopt(h)
+        return self
+
+    def load(self, path, shard_rank=0, shard_count=1):
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_index_load(str(path).encode(), self.device, shard_rank, shard_count, C.byref(h)))
+        self._adopt(h)
+
+    def save(self, path):
+        _check(_ffi.lib().rbq_index_save(self._need(), str(path).encode()))
+
+    def save_to_bytes(self):
+        n = C.c_size_t()
+        _check(_ffi.lib().rbq_index_save_mem(self._need(), None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _check(_ffi.lib().rbq_index_save_mem(self._need(), _ptr(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
+
+    # ---- build (train_with_clusters / train) ----------------------------------------------------
+    def fit_with_clusters(self, data, centroids, assignments, total_bits=7, rotator_type="random", seed=42,
+                          faster_config=True, rotator_state=None):
+        data = np.ascontiguousarray(data, np.float32)
+        centroids = np.ascontiguousarray(centroids, np.float32)
+        assignments = np.ascontiguousarray(assignments, np.uint32)
+        if data.ndim != 2 or centroids.ndim != 2:
+            raise ValueError("Data and centroids must be 2D arrays")
+        if self.dimension is not None and (data.shape[1] != self.dimension or centroids.shape[1] != self.dimension):
+            raise ValueError(f"Data/centroids dimension must match expected {self.dimension}")
+        if data.shape[0] != assignments.shape[0]:
+            raise ValueError("Data and assignments must have same length")
+        rt = _rotator_from_str(rotator_type)
+        rs = None if rotator_state is None else np.ascontiguousarray(rotator_state, np.uint8)
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_index_build(_ptr(data), data.shape[0], data.shape[1], _ptr(centroids), centroids.shape[0],
+                                          _ptr(assignments), int(total_bits), int(self.metric), int(rt), int(seed),
+                                          int(bool(faster_config)), _ptr(rs), self.device, C.byref(h)))
+        self._adopt(h)
+
+    def fit(self, data, nlist, total_bits=7, rotator_type="random", seed=42, faster_config=True, kmeans_iters=10):
+        """k-means (torch, on the GPU) followed by fit_with_clusters.  The reference's k-means
+        (src/kmeans.rs) is outside the drop-in scope; any clustering yields a valid index."""
+        from .kmeans import kmeans_gpu
+
+        data = np.ascontiguousarray(data, np.float32)
+        if data.ndim != 2:
+            raise ValueError("Data must be 2D array (N x D)")
+        cents, assign = kmeans_gpu(data, nlist, iters=kmeans_iters, seed=seed, device=self.device)
+        self.fit_with_clusters(data, cents, assign, total_bits, rotator_type, seed, faster_config)
+
+    # ---- accessors ----------------------------------------------------------------------------
+    def __len__(self):
+        return int(_ffi.lib().rbq_index_len(self._need()))
+
+    def local_len(self):
+        return int(_ffi.lib().rbq_index_local_len(self._need()))
+
+    def cluster_count(self):
+        return int(_ffi.lib().rbq_index_cluster_count(self._need()))
+
+    @property
+    def padded_dim(self):
+        return int(_ffi.lib().rbq_index_padded_dim(self._need()))
+
+    @property
+    def ex_bits(self):
+        return int(_ffi.lib().rbq_index_ex_bits(self._need()))
+
+    @property
+    def handle(self):
+        return self._need()
+
+    def __repr__(self):
+        return (f"IvfRabitqIndex(dimension={self.dimension}, metric={self.metric.name}, built={self._h is not None}, "
+                f"clusters={self.cluster_count() if self._h is not None else 0})")
+
+    # ---- search ---------------------------------------------------------------------------------
+    def batch_search(self, queries, params, filter_bits=None):
+        """IvfRabitqIndex::batch_search: returns (ids[nq,k] u64, scores[nq,k] f32, counts[nq] u32)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, dim = q.shape
+        k = int(params.top_k)
+        ids = np.full((nq, max(k, 1)), np.iinfo(np.uint64).max, np.uint64)
+        scores = np.zeros((nq, max(k, 1)), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        L = _ffi.lib()
+        if filter_bits is None:
+            rc = L.rbq_search_batch(self._need(), _ptr(q), nq, dim, k, int(params.nprobe), _ptr(ids), _ptr(scores),
+                                    _ptr(counts))
+        else:
+            fb = np.ascontiguousarray(filter_bits, np.uint64)
+            rc = L.rbq_search_batch_filtered(self._need(), _ptr(q), nq, dim, k, int(params.nprobe), _ptr(fb),
+                                             fb.size * 64, _ptr(ids), _ptr(scores), _ptr(counts))
+        _check(rc)
+        return ids[:, :k], scores[:, :k], counts
+
+    def search(self, query, params):
+        """IvfRabitqIndex::search: list of (id, score)."""
+        ids, scores, counts = self.batch_search(np.asarray(query, np.float32)[None, :], params)
+        return [(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+    def search_filtered(self, query, params, allowed_ids):
+        """IvfRabitqIndex::search_filtered; `allowed_ids` plays the RoaringBitmap (u32 ids)."""
+        fb = ids_to_bitset(allowed_ids)
+        ids, scores, counts = self.batch_search(np.asarray(query, np.float32)[None, :], params, fb)
+        return [(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+    def query(self, query, k, nprobe=1):
+        """pyo3 `query`: (k, 2) float32 array [id, score] (src/python_bindings.rs:536-583)."""
+        q = np.asarray(query, np.float32)
+        if q.ndim != 1 or (self.dimension is not None and q.shape[0] != self.dimension):
+            raise ValueError(f"Query dimension {q.shape[-1]} does not match expected {self.dimension}")
+        return self.batch_query(q[None, :], k, nprobe)[0]
+
+    def batch_query(self, queries, k, nprobe=1):
+        """pyo3 `batch_query`: list of (n_i, 2) float32 arrays (src/python_bindings.rs:593-665)."""
+        q = np.asarray(queries, np.float32)
+        if q.ndim != 2:
+            raise ValueError("Queries must be 2D array (N x D)")
+        if self.dimension is not None and q.shape[1] != self.dimension:
+            raise ValueError(f"Query dimension {q.shape[1]} does not match expected {self.dimension}")
+        ids, scores, counts = self.batch_search(q, SearchParams(k, nprobe))
+        out = []
+        for i in range(q.shape[0]):
+            n = int(counts[i])
+            out.append(np.stack([ids[i, :n].astype(np.float32), scores[i, :n]], axis=1))
+        return out
+
+    # device-resident entry (torch tensors on this index's device; no host copies, no sync)
+    def batch_search_device(self, queries, top_k, nprobe, out_ids, out_scores, out_counts, filter_bits=None, stream=None):
+        import torch
+
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        nq, dim = queries.shape
+        st = C.c_void_p(stream) if stream else C.c_void_p(torch.cuda.current_stream(queries.device).cuda_stream)
+        fb, fn = (None, 0) if filter_bits is None else (C.c_void_p(filter_bits.data_ptr()), filter_bits.numel() * 64)
+        _check(_ffi.lib().rbq_search_batch_device(self._need(), C.c_void_p(queries.data_ptr()), nq, dim, int(top_k),
+                                                  int(nprobe), fb, fn, C.c_void_p(out_ids.data_ptr()),
+                                                  C.c_void_p(out_scores.data_ptr()), C.c_void_p(out_counts.data_ptr()), st))
+
+    def stats(self):
+        s = _ffi.SearchStats()
+        _check(_ffi.lib().rbq_last_search_stats(self._need(), C.byref(s)))
+        return {f: getattr(s, f) for f, _ in _ffi.SearchStats._fields_}
+
+    def set_profiling(self, on):
+        _check(_ffi.lib().rbq_set_profiling(self._need(), int(bool(on))))
+
+    def set_coarse_mode(self, mode):
+        _check(_ffi.lib().rbq_set_coarse_mode(self._need(), int(mode)))
+
+    # ---- stage probes (tests) ---------------------------------------------------------------------
+    def debug_query_prep(self, queries):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq, dim = q.shape
+        D = self.padded_dim
+        rot = np.empty((nq, D), np.float32)
+        lut = np.empty((nq, 4 * D), np.uint8)
+        sc = np.empty((nq, 8), np.float32)
+        _check(_ffi.lib().rbq_debug_query_prep(self._need(), _ptr(q), nq, dim, _ptr(rot), _ptr(lut), _ptr(sc)))
+        return rot, lut, sc
+
+    def debug_probe(self, queries, nprobe):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq, dim = q.shape
+        npb = min(max(int(nprobe), 1), self.cluster_count())
+        cids = np.empty((nq, npb), np.uint32)
+        consts = np.empty((nq, npb, 3), np.float32)
+        _check(_ffi.lib().rbq_debug_probe(self._need(), _ptr(q), nq, dim, npb, _ptr(cids), _ptr(consts)))
+        return cids, consts
+
+    def debug_scan_list(self, query, cluster, list_len):
+        q = np.ascontiguousarray(query, np.float32)
+        slots = (list_len + 31) // 32 * 32
+        accu = np.zeros(max(slots, 1), np.uint32)
+        ip, est, lb = (np.zeros(max(slots, 1), np.float32) for _ in range(3))
+        _check(_ffi.lib().rbq_debug_scan_list(self._need(), _ptr(q), q.size, int(cluster), _ptr(accu), _ptr(ip),
+                                              _ptr(est), _ptr(lb), max(slots, 1)))
+        return accu[:slots], ip[:slots], est[:slots], lb[:slots]
+
+
+def ids_to_bitset(allowed_ids, nbits=None):
+    """Dense u64 bitset over u32 ids (the C ABI's stand-in for RoaringBitmap)."""
+    a = np.asarray(list(allowed_ids) if not isinstance(allowed_ids, np.ndarray) else allowed_ids, np.uint64)
+    n = int(nbits if nbits is not None else (int(a.max()) + 1 if a.size else 0))
+    words = np.zeros((n + 63) // 64, np.uint64)
+    if a.size:
+        np.bitwise_or.at(words, (a // 64).astype(np.int64), np.uint64(1) << (a % np.uint64(64)))
+    return words

@@ -1,0 +1,275 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical index
+bytes and queries.  Bar (BASELINE.json north_star): integer accumulations and probed-list
+selection bit-exact; estimated distances within 1e-5 relative (asserted bit-exact wherever the
+kernel reproduces the reference's float order); top-k ids identical except documented near-ties."""
+import numpy as np
+import pytest
+
+from helpers import assert_results_match, oracle_index
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star tolerance for estimated distances (relative)
+
+
+@pytest.fixture(scope="module")
+def rbq():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import rabitq_rs_b200 as r
+
+    return r
+
+
+def _load(rbq, blob, **kw):
+    return rbq.IvfRabitqIndex.load_from_bytes(blob, **kw)
+
+
+def _queries(data, nq, seed):
+    rng = np.random.default_rng(seed)
+    base = data[rng.integers(0, data.shape[0], nq)]
+    return (base + 0.05 * rng.standard_normal(base.shape)).astype(np.float32)
+
+
+GEOMS = [  # (n, dim, nlist, bits, metric, rotator)
+    (600, 128, 8, 7, 0, 1),   # power-of-two FHT
+    (600, 960, 8, 3, 0, 1),   # GIST geometry: trunc 512, window start 448
+    (600, 768, 8, 7, 1, 1),   # trunc 512, start 256, inner product
+    (600, 100, 8, 7, 0, 1),   # padded 128, trunc 64
+    (400, 24, 8, 1, 1, 1),    # padded 64, 1-bit
+    (400, 32, 8, 3, 0, 0),    # MatrixRotator
+    (600, 1536, 4, 3, 0, 1),  # > 1024 dims: wide (32-bit) reduction with u16 wrap semantics
+]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_query_prep_bit_exact(rbq, oracle, geom):
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = _queries(data, 9, 1)
+    q[0] = 0.0  # degenerate: delta == 0 -> all-zero LUT
+    rot_g, lut_g, sc_g = gix.debug_query_prep(q)
+    for i in range(q.shape[0]):
+        d = oix.search_dump(q[i], 5, 4)
+        assert np.array_equal(rot_g[i].view(np.uint32), d["rotated"].view(np.uint32)), "rotation not bit-exact"
+        assert np.array_equal(lut_g[i], d["lut"]), "LUT bytes differ"
+        exp = np.array([d["delta"], d["sum_vl"], d["k1x"], d["kbx"], d["qnorm"], d["sum_q"]], np.float32)
+        assert np.array_equal(sc_g[i, :6].view(np.uint32), exp.view(np.uint32)), "query scalars not bit-exact"
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_probe_selection_bit_exact(rbq, oracle, geom):
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = _queries(data, 7, 2)
+    for nprobe in (1, 3, nlist):
+        cids, consts = gix.debug_probe(q, nprobe)
+        for i in range(q.shape[0]):
+            d = oix.search_dump(q[i], 5, nprobe)
+            assert np.array_equal(cids[i], d["probe"]), "probed lists / order differ"
+            assert np.array_equal(consts[i].view(np.uint32), d["probe_f"].view(np.uint32)), "g_add/g_error/dot_qc not bit-exact"
+
+
+def test_probe_selection_ties_break_on_cluster_id(rbq, oracle):
+    # duplicate centroids -> equal scores; the reference orders ties by cluster id (ivf.rs:1808-1823)
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((400, 64)).astype(np.float32)
+    cents = np.repeat(rng.standard_normal((4, 64)).astype(np.float32), 4, axis=0)  # 16 lists, 4 distinct centroids
+    assign = (np.arange(400) % 16).astype(np.uint32)
+    for metric in (0, 1):
+        oix = orc.Index.train_with_clusters(data, cents, assign, 3, metric)
+        gix = _load(rbq, oix.save_bytes())
+        for nprobe in (2, 5, 9, 16):
+            cids, _ = gix.debug_probe(data[:6], nprobe)
+            for i in range(6):
+                assert np.array_equal(cids[i], oix.search_dump(data[i], 3, nprobe)["probe"])
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_fastscan_accumulate_and_distances(rbq, oracle, geom):
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = _queries(data, 1, 3)[0]
+    d = oix.search_dump(q, 5, nlist)
+    D = oix.padded_dim
+    for c in (0, nlist - 1):
+        nv = oix.list_len(c)
+        accu, ip, est, lb = gix.debug_scan_list(q, c, nv)
+        blocks = oix.list_blocks(c).reshape(-1, 4 * D + 384)
+        rank = int(np.where(d["probe"] == c)[0][0])
+        g_add, g_err = d["probe_f"][rank, 0], d["probe_f"][rank, 1]
+        for b in range(blocks.shape[0]):
+            ea = oracle.accumulate_block(blocks[b, :4 * D], d["lut"], D)
+            assert np.array_equal(accu[b * 32:(b + 1) * 32].astype(np.uint16), ea), "integer accumulation differs"
+            fac = blocks[b, 4 * D:].view(np.float32)
+            eip, eest, elb = oracle.batch_distances(ea, d["delta"], d["sum_vl"], fac[:32], fac[32:64], fac[64:], g_add, g_err, d["k1x"])
+            for got, exp in ((ip, eip), (est, eest), (lb, elb)):
+                assert np.array_equal(got[b * 32:(b + 1) * 32].view(np.uint32), exp.view(np.uint32))
+
+
+SEARCH_CASES = [  # (n, dim, nlist, bits, metric, rot, kind, k, nprobe)
+    (10000, 128, 256, 7, 0, 1, "uniform01", 10, 32),   # BASELINE config 1 (README quickstart)
+    (10000, 128, 256, 3, 0, 1, "uniform01", 10, 32),
+    (10000, 128, 256, 1, 0, 1, "uniform01", 10, 32),
+    (4000, 96, 64, 7, 1, 1, "clustered", 10, 16),      # inner product, normalised, non-pow2 FHT
+    (3000, 960, 32, 3, 0, 1, "clustered", 10, 8),      # GIST geometry
+    (3000, 960, 32, 7, 0, 1, "clustered", 100, 8),
+    (2000, 32, 16, 7, 0, 0, "uniform11", 5, 16),       # MatrixRotator
+    (2000, 1280, 16, 3, 0, 1, "clustered", 10, 4),     # wide path
+]
+
+
+@pytest.mark.parametrize("case", SEARCH_CASES)
+def test_search_end_to_end(rbq, oracle, case):
+    n, dim, nlist, bits, metric, rot, kind, k, nprobe = case
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind=kind)
+    gix = _load(rbq, blob)
+    assert len(gix) == n and gix.cluster_count() == nlist
+    q = np.concatenate([data[:32], _queries(data, 224, 4)])
+    exp = oix.search_batch(q, k, nprobe, want_diag=True)
+    got = gix.batch_search(q, rbq.SearchParams(k, nprobe))
+    exact = assert_results_match(got, exp[:3], TOL, f"case {case}")
+    assert exact == q.shape[0], f"only {exact}/{q.shape[0]} queries bit-identical"
+    st = gix.stats()
+    assert st["blocks_scanned"] == int(exp[3][:, 3].sum())           # same lists, same blocks
+    assert st["admitted"] == int(exp[3][:, 0].sum()) or bits > 1     # estimated (+ non-finite) in reference order
+    assert st["refined"] >= int(exp[3][:, 2].sum()) or bits == 1     # refined set is a superset
+
+
+def test_search_edge_cases(rbq, oracle):
+    data, oix, blob = oracle_index(2000, 64, 16, 7, 0, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = data[:5]
+    P = rbq.SearchParams
+    ids, sc, cnt = gix.batch_search(q, P(0, 4))
+    assert np.all(cnt == 0)                                           # top_k == 0 (ivf.rs:1792)
+    assert_results_match(gix.batch_search(q, P(5, 0)), oix.search_batch(q, 5, 1))            # nprobe clamps up
+    assert_results_match(gix.batch_search(q, P(5, 10 ** 6)), oix.search_batch(q, 5, 16))     # nprobe clamps down
+    assert_results_match(gix.batch_search(q, P(300, 2)), oix.search_batch(q, 300, 2))        # fewer than k results
+    with pytest.raises(rbq.DimensionMismatch) as e:
+        gix.batch_search(np.zeros((2, 65), np.float32), P(5, 4))
+    assert "expected 64, got 65" in str(e.value)
+    with pytest.raises(rbq.InvalidConfig):
+        gix.batch_search(q, P(5000, 4))
+    assert gix.search(q[0], P(3, 4))[0][0] == int(oix.search_batch(q[:1], 3, 4)[0][0, 0])
+    r = gix.batch_query(q, 4, 8)                                      # pyo3 surface
+    assert len(r) == 5 and r[0].shape == (4, 2) and r[0].dtype == np.float32
+    one = gix.query(q[1], 4, 8)
+    assert np.array_equal(one, r[1])
+    nanq = q.copy()
+    nanq[0, 3] = np.nan                                               # NaN query -> no finite distance -> empty
+    ids, sc, cnt = gix.batch_search(nanq, P(5, 4))
+    assert cnt[0] == 0 and cnt[1] == oix.search_batch(q[1:2], 5, 4)[2][0]
+
+
+def test_empty_index_and_empty_lists(rbq, oracle):
+    import struct
+    import zlib
+
+    # header-only stream: zero clusters, zero vectors -> loads, search reports EmptyIndex
+    body = struct.pack("<IIBBBBQQQ", 16, 64, 0, 1, 6, 7, 0, 0, 32) + bytes(32)
+    blob = b"RBQ1" + struct.pack("<I", 3) + body + struct.pack("<I", zlib.crc32(body))
+    gix = _load(rbq, blob)
+    assert len(gix) == 0
+    with pytest.raises(rbq.EmptyIndex):
+        gix.batch_search(np.zeros((1, 16), np.float32), rbq.SearchParams(5, 4))
+    # lists with zero vectors and ragged tails (n not a multiple of 32)
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((333, 48)).astype(np.float32)
+    cents = rng.standard_normal((12, 48)).astype(np.float32)
+    assign = rng.integers(0, 9, 333).astype(np.uint32)  # lists 9..11 stay empty
+    oix = orc.Index.train_with_clusters(data, cents, assign, 7, 0)
+    gix = _load(rbq, oix.save_bytes())
+    q = data[:40]
+    assert_results_match(gix.batch_search(q, rbq.SearchParams(7, 12)), oix.search_batch(q, 7, 12))
+
+
+def test_filtered_search(rbq, oracle):
+    data, oix, blob = oracle_index(3000, 64, 16, 7, 0, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = _queries(data, 64, 9)
+    allow = np.arange(0, 3000, 3)
+    bits = rbq.ids_to_bitset(allow, 3000)
+    got = gix.batch_search(q, rbq.SearchParams(10, 16), filter_bits=bits)
+    exp = oix.search_batch(q, 10, 16, filter_bits=bits)
+    assert assert_results_match(got, exp) == 64
+    assert np.all(got[0][got[0] != np.iinfo(np.uint64).max] % 3 == 0)
+    got = gix.batch_search(q, rbq.SearchParams(10, 16), filter_bits=np.zeros_like(bits))
+    assert np.all(got[2] == 0)                                        # empty filter -> empty results
+    res = gix.search_filtered(q[0], rbq.SearchParams(5, 16), allow)
+    assert [r[0] for r in res] == exp[0][0, :5].tolist()
+
+
+def test_persistence_roundtrip_through_device(rbq, oracle):
+    for bits, metric in ((7, 1), (3, 0), (1, 0)):
+        data, oix, blob = oracle_index(500, 24, 32, bits, metric, seed=7412, faster=False, kind="uniform11")
+        gix = _load(rbq, blob)
+        assert gix.save_to_bytes() == blob                            # byte-identical RBQ1 v3 stream
+        again = _load(rbq, gix.save_to_bytes())
+        a = gix.batch_search(data[:5], rbq.SearchParams(5, 12))
+        b = again.batch_search(data[:5], rbq.SearchParams(5, 12))
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))       # tests.rs:393-431
+
+
+def test_sharded_lists_and_device_merge(rbq, oracle):
+    import ctypes as C
+
+    import torch
+
+    from rabitq_rs_b200 import _ffi
+
+    data, oix, blob = oracle_index(6000, 64, 64, 7, 0, kind="clustered")
+    full = _load(rbq, blob)
+    nsh, k, nprobe = 4, 10, 16
+    shards = [_load(rbq, blob, shard_rank=r, shard_count=nsh) for r in range(nsh)]
+    assert sum(s.local_len() for s in shards) == 6000 and all(len(s) == 6000 for s in shards)
+    sizes = [s.local_len() for s in shards]
+    assert max(sizes) - min(sizes) < 0.1 * 6000 / nsh                 # size-balanced
+    q = _queries(data, 200, 11)
+    dq = torch.from_numpy(q).cuda()
+    ids = torch.empty((nsh, 200, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((nsh, 200, k), dtype=torch.float32, device="cuda")
+    cn = torch.empty((nsh, 200), dtype=torch.int32, device="cuda")
+    for r, s in enumerate(shards):
+        s.batch_search_device(dq, k, nprobe, ids[r], sc[r], cn[r])
+    oi = torch.empty((200, k), dtype=torch.int64, device="cuda")
+    os_ = torch.empty((200, k), dtype=torch.float32, device="cuda")
+    oc = torch.empty(200, dtype=torch.int32, device="cuda")
+    rc = _ffi.lib().rbq_merge_topk_device(full.handle, nsh, 200, k, C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                          C.c_void_p(cn.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(os_.data_ptr()),
+                                          C.c_void_p(oc.data_ptr()), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    exp = full.batch_search(q, rbq.SearchParams(k, nprobe))
+    gid = oi.cpu().numpy().astype(np.uint64)
+    # per-shard thresholds can admit bound-violating candidates the single sequence skipped (class D2):
+    # results must agree on (almost) every id and never be worse than the single-GPU answer
+    agree = np.mean([len(set(gid[i]) & set(exp[0][i])) / k for i in range(200)])
+    assert agree >= 0.995
+    assert np.all(os_.cpu().numpy() <= exp[1] + 1e-6)
+    assert np.array_equal(oc.cpu().numpy().astype(np.uint32), exp[2])
+
+
+def test_device_resident_entry_matches_host_entry(rbq, oracle):
+    import torch
+
+    data, oix, blob = oracle_index(10000, 128, 256, 7, 0, kind="uniform01")
+    gix = _load(rbq, blob)
+    q = _queries(data, 300, 12)
+    host = gix.batch_search(q, rbq.SearchParams(10, 32))
+    dq = torch.from_numpy(q).cuda()
+    ids = torch.empty((300, 10), dtype=torch.int64, device="cuda")
+    sc = torch.empty((300, 10), dtype=torch.float32, device="cuda")
+    cn = torch.empty(300, dtype=torch.int32, device="cuda")
+    gix.batch_search_device(dq, 10, 32, ids, sc, cn)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy().astype(np.uint64), host[0])
+    assert np.array_equal(sc.cpu().numpy(), host[1])
