@@ -101,8 +101,8 @@ int upload_index(rbq_index* h) {
     std::vector<float>().swap(hi.f_add_ex);
     std::vector<float>().swap(hi.f_rescale_ex);
     void* st = nullptr;
-    RBQ_CUDA(cudaMalloc(&st, sizeof(DevStats)));
-    RBQ_CUDA(cudaMemset(st, 0, sizeof(DevStats)));
+    RBQ_CUDA(cudaMalloc(&st, sizeof(DevStats) + 64));
+    RBQ_CUDA(cudaMemset(st, 0, sizeof(DevStats) + 64));
     h->allocations.push_back(st);
     h->d_stats = reinterpret_cast<DevStats*>(st);
     return RBQ_OK;
@@ -176,7 +176,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         if ((rc = launch_probe_select(ix, d_rot, d_sc, n, nprobe, d_pr, st))) return rc;
         if (h->profiling) cudaEventRecord(h->ev[3], st);
         if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                              d_scores + q0 * top_k, d_counts + q0, h->d_stats, st)))
+                              d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), st)))
             return rc;
         *launches += 4;
         if (h->profiling) {
@@ -465,7 +465,7 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     const size_t D = h->dev.D, nl = h->dev.nlist;
-    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * 16) + 8192))) return rc;
+    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * sizeof(Probe)) + 8192))) return rc;
     Carver cv{(char*)h->ws};
     float* d_q = cv.take<float>(nq * dim);
     float* d_rot = cv.take<float>(nq * D);
@@ -499,7 +499,7 @@ int rbq_debug_scan_list(const rbq_index* h, const float* query, size_t dim, size
     const size_t D = h->dev.D, nl = h->dev.nlist;
     const size_t nv = h->host.list_n[cluster], nb = (nv + kBatch - 1) / kBatch, slots = nb * kBatch;
     if (cap_vectors < slots) return fail(RBQ_INVALID_CONFIG, "output buffers too small");
-    if ((rc = ensure_ws(h, dim * 4 + D * 8 + 64 + nl * 4 + 64 + slots * 16 + 8192))) return rc;
+    if ((rc = ensure_ws(h, dim * 4 + D * 8 + 64 + nl * 4 + nl * sizeof(Probe) + slots * 16 + 16384))) return rc;
     Carver cv{(char*)h->ws};
     float* d_q = cv.take<float>(dim);
     float* d_rot = cv.take<float>(D);

@@ -683,8 +683,8 @@ extern "C" int rbq_index_build(const float* data, size_t n, size_t dim, const fl
     dv.f_add_ex = d_fae;
     dv.f_rescale_ex = d_fre;
     void* stp = nullptr;
-    RBQ_CUDA(cudaMalloc(&stp, sizeof(DevStats)));
-    RBQ_CUDA(cudaMemset(stp, 0, sizeof(DevStats)));
+    RBQ_CUDA(cudaMalloc(&stp, sizeof(DevStats) + 64));
+    RBQ_CUDA(cudaMemset(stp, 0, sizeof(DevStats) + 64));
     h->allocations.push_back(stp);
     h->d_stats = reinterpret_cast<DevStats*>(stp);
     for (auto& e : h->ev) cudaEventCreate(&e);

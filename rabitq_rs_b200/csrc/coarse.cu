@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, 
             pr.g_add = desc ? -ip : l2;
             pr.g_error = sqrtf(l2);
             pr.dot_qc = ip;
+            pr.nv = ix.list_n[cid];
+            pr.blk_off = ix.blk_off[cid];
+            pr.vec_off = ix.vec_off[cid];
             probes[q * (size_t)nprobe + r] = pr;
         }
     }

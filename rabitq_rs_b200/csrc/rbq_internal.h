@@ -75,9 +75,12 @@ struct DevIndex {
 struct QueryScalars {  // one per query, written by the prep kernel
     float delta, sum_vl, k1x, kbx, qnorm, sum_q, bscale, pad;
 };
-struct Probe {  // one per (query, probe rank), written by the probe kernel
+struct Probe {  // one per (query, probe rank), written by the probe kernel (32 bytes)
     uint32_t cid;
     float g_add, g_error, dot_qc;
+    uint32_t nv;        // vectors of the list on this shard (0: empty or owned elsewhere)
+    uint32_t blk_off;   // first 32-vector block of the list
+    uint64_t vec_off;   // first vector of the list
 };
 struct DevStats {
     unsigned long long blocks, candidates, refined, admitted;
@@ -92,7 +95,7 @@ int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_s
 int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
                 const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter,
                 size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
-                cudaStream_t st);
+                unsigned int* d_work_counter, cudaStream_t st);
 int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, uint32_t cluster,
                       float g_add, float g_error, uint32_t* d_accu, float* d_ip, float* d_est, float* d_lb,
                       cudaStream_t st);
@@ -127,7 +130,8 @@ struct rbq_index {
     mutable std::mutex mu;
     mutable void* ws = nullptr;
     mutable size_t ws_bytes = 0;
-    mutable rbq::DevStats* d_stats = nullptr;
+    mutable rbq::DevStats* d_stats = nullptr;     // followed by the scan kernel's work counter
+    unsigned int* work_counter() const { return reinterpret_cast<unsigned int*>(d_stats + 1); }
     mutable rbq_search_stats last_stats{};
     mutable cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool profiling = false;

@@ -6,21 +6,28 @@
 //   K10  packed ex-code dot    ip_packed_ex2_f32 / ip_packed_ex6_f32 (AVX2 lane order) (src/simd.rs:1722-1825)
 //   K11  top-k                 BinaryHeap<HeapEntry> keep-k-smallest    (reference src/ivf.rs:1844, 2116-2126)
 //
-// Data layout consumed as stored in the index file: a 32-vector block is
-// 4*D code bytes followed by f_add[32], f_rescale[32], f_error[32].  The 16 code bytes at offset
-// 16*cb belong to codebook cb (dims 4cb..4cb+3) and so do the 16 LUT bytes at the same offset:
-// lane l of the warp owns codebooks l, l+32, ... -> one coalesced 128-bit load per lane per 512 B of
-// block, its LUT rows live in registers for the whole query, and the 16-entry byte lookup is two
-// PRMTs (entries 0-7 / 8-15) blended by a PRMT-generated mask (the GPU analogue of pshufb).  Per-lane
-// partial sums are kept as packed u16 pairs and reduced across lanes with a 16-shuffle
-// reduce-scatter that leaves lane v holding accu[v]; the block's factors are then read by lane v.
+// Layout consumed as stored in the index file: a 32-vector block = 4*D code
+// bytes + f_add[32] + f_rescale[32] + f_error[32].  The 16 code bytes at offset 16*cb belong to
+// codebook cb (dims 4cb..4cb+3), like the 16 LUT bytes at the same offset of the query's LUT.
 //
-// Exact pruning order: lanes whose lower bound beats the threshold at block entry
-// (a superset of what the reference admits) are refined in parallel, then replayed in lane order
-// against the live threshold, which reproduces the reference's sequential decisions exactly.
+// Kernel structure (persistent CTAs, warps fetch queries from a global counter):
+//   * every warp owns a ring of NST block-sized shared-memory stages fed by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), so the next blocks of the query's probe sequence are in
+//     flight while the current one is processed -- the stream never waits on a register load;
+//   * lane l owns codebooks l, l+32, ...: its LUT rows stay in registers for the whole query, its
+//     code bytes are one LDS.128 per codebook; the 16-entry byte lookup is two PRMTs (entries 0-7 /
+//     8-15) blended by a PRMT-generated mask (the GPU analogue of pshufb); the four looked-up bytes of
+//     a PRMT are accumulated with dp4a against one-hot selectors (FMA pipe, balancing the ALU pipe);
+//   * per-lane partial sums are packed to u16 pairs and reduced across lanes with a 16-shuffle
+//     reduce-scatter that leaves lane v holding accu[v]; factors are read from the same stage;
+//   * pruning is exact: lanes whose lower bound beats a (possibly stale, hence looser)
+//     threshold are queued; at the end of each list the queue is refined 4 candidates x 8 lanes at a
+//     time (ex-codes staged through shared memory with 128-bit loads) and then replayed in visit
+//     order against the live threshold -- the reference's sequential decisions, reproduced exactly.
 //
-// Integer sums are exact (== the reference's u16 wrap-around value); float ops follow the AVX2
+// Integer sums are exact (== the reference's wrapping-u16 value); float ops follow the AVX2
 // variants' order (fma only where the reference uses fmadd).  Compiled with -fmad=false.
+#include <algorithm>
 #include <cfloat>
 
 #include "rbq_internal.h"
@@ -29,47 +36,83 @@ namespace rbq {
 
 constexpr int kWarps = 4;
 constexpr int kMaxTopK = 1024;
+constexpr int kRefineSlots = 4;  // candidates refined per round (4 x 8 lanes)
 size_t scan_max_topk() { return kMaxTopK; }
 
+// ---- PTX helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// 32 nibble lookups of one codebook.  C = the 16 code bytes (4 regs), T = the codebook's 16 LUT bytes.
-// E[m] accumulates (vector m | vector m+8 << 16), O[m] (vector m+16 | vector m+24 << 16), m = 0..7.
-__device__ __forceinline__ void lookup_accumulate(const uint4& Cv, const uint4& T, uint32_t (&E)[8], uint32_t (&O)[8]) {
+// ---- K7: lookups ---------------------------------------------------------------------------------
+// 32 nibble lookups of one codebook.  C = its 16 code bytes, T = its 16 LUT bytes.  acc[v] += lut[nibble(v)].
+// Byte j of C holds vector KPERM0[j] (low nibble) and KPERM0[j]+16 (high nibble); bytes 4k+2h, 4k+2h+1
+// form PRMT selector half h of register k and carry vectors m, m+16, m+8, m+24 with m = 2k+h.
+__device__ __forceinline__ void lookup_accumulate(const uint4& Cv, const uint4& T, uint32_t (&acc)[32]) {
     const uint32_t C[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t c = C[k];
-        const uint32_t s = c & 0x77777777u;  // 3-bit byte selectors (bit 3 of a PRMT selector = sign mode)
-        const uint32_t sh = c << 4;          // moves the low nibbles' msb into byte-sign position
+        const uint32_t s = c & 0x77777777u;  // 3-bit byte selectors (bit 3 of a PRMT selector = sign-replicate mode)
+        const uint32_t sh = c << 4;          // brings the low nibbles' msb into byte-sign position
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t sel = h ? (s >> 16) : s;
-            const uint32_t lo = prmt(T.x, T.y, sel);                    // entries 0..7
-            const uint32_t hi = prmt(T.z, T.w, sel);                    // entries 8..15
-            const uint32_t m = prmt(c, sh, h ? 0xBFAEu : 0x9D8Cu);      // 0xFF where the nibble's msb is set
-            const uint32_t r = (lo & ~m) | (hi & m);                    // 4 looked-up bytes
-            E[2 * k + h] += prmt(r, 0u, 0x4240u);                       // bytes 0,2 -> u16 pair
-            O[2 * k + h] += prmt(r, 0u, 0x4341u);                       // bytes 1,3 -> u16 pair
+            const uint32_t lo = prmt(T.x, T.y, sel);                // entries 0..7
+            const uint32_t hi = prmt(T.z, T.w, sel);                // entries 8..15
+            const uint32_t m = prmt(c, sh, h ? 0xBFAEu : 0x9D8Cu);  // 0xFF where the nibble's msb is set
+            const uint32_t r = (lo & ~m) | (hi & m);                // 4 looked-up bytes
+            const int v = 2 * k + h;
+            acc[v] = __dp4a(r, 0x00000001u, acc[v]);
+            acc[v + 16] = __dp4a(r, 0x00000100u, acc[v + 16]);
+            acc[v + 8] = __dp4a(r, 0x00010000u, acc[v + 8]);
+            acc[v + 24] = __dp4a(r, 0x01000000u, acc[v + 24]);
         }
     }
 }
 
-// Cross-lane reduce-scatter: on return lane v holds sum over lanes of the partial for vector v.
+// Cross-lane reduce-scatter: on return lane v holds the sum over lanes of acc[v].
 template <bool WIDE>
-__device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&E)[8], uint32_t (&O)[8], int lane) {
+__device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&acc)[32], int lane) {
     const unsigned full = 0xffffffffu;
     if (!WIDE) {
+        // totals fit 16 bits (padded_dim <= 1024): pack vector pairs (v, v+8) and halve the shuffles
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
         uint32_t X[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const uint32_t keep = b4 ? O[m] : E[m], send = b4 ? E[m] : O[m];
+            const uint32_t E = acc[m] + (acc[m + 8] << 16), O = acc[m + 16] + (acc[m + 24] << 16);
+            const uint32_t keep = b4 ? O : E, send = b4 ? E : O;
             X[m] = keep + __shfl_xor_sync(full, send, 16);
         }
         uint32_t Y[4];
@@ -89,62 +132,56 @@ __device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&E)[8], uint32_t (&
         return keep + __shfl_xor_sync(full, send, 8);
     } else {
         // padded_dim > 1024: totals can exceed 16 bits, reduce in 32-bit (the caller applies the u16 wrap)
-        uint32_t x[32];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            x[m] = E[m] & 0xffffu;
-            x[m + 8] = E[m] >> 16;
-            x[m + 16] = O[m] & 0xffffu;
-            x[m + 24] = O[m] >> 16;
-        }
 #pragma unroll
         for (int w = 16; w >= 1; w >>= 1) {
             const bool up = lane & w;
 #pragma unroll
             for (int i = 0; i < w; ++i) {
-                const uint32_t keep = up ? x[i + w] : x[i], send = up ? x[i] : x[i + w];
-                x[i] = keep + __shfl_xor_sync(full, send, w);
+                const uint32_t keep = up ? acc[i + w] : acc[i], send = up ? acc[i] : acc[i + w];
+                acc[i] = keep + __shfl_xor_sync(full, send, w);
             }
         }
-        return x[0];
+        return acc[0];
     }
 }
 
-// K7 for one block: returns accu[lane] (exact integer sum, before the u16 wrap)
+// K7 for one block resident in shared memory: returns accu[lane] (exact integer sum, before the u16 wrap)
 template <int NCB, bool WIDE>
-__device__ __forceinline__ uint32_t accumulate_block(const uint8_t* __restrict__ blk, const uint4 (&T)[NCB], int ncb,
-                                                     int lane) {
-    uint32_t E[8], O[8];
+__device__ __forceinline__ uint32_t accumulate_block(const uint8_t* blk, const uint4 (&T)[NCB], int ncb, int lane) {
+    uint32_t acc[32];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) E[m] = O[m] = 0u;
-    uint4 C[NCB];
+    for (int v = 0; v < 32; ++v) acc[v] = 0u;
 #pragma unroll
     for (int i = 0; i < NCB; ++i) {
         const int cb = lane + 32 * i;
-        C[i] = (cb < ncb) ? ldg128(blk + 16 * cb) : make_uint4(0, 0, 0, 0);
+        if (NCB * 32 == ncb || cb < ncb) {
+            const uint4 C = *reinterpret_cast<const uint4*>(blk + 16 * cb);
+            lookup_accumulate(C, T[i], acc);
+        }
     }
-#pragma unroll
-    for (int i = 0; i < NCB; ++i) lookup_accumulate(C[i], T[i], E, O);
-    return reduce_scatter<WIDE>(E, O, lane);
+    return reduce_scatter<WIDE>(acc, lane);
 }
 
-// K10: one of the 8 "AVX lanes" (j) of the packed ex-code dot product: dims j, j+8, j+16, ... with fma.
+// ---- K10: packed ex-code dot, AVX2 lane order -------------------------------------------------------
+// One of the 8 "AVX lanes" (j): dims j, j+8, j+16, ... accumulated with fma, like the two fmadd steps
+// per 16 dims of the reference.  p points at the vector's packed ex-code (shared memory staging).
 // EXK: 2 / 6 = the reference's C++-compatible layouts; 1 = generic LSB-first bit stream (extension).
 template <int EXK>
-__device__ __forceinline__ float ex_dot_lane(const uint8_t* __restrict__ p, const float* __restrict__ rq, int D, int j,
-                                             int ex_bits) {
+__device__ __forceinline__ float ex_dot_lane(const uint8_t* p, const float* rq, int D, int j, int ex_bits) {
     float acc = 0.0f;
     const int sh_lo = 8 * (j & 3) + 2 * (j >> 2);  // bit position of code j in the 2-bit word; code j+8: +4
     if (EXK == 2) {
+#pragma unroll 4
         for (int c = 0; c < D / 16; ++c) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + 4 * c));
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(p + 4 * c);
             acc = __fmaf_rn((float)((w >> sh_lo) & 3u), rq[16 * c + j], acc);
             acc = __fmaf_rn((float)((w >> (sh_lo + 4)) & 3u), rq[16 * c + 8 + j], acc);
         }
     } else if (EXK == 6) {
+#pragma unroll 4
         for (int c = 0; c < D / 16; ++c) {
-            const uint32_t b = __ldg(p + 12 * c + j);
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + 12 * c + 8));
+            const uint32_t b = p[12 * c + j];
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(p + 12 * c + 8);
             const uint32_t c0 = (b & 15u) | (((w >> sh_lo) & 3u) << 4);
             const uint32_t c1 = (b >> 4) | (((w >> (sh_lo + 4)) & 3u) << 4);
             acc = __fmaf_rn((float)c0, rq[16 * c + j], acc);
@@ -154,7 +191,7 @@ __device__ __forceinline__ float ex_dot_lane(const uint8_t* __restrict__ p, cons
         const uint32_t mask = (1u << ex_bits) - 1u;
         for (int d = j; d < D; d += 8) {
             const uint32_t pos = (uint32_t)d * (uint32_t)ex_bits;
-            const uint32_t two = (uint32_t)__ldg(p + (pos >> 3)) | ((uint32_t)__ldg(p + (pos >> 3) + 1) << 8);
+            const uint32_t two = (uint32_t)p[pos >> 3] | ((uint32_t)p[(pos >> 3) + 1] << 8);
             acc = __fmaf_rn((float)((two >> (pos & 7u)) & mask), rq[d], acc);
         }
     }
@@ -168,7 +205,7 @@ __device__ __forceinline__ float hsum8(float a) {
     return a;
 }
 
-// K11: warp-cooperative insertion into an ascending list of at most k (distance, id) pairs.
+// ---- K11: warp-cooperative insertion into an ascending list of at most k (distance, id) pairs -----
 // Equal distances keep the earlier-visited entry first (and drop the newcomer at the boundary).
 __device__ __forceinline__ void topk_insert(float* sd, unsigned long long* si, int& cnt, int k, float d,
                                             unsigned long long id, int lane) {
@@ -215,157 +252,333 @@ struct ScanArgs {
     float* out_scores;
     uint32_t* out_counts;
     DevStats* stats;
+    unsigned int* work_counter;  // next query to hand out
+    uint32_t nst;                // ring stages per warp
+    uint32_t ex_stage_stride;    // bytes per refine staging slot (16-byte multiple)
+};
+
+// Per-warp shared memory carve-up (bytes), all offsets 16-byte aligned.
+struct WarpSmem {
+    uint32_t ring, bars, exst, rq, si, sd, total;
+};
+__host__ __device__ inline WarpSmem warp_smem_layout(uint32_t block_stride, uint32_t nst, uint32_t ex_stage_stride,
+                                                     uint32_t D, uint32_t k, bool has_ex) {
+    WarpSmem w;
+    uint32_t o = 0;
+    w.ring = o;
+    o += nst * block_stride;
+    w.bars = o;
+    o += ((nst * 8 + 15) / 16) * 16;
+    w.exst = o;
+    o += has_ex ? kRefineSlots * ex_stage_stride : 0;
+    w.rq = o;
+    o += has_ex ? ((D * 4 + 15) / 16) * 16 : 0;
+    w.si = o;
+    o += ((k * 8 + 15) / 16) * 16;
+    w.sd = o;
+    o += ((k * 4 + 15) / 16) * 16;
+    w.total = o;
+    return w;
+}
+
+// Walks a query's block sequence: probes in order, blocks of a list in order; lists with no local
+// vectors (empty, or owned by another shard) are skipped.
+struct Cursor {
+    uint32_t pi, b, nb;  // probe rank, block inside the list, blocks in the list
+    const uint8_t* base; // first block of the current list
+    __device__ __forceinline__ void seek(const DevIndex& ix, const Probe* pr, uint32_t nprobe) {
+        while (pi < nprobe) {
+            const uint32_t nv = pr[pi].nv;
+            if (nv != 0) {
+                nb = (nv + kBatch - 1) / kBatch;
+                base = ix.blocks + (size_t)pr[pi].blk_off * ix.block_stride;
+                b = 0;
+                return;
+            }
+            ++pi;
+        }
+        nb = 0;
+    }
+    __device__ __forceinline__ bool valid(uint32_t nprobe) const { return pi < nprobe; }
+    __device__ __forceinline__ void next(const DevIndex& ix, const Probe* pr, uint32_t nprobe) {
+        if (++b >= nb) {
+            ++pi;
+            seek(ix, pr, nprobe);
+        }
+    }
 };
 
 template <int NCB, int EXK, bool WIDE>
 __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs a) {
-    extern __shared__ __align__(16) unsigned char scan_smem[];
+    extern __shared__ __align__(128) unsigned char scan_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * kWarps + warp;
-    if (q >= a.nq) return;  // whole warp exits together; no block-level sync below
     const int D = ix.D, ncb = D / 4, k = (int)a.top_k;
-    // per-warp shared memory: top-k ids (8B) | top-k distances | rotated query
-    unsigned long long* si = reinterpret_cast<unsigned long long*>(scan_smem) + (size_t)warp * k;
-    float* sd = reinterpret_cast<float*>(scan_smem + (size_t)kWarps * k * 8) + (size_t)warp * k;
-    float* rq = reinterpret_cast<float*>(scan_smem + (size_t)kWarps * k * 12) + (size_t)warp * D;
-    if (EXK != 0)
-        for (int i = lane; i < D; i += 32) rq[i] = a.rot[(size_t)q * D + i];
-    __syncwarp();
-
-    uint4 T[NCB];
-#pragma unroll
-    for (int i = 0; i < NCB; ++i) {
-        const int cb = lane + 32 * i;
-        T[i] = (cb < ncb) ? ldg128(a.lut + (size_t)q * D * 4 + 16 * cb) : make_uint4(0, 0, 0, 0);
-    }
-    const QueryScalars s = a.qs[q];
+    const uint32_t B = ix.block_stride, NST = a.nst;
+    const WarpSmem L = warp_smem_layout(B, NST, a.ex_stage_stride, D, k, EXK != 0);
+    unsigned char* wbase = scan_smem + (size_t)warp * L.total;
+    uint8_t* ring = wbase + L.ring;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(wbase + L.bars);
+    uint8_t* exst = wbase + L.exst;
+    float* rq = reinterpret_cast<float*>(wbase + L.rq);
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
+    float* sd = reinterpret_cast<float*>(wbase + L.sd);
     const bool l2 = ix.metric == RBQ_METRIC_L2;
-    int cnt = 0;
+
+    if (lane == 0) {
+        for (uint32_t s = 0; s < NST; ++s) mbar_init(bars_u32 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t it_issue = 0, it_use = 0;  // blocks issued / consumed by this warp since kernel start (ring phase)
     unsigned long long st_blocks = 0, st_cand = 0, st_ref = 0, st_adm = 0;
 
-    for (uint32_t pi = 0; pi < a.nprobe; ++pi) {
-        const Probe pr = a.probes[(size_t)q * a.nprobe + pi];
-        const uint32_t nv = ix.list_n[pr.cid];
-        if (nv == 0) continue;  // empty list, or a list owned by another shard
-        const uint8_t* base = ix.blocks + (size_t)ix.blk_off[pr.cid] * ix.block_stride;
-        const unsigned long long vbase = ix.vec_off[pr.cid];
-        const uint32_t nb = (nv + kBatch - 1) / kBatch;
-        st_blocks += nb;
-        for (uint32_t b = 0; b < nb; ++b) {
-            const uint8_t* blk = base + (size_t)b * ix.block_stride;
-            uint32_t accu = accumulate_block<NCB, WIDE>(blk, T, ncb, lane);
-            if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
-            const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
-            const float f_add = __ldg(fac + lane), f_rescale = __ldg(fac + 32 + lane), f_error = __ldg(fac + 64 + lane);
-            // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
-            const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
-            const float t1 = ip + s.k1x;
-            const float t2 = f_rescale * t1;
-            const float t3 = f_add + pr.g_add;
-            const float est = t3 + t2;
-            const float t4 = f_error * pr.g_error;
-            float lower = est - t4;
-            // K9
-            const uint32_t li = b * kBatch + lane;
-            bool valid = li < nv;
-            unsigned long long vid = 0;
-            if (a.filter != nullptr) {
-                if (valid) {
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(a.work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.nq) break;
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+
+        // producer side: prime the ring (all stages are free: everything issued so far was consumed)
+        if (lane == 0) fence_proxy_async();
+        Cursor pc;
+        pc.pi = 0;
+        pc.seek(ix, pr, a.nprobe);
+        for (uint32_t s = 0; s < NST && pc.valid(a.nprobe); ++s) {
+            if (lane == 0) {
+                const uint32_t st = it_issue % NST;
+                mbar_expect_tx(bars_u32 + 8 * st, B);
+                tma_load_1d(ring_u32 + st * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * st);
+            }
+            ++it_issue;
+            pc.next(ix, pr, a.nprobe);
+        }
+
+        if (EXK != 0)
+            for (int i = lane; i < D; i += 32) rq[i] = a.rot[(size_t)q * D + i];
+        uint4 T[NCB];
+#pragma unroll
+        for (int i = 0; i < NCB; ++i) {
+            const int cb = lane + 32 * i;
+            T[i] = (cb < ncb) ? ldg128(a.lut + (size_t)q * D * 4 + 16 * cb) : make_uint4(0, 0, 0, 0);
+        }
+        const QueryScalars s = a.qs[q];
+        __syncwarp();
+        int cnt = 0;
+
+        // candidate queue: slot i lives in lane i (candidates of ONE list, in visit order)
+        int qn = 0;
+        float q_lower = 0.0f, q_ip = 0.0f;
+        uint32_t q_li = 0;
+        unsigned long long q_vid = 0;
+
+        Cursor cc;
+        cc.pi = 0;
+        cc.seek(ix, pr, a.nprobe);
+        while (cc.valid(a.nprobe)) {
+            const Probe p = pr[cc.pi];
+            const uint32_t nv = p.nv;
+            const unsigned long long vbase = p.vec_off;
+            st_blocks += cc.nb;
+
+            // refine + replay everything queued for this list (reference order, live threshold)
+            auto flush = [&]() {
+                if (qn == 0) return;
+                float dist = 0.0f;
+                const bool mine = lane < qn;
+                const unsigned long long gv = vbase + q_li;
+                float fae = 0.0f, fre = 0.0f;
+                if (mine) {
+                    fae = __ldg(ix.f_add_ex + gv);
+                    fre = __ldg(ix.f_rescale_ex + gv);
+                    if (a.filter == nullptr) q_vid = ix.ids[gv];
+                }
+                float exdot = 0.0f;
+                const int g = lane >> 3, j = lane & 7;
+                for (int r0 = 0; r0 < qn; r0 += kRefineSlots) {
+                    const int c = r0 + g;  // candidate served by this 8-lane group
+                    const uint32_t li_c = __shfl_sync(0xffffffffu, q_li, c & 31);
+                    uint8_t* stg = exst + (size_t)g * a.ex_stage_stride;
+                    if (c < qn) {
+                        const uint8_t* src = ix.ex + (vbase + li_c) * ix.ex_stride;
+                        if ((ix.ex_stride & 15u) == 0) {
+                            for (uint32_t o = 16 * j; o < ix.ex_stride; o += 128)
+                                *reinterpret_cast<uint4*>(stg + o) = ldg128(src + o);
+                        } else {
+                            for (uint32_t o = 4 * j; o < ix.ex_stride; o += 32)
+                                *reinterpret_cast<uint32_t*>(stg + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
+                        }
+                    }
+                    __syncwarp();
+                    float part = 0.0f;
+                    if (c < qn) part = ex_dot_lane<EXK>(stg, rq, D, j, ix.ex_bits);
+                    part = hsum8(part);
+                    const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
+                    if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
+                    __syncwarp();
+                }
+                st_ref += qn;
+                if (mine) {
+                    // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                    float tt = s.bscale * q_ip;
+                    tt = tt + exdot;
+                    tt = tt + s.kbx;
+                    const float mm2 = fre * tt;
+                    const float aa = fae + p.g_add;
+                    dist = aa + mm2;
+                }
+                for (int c = 0; c < qn; ++c) {
+                    const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
+                    const float d_s = __shfl_sync(0xffffffffu, dist, c);
+                    const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
+                    const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                    if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                    st_adm += 1;
+                    if (!isfinite(d_s)) continue;
+                    topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                }
+                qn = 0;
+            };
+
+            const uint32_t list_pi = cc.pi;
+            while (cc.valid(a.nprobe) && cc.pi == list_pi) {
+                const uint32_t b = cc.b;
+                const uint32_t st = it_use % NST;
+                mbar_wait(bars_u32 + 8 * st, (it_use / NST) & 1u);
+                const uint8_t* blk = ring + (size_t)st * B;
+                uint32_t accu = accumulate_block<NCB, WIDE>(blk, T, ncb, lane);
+                if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
+                const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
+                const float f_add = fac[lane], f_rescale = fac[32 + lane], f_error = fac[64 + lane];
+                // the stage has been read: hand it back to the TMA engine for the block NST ahead
+                __syncwarp();
+                ++it_use;
+                if (pc.valid(a.nprobe)) {
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        const uint32_t ns = it_issue % NST;
+                        mbar_expect_tx(bars_u32 + 8 * ns, B);
+                        tma_load_1d(ring_u32 + ns * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * ns);
+                    }
+                    ++it_issue;
+                    pc.next(ix, pr, a.nprobe);
+                }
+                // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
+                const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
+                const float t1 = ip + s.k1x;
+                const float t2 = f_rescale * t1;
+                const float t3 = f_add + p.g_add;
+                const float est = t3 + t2;
+                const float t4 = f_error * p.g_error;
+                float lower = est - t4;
+                // K9
+                const uint32_t li = b * kBatch + lane;
+                bool valid = li < nv;
+                unsigned long long vid = 0;
+                if (a.filter != nullptr && valid) {
                     vid = ix.ids[vbase + li];
                     const uint32_t id32 = (uint32_t)vid;
                     valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
                 }
-            }
-            if (!isfinite(lower)) lower = l2 ? 0.0f : -(pr.dot_qc + s.qnorm);
-            const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;
-            const bool cand = valid && (lower < theta0);
-            const unsigned mask = __ballot_sync(0xffffffffu, cand);
-            st_cand += __popc(__ballot_sync(0xffffffffu, valid));
-            if (mask == 0u) continue;
-            if (cand && a.filter == nullptr) vid = ix.ids[vbase + li];
-            float dist = est;
-            if (EXK != 0) {
-                // refine the superset: 4 candidates at a time, 8 lanes each
-                float exdot = 0.0f;
-                unsigned m = mask;
-                const int g = lane >> 3, j = lane & 7;
-                while (m) {
-                    int src = -1;  // the candidate lane served by this 8-lane group in this round
-                    unsigned mm = m;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (mm) {
-                            const int sl = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            if (t == g) src = sl;
+                if (!isfinite(lower)) lower = l2 ? 0.0f : -(p.dot_qc + s.qnorm);
+                const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                const bool cand = valid && (lower < theta0);
+                const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                st_cand += __popc(__ballot_sync(0xffffffffu, valid));
+                if (mask != 0u) {
+                    if (EXK == 0) {
+                        // 1-bit index: distance == estimate, replay right away
+                        if (cand && a.filter == nullptr) vid = ix.ids[vbase + li];
+                        unsigned m = mask;
+                        while (m) {
+                            const int sl = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
+                            const float d_s = __shfl_sync(0xffffffffu, est, sl);
+                            const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
+                            const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                            if (lb_s >= theta) continue;
+                            st_adm += 1;
+                            if (!isfinite(d_s)) continue;
+                            topk_insert(sd, si, cnt, k, d_s, id_s, lane);
                         }
+                    } else {
+                        const int n_new = __popc(mask);
+                        if (qn + n_new > 32) flush();
+                        // append in lane order: queue slot qn + r takes the r-th set lane of mask
+                        const int r = lane - qn;
+                        const int src = (r >= 0 && r < n_new) ? (int)__fns(mask, 0, r + 1) : 0;
+                        const float nl = __shfl_sync(0xffffffffu, lower, src);
+                        const float nip = __shfl_sync(0xffffffffu, ip, src);
+                        const unsigned long long nvid = __shfl_sync(0xffffffffu, vid, src);
+                        if (r >= 0 && r < n_new) {
+                            q_lower = nl;
+                            q_ip = nip;
+                            q_li = b * kBatch + (uint32_t)src;
+                            q_vid = nvid;
+                            // warm L2 with the candidate's ex-code while the list is still being scanned
+                            const uint8_t* ep = ix.ex + (vbase + q_li) * ix.ex_stride;
+                            for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                        }
+                        qn += n_new;
                     }
-                    float part = 0.0f;
-                    if (src >= 0) {
-                        const unsigned long long gv = vbase + (unsigned long long)b * kBatch + src;
-                        part = ex_dot_lane<EXK>(ix.ex + gv * ix.ex_stride, rq, D, j, ix.ex_bits);
-                    }
-                    part = hsum8(part);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int sl = __shfl_sync(0xffffffffu, src, t * 8);
-                        const float v = __shfl_sync(0xffffffffu, part, t * 8);
-                        if (sl == lane) exdot = v;
-                    }
-                    st_ref += __popc(m) < 4 ? __popc(m) : 4;
-                    m = mm;
                 }
-                if (cand) {
-                    // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
-                    const unsigned long long gv = vbase + li;
-                    float tt = s.bscale * ip;
-                    tt = tt + exdot;
-                    tt = tt + s.kbx;
-                    const float mm2 = __ldg(ix.f_rescale_ex + gv) * tt;
-                    const float aa = __ldg(ix.f_add_ex + gv) + pr.g_add;
-                    dist = aa + mm2;
-                }
+                cc.next(ix, pr, a.nprobe);
             }
-            // replay in reference order against the live threshold
-            unsigned m = mask;
-            while (m) {
-                const int sl = __ffs(m) - 1;
-                m &= m - 1;
-                const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
-                const float d_s = __shfl_sync(0xffffffffu, dist, sl);
-                const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
-                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
-                if (lb_s >= theta) continue;  // skipped_by_lower_bound
-                st_adm += 1;
-                if (!isfinite(d_s)) continue;
-                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
-            }
+            if (EXK != 0) flush();
         }
-    }
-    for (int i = lane; i < k; i += 32) {
-        const bool have = i < cnt;
-        a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
-        a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
-    }
-    if (lane == 0) {
-        a.out_counts[q] = (uint32_t)cnt;
-        if (a.stats) {
-            atomicAdd(&a.stats->blocks, st_blocks);
-            atomicAdd(&a.stats->candidates, st_cand);
-            atomicAdd(&a.stats->refined, st_ref);
-            atomicAdd(&a.stats->admitted, st_adm);
+        for (int i = lane; i < k; i += 32) {
+            const bool have = i < cnt;
+            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
         }
+        if (lane == 0) a.out_counts[q] = (uint32_t)cnt;
+        __syncwarp();
+    }
+    if (lane == 0 && a.stats) {
+        atomicAdd(&a.stats->blocks, st_blocks);
+        atomicAdd(&a.stats->candidates, st_cand);
+        atomicAdd(&a.stats->refined, st_ref);
+        atomicAdd(&a.stats->admitted, st_adm);
     }
 }
 
+static int g_num_sms = 0;
+static size_t g_smem_optin = 0;
+static int device_limits() {
+    if (g_num_sms) return RBQ_OK;
+    int dev = 0, v = 0;
+    RBQ_CUDA(cudaGetDevice(&dev));
+    RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = v;
+    RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_smem_optin = (size_t)v;
+    return RBQ_OK;
+}
+
 template <int NCB, bool WIDE>
-static int launch_scan_ex(const DevIndex& ix, const ScanArgs& a, size_t smem, cudaStream_t st) {
-    const unsigned grid = (a.nq + kWarps - 1) / kWarps;
+static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
+    int rc = device_limits();
+    if (rc) return rc;
+    const bool has_ex = ix.ex_bits != 0;
+    a.ex_stage_stride = ((ix.ex_stride + 15u) / 16u) * 16u + 16u;
+    // ring depth: as many stages as fit 3 CTAs/SM, between 2 and 4
+    const size_t per_sm = 227 * 1024;
+    uint32_t nst = 4;
+    for (; nst > 2; --nst) {
+        const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex);
+        if ((size_t)w.total * kWarps * 3 + 3 * 1024 <= per_sm) break;
+    }
+    a.nst = nst;
+    const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex);
+    const size_t smem = (size_t)w.total * kWarps;
+    if (smem > g_smem_optin) return fail(RBQ_INVALID_CONFIG, "scan kernel shared memory exceeds the device limit");
+    const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (smem + 1024)));
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)a.nq + kWarps - 1) / kWarps, (size_t)g_num_sms * ctas_per_sm);
 #define RBQ_LAUNCH(EXK)                                                                                        \
     do {                                                                                                       \
-        if (smem > 48 * 1024)                                                                                  \
-            RBQ_CUDA(cudaFuncSetAttribute(scan_kernel<NCB, EXK, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                         \
+        RBQ_CUDA(cudaFuncSetAttribute(scan_kernel<NCB, EXK, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                             \
         scan_kernel<NCB, EXK, WIDE><<<grid, kWarps * 32, smem, st>>>(ix, a);                                   \
     } while (0)
     if (ix.ex_bits == 0) RBQ_LAUNCH(0);
@@ -380,9 +593,11 @@ static int launch_scan_ex(const DevIndex& ix, const ScanArgs& a, size_t smem, cu
 int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
                 const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter,
                 size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
-                cudaStream_t st) {
+                unsigned int* d_work_counter, cudaStream_t st) {
     if (nq == 0) return RBQ_OK;
     if (top_k > (size_t)kMaxTopK) return fail(RBQ_INVALID_CONFIG, "top_k exceeds the device limit (1024)");
+    if (ix.D > 2048) return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
+    RBQ_CUDA(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned int), st));
     ScanArgs a;
     a.rot = d_rot;
     a.lut = d_lut;
@@ -397,21 +612,22 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     a.out_scores = d_scores;
     a.out_counts = d_counts;
     a.stats = d_stats;
-    const size_t smem = (size_t)kWarps * top_k * 12 + (size_t)kWarps * ix.D * 4;
+    a.work_counter = d_work_counter;
+    a.nst = 2;
+    a.ex_stage_stride = 16;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
-    if (ix.D > 2048) return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
     if (ix.D > 1024) {
-        if (ncb_lane <= 12) return launch_scan_ex<12, true>(ix, a, smem, st);
-        return launch_scan_ex<16, true>(ix, a, smem, st);
+        if (ncb_lane <= 12) return launch_scan_ex<12, true>(ix, a, st);
+        return launch_scan_ex<16, true>(ix, a, st);
     }
     switch (ncb_lane) {
-        case 1: return launch_scan_ex<1, false>(ix, a, smem, st);
-        case 2: return launch_scan_ex<2, false>(ix, a, smem, st);
-        case 3: return launch_scan_ex<3, false>(ix, a, smem, st);
-        case 4: return launch_scan_ex<4, false>(ix, a, smem, st);
+        case 1: return launch_scan_ex<1, false>(ix, a, st);
+        case 2: return launch_scan_ex<2, false>(ix, a, st);
+        case 3: return launch_scan_ex<3, false>(ix, a, st);
+        case 4: return launch_scan_ex<4, false>(ix, a, st);
         case 5:
-        case 6: return launch_scan_ex<6, false>(ix, a, smem, st);
-        default: return launch_scan_ex<8, false>(ix, a, smem, st);
+        case 6: return launch_scan_ex<6, false>(ix, a, st);
+        default: return launch_scan_ex<8, false>(ix, a, st);
     }
 }
 
@@ -425,22 +641,19 @@ __global__ void scan_debug_kernel(DevIndex ix, const uint8_t* __restrict__ lut, 
     const QueryScalars s = qs[0];
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         const uint8_t* blk = base + (size_t)b * ix.block_stride;
-        // generic (slow) formulation of the same mapping: 16 codebooks per pass so any D works
-        uint32_t E[8], O[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) E[m] = O[m] = 0u;
         uint32_t total = 0;
-        for (int c0 = 0; c0 < ncb; c0 += 32) {
+        for (int c0 = 0; c0 < ncb; c0 += 32) {  // 32 codebooks per pass so that any D works
             const int cb = c0 + lane;
             uint4 C = make_uint4(0, 0, 0, 0), T = make_uint4(0, 0, 0, 0);
             if (cb < ncb) {
                 C = ldg128(blk + 16 * cb);
                 T = ldg128(lut + 16 * cb);
             }
+            uint32_t acc[32];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) E[m] = O[m] = 0u;
-            lookup_accumulate(C, T, E, O);
-            total += reduce_scatter<true>(E, O, lane);
+            for (int v = 0; v < 32; ++v) acc[v] = 0u;
+            lookup_accumulate(C, T, acc);
+            total += reduce_scatter<true>(acc, lane);
         }
         const uint32_t accu = total & 0xffffu;
         const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
@@ -484,7 +697,6 @@ __global__ void merge_kernel(int metric, int nshards, uint32_t nq, uint32_t k, c
             float sc = in_scores[((size_t)lane * nq + q) * k + head];
             key = metric == RBQ_METRIC_L2 ? sc : -sc;
         }
-        // warp argmin over (have, key, lane)
         float best = key;
         int who = have ? lane : 64;
 #pragma unroll
