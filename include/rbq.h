@@ -110,13 +110,15 @@ typedef struct rbq_search_stats {
     uint64_t refined;           /* ex-code dot products evaluated on device (>= reference's extended_evaluations) */
     uint64_t admitted;          /* candidates that passed lb < distk in reference order (== estimated + non-finite) */
     uint64_t kernel_launches;   /* CUDA kernels launched by the call */
+    uint64_t coarse_fallbacks;  /* queries whose tensor-core candidate set overflowed and were scored exactly */
     float ms_prep, ms_coarse, ms_select, ms_scan; /* CUDA-event times of the last *profiled* call */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */
 int rbq_set_profiling(rbq_index* ix, int on);
 /* Coarse-stage implementation: 0 = exact FP32 scoring of every centroid (CUDA cores),
- * 1 = tensor-core candidate GEMM + exact FP32 re-score (default when available). */
+ * 1 = tensor-core (tcgen05) candidate GEMM + exact FP32 re-score of the near-threshold centroids
+ * (default).  Both produce the reference's probe list bit for bit. */
 int rbq_set_coarse_mode(rbq_index* ix, int mode);
 
 /* ---- stage probes (parity tests call each device stage in isolation; host buffers) ----

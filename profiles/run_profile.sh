@@ -8,6 +8,6 @@ mkdir -p gpurun_out
 KREGEX='regex:query_prep_kernel|coarse_|probe_select_kernel|scan_kernel|merge_kernel|rescore'
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 60 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -f -o gpurun_out/scan_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 9 -c 1 -f -o gpurun_out/scan_${TAG} \
     python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/scan_${TAG}.log 2>&1
 ls -la gpurun_out/

@@ -12,7 +12,7 @@ OK, DIMENSION_MISMATCH, INVALID_CONFIG, EMPTY_INDEX, IO, INVALID_PERSISTENCE, CU
 class SearchStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("blocks_scanned", C.c_uint64), ("bytes_scanned", C.c_uint64),
                 ("candidates", C.c_uint64), ("refined", C.c_uint64), ("admitted", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("ms_prep", C.c_float), ("ms_coarse", C.c_float),
+                ("kernel_launches", C.c_uint64), ("coarse_fallbacks", C.c_uint64), ("ms_prep", C.c_float), ("ms_coarse", C.c_float),
                 ("ms_select", C.c_float), ("ms_scan", C.c_float)]
 
 

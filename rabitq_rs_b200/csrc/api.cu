@@ -87,6 +87,7 @@ int upload_index(rbq_index* h) {
         if ((rc = upload(h, mt.data(), mt.size(), &d.matrix_t))) return rc;
     }
     if ((rc = upload(h, hi.centroids.data(), hi.centroids.size(), &d.centroids))) return rc;
+    if ((rc = prepare_coarse_tc(h))) return rc;
     if ((rc = upload(h, hi.list_n.data(), hi.list_n.size(), &d.list_n))) return rc;
     if ((rc = upload(h, hi.blk_off.data(), hi.blk_off.size(), &d.blk_off))) return rc;
     if ((rc = upload(h, hi.vec_off.data(), hi.vec_off.size(), &d.vec_off))) return rc;
@@ -107,6 +108,35 @@ int upload_index(rbq_index* h) {
     h->d_stats = reinterpret_cast<DevStats*>(st);
     return RBQ_OK;
 }
+
+}  // namespace
+
+// Tensor-core coarse stage operands: bf16 split of the (rotated) centroids, |c|^2 and max |c|.
+int rbq::prepare_coarse_tc(rbq_index* h) {
+    DevIndex& d = h->dev;
+    const size_t nl = d.nlist, D = d.D;
+    void* sp = nullptr;
+    float* n2 = nullptr;
+    RBQ_CUDA(cudaMalloc(&sp, std::max<size_t>(nl * 3 * D * 2, 16)));
+    h->allocations.push_back(sp);
+    RBQ_CUDA(cudaMalloc(&n2, std::max<size_t>(nl * 4, 16)));
+    h->allocations.push_back(n2);
+    int rc = launch_split_bf16(d.centroids, nl, (int)D, 1, sp, n2, nullptr);
+    if (rc) return rc;
+    RBQ_CUDA(cudaDeviceSynchronize());
+    double mx = 0.0;
+    for (size_t c = 0; c < nl; ++c) {
+        double s = 0.0;
+        for (size_t k = 0; k < D; ++k) s += (double)h->host.centroids[c * D + k] * (double)h->host.centroids[c * D + k];
+        mx = std::max(mx, s);
+    }
+    d.cent_split = sp;
+    d.cent_n2 = n2;
+    d.cmax_norm = (float)(std::sqrt(mx) * (1.0 + 1e-6));
+    return RBQ_OK;
+}
+
+namespace {
 
 int ensure_ws(const rbq_index* h, size_t bytes) {
     if (h->ws_bytes >= bytes) return RBQ_OK;
@@ -144,6 +174,7 @@ size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_
     n += qt * sizeof(QueryScalars) + 256;
     n += qt * (size_t)h->dev.nlist * 4 + 256;  // scores
     n += qt * nprobe * sizeof(Probe) + 256;
+    n += qt * 3 * D * 2 + qt * 4 + 512;    // bf16 split of the rotated queries + |q|^2 (tensor-core coarse stage)
     if (host_io) {
         n += qt * dim * 4 + 256;
         n += qt * top_k * 12 + qt * 4 + 768;
@@ -164,6 +195,8 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
     QueryScalars* d_qs = cv.take<QueryScalars>(qt);
     float* d_sc = cv.take<float>(qt * (size_t)ix.nlist);
     Probe* d_pr = cv.take<Probe>(qt * nprobe);
+    uint16_t* d_qsplit = cv.take<uint16_t>(qt * 3 * D);
+    float* d_qn2 = cv.take<float>(qt);
     float ms[4] = {0, 0, 0, 0};
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
@@ -171,9 +204,18 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         if (h->profiling) cudaEventRecord(h->ev[0], st);
         if ((rc = launch_query_prep(ix, d_queries + q0 * ix.dim, n, d_rot, d_lut, d_qs, st))) return rc;
         if (h->profiling) cudaEventRecord(h->ev[1], st);
-        if ((rc = launch_coarse_exact(ix, d_rot, n, d_sc, st))) return rc;
-        if (h->profiling) cudaEventRecord(h->ev[2], st);
-        if ((rc = launch_probe_select(ix, d_rot, d_sc, n, nprobe, d_pr, st))) return rc;
+        if (h->coarse_mode == 0) {
+            if ((rc = launch_coarse_exact(ix, d_rot, n, d_sc, st))) return rc;
+            if (h->profiling) cudaEventRecord(h->ev[2], st);
+            if ((rc = launch_probe_select(ix, d_rot, d_sc, n, nprobe, d_pr, st))) return rc;
+        } else {
+            if ((rc = launch_split_bf16(d_rot, n, (int)D, 0, d_qsplit, d_qn2, st))) return rc;
+            if ((rc = launch_coarse_tc(ix, d_qsplit, d_qn2, n, d_sc, st))) return rc;
+            if (h->profiling) cudaEventRecord(h->ev[2], st);
+            if ((rc = launch_probe_select_tc(ix, d_rot, d_sc, d_qs, n, nprobe, h->coarse_eps, d_pr, h->fallback_counter(), st)))
+                return rc;
+            *launches += 1;
+        }
         if (h->profiling) cudaEventRecord(h->ev[3], st);
         if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                               d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), st)))
@@ -331,7 +373,7 @@ int rbq_set_profiling(rbq_index* h, int on) {
 }
 int rbq_set_coarse_mode(rbq_index* h, int mode) {
     if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
-    if (mode != 0) return fail(RBQ_INVALID_CONFIG, "coarse mode not available in this build");
+    if (mode != 0 && mode != 1) return fail(RBQ_INVALID_CONFIG, "coarse mode must be 0 (exact) or 1 (tensor-core candidates)");
     h->coarse_mode = mode;
     return RBQ_OK;
 }
@@ -347,6 +389,9 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     h->last_stats.candidates = ds.candidates;
     h->last_stats.refined = ds.refined;
     h->last_stats.admitted = ds.admitted;
+    unsigned int fb = 0;
+    RBQ_CUDA(cudaMemcpy(&fb, h->fallback_counter(), sizeof(fb), cudaMemcpyDeviceToHost));
+    h->last_stats.coarse_fallbacks = fb;
     *out = h->last_stats;
     return RBQ_OK;
 }
@@ -368,7 +413,7 @@ int rbq_search_batch_device(const rbq_index* h, const float* d_queries, size_t n
     }
     const size_t qt = tile_queries(h, nq);
     if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, false, 0)))) return rc;
-    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), st));
+    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     uint64_t launches = 0;
     rc = search_device(h, d_queries, nq, top_k, nprobe, d_filter_bits, filter_nbits, d_ids, d_scores, d_counts,
                        (char*)h->ws, qt, st, &launches);
@@ -404,7 +449,7 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     uint64_t* d_f = fwords ? cv.take<uint64_t>(fwords) : nullptr;
     cudaStream_t st = nullptr;
     if (d_f) RBQ_CUDA(cudaMemcpyAsync(d_f, filter_bits, fwords * 8, cudaMemcpyHostToDevice, st));
-    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), st));
+    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     uint64_t launches = 0;
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
@@ -465,7 +510,7 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     const size_t D = h->dev.D, nl = h->dev.nlist;
-    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * sizeof(Probe)) + 8192))) return rc;
+    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * sizeof(Probe) + D * 6 + 4) + 16384))) return rc;
     Carver cv{(char*)h->ws};
     float* d_q = cv.take<float>(nq * dim);
     float* d_rot = cv.take<float>(nq * D);
@@ -475,8 +520,18 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
     Probe* d_pr = cv.take<Probe>(nq * nprobe);
     RBQ_CUDA(cudaMemcpy(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice));
     if ((rc = launch_query_prep(h->dev, d_q, nq, d_rot, d_lut, d_qs, nullptr))) return rc;
-    if ((rc = launch_coarse_exact(h->dev, d_rot, nq, d_sc, nullptr))) return rc;
-    if ((rc = launch_probe_select(h->dev, d_rot, d_sc, nq, nprobe, d_pr, nullptr))) return rc;
+    if (h->coarse_mode == 0) {
+        if ((rc = launch_coarse_exact(h->dev, d_rot, nq, d_sc, nullptr))) return rc;
+        if ((rc = launch_probe_select(h->dev, d_rot, d_sc, nq, nprobe, d_pr, nullptr))) return rc;
+    } else {
+        uint16_t* d_qsplit = cv.take<uint16_t>(nq * 3 * D);
+        float* d_qn2 = cv.take<float>(nq);
+        RBQ_CUDA(cudaMemset(h->fallback_counter(), 0, 4));
+        if ((rc = launch_split_bf16(d_rot, nq, (int)D, 0, d_qsplit, d_qn2, nullptr))) return rc;
+        if ((rc = launch_coarse_tc(h->dev, d_qsplit, d_qn2, nq, d_sc, nullptr))) return rc;
+        if ((rc = launch_probe_select_tc(h->dev, d_rot, d_sc, d_qs, nq, nprobe, h->coarse_eps, d_pr, h->fallback_counter(), nullptr)))
+            return rc;
+    }
     std::vector<Probe> pr(nq * nprobe);
     RBQ_CUDA(cudaMemcpy(pr.data(), d_pr, pr.size() * sizeof(Probe), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < pr.size(); ++i) {

@@ -12,6 +12,8 @@
 // probe_select_kernel picks the nprobe best per query with an exact radix select on the
 // total_cmp-ordered key (ties broken by cluster id like the reference), sorts them, and re-derives
 // the K6 constants with the same lane order.
+#include <algorithm>
+
 #include "rbq_internal.h"
 
 namespace rbq {
@@ -110,58 +112,67 @@ __device__ __forceinline__ uint32_t order_key(float f, bool descending) {
     return descending ? ~u : u;
 }
 
-__global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, const float* __restrict__ rot,
-                                                                  const float* __restrict__ scores, int nprobe,
-                                                                  int sort_n, Probe* __restrict__ probes) {
-    extern __shared__ __align__(16) unsigned char sel_smem[];
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
-    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned int s_prefix, s_remaining, s_nless, s_eqbase, s_warp_tot[kSelThreads / 32];
-    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
-    const size_t q = blockIdx.x;
-    const float* sc = scores + q * (size_t)nl;
-    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+__device__ __forceinline__ float key_to_float(uint32_t u, bool descending) {
+    if (descending) u = ~u;
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
 
-    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
-    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+struct SelShared {
+    unsigned int hist[256];
+    unsigned int prefix, remaining, nless, eqbase, warp_tot[kSelThreads / 32];
+    unsigned int count;
+};
+
+// Radix select (8 bits per pass, most significant first): key of the n-th smallest order_key among
+// sc[0..nl).  Returns the key; *take_eq = how many entries equal to it belong to the n smallest.
+__device__ __forceinline__ uint32_t radix_select(const float* __restrict__ sc, int nl, int n, bool desc, SelShared& sh,
+                                                 unsigned int* take_eq) {
+    const int tid = threadIdx.x;
     if (tid == 0) {
-        s_prefix = 0;
-        s_remaining = (unsigned)nprobe;
-        s_nless = 0;
-        s_eqbase = 0;
+        sh.prefix = 0;
+        sh.remaining = (unsigned)n;
     }
     __syncthreads();
-
-    // radix select (8 bits per pass, most significant first) of the nprobe-th smallest key
     uint32_t mask = 0;
     for (int pass = 3; pass >= 0; --pass) {
-        for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+        for (int i = tid; i < 256; i += kSelThreads) sh.hist[i] = 0;
         __syncthreads();
-        const uint32_t prefix = s_prefix;
+        const uint32_t prefix = sh.prefix;
         for (int c = tid; c < nl; c += kSelThreads) {
-            uint32_t u = order_key(sc[c], desc);
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
+            const uint32_t u = order_key(sc[c], desc);
+            if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> (8 * pass)) & 255u], 1u);
         }
         __syncthreads();
         if (tid == 0) {
-            unsigned int cum = 0, rem = s_remaining;
+            unsigned int cum = 0, rem = sh.remaining;
             int b = 0;
             for (; b < 256; ++b) {
-                if (cum + hist[b] >= rem) break;
-                cum += hist[b];
+                if (cum + sh.hist[b] >= rem) break;
+                cum += sh.hist[b];
             }
-            s_remaining = rem - cum;
-            s_prefix = prefix | ((uint32_t)b << (8 * pass));
+            sh.remaining = rem - cum;
+            sh.prefix = prefix | ((uint32_t)b << (8 * pass));
         }
         mask |= 255u << (8 * pass);
         __syncthreads();
     }
-    const uint32_t vstar = s_prefix;          // key of the nprobe-th best list
-    const unsigned int take_eq = s_remaining;  // how many lists with key == vstar belong to the result
-    const unsigned int n_less = (unsigned)nprobe - take_eq;
+    *take_eq = sh.remaining;
+    return sh.prefix;
+}
 
-    // gather: keys < vstar in any order; keys == vstar in increasing cluster id (the reference's tie-break)
+// Exact top-nprobe keys from exact scores: keys < vstar in any order, keys == vstar in increasing
+// cluster id (the reference's tie-break, src/ivf.rs:1808-1823).  Leaves nprobe keys in sel[0..nprobe).
+__device__ __forceinline__ void gather_exact(const float* __restrict__ sc, int nl, int nprobe, bool desc, SelShared& sh,
+                                             unsigned long long* sel) {
+    const int tid = threadIdx.x;
+    unsigned int take_eq;
+    const uint32_t vstar = radix_select(sc, nl, nprobe, desc, sh, &take_eq);
+    const unsigned int n_less = (unsigned)nprobe - take_eq;
+    if (tid == 0) {
+        sh.nless = 0;
+        sh.eqbase = 0;
+    }
+    __syncthreads();
     for (int base = 0; base < nl; base += kSelThreads) {
         const int c = base + tid;
         uint32_t u = 0;
@@ -172,33 +183,60 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, 
             eq = u == vstar;
         }
         if (less) {
-            unsigned int slot = atomicAdd(&s_nless, 1u);
+            const unsigned int slot = atomicAdd(&sh.nless, 1u);
             sel[slot] = ((unsigned long long)u << 32) | (unsigned)c;
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, eq);
-        if ((tid & 31) == 0) s_warp_tot[tid >> 5] = __popc(bal);
+        if ((tid & 31) == 0) sh.warp_tot[tid >> 5] = __popc(bal);
         __syncthreads();
-        unsigned int before = s_eqbase;
-        for (int w = 0; w < (tid >> 5); ++w) before += s_warp_tot[w];
+        unsigned int before = sh.eqbase;
+        for (int w = 0; w < (tid >> 5); ++w) before += sh.warp_tot[w];
         const unsigned int pos = before + __popc(bal & ((1u << (tid & 31)) - 1u));
         if (eq && pos < take_eq) sel[n_less + pos] = ((unsigned long long)u << 32) | (unsigned)c;
         __syncthreads();
         if (tid == 0) {
             unsigned int t = 0;
-            for (int w = 0; w < kSelThreads / 32; ++w) t += s_warp_tot[w];
-            s_eqbase += t;
+            for (int w = 0; w < kSelThreads / 32; ++w) t += sh.warp_tot[w];
+            sh.eqbase += t;
         }
         __syncthreads();
     }
+}
 
-    // bitonic sort of the selected keys (ascending; padding = all ones)
+// l2_distance_sqr and dot of the query against one centroid, AVX2 lane order; all 8 lanes of the
+// group return both values.
+__device__ __forceinline__ void exact_pair(const float* __restrict__ rq, const float* __restrict__ ce, int D, int lane8,
+                                           unsigned gmask, float* l2_out, float* ip_out) {
+    float al2 = 0.0f, aip = 0.0f;
+    for (int i = lane8; i < D; i += 8) {
+        const float a = rq[i], b = ce[i];
+        const float d = a - b;
+        const float p = d * d;
+        al2 = al2 + p;
+        const float m = a * b;
+        aip = aip + m;
+    }
+    float l2 = 0.0f, ip = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        l2 = l2 + __shfl_sync(gmask, al2, l, 8);
+        ip = ip + __shfl_sync(gmask, aip, l, 8);
+    }
+    *l2_out = l2;
+    *ip_out = ip;
+}
+
+// bitonic sort of sel[0..sort_n) ascending, then K6 for the first nprobe entries
+__device__ __forceinline__ void sort_and_emit(const DevIndex& ix, const float* __restrict__ rq, unsigned long long* sel,
+                                              int sort_n, int nprobe, bool desc, Probe* __restrict__ out) {
+    const int tid = threadIdx.x, D = ix.D;
     for (int k = 2; k <= sort_n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < sort_n; i += kSelThreads) {
-                int ixj = i ^ j;
+                const int ixj = i ^ j;
                 if (ixj > i) {
-                    unsigned long long a = sel[i], b = sel[ixj];
-                    bool up = (i & k) == 0;
+                    const unsigned long long a = sel[i], b = sel[ixj];
+                    const bool up = (i & k) == 0;
                     if ((a > b) == up) {
                         sel[i] = b;
                         sel[ixj] = a;
@@ -207,28 +245,12 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, 
             }
             __syncthreads();
         }
-
-    // K6 for every selected list: 8 threads = the 8 AVX lanes of l2_distance_sqr / dot
     const int lane8 = tid & 7, grp = tid >> 3;
     const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
     for (int r = grp; r < nprobe; r += kSelThreads / 8) {
         const uint32_t cid = (uint32_t)(sel[r] & 0xffffffffull);
-        const float* ce = ix.centroids + (size_t)cid * D;
-        float al2 = 0.0f, aip = 0.0f;
-        for (int i = lane8; i < D; i += 8) {
-            const float a = rq[i], b = ce[i];
-            const float d = a - b;
-            const float p = d * d;
-            al2 = al2 + p;
-            const float m = a * b;
-            aip = aip + m;
-        }
-        float l2 = 0.0f, ip = 0.0f;
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            l2 = l2 + __shfl_sync(gmask, al2, l, 8);
-            ip = ip + __shfl_sync(gmask, aip, l, 8);
-        }
+        float l2, ip;
+        exact_pair(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
         if (lane8 == 0) {
             Probe pr;
             pr.cid = cid;
@@ -238,9 +260,103 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, 
             pr.nv = ix.list_n[cid];
             pr.blk_off = ix.blk_off[cid];
             pr.vec_off = ix.vec_off[cid];
-            probes[q * (size_t)nprobe + r] = pr;
+            out[r] = pr;
         }
     }
+}
+
+// mode 0: scores are exact (coarse_exact_kernel)
+__global__ void __launch_bounds__(kSelThreads) probe_select_kernel(DevIndex ix, const float* __restrict__ rot,
+                                                                  const float* __restrict__ scores, int nprobe,
+                                                                  int sort_n, Probe* __restrict__ probes) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
+    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
+    __shared__ SelShared sh;
+    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
+    const size_t q = blockIdx.x;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+    __syncthreads();
+    gather_exact(scores + q * (size_t)nl, nl, nprobe, desc, sh, sel);
+    sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
+}
+
+// mode 1: scores are the tensor-core approximations.  Every centroid whose approximate score is within
+// 2*delta of the nprobe-th best is re-scored exactly (delta bounds |approx - reference score|, see
+// DESIGN.md), which provably contains the reference's top-nprobe; the exact keys are then sorted with the
+// reference's comparator.  If the candidate set overflows the sort buffer the query falls back to exact
+// scoring of every centroid inside this kernel.
+__global__ void __launch_bounds__(kSelThreads) probe_select_tc_kernel(DevIndex ix, const float* __restrict__ rot,
+                                                                     float* __restrict__ scores,
+                                                                     const QueryScalars* __restrict__ qs, int nprobe,
+                                                                     int sort_n, float eps_g, Probe* __restrict__ probes,
+                                                                     unsigned int* __restrict__ fallbacks) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
+    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
+    uint32_t* cand = reinterpret_cast<uint32_t*>(rq + ix.D);                    // sort_n candidate ids
+    __shared__ SelShared sh;
+    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
+    const size_t q = blockIdx.x;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    float* sc = scores + q * (size_t)nl;
+    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+    __syncthreads();
+
+    unsigned int take_eq;
+    const uint32_t tkey = radix_select(sc, nl, nprobe, desc, sh, &take_eq);
+    const float T = key_to_float(tkey, desc);
+    const float qn = qs[q].qnorm, cm = ix.cmax_norm;
+    const float round_terms = (1.2f * (float)D + 20.0f) * 5.9604645e-8f;
+    float thr;
+    if (!desc) {
+        const float s2 = (qn + cm) * (qn + cm);
+        thr = T + 2.0f * (0.5f * eps_g + round_terms) * s2;
+    } else {
+        thr = T - 2.0f * (eps_g + round_terms) * qn * cm;
+    }
+    const uint32_t thr_key = order_key(thr, desc);
+    if (tid == 0) sh.count = 0;
+    __syncthreads();
+    for (int c = tid; c < nl; c += kSelThreads) {
+        if (order_key(sc[c], desc) <= thr_key) {
+            const unsigned int slot = atomicAdd(&sh.count, 1u);
+            if (slot < (unsigned)sort_n) cand[slot] = (uint32_t)c;
+        }
+    }
+    __syncthreads();
+    const unsigned int m = sh.count;
+    const int lane8 = tid & 7, grp = tid >> 3;
+    const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
+    if (m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
+        for (unsigned int i = grp; i < m; i += kSelThreads / 8) {
+            const uint32_t cid = cand[i];
+            float l2, ip;
+            exact_pair(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            if (lane8 == 0) sel[i] = ((unsigned long long)order_key(desc ? ip : l2, desc) << 32) | cid;
+        }
+        __syncthreads();
+    } else {
+        // rare: exact scores for every centroid of this query, then the exact selection
+        if (tid == 0) atomicAdd(fallbacks, 1u);
+        for (int c = grp; c < nl; c += kSelThreads / 8) {
+            float l2, ip;
+            exact_pair(rq, ix.centroids + (size_t)c * D, D, lane8, gmask, &l2, &ip);
+            if (lane8 == 0) sc[c] = desc ? ip : l2;
+        }
+        __syncthreads();
+        gather_exact(sc, nl, nprobe, desc, sh, sel);
+    }
+    sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
+}
+
+static int sort_size(size_t n) {
+    int s = 32;
+    while ((size_t)s < n) s <<= 1;
+    return s;
 }
 
 int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_scores, size_t nq, size_t nprobe,
@@ -248,12 +364,26 @@ int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_s
     if (nq == 0) return RBQ_OK;
     if (nprobe > (size_t)kMaxNprobe)
         return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
-    int sort_n = 32;
-    while ((size_t)sort_n < nprobe) sort_n <<= 1;
-    size_t smem = (size_t)sort_n * 8 + (size_t)ix.D * 4;
+    const int sort_n = sort_size(nprobe);
+    const size_t smem = (size_t)sort_n * 8 + (size_t)ix.D * 4;
     if (smem > 48 * 1024)
         RBQ_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_select_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ix, d_rot, d_scores, (int)nprobe, sort_n, d_probes);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scores, const QueryScalars* d_qs, size_t nq,
+                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st) {
+    if (nq == 0) return RBQ_OK;
+    if (nprobe > (size_t)kMaxNprobe)
+        return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
+    const int sort_n = sort_size(std::min<size_t>(nprobe + 48, (size_t)kMaxNprobe));
+    const size_t smem = (size_t)sort_n * 12 + (size_t)ix.D * 4;
+    if (smem > 48 * 1024)
+        RBQ_CUDA(cudaFuncSetAttribute(probe_select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_select_tc_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
+                                                                   d_probes, d_fallbacks);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

@@ -1,0 +1,287 @@
+// coarse_tc.cu -- K4 on the tensor cores: query x centroid GEMM (the only dense contraction of the
+// search path) as a hand-written sm_100a kernel: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared
+// memory -> tcgen05.mma (kind::f16, BF16 in / FP32 accumulate in TMEM) -> tcgen05.ld epilogue.
+//
+// Replaces the all-pairs loop of the reference (src/ivf.rs:1782-1789 -> math::l2_distance_sqr / dot)
+// as a CANDIDATE GENERATOR only: probe selection must be bit-exact, so the approximate scores are
+// followed by an exact FP32 re-score of the near-threshold centroids in the reference's float order
+// (coarse.cu, probe_select_tc_kernel).
+//
+// Precision: operands are split into two bf16 terms, x = hi + lo (+ O(2^-18 |x|)), and the GEMM runs
+// over the K-concatenation A' = [q_hi | q_hi | q_lo], B' = [c_hi | c_lo | c_hi], so that
+// A'.B'^T = q_hi.c_hi + q_hi.c_lo + q_lo.c_hi = q.c up to 2^-16-relative terms -- one plain GEMM with
+// K' = 3*D, no second accumulator.  Scores written: L2: |q|^2 + |c|^2 - 2 q.c ; IP: q.c.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "rbq_internal.h"
+
+namespace rbq {
+
+namespace tc {
+constexpr int BM = 128;      // queries per tile (UMMA M)
+constexpr int BN = 256;      // centroids per tile (UMMA N), fp32 accumulator = 256 TMEM columns
+constexpr int BK = 64;       // bf16 per k-block = 128 bytes = one swizzle row
+constexpr int UK = 16;       // UMMA K for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int THREADS = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+}  // namespace tc
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 8 rows * 128 B |
+// version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// A,B K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(tc::THREADS, 1)
+    coarse_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nq, int nlist,
+                       int num_kb, int metric, const float* __restrict__ qn2, const float* __restrict__ cn2,
+                       float* __restrict__ scores) {
+    using namespace tc;
+    extern __shared__ unsigned char gsm_raw[];
+    unsigned char* gsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = gsm;
+    unsigned char* sB = gsm + (size_t)STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES));
+    // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull = s_u32(bars + 2 * STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            bar_init(full0 + 8 * s, 1);
+            bar_init(empty0 + 8 * s, 1);
+        }
+        bar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 256 columns x 128 lanes of fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                bar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+                tma_load_2d(s_u32(sA + (size_t)s * A_BYTES), &map_a, full0 + 8 * s, kb * BK, m_blk * BM);
+                tma_load_2d(s_u32(sB + (size_t)s * B_BYTES), &map_b, full0 + 8 * s, kb * BK, n_blk * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer (one thread) =====
+            constexpr uint32_t idesc = umma_idesc(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                bar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc(s_u32(sA + (size_t)s * A_BYTES));
+                const uint64_t db = umma_desc(s_u32(sB + (size_t)s * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                    const uint32_t acc = (kb | k) ? 1u : 0u;
+                    // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p;\n"
+                        "setp.ne.b32 p, %4, 0;\n"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+                        "}" ::"r"(tmem),
+                        "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
+                        : "memory");
+                }
+                // frees the smem stage once the MMAs above have read it (implies fence::before_thread_sync)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
+                             : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> scores =====
+        const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        bar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m_blk * BM + quarter * 32 + lane;
+        const float qq = (row < nq && metric == RBQ_METRIC_L2) ? qn2[row] : 0.0f;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n0 = n_blk * BN + c0;
+            if (row < nq) {
+                float* out = scores + (size_t)row * nlist + n0;
+                if (n0 + 32 <= nlist && (nlist & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        float* pv = &v.x;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float g = __uint_as_float(r[j + t]);
+                            pv[t] = metric == RBQ_METRIC_L2 ? (qq + cn2[n0 + j + t]) - 2.0f * g : g;
+                        }
+                        *reinterpret_cast<float4*>(out + j) = v;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < nlist) {
+                            const float g = __uint_as_float(r[j]);
+                            out[j] = metric == RBQ_METRIC_L2 ? (qq + cn2[n0 + j]) - 2.0f * g : g;
+                        }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+// ---- operand preparation ------------------------------------------------------------------------------
+// rows x D fp32 -> rows x 3D bf16 in the order the GEMM wants, plus |x|^2 per row.
+// query side: [hi | hi | lo]; centroid side: [hi | lo | hi]
+__global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int D, int centroid_side,
+                                  __nv_bfloat16* __restrict__ out, float* __restrict__ n2) {
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * D;
+    __nv_bfloat16* o = out + (size_t)row * 3 * D;
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = xr[i];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        o[i] = hi;
+        o[D + i] = centroid_side ? lo : hi;
+        o[2 * D + i] = centroid_side ? hi : lo;
+        acc += v * v;
+    }
+    __shared__ float red[32];
+    for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        n2[row] = t;
+    }
+}
+
+int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st) {
+    if (rows == 0) return RBQ_OK;
+    split_bf16_kernel<<<(unsigned)rows, 128, 0, st>>>(d_x, (int)rows, D, centroid_side, reinterpret_cast<__nv_bfloat16*>(d_out), d_n2);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+// ---- tensor maps + launch ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return RBQ_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RBQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) return fail(RBQ_CUDA_ERROR, "cuTensorMapEncodeTiled is not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return RBQ_OK;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous), box = [box_rows][64 cols], 128-byte swizzle, OOB -> 0
+static int make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols, int box_rows) {
+    int rc = get_encode();
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RBQ_CUDA_ERROR, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return RBQ_OK;
+}
+
+// scores[nq][nlist] (approximate).  d_qsplit: nq x 3D bf16, d_csplit: nlist x 3D bf16.
+int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st) {
+    if (nq == 0) return RBQ_OK;
+    const size_t K3 = (size_t)3 * ix.D;
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, d_qsplit, nq, K3, tc::BM))) return rc;
+    if ((rc = make_map(&mb, ix.cent_split, ix.nlist, K3, tc::BN))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+        attr_set = true;
+    }
+    const int num_kb = (int)((K3 + tc::BK - 1) / tc::BK);
+    dim3 grid((ix.nlist + tc::BN - 1) / tc::BN, (unsigned)((nq + tc::BM - 1) / tc::BM));
+    coarse_gemm_kernel<<<grid, tc::THREADS, tc::SMEM, st>>>(ma, mb, (int)nq, (int)ix.nlist, num_kb, ix.metric, d_qn2, ix.cent_n2,
+                                                           d_scores);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+}  // namespace rbq

@@ -9,6 +9,8 @@
 
 #include "../../include/rbq.h"
 
+struct rbq_index;
+
 namespace rbq {
 
 constexpr int kBatch = 32;  // FASTSCAN_BATCH_SIZE (reference src/simd.rs:768)
@@ -62,6 +64,9 @@ struct DevIndex {
     const uint8_t* flip;    // 4*D/8
     const float* matrix_t;  // Matrix rotator, TRANSPOSED (k-major) for coalesced reads
     const float* centroids; // nlist*D
+    const void* cent_split; // nlist*3D bf16: [hi | lo | hi] split of the centroids (tensor-core coarse stage)
+    const float* cent_n2;   // |c|^2 per centroid
+    float cmax_norm;        // max |c|
     const uint32_t* list_n; // nlist
     const uint32_t* blk_off;
     const uint64_t* vec_off;
@@ -102,6 +107,11 @@ int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScala
 int launch_merge(int metric, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids, const float* in_scores,
                  const uint32_t* in_counts, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
                  cudaStream_t st);
+int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scores, const QueryScalars* d_qs, size_t nq,
+                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st);
+int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
+int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st);
+int prepare_coarse_tc(rbq_index* h);  // builds cent_split / cent_n2 / cmax_norm from dev.centroids (api.cu)
 size_t probe_select_max_nprobe();
 size_t scan_max_topk();
 
@@ -132,8 +142,10 @@ struct rbq_index {
     mutable size_t ws_bytes = 0;
     mutable rbq::DevStats* d_stats = nullptr;     // followed by the scan kernel's work counter
     unsigned int* work_counter() const { return reinterpret_cast<unsigned int*>(d_stats + 1); }
+    unsigned int* fallback_counter() const { return work_counter() + 1; }
     mutable rbq_search_stats last_stats{};
     mutable cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool profiling = false;
-    int coarse_mode = 0;
+    int coarse_mode = 1;       // 0: exact FP32 all-pairs, 1: tensor-core candidates + exact re-score
+    float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|)
 };

@@ -273,3 +273,39 @@ def test_device_resident_entry_matches_host_entry(rbq, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(ids.cpu().numpy().astype(np.uint64), host[0])
     assert np.array_equal(sc.cpu().numpy(), host[1])
+
+
+COARSE_CASES = [  # (n, dim, nlist, metric, rotator, kind)
+    (20000, 128, 512, 0, 1, "clustered"),
+    (20000, 960, 300, 0, 1, "clustered"),     # nlist not a multiple of the GEMM tile, K' = 2880
+    (20000, 768, 256, 1, 1, "clustered"),     # inner product
+    (6000, 96, 64, 0, 1, "uniform11"),        # padded 128
+    (3000, 48, 40, 1, 0, "uniform11"),        # MatrixRotator, K' = 144 (not a multiple of 64: TMA zero fill)
+]
+
+
+@pytest.mark.parametrize("case", COARSE_CASES)
+def test_tensor_core_coarse_matches_exact_coarse(rbq, oracle, case):
+    """Mode 1 (tcgen05 GEMM candidates + exact re-score) must give the reference's probe list bit for bit,
+    exactly like mode 0 (exact FP32 scoring of every centroid) and the oracle."""
+    n, dim, nlist, metric, rot, kind = case
+    data, oix, blob = oracle_index(n, dim, nlist, 1, metric, rotator=rot, kind=kind)
+    gix = _load(rbq, blob)
+    q = np.concatenate([data[:100], _queries(data, 412, 21)])
+    for nprobe in (1, 16, 64):
+        nprobe = min(nprobe, nlist)
+        gix.set_coarse_mode(0)
+        c0, f0 = gix.debug_probe(q, nprobe)
+        gix.set_coarse_mode(1)
+        c1, f1 = gix.debug_probe(q, nprobe)
+        assert np.array_equal(c0, c1), "tensor-core candidate path changed the probe list"
+        assert np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
+        for i in range(0, q.shape[0], 37):
+            assert np.array_equal(c1[i], oix.search_dump(q[i], 1, nprobe)["probe"])
+    gix.set_coarse_mode(1)
+    got = gix.batch_search(q, rbq.SearchParams(10, min(16, nlist)))
+    st = gix.stats()
+    assert st["coarse_fallbacks"] <= q.shape[0] // 20, st       # the margin is tight enough to avoid the slow path
+    gix.set_coarse_mode(0)
+    ref = gix.batch_search(q, rbq.SearchParams(10, min(16, nlist)))
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
