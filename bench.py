@@ -85,38 +85,43 @@ def recall_at_k(ids, gt):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled through NVML while the timed region runs (the same counters
+    as the nvidia-smi clocks line of B200_PROFILING.md, polled every ~2 ms so short regions are covered)."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag, self.proc = gpu_index, [], False, None
+        self.gpu, self.sm, self.reasons, self.stop_flag, self.max_mhz, self.window = gpu_index, [], set(), False, None, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.sm.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), r))
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report no samples rather than failing the bench
+            self.err = repr(e)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=2.0)
+        rows = self.sm
+        if self.window:  # keep the samples taken inside the timed region (fall back to all if none landed in it)
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1]]
+            rows = inside or rows
+        import pynvml as nv
+
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted({n for _, _, r in rows for n, bit in names.items() if r & bit})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(rows)}
 
 
 def build_index(wl, device_index, log):
@@ -183,7 +188,7 @@ def oracle_baseline(blob, queries, top_k, nprobe, seconds=12.0, log=lambda s: No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("RBQ_BENCH_WORKLOAD", "gist1m"), choices=sorted(WORKLOADS))
@@ -288,14 +293,15 @@ def main():
         torch.cuda.synchronize(dev)
 
     ix.set_profiling(True)  # CUDA events around every stage on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         flush.fill_(1)
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     scan_ms, scan_bytes, stage_ms, launches = 0.0, 0, np.zeros(4), 0
+    prune = np.zeros(4)
     barrier()
     wall0 = time.time()
     for s in range(args.steps):
@@ -309,8 +315,10 @@ def main():
         scan_bytes += st["bytes_scanned"]
         stage_ms += np.array([st["ms_prep"], st["ms_coarse"], st["ms_select"], st["ms_scan"]])
         launches += st["kernel_launches"] + (1 if world > 1 else 0)
+        prune += np.array([st["candidates"], st["refined"], st["admitted"], st["coarse_fallbacks"]])
     barrier()
     wall = time.time() - wall0
+    sampler.window = (wall0, wall0 + wall)
     clocks = sampler.finish()
     ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -387,6 +395,8 @@ def main():
                         "traffic": None, "bytes_per_launch": scan_bytes / max(args.steps, 1),
                         "ms_per_launch": scan_ms / max(args.steps, 1)},
            "stage_ms_per_step": {n: float(v) / args.steps for n, v in zip(("prep", "coarse", "select", "scan"), stage_ms)},
+           "per_query": {"vectors_scanned": prune[0] / args.steps / nq, "refined": prune[1] / args.steps / nq,
+                         "admitted": prune[2] / args.steps / nq, "coarse_fallbacks": prune[3] / args.steps / nq},
            "wall_s_timed_region": wall}
     if merged_recall is not None:
         out["config"]["recall_at_10_merged"] = round(merged_recall, 4)

@@ -71,6 +71,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("{\n.reg .u16 t;\nld.shared.u16 t, [%1];\ncvt.u32.u16 %0, t;\n}" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -145,55 +169,74 @@ __device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&acc)[32], int lane
     }
 }
 
-// K7 for one block resident in shared memory: returns accu[lane] (exact integer sum, before the u16 wrap)
+// K7 for one block resident in shared memory (blk = 32-bit shared address): returns accu[lane] (exact
+// integer sum, before the u16 wrap).  Branch-free: lanes past the last codebook hold an all-zero LUT row, so
+// whatever (clamped, valid) code bytes they read contribute nothing.
 template <int NCB, bool WIDE>
-__device__ __forceinline__ uint32_t accumulate_block(const uint8_t* blk, const uint4 (&T)[NCB], int ncb, int lane) {
+__device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (&T)[NCB], int ncb, int lane) {
     uint32_t acc[32];
 #pragma unroll
     for (int v = 0; v < 32; ++v) acc[v] = 0u;
 #pragma unroll
     for (int i = 0; i < NCB; ++i) {
-        const int cb = lane + 32 * i;
-        if (NCB * 32 == ncb || cb < ncb) {
-            const uint4 C = *reinterpret_cast<const uint4*>(blk + 16 * cb);
-            lookup_accumulate(C, T[i], acc);
-        }
+        const int cb = min(lane + 32 * i, ncb - 1);
+        const uint4 C = lds128(blk + 16u * (uint32_t)cb);
+        lookup_accumulate(C, T[i], acc);
     }
     return reduce_scatter<WIDE>(acc, lane);
 }
 
 // ---- K10: packed ex-code dot, AVX2 lane order -------------------------------------------------------
-// One of the 8 "AVX lanes" (j): dims j, j+8, j+16, ... accumulated with fma, like the two fmadd steps
-// per 16 dims of the reference.  p points at the vector's packed ex-code (shared memory staging).
-// EXK: 2 / 6 = the reference's C++-compatible layouts; 1 = generic LSB-first bit stream (extension).
+// Staging: the 8 lanes of a group expand one candidate's packed ex-code (global memory) into one byte per
+// code in shared memory, 16 bytes per 16-dim chunk ordered (c0,c8,c1,c9,...,c7,c15) so that "AVX lane" j
+// later reads its two codes of the chunk (dims 16c+j and 16c+8+j) as one 16-bit load.
+// EXK: 2 / 6 = the reference's C++-compatible layouts (src/simd.rs:2478-2695); 1 = generic LSB-first
+// bit stream (src/simd.rs:166-191), used for bit widths the reference cannot search (extension).
 template <int EXK>
-__device__ __forceinline__ float ex_dot_lane(const uint8_t* p, const float* rq, int D, int j, int ex_bits) {
+__device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
+    for (int c = j; c < D / 16; c += 8) {
+        uint32_t A, Bq, Cq, Dq;  // codes 0-3, 4-7, 8-11, 12-15 of the chunk, one per byte
+        if (EXK == 2) {
+            const uint32_t w = ldg32(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
+            A = w & 0x03030303u;
+            Bq = (w >> 2) & 0x03030303u;
+            Cq = (w >> 4) & 0x03030303u;
+            Dq = (w >> 6) & 0x03030303u;
+        } else if (EXK == 6) {
+            const uint32_t w0 = ldg32(src + 12 * c), w1 = ldg32(src + 12 * c + 4), w2 = ldg32(src + 12 * c + 8);
+            // bytes 0-7: low nibble = low 4 bits of code b, high nibble = low 4 bits of code b+8; w2: the 2-bit layout
+            A = (w0 & 0x0F0F0F0Fu) | ((w2 << 4) & 0x30303030u);
+            Bq = (w1 & 0x0F0F0F0Fu) | ((w2 << 2) & 0x30303030u);
+            Cq = ((w0 >> 4) & 0x0F0F0F0Fu) | (w2 & 0x30303030u);
+            Dq = ((w1 >> 4) & 0x0F0F0F0Fu) | ((w2 >> 2) & 0x30303030u);
+        } else {
+            const uint32_t mask = (1u << ex_bits) - 1u;
+            uint32_t x[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t pos = (uint32_t)(16 * c + k) * (uint32_t)ex_bits;
+                const uint32_t two = (uint32_t)__ldg(src + (pos >> 3)) | ((uint32_t)__ldg(src + (pos >> 3) + 1) << 8);
+                x[k >> 2] |= ((two >> (pos & 7u)) & mask) << (8 * (k & 3));
+            }
+            A = x[0];
+            Bq = x[1];
+            Cq = x[2];
+            Dq = x[3];
+        }
+        sts128(stg + 16u * (uint32_t)c, prmt(A, Cq, 0x5140u), prmt(A, Cq, 0x7362u), prmt(Bq, Dq, 0x5140u), prmt(Bq, Dq, 0x7362u));
+    }
+}
+// One of the 8 "AVX lanes" (j): dims j, j+8, j+16, ... accumulated with fma, in the order of the two fmadd
+// steps per 16 dims of the reference (src/simd.rs:1749-1757, 1804-1812).  rq2 holds the rotated query
+// interleaved the same way: float2 (rq[16c+j], rq[16c+8+j]) at index 8c+j.
+__device__ __forceinline__ float ex_dot_lane(uint32_t stg, uint32_t rq2, int D, int j) {
     float acc = 0.0f;
-    const int sh_lo = 8 * (j & 3) + 2 * (j >> 2);  // bit position of code j in the 2-bit word; code j+8: +4
-    if (EXK == 2) {
 #pragma unroll 4
-        for (int c = 0; c < D / 16; ++c) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(p + 4 * c);
-            acc = __fmaf_rn((float)((w >> sh_lo) & 3u), rq[16 * c + j], acc);
-            acc = __fmaf_rn((float)((w >> (sh_lo + 4)) & 3u), rq[16 * c + 8 + j], acc);
-        }
-    } else if (EXK == 6) {
-#pragma unroll 4
-        for (int c = 0; c < D / 16; ++c) {
-            const uint32_t b = p[12 * c + j];
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(p + 12 * c + 8);
-            const uint32_t c0 = (b & 15u) | (((w >> sh_lo) & 3u) << 4);
-            const uint32_t c1 = (b >> 4) | (((w >> (sh_lo + 4)) & 3u) << 4);
-            acc = __fmaf_rn((float)c0, rq[16 * c + j], acc);
-            acc = __fmaf_rn((float)c1, rq[16 * c + 8 + j], acc);
-        }
-    } else {
-        const uint32_t mask = (1u << ex_bits) - 1u;
-        for (int d = j; d < D; d += 8) {
-            const uint32_t pos = (uint32_t)d * (uint32_t)ex_bits;
-            const uint32_t two = (uint32_t)p[pos >> 3] | ((uint32_t)p[(pos >> 3) + 1] << 8);
-            acc = __fmaf_rn((float)((two >> (pos & 7u)) & mask), rq[d], acc);
-        }
+    for (int c = 0; c < D / 16; ++c) {
+        const uint32_t pair = lds_u16(stg + 16u * (uint32_t)c + 2u * (uint32_t)j);
+        const float2 qv = lds_f32x2(rq2 + 8u * (uint32_t)(8 * c + j));
+        acc = __fmaf_rn((float)(pair & 0xffu), qv.x, acc);
+        acc = __fmaf_rn((float)(pair >> 8), qv.y, acc);
     }
     return acc;
 }
@@ -316,10 +359,9 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
     const uint32_t B = ix.block_stride, NST = a.nst;
     const WarpSmem L = warp_smem_layout(B, NST, a.ex_stage_stride, D, k, EXK != 0);
     unsigned char* wbase = scan_smem + (size_t)warp * L.total;
-    uint8_t* ring = wbase + L.ring;
-    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(wbase + L.bars);
-    uint8_t* exst = wbase + L.exst;
-    float* rq = reinterpret_cast<float*>(wbase + L.rq);
+    const uint32_t ring_u32 = smem_u32(wbase + L.ring), bars_u32 = smem_u32(wbase + L.bars);
+    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq);
+    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);  // rotated query, (j, j+8) interleaved per 16 dims
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
     const bool l2 = ix.metric == RBQ_METRIC_L2;
@@ -329,7 +371,7 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    uint32_t it_issue = 0, it_use = 0;  // blocks issued / consumed by this warp since kernel start (ring phase)
+    uint32_t iss_stage = 0, use_stage = 0, use_phase = 0;  // ring cursors (persist across queries)
     unsigned long long st_blocks = 0, st_cand = 0, st_ref = 0, st_adm = 0;
 
     for (;;) {
@@ -346,16 +388,16 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
         pc.seek(ix, pr, a.nprobe);
         for (uint32_t s = 0; s < NST && pc.valid(a.nprobe); ++s) {
             if (lane == 0) {
-                const uint32_t st = it_issue % NST;
-                mbar_expect_tx(bars_u32 + 8 * st, B);
-                tma_load_1d(ring_u32 + st * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * st);
+                mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
+                tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
             }
-            ++it_issue;
+            if (++iss_stage == NST) iss_stage = 0;
             pc.next(ix, pr, a.nprobe);
         }
 
         if (EXK != 0)
-            for (int i = lane; i < D; i += 32) rq[i] = a.rot[(size_t)q * D + i];
+            for (int i = lane; i < D; i += 32)  // dim 16c + r -> float2 slot 8c + (r & 7), component r >> 3
+                rq2[2 * (8 * (i >> 4) + (i & 7)) + ((i >> 3) & 1)] = a.rot[(size_t)q * D + i];
         uint4 T[NCB];
 #pragma unroll
         for (int i = 0; i < NCB; ++i) {
@@ -398,20 +440,11 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
                 for (int r0 = 0; r0 < qn; r0 += kRefineSlots) {
                     const int c = r0 + g;  // candidate served by this 8-lane group
                     const uint32_t li_c = __shfl_sync(0xffffffffu, q_li, c & 31);
-                    uint8_t* stg = exst + (size_t)g * a.ex_stage_stride;
-                    if (c < qn) {
-                        const uint8_t* src = ix.ex + (vbase + li_c) * ix.ex_stride;
-                        if ((ix.ex_stride & 15u) == 0) {
-                            for (uint32_t o = 16 * j; o < ix.ex_stride; o += 128)
-                                *reinterpret_cast<uint4*>(stg + o) = ldg128(src + o);
-                        } else {
-                            for (uint32_t o = 4 * j; o < ix.ex_stride; o += 32)
-                                *reinterpret_cast<uint32_t*>(stg + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
-                        }
-                    }
+                    const uint32_t stg = exst_u32 + (uint32_t)g * a.ex_stage_stride;
+                    if (c < qn) stage_expand<EXK>(ix.ex + (vbase + li_c) * ix.ex_stride, stg, D, j, ix.ex_bits);
                     __syncwarp();
                     float part = 0.0f;
-                    if (c < qn) part = ex_dot_lane<EXK>(stg, rq, D, j, ix.ex_bits);
+                    if (c < qn) part = ex_dot_lane(stg, rq2_u32, D, j);
                     part = hsum8(part);
                     const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
                     if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
@@ -443,24 +476,25 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
             const uint32_t list_pi = cc.pi;
             while (cc.valid(a.nprobe) && cc.pi == list_pi) {
                 const uint32_t b = cc.b;
-                const uint32_t st = it_use % NST;
-                mbar_wait(bars_u32 + 8 * st, (it_use / NST) & 1u);
-                const uint8_t* blk = ring + (size_t)st * B;
+                mbar_wait(bars_u32 + 8 * use_stage, use_phase);
+                const uint32_t blk = ring_u32 + use_stage * B;
                 uint32_t accu = accumulate_block<NCB, WIDE>(blk, T, ncb, lane);
                 if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
-                const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
-                const float f_add = fac[lane], f_rescale = fac[32 + lane], f_error = fac[64 + lane];
+                const uint32_t fac = blk + (uint32_t)D * 4u + 4u * (uint32_t)lane;
+                const float f_add = lds_f32(fac), f_rescale = lds_f32(fac + 128u), f_error = lds_f32(fac + 256u);
                 // the stage has been read: hand it back to the TMA engine for the block NST ahead
                 __syncwarp();
-                ++it_use;
+                if (++use_stage == NST) {
+                    use_stage = 0;
+                    use_phase ^= 1u;
+                }
                 if (pc.valid(a.nprobe)) {
                     if (lane == 0) {
                         fence_proxy_async();
-                        const uint32_t ns = it_issue % NST;
-                        mbar_expect_tx(bars_u32 + 8 * ns, B);
-                        tma_load_1d(ring_u32 + ns * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * ns);
+                        mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
+                        tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
                     }
-                    ++it_issue;
+                    if (++iss_stage == NST) iss_stage = 0;
                     pc.next(ix, pr, a.nprobe);
                 }
                 // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
@@ -561,7 +595,7 @@ static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
     int rc = device_limits();
     if (rc) return rc;
     const bool has_ex = ix.ex_bits != 0;
-    a.ex_stage_stride = ((ix.ex_stride + 15u) / 16u) * 16u + 16u;
+    a.ex_stage_stride = (uint32_t)ix.D;  // refine staging: one byte per code, 16 bytes per 16-dim chunk
     // ring depth: as many stages as fit 3 CTAs/SM, between 2 and 4
     const size_t per_sm = 227 * 1024;
     uint32_t nst = 4;
