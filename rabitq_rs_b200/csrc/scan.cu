@@ -194,6 +194,7 @@ __device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (
 // bit stream (src/simd.rs:166-191), used for bit widths the reference cannot search (extension).
 template <int EXK>
 __device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
+#pragma unroll 4
     for (int c = j; c < D / 16; c += 8) {
         uint32_t A, Bq, Cq, Dq;  // codes 0-3, 4-7, 8-11, 12-15 of the chunk, one per byte
         if (EXK == 2) {
@@ -555,6 +556,7 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
                             for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
                         }
                         qn += n_new;
+                        if (qn >= 2 * kRefineSlots) flush();  // keeps rounds full and the threshold fresh
                     }
                 }
                 cc.next(ix, pr, a.nprobe);
@@ -595,7 +597,9 @@ static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
     int rc = device_limits();
     if (rc) return rc;
     const bool has_ex = ix.ex_bits != 0;
-    a.ex_stage_stride = (uint32_t)ix.D;  // refine staging: one byte per code, 16 bytes per 16-dim chunk
+    // refine staging: one byte per code (16 bytes per 16-dim chunk); stride = 32 (mod 128) so the four
+    // 8-lane groups hit disjoint shared-memory banks
+    a.ex_stage_stride = ((uint32_t)ix.D + 127u) / 128u * 128u + 32u;
     // ring depth: as many stages as fit 3 CTAs/SM, between 2 and 4
     const size_t per_sm = 227 * 1024;
     uint32_t nst = 4;
