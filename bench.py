@@ -218,21 +218,45 @@ def main():
 
     import rabitq_rs_b200 as rbq
 
-    ix_full, base, queries, gt = build_index(wl, local, log)
-    nq, k, D = wl["nq"], wl["top_k"], ix_full.padded_dim
-    if args.nprobe:
-        nprobe, table = args.nprobe, []
-    else:
-        nprobe, table = pick_nprobe(ix_full, queries, gt, k, wl["nlist"], args.recall, log)
-    ids, _, _ = ix_full.batch_search(queries, rbq.SearchParams(k, nprobe))
-    recall = recall_at_k(ids, gt)
+    # Rank 0 generates the data, builds the index once and picks nprobe; the other ranks receive the
+    # serialized RBQ1 stream, the queries and nprobe (one index file, every rank loads its shard of it).
+    multi = world > 1 and args.impl == "ours"
+    nq, k = wl["nq"], wl["top_k"]
+    ix_full = base = gt = None
+    blob = None
+    if rank == 0:
+        ix_full, base, queries, gt = build_index(wl, local, log)
+        if args.nprobe:
+            nprobe, table = args.nprobe, []
+        else:
+            nprobe, table = pick_nprobe(ix_full, queries, gt, k, wl["nlist"], args.recall, log)
+        ids, _, _ = ix_full.batch_search(queries, rbq.SearchParams(k, nprobe))
+        recall = recall_at_k(ids, gt)
+        D = ix_full.padded_dim
+    if multi:
+        meta = torch.zeros(4, dtype=torch.int64, device=dev)
+        if rank == 0:
+            blob = ix_full.save_to_bytes()
+            meta[:] = torch.tensor([len(blob), nprobe, D, int(recall * 1e6)], dtype=torch.int64)
+        dist.broadcast(meta, 0)
+        nbytes, nprobe, D, recall = int(meta[0]), int(meta[1]), int(meta[2]), float(meta[3]) / 1e6
+        tb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        tq = torch.empty((nq, wl["dim"]), dtype=torch.float32, device=dev)
+        if rank == 0:
+            tb.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+            tq.copy_(torch.from_numpy(queries))
+        dist.broadcast(tb, 0)
+        dist.broadcast(tq, 0)
+        if rank != 0:
+            blob = tb.cpu().numpy().tobytes()
+            queries = tq.cpu().numpy()
+        del tb, tq
     config = {"workload": f"{args.workload}: {wl['n']}x{wl['dim']} synthetic (latent-{GEN['latent']} Gaussian mixture), nlist={wl['nlist']}, "
                           f"total_bits={wl['total_bits']}, {'L2' if wl['metric'] == 0 else 'IP'}, FhtKacRotator, {nq}-query batch, top-{k}",
               "nprobe": nprobe, "recall_at_10": round(recall, 4), "recall_target": args.recall, "padded_dim": D,
               "l2_policy": "256 MiB L2 flush between timed steps; scanned blocks+ex-codes also exceed the 126 MB L2",
               "parallelism": f"lists sharded over {world} GPU(s), centroids replicated" if world > 1 else "1 GPU",
               "generator": GEN}
-    blob = None
 
     if args.impl == "reference":
         blob = ix_full.save_to_bytes()
@@ -256,7 +280,6 @@ def main():
 
     # ---- our arm -------------------------------------------------------------------------------
     if world > 1:
-        blob = ix_full.save_to_bytes()
         ix = rbq.IvfRabitqIndex.load_from_bytes(blob, device=local, shard_rank=rank, shard_count=world)
         log(f"shard {rank}/{world}: {ix.local_len()} of {len(ix)} vectors")
     else:
@@ -328,9 +351,11 @@ def main():
     value = nq * args.steps / (ms_total / 1000.0)
 
     # correctness of the distributed result vs the single-GPU result (not timed)
-    merged_recall = None
-    if world > 1:
-        merged_recall = recall_at_k(m_ids.cpu().numpy().astype(np.uint64), gt)
+    merged_recall = merged_same = None
+    if world > 1 and rank == 0:
+        merged = m_ids.cpu().numpy().astype(np.uint64)
+        merged_recall = recall_at_k(merged, gt)
+        merged_same = float(np.mean([len(set(merged[i].tolist()) & set(ids[i, :k].tolist())) / k for i in range(nq)]))
 
     # ---- e2e through the C ABI with pinned host buffers ------------------------------------------
     ix.set_profiling(False)
@@ -400,6 +425,7 @@ def main():
            "wall_s_timed_region": wall}
     if merged_recall is not None:
         out["config"]["recall_at_10_merged"] = round(merged_recall, 4)
+        out["config"]["merged_ids_equal_single_gpu"] = round(merged_same, 5)
     if not args.no_cpu_baseline and world == 1:
         blob = blob or ix_full.save_to_bytes()
         qps, cores, sample, res, _ = oracle_baseline(blob, queries, k, nprobe, log=log)

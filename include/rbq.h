@@ -101,6 +101,12 @@ int rbq_merge_topk_device(const rbq_index* ix, int nshards, size_t nq, size_t to
                           const uint64_t* in_ids, const float* in_scores, const uint32_t* in_counts,
                           uint64_t* out_ids, float* out_scores, uint32_t* out_counts, void* stream);
 
+/* Host-only: the shard every inverted list of an RBQ1 stream is assigned to for `shard_count` shards
+ * (the same deterministic size-balanced map rbq_index_load uses; no GPU needed).  owner[i] in
+ * [0, shard_count); list_sizes (optional) receives the vector count of every list. */
+int rbq_shard_assignment(const uint8_t* bytes, size_t len, int shard_count, int32_t* owner, uint32_t* list_sizes,
+                         size_t cap_lists, size_t* nlist_out);
+
 /* ---- diagnostics (SearchDiagnostics, src/ivf.rs:151-155, plus roofline accounting) ---- */
 typedef struct rbq_search_stats {
     uint64_t queries;           /* queries in the last search call on this handle */

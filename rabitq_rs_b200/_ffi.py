@@ -24,7 +24,7 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m rabitq_rs_b200.build` "
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python rabitq_rs_b200/build.py` "
                           "(rabitq_rs_b200 has no CPU fallback)")
     L = C.CDLL(LIB_PATH)
     vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
@@ -47,6 +47,7 @@ def lib():
     L.rbq_search_batch_filtered.argtypes = [vp, vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
     L.rbq_search_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
     L.rbq_merge_topk_device.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.rbq_shard_assignment.argtypes = [vp, sz, i32, vp, vp, sz, C.POINTER(sz)]
     L.rbq_last_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.rbq_set_profiling.argtypes = [vp, i32]
     L.rbq_set_coarse_mode.argtypes = [vp, i32]

@@ -1,6 +1,7 @@
 """Builds librbq.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-Run as `python -m rabitq_rs_b200.build` or through __graft_entry__.build().  nvcc cross-compiles
+Run as `python rabitq_rs_b200/build.py` or through __graft_entry__.build() (loaded by path, because
+importing the package requires the library to exist).  nvcc cross-compiles
 without a GPU.  Flags that matter for parity: -fmad=false (no implicit mul+add contraction; the
 kernels spell out every fma the reference uses), IEEE division and square root (nvcc defaults).
 """

@@ -301,3 +301,26 @@ void write_rbq1(const HostIndex& ix, std::vector<uint8_t>& out) {
 }  // namespace rbq
 
 extern "C" const char* rbq_last_error(void) { return rbq::last_error_cstr(); }
+
+extern "C" int rbq_shard_assignment(const uint8_t* bytes, size_t len, int shard_count, int32_t* owner, uint32_t* list_sizes,
+                                    size_t cap_lists, size_t* nlist_out) {
+    if (!bytes || !nlist_out) return rbq::fail(RBQ_INVALID_CONFIG, "null argument");
+    rbq::HostIndex hi;
+    // parse as shard 0 of shard_count: validates the stream and yields every list's size
+    int rc = rbq::parse_rbq1(bytes, len, 0, shard_count, hi);
+    if (rc) return rc;
+    *nlist_out = hi.nlist;
+    if (cap_lists < hi.nlist) return owner ? rbq::fail(RBQ_INVALID_CONFIG, "output buffer too small") : (int)RBQ_OK;
+    std::vector<uint64_t> bytes_per_list(hi.nlist);
+    const size_t stride = hi.block_stride(), exs = hi.ex_stride();
+    for (size_t c = 0; c < hi.nlist; ++c) {
+        const uint64_t nv = hi.list_n_all[c];
+        bytes_per_list[c] = (nv + rbq::kBatch - 1) / rbq::kBatch * stride + nv * (exs + 16);
+        if (list_sizes) list_sizes[c] = (uint32_t)nv;
+    }
+    std::vector<int> own;
+    rbq::assign_shards(bytes_per_list, shard_count, own);
+    if (owner)
+        for (size_t c = 0; c < hi.nlist; ++c) owner[c] = own[c];
+    return RBQ_OK;
+}

@@ -327,6 +327,18 @@ class IvfRabitqIndex:
         return accu[:slots], ip[:slots], est[:slots], lb[:slots]
 
 
+def shard_assignment(blob, shard_count):
+    """(owner[nlist] int32, list_sizes[nlist] uint32): the deterministic size-balanced list -> shard map
+    used by load(..., shard_rank, shard_count).  Host-only (no GPU needed)."""
+    buf = np.frombuffer(bytes(blob), np.uint8)
+    n = C.c_size_t()
+    _check(_ffi.lib().rbq_shard_assignment(_ptr(buf), buf.size, int(shard_count), None, None, 0, C.byref(n)))
+    owner = np.empty(n.value, np.int32)
+    sizes = np.empty(n.value, np.uint32)
+    _check(_ffi.lib().rbq_shard_assignment(_ptr(buf), buf.size, int(shard_count), _ptr(owner), _ptr(sizes), n.value, C.byref(n)))
+    return owner, sizes
+
+
 def ids_to_bitset(allowed_ids, nbits=None):
     """Dense u64 bitset over u32 ids (the C ABI's stand-in for RoaringBitmap)."""
     a = np.asarray(list(allowed_ids) if not isinstance(allowed_ids, np.ndarray) else allowed_ids, np.uint64)

@@ -26,3 +26,13 @@ def oracle():
 
     orc.lib()
     return orc
+
+
+def build_librbq():
+    """Build librbq.so in-tree (loaded by path: importing the package needs the library to exist)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("rbq_build", os.path.join(ROOT, "rabitq_rs_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()

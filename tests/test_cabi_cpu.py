@@ -15,9 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def rbq():
-    from rabitq_rs_b200 import build as b
+    from conftest import build_librbq
 
-    b.build()
+    build_librbq()
     import rabitq_rs_b200 as r
 
     return r
