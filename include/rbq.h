@@ -118,10 +118,22 @@ typedef struct rbq_search_stats {
     uint64_t kernel_launches;   /* CUDA kernels launched by the call */
     uint64_t coarse_fallbacks;  /* queries whose tensor-core candidate set overflowed and were scored exactly */
     float ms_prep, ms_coarse, ms_select, ms_scan; /* CUDA-event times of the last *profiled* call */
+    /* list-major scan (large batches): head pass / tail kernel / replay pass */
+    uint64_t tail_blocks;       /* (query, block) FastScan evaluations done by the list-major tail kernel */
+    uint64_t tail_bytes;        /* tail_blocks * (4*padded_dim + 384): the tail kernel's algorithmic bytes */
+    uint64_t tail_pairs;        /* (query, list) pairs handled by the tail kernel */
+    uint64_t survivors;         /* tail vectors with lower bound < the head threshold (replayed in reference order) */
+    uint64_t overflow_queries;  /* queries whose survivor buffer overflowed (their tail was re-walked sequentially) */
+    float ms_scan_head, ms_scan_tail, ms_scan_replay; /* split of ms_scan (sequential mode: all in head) */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */
 int rbq_set_profiling(rbq_index* ix, int on);
+/* Scan-stage schedule: 0 = auto (list-major for large batches), 1 = sequential (one warp walks one query's
+ * probe sequence, the reference's loop order), 2 = list-major (head pass until the heap is full, then all
+ * remaining (query, list) pairs grouped by list, then an ordered replay of the surviving candidates).
+ * Both reproduce search_cluster_v2_batched's decisions exactly (src/ivf.rs:2013-2127). */
+int rbq_set_scan_mode(rbq_index* ix, int mode);
 /* Coarse-stage implementation: 0 = exact FP32 scoring of every centroid (CUDA cores),
  * 1 = tensor-core (tcgen05) candidate GEMM + exact FP32 re-score of the near-threshold centroids
  * (default).  Both produce the reference's probe list bit for bit. */
@@ -141,6 +153,10 @@ int rbq_debug_probe(const rbq_index* ix, const float* queries, size_t nq, size_t
  * (simd::accumulate_batch_avx2 src/simd.rs:972, compute_batch_distances_u16 :1932). */
 int rbq_debug_scan_list(const rbq_index* ix, const float* query, size_t dim, size_t cluster,
                         uint32_t* accu, float* ip, float* est, float* lb, size_t cap_vectors);
+
+/* Test knob (process-wide): capacity of the per-query survivor buffer of the list-major scan; 0 restores the
+ * default (derived from top_k).  A query that overflows it has its tail re-walked sequentially (still exact). */
+int rbq_debug_set_survivor_cap(uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,10 @@ class SearchStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("blocks_scanned", C.c_uint64), ("bytes_scanned", C.c_uint64),
                 ("candidates", C.c_uint64), ("refined", C.c_uint64), ("admitted", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("coarse_fallbacks", C.c_uint64), ("ms_prep", C.c_float), ("ms_coarse", C.c_float),
-                ("ms_select", C.c_float), ("ms_scan", C.c_float)]
+                ("ms_select", C.c_float), ("ms_scan", C.c_float),
+                ("tail_blocks", C.c_uint64), ("tail_bytes", C.c_uint64), ("tail_pairs", C.c_uint64),
+                ("survivors", C.c_uint64), ("overflow_queries", C.c_uint64),
+                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float)]
 
 
 _lib = None
@@ -51,6 +54,8 @@ def lib():
     L.rbq_last_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.rbq_set_profiling.argtypes = [vp, i32]
     L.rbq_set_coarse_mode.argtypes = [vp, i32]
+    L.rbq_set_scan_mode.argtypes = [vp, i32]
+    L.rbq_debug_set_survivor_cap.argtypes = [C.c_uint32]
     L.rbq_debug_query_prep.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.rbq_debug_probe.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.rbq_debug_scan_list.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, sz]

@@ -175,6 +175,7 @@ size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_
     n += qt * (size_t)h->dev.nlist * 4 + 256;  // scores
     n += qt * nprobe * sizeof(Probe) + 256;
     n += qt * 3 * D * 2 + qt * 4 + 512;    // bf16 split of the rotated queries + |q|^2 (tensor-core coarse stage)
+    n += tail_ws_bytes(h->dev, qt, nprobe, top_k) + 256;  // head/tail/replay pipeline (scan_tail.cu)
     if (host_io) {
         n += qt * dim * 4 + 256;
         n += qt * top_k * 12 + qt * 4 + 768;
@@ -197,7 +198,9 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
     Probe* d_pr = cv.take<Probe>(qt * nprobe);
     uint16_t* d_qsplit = cv.take<uint16_t>(qt * 3 * D);
     float* d_qn2 = cv.take<float>(qt);
-    float ms[4] = {0, 0, 0, 0};
+    TailWs tw;
+    tail_ws_carve(ix, qt, nprobe, top_k, cv.take<char>(tail_ws_bytes(ix, qt, nprobe, top_k)), tw);
+    float ms[7] = {0, 0, 0, 0, 0, 0, 0};
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
         int rc;
@@ -217,14 +220,37 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
             *launches += 1;
         }
         if (h->profiling) cudaEventRecord(h->ev[3], st);
-        if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                              d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), st)))
-            return rc;
-        *launches += 4;
+        // Scan stage.  Sequential: one warp walks one query's whole probe sequence.  List-major (large batches):
+        // head pass (sequential, until the heap is full) -> tail kernel (all remaining pairs grouped by list)
+        // -> replay pass (survivors in reference order).  Both are exact.
+        const bool list_major = h->scan_mode == 2 || (h->scan_mode == 0 && nprobe >= 4 && n * nprobe >= 8 * (size_t)ix.nlist);
+        if (!list_major) {
+            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFull, nullptr, st)))
+                return rc;
+            *launches += 4;
+            if (h->profiling) {
+                cudaEventRecord(h->ev[4], st);
+                cudaEventRecord(h->ev[5], st);
+                cudaEventRecord(h->ev[6], st);
+            }
+        } else {
+            RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + 8) * 4, st));  // + list_cnt, list_fill, counters
+            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanHead, &tw, st)))
+                return rc;
+            if (h->profiling) cudaEventRecord(h->ev[4], st);
+            if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches))) return rc;
+            if (h->profiling) cudaEventRecord(h->ev[5], st);
+            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanReplay, &tw, st)))
+                return rc;
+            *launches += 9;
+            if (h->profiling) cudaEventRecord(h->ev[6], st);
+        }
         if (h->profiling) {
-            cudaEventRecord(h->ev[4], st);
-            RBQ_CUDA(cudaEventSynchronize(h->ev[4]));
-            for (int i = 0; i < 4; ++i) {
+            RBQ_CUDA(cudaEventSynchronize(h->ev[6]));
+            for (int i = 0; i < 6; ++i) {
                 float t = 0;
                 cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
                 ms[i] += t;
@@ -235,7 +261,10 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         h->last_stats.ms_prep = ms[0];
         h->last_stats.ms_coarse = ms[1];
         h->last_stats.ms_select = ms[2];
-        h->last_stats.ms_scan = ms[3];
+        h->last_stats.ms_scan = ms[3] + ms[4] + ms[5];
+        h->last_stats.ms_scan_head = ms[3];
+        h->last_stats.ms_scan_tail = ms[4];
+        h->last_stats.ms_scan_replay = ms[5];
     }
     return RBQ_OK;
 }
@@ -378,6 +407,19 @@ int rbq_set_coarse_mode(rbq_index* h, int mode) {
     return RBQ_OK;
 }
 
+int rbq_set_scan_mode(rbq_index* h, int mode) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (mode < 0 || mode > 2) return fail(RBQ_INVALID_CONFIG, "scan mode must be 0 (auto), 1 (sequential) or 2 (list-major)");
+    h->scan_mode = mode;
+    return RBQ_OK;
+}
+
+int rbq_debug_set_survivor_cap(uint32_t cap) {
+    if (cap > 1024) return fail(RBQ_INVALID_CONFIG, "survivor cap must be <= 1024");
+    tail_debug_set_survivor_cap(cap);
+    return RBQ_OK;
+}
+
 int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     if (!h || !out) return fail(RBQ_INVALID_CONFIG, "null argument");
     DeviceGuard g(h->device);
@@ -389,6 +431,11 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     h->last_stats.candidates = ds.candidates;
     h->last_stats.refined = ds.refined;
     h->last_stats.admitted = ds.admitted;
+    h->last_stats.tail_blocks = ds.tail_blocks;
+    h->last_stats.tail_bytes = ds.tail_blocks * (uint64_t)h->dev.block_stride;
+    h->last_stats.tail_pairs = ds.tail_pairs;
+    h->last_stats.survivors = ds.survivors;
+    h->last_stats.overflow_queries = ds.overflow_queries;
     unsigned int fb = 0;
     RBQ_CUDA(cudaMemcpy(&fb, h->fallback_counter(), sizeof(fb), cudaMemcpyDeviceToHost));
     h->last_stats.coarse_fallbacks = fb;

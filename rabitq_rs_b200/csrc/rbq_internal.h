@@ -89,6 +89,37 @@ struct Probe {  // one per (query, probe rank), written by the probe kernel (32 
 };
 struct DevStats {
     unsigned long long blocks, candidates, refined, admitted;
+    // list-major tail stage (scan_tail.cu)
+    unsigned long long tail_blocks;      // (query, block) evaluations done by the tail kernel
+    unsigned long long tail_pairs;       // (query, list) pairs handed to the tail kernel
+    unsigned long long survivors;        // tail candidates with lower bound < the query's head threshold
+    unsigned long long overflow_queries; // queries whose survivor buffer overflowed (re-walked sequentially)
+};
+// A tail candidate that may still enter the top-k: replayed in (rank, pos) order by the replay pass.
+struct Survivor {
+    uint32_t rank;   // probe rank of its list
+    uint32_t pos;    // position inside the list (visit order)
+    float lower;     // lower bound (after the non-finite fallback)
+    float x;         // ex_bits > 0: ip_x0_qr (feeds the ex-code distance); ex_bits == 0: the estimate
+};
+struct TailItem {  // work item of the tail kernel: a chunk of the (query, rank) pairs probing one list
+    uint32_t cid, pair_begin, pair_count, pad;
+};
+enum ScanMode { kScanFull = 0, kScanHead = 1, kScanReplay = 2 };
+struct TailWs {  // device workspace of the head/tail/replay pipeline (per query tile)
+    uint32_t* tail_start;  // [nq] first probe rank left to the tail stage (== nprobe: none)
+    float* tau;            // [nq] k-th distance after the head stage (INF if the heap is not full)
+    uint32_t* surv_cnt;    // [nq]
+    Survivor* surv;        // [nq * surv_cap]
+    uint32_t surv_cap;
+    uint32_t* list_cnt;    // [nlist] pairs per list      } zeroed together with surv_cnt and the counters
+    uint32_t* list_fill;   // [nlist] scatter cursors     }
+    uint32_t* list_off;    // [nlist + 1]
+    uint32_t* pairs;       // [nq * nprobe] pair ids (q * nprobe + rank) grouped by list
+    TailItem* items;       // [max_items]
+    uint32_t* counters;    // [0] n_items, [1] item cursor
+    uint32_t max_items;
+    uint32_t pairs_per_item;
 };
 
 // kernels (each .cu exposes a launcher)
@@ -97,10 +128,20 @@ int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, flo
 int launch_coarse_exact(const DevIndex& ix, const float* d_rot, size_t nq, float* d_scores, cudaStream_t st);
 int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_scores, size_t nq, size_t nprobe,
                         Probe* d_probes, cudaStream_t st);
+// mode kScanFull: the whole probe sequence per query.  kScanHead: stop after the first list that leaves the
+// heap full (writes tw->tail_start / tw->tau).  kScanReplay: continue from the head state with the tail
+// kernel's survivors.  tw may be null for kScanFull.
 int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
                 const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter,
                 size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
-                unsigned int* d_work_counter, cudaStream_t st);
+                unsigned int* d_work_counter, int mode, const TailWs* tw, cudaStream_t st);
+// scan_tail.cu: group the tail (query, rank) pairs by list, then FastScan list-major; survivors -> tw.
+int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
+                size_t nprobe, const uint64_t* d_filter, size_t filter_nbits, DevStats* d_stats, const TailWs& tw,
+                cudaStream_t st, uint64_t* launches);
+void tail_debug_set_survivor_cap(uint32_t cap);  // 0 = default
+size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k);
+void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, char* base, TailWs& tw);
 int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, uint32_t cluster,
                       float g_add, float g_error, uint32_t* d_accu, float* d_ip, float* d_est, float* d_lb,
                       cudaStream_t st);
@@ -144,8 +185,9 @@ struct rbq_index {
     unsigned int* work_counter() const { return reinterpret_cast<unsigned int*>(d_stats + 1); }
     unsigned int* fallback_counter() const { return work_counter() + 1; }
     mutable rbq_search_stats last_stats{};
-    mutable cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    mutable cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool profiling = false;
+    int scan_mode = 0;         // 0: auto, 1: sequential per-query walk, 2: list-major head/tail/replay
     int coarse_mode = 1;       // 0: exact FP32 all-pairs, 1: tensor-core candidates + exact re-score
     float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|)
 };

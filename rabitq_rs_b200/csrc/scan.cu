@@ -28,75 +28,14 @@
 // Integer sums are exact (== the reference's wrapping-u16 value); float ops follow the AVX2
 // variants' order (fma only where the reference uses fmadd).  Compiled with -fmad=false.
 #include <algorithm>
-#include <cfloat>
 
-#include "rbq_internal.h"
+#include "scan_common.cuh"
 
 namespace rbq {
 
 constexpr int kWarps = 4;
 constexpr int kMaxTopK = 1024;
-constexpr int kRefineSlots = 4;  // candidates refined per round (4 x 8 lanes)
 size_t scan_max_topk() { return kMaxTopK; }
-
-// ---- PTX helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint32_t v;
-    asm volatile("{\n.reg .u16 t;\nld.shared.u16 t, [%1];\ncvt.u32.u16 %0, t;\n}" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- K7: lookups ---------------------------------------------------------------------------------
 // 32 nibble lookups of one codebook.  C = its 16 code bytes, T = its 16 LUT bytes.  acc[v] += lut[nibble(v)].
@@ -186,104 +125,6 @@ __device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (
     return reduce_scatter<WIDE>(acc, lane);
 }
 
-// ---- K10: packed ex-code dot, AVX2 lane order -------------------------------------------------------
-// Staging: the 8 lanes of a group expand one candidate's packed ex-code (global memory) into one byte per
-// code in shared memory, 16 bytes per 16-dim chunk ordered (c0,c8,c1,c9,...,c7,c15) so that "AVX lane" j
-// later reads its two codes of the chunk (dims 16c+j and 16c+8+j) as one 16-bit load.
-// EXK: 2 / 6 = the reference's C++-compatible layouts (src/simd.rs:2478-2695); 1 = generic LSB-first
-// bit stream (src/simd.rs:166-191), used for bit widths the reference cannot search (extension).
-template <int EXK>
-__device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
-#pragma unroll 4
-    for (int c = j; c < D / 16; c += 8) {
-        uint32_t A, Bq, Cq, Dq;  // codes 0-3, 4-7, 8-11, 12-15 of the chunk, one per byte
-        if (EXK == 2) {
-            const uint32_t w = ldg32(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
-            A = w & 0x03030303u;
-            Bq = (w >> 2) & 0x03030303u;
-            Cq = (w >> 4) & 0x03030303u;
-            Dq = (w >> 6) & 0x03030303u;
-        } else if (EXK == 6) {
-            const uint32_t w0 = ldg32(src + 12 * c), w1 = ldg32(src + 12 * c + 4), w2 = ldg32(src + 12 * c + 8);
-            // bytes 0-7: low nibble = low 4 bits of code b, high nibble = low 4 bits of code b+8; w2: the 2-bit layout
-            A = (w0 & 0x0F0F0F0Fu) | ((w2 << 4) & 0x30303030u);
-            Bq = (w1 & 0x0F0F0F0Fu) | ((w2 << 2) & 0x30303030u);
-            Cq = ((w0 >> 4) & 0x0F0F0F0Fu) | (w2 & 0x30303030u);
-            Dq = ((w1 >> 4) & 0x0F0F0F0Fu) | ((w2 >> 2) & 0x30303030u);
-        } else {
-            const uint32_t mask = (1u << ex_bits) - 1u;
-            uint32_t x[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t pos = (uint32_t)(16 * c + k) * (uint32_t)ex_bits;
-                const uint32_t two = (uint32_t)__ldg(src + (pos >> 3)) | ((uint32_t)__ldg(src + (pos >> 3) + 1) << 8);
-                x[k >> 2] |= ((two >> (pos & 7u)) & mask) << (8 * (k & 3));
-            }
-            A = x[0];
-            Bq = x[1];
-            Cq = x[2];
-            Dq = x[3];
-        }
-        sts128(stg + 16u * (uint32_t)c, prmt(A, Cq, 0x5140u), prmt(A, Cq, 0x7362u), prmt(Bq, Dq, 0x5140u), prmt(Bq, Dq, 0x7362u));
-    }
-}
-// One of the 8 "AVX lanes" (j): dims j, j+8, j+16, ... accumulated with fma, in the order of the two fmadd
-// steps per 16 dims of the reference (src/simd.rs:1749-1757, 1804-1812).  rq2 holds the rotated query
-// interleaved the same way: float2 (rq[16c+j], rq[16c+8+j]) at index 8c+j.
-__device__ __forceinline__ float ex_dot_lane(uint32_t stg, uint32_t rq2, int D, int j) {
-    float acc = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < D / 16; ++c) {
-        const uint32_t pair = lds_u16(stg + 16u * (uint32_t)c + 2u * (uint32_t)j);
-        const float2 qv = lds_f32x2(rq2 + 8u * (uint32_t)(8 * c + j));
-        acc = __fmaf_rn((float)(pair & 0xffu), qv.x, acc);
-        acc = __fmaf_rn((float)(pair >> 8), qv.y, acc);
-    }
-    return acc;
-}
-// horizontal sum of the 8 lanes exactly as the AVX2 code: ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
-__device__ __forceinline__ float hsum8(float a) {
-    a = a + __shfl_xor_sync(0xffffffffu, a, 4);
-    a = a + __shfl_xor_sync(0xffffffffu, a, 2);
-    a = a + __shfl_xor_sync(0xffffffffu, a, 1);
-    return a;
-}
-
-// ---- K11: warp-cooperative insertion into an ascending list of at most k (distance, id) pairs -----
-// Equal distances keep the earlier-visited entry first (and drop the newcomer at the boundary).
-__device__ __forceinline__ void topk_insert(float* sd, unsigned long long* si, int& cnt, int k, float d,
-                                            unsigned long long id, int lane) {
-    int pos = 0;
-    for (int base = 0; base < cnt; base += 32) {
-        const int i = base + lane;
-        pos += __popc(__ballot_sync(0xffffffffu, i < cnt && sd[i] <= d));
-    }
-    if (pos >= k) return;
-    const int newcnt = cnt < k ? cnt + 1 : k;
-    for (int base = ((newcnt - 1) >> 5) << 5; base >= 0 && base + 32 > pos; base -= 32) {
-        const int i = base + lane;
-        const bool mv = i >= pos && i < newcnt - 1;
-        float td = 0.0f;
-        unsigned long long ti = 0;
-        if (mv) {
-            td = sd[i];
-            ti = si[i];
-        }
-        __syncwarp();
-        if (mv) {
-            sd[i + 1] = td;
-            si[i + 1] = ti;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) {
-        sd[pos] = d;
-        si[pos] = id;
-    }
-    __syncwarp();
-    cnt = newcnt;
-}
-
 struct ScanArgs {
     const float* rot;
     const uint8_t* lut;
@@ -299,14 +140,21 @@ struct ScanArgs {
     unsigned int* work_counter;  // next query to hand out
     uint32_t nst;                // ring stages per warp
     uint32_t ex_stage_stride;    // bytes per refine staging slot (16-byte multiple)
+    // head / replay passes of the list-major pipeline (see scan_tail.cu)
+    uint32_t mode;               // ScanMode
+    uint32_t* tail_start;
+    float* tau;
+    const Survivor* surv;
+    const uint32_t* surv_cnt;
+    uint32_t surv_cap;
 };
 
 // Per-warp shared memory carve-up (bytes), all offsets 16-byte aligned.
 struct WarpSmem {
-    uint32_t ring, bars, exst, rq, si, sd, total;
+    uint32_t ring, bars, exst, rq, si, sd, ord, total;
 };
 __host__ __device__ inline WarpSmem warp_smem_layout(uint32_t block_stride, uint32_t nst, uint32_t ex_stage_stride,
-                                                     uint32_t D, uint32_t k, bool has_ex) {
+                                                     uint32_t D, uint32_t k, bool has_ex, uint32_t surv_cap) {
     WarpSmem w;
     uint32_t o = 0;
     w.ring = o;
@@ -321,6 +169,10 @@ __host__ __device__ inline WarpSmem warp_smem_layout(uint32_t block_stride, uint
     o += ((k * 8 + 15) / 16) * 16;
     w.sd = o;
     o += ((k * 4 + 15) / 16) * 16;
+    w.ord = o;  // replay pass: sort keys of the survivors (capacity rounded up to a power of two >= 32)
+    uint32_t cap2 = surv_cap ? 32 : 0;
+    while (cap2 < surv_cap) cap2 <<= 1;
+    o += cap2 * 8;
     w.total = o;
     return w;
 }
@@ -358,13 +210,14 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, ncb = D / 4, k = (int)a.top_k;
     const uint32_t B = ix.block_stride, NST = a.nst;
-    const WarpSmem L = warp_smem_layout(B, NST, a.ex_stage_stride, D, k, EXK != 0);
+    const WarpSmem L = warp_smem_layout(B, NST, a.ex_stage_stride, D, k, EXK != 0, a.mode == kScanReplay ? a.surv_cap : 0);
     unsigned char* wbase = scan_smem + (size_t)warp * L.total;
     const uint32_t ring_u32 = smem_u32(wbase + L.ring), bars_u32 = smem_u32(wbase + L.bars);
     const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq);
     float* rq2 = reinterpret_cast<float*>(wbase + L.rq);  // rotated query, (j, j+8) interleaved per 16 dims
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
+    unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);  // replay: survivor sort keys
     const bool l2 = ix.metric == RBQ_METRIC_L2;
 
     if (lane == 0) {
@@ -373,7 +226,7 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
     }
     __syncwarp();
     uint32_t iss_stage = 0, use_stage = 0, use_phase = 0;  // ring cursors (persist across queries)
-    unsigned long long st_blocks = 0, st_cand = 0, st_ref = 0, st_adm = 0;
+    unsigned long long st_blocks = 0, st_cand = 0, st_ref = 0, st_adm = 0, st_ovf = 0;
 
     for (;;) {
         uint32_t q = 0;
@@ -382,184 +235,267 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
         if (q >= a.nq) break;
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
 
-        // producer side: prime the ring (all stages are free: everything issued so far was consumed)
-        if (lane == 0) fence_proxy_async();
-        Cursor pc;
-        pc.pi = 0;
-        pc.seek(ix, pr, a.nprobe);
-        for (uint32_t s = 0; s < NST && pc.valid(a.nprobe); ++s) {
-            if (lane == 0) {
-                mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
-                tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
+        // what this pass does for the query
+        uint32_t start_pi = 0, n_surv = 0;
+        bool walk = true;  // walk lists start_pi.. sequentially (full / head / overflowed replay)
+        int cnt = 0;
+        if (a.mode == kScanReplay) {
+            start_pi = a.tail_start[q];
+            n_surv = a.surv_cnt[q];
+            if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
+            walk = n_surv > a.surv_cap;                          // survivor buffer overflowed: re-walk the tail
+            if (walk) st_ovf += 1;
+            // resume from the head pass' top-k (stored best-first in the output arrays)
+            cnt = (int)a.out_counts[q];
+            for (int i = lane; i < cnt; i += 32) {
+                const float sc = a.out_scores[(size_t)q * k + i];
+                sd[i] = l2 ? sc : -sc;
+                si[i] = a.out_ids[(size_t)q * k + i];
             }
-            if (++iss_stage == NST) iss_stage = 0;
-            pc.next(ix, pr, a.nprobe);
+        }
+
+        // producer side: prime the ring (all stages are free: everything issued so far was consumed)
+        Cursor pc;
+        pc.pi = start_pi;
+        uint32_t inflight = 0;
+        if (walk) {
+            if (lane == 0) fence_proxy_async();
+            pc.seek(ix, pr, a.nprobe);
+            for (uint32_t s = 0; s < NST && pc.valid(a.nprobe); ++s) {
+                if (lane == 0) {
+                    mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
+                    tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
+                }
+                if (++iss_stage == NST) iss_stage = 0;
+                ++inflight;
+                pc.next(ix, pr, a.nprobe);
+            }
         }
 
         if (EXK != 0)
             for (int i = lane; i < D; i += 32)  // dim 16c + r -> float2 slot 8c + (r & 7), component r >> 3
                 rq2[2 * (8 * (i >> 4) + (i & 7)) + ((i >> 3) & 1)] = a.rot[(size_t)q * D + i];
         uint4 T[NCB];
+        if (walk) {
 #pragma unroll
-        for (int i = 0; i < NCB; ++i) {
-            const int cb = lane + 32 * i;
-            T[i] = (cb < ncb) ? ldg128(a.lut + (size_t)q * D * 4 + 16 * cb) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < NCB; ++i) {
+                const int cb = lane + 32 * i;
+                T[i] = (cb < ncb) ? ldg128(a.lut + (size_t)q * D * 4 + 16 * cb) : make_uint4(0, 0, 0, 0);
+            }
         }
         const QueryScalars s = a.qs[q];
         __syncwarp();
-        int cnt = 0;
 
-        // candidate queue: slot i lives in lane i (candidates of ONE list, in visit order)
+        // candidate queue: slot i lives in lane i, in visit order
         int qn = 0;
-        float q_lower = 0.0f, q_ip = 0.0f;
-        uint32_t q_li = 0;
-        unsigned long long q_vid = 0;
+        float q_lower = 0.0f, q_ip = 0.0f, q_gadd = 0.0f;
+        unsigned long long q_gv = 0;  // global vector index (list's vec_off + position)
 
-        Cursor cc;
-        cc.pi = 0;
-        cc.seek(ix, pr, a.nprobe);
-        while (cc.valid(a.nprobe)) {
-            const Probe p = pr[cc.pi];
-            const uint32_t nv = p.nv;
-            const unsigned long long vbase = p.vec_off;
-            st_blocks += cc.nb;
-
-            // refine + replay everything queued for this list (reference order, live threshold)
-            auto flush = [&]() {
-                if (qn == 0) return;
-                float dist = 0.0f;
-                const bool mine = lane < qn;
-                const unsigned long long gv = vbase + q_li;
-                float fae = 0.0f, fre = 0.0f;
-                if (mine) {
-                    fae = __ldg(ix.f_add_ex + gv);
-                    fre = __ldg(ix.f_rescale_ex + gv);
-                    if (a.filter == nullptr) q_vid = ix.ids[gv];
-                }
-                float exdot = 0.0f;
-                const int g = lane >> 3, j = lane & 7;
-                for (int r0 = 0; r0 < qn; r0 += kRefineSlots) {
-                    const int c = r0 + g;  // candidate served by this 8-lane group
-                    const uint32_t li_c = __shfl_sync(0xffffffffu, q_li, c & 31);
-                    const uint32_t stg = exst_u32 + (uint32_t)g * a.ex_stage_stride;
-                    if (c < qn) stage_expand<EXK>(ix.ex + (vbase + li_c) * ix.ex_stride, stg, D, j, ix.ex_bits);
-                    __syncwarp();
-                    float part = 0.0f;
-                    if (c < qn) part = ex_dot_lane(stg, rq2_u32, D, j);
-                    part = hsum8(part);
-                    const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
-                    if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
-                    __syncwarp();
-                }
-                st_ref += qn;
-                if (mine) {
-                    // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
-                    float tt = s.bscale * q_ip;
-                    tt = tt + exdot;
-                    tt = tt + s.kbx;
-                    const float mm2 = fre * tt;
-                    const float aa = fae + p.g_add;
-                    dist = aa + mm2;
-                }
-                for (int c = 0; c < qn; ++c) {
-                    const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
-                    const float d_s = __shfl_sync(0xffffffffu, dist, c);
-                    const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
-                    const float theta = cnt >= k ? sd[k - 1] : INFINITY;
-                    if (lb_s >= theta) continue;  // skipped_by_lower_bound
-                    st_adm += 1;
-                    if (!isfinite(d_s)) continue;
-                    topk_insert(sd, si, cnt, k, d_s, id_s, lane);
-                }
-                qn = 0;
-            };
-
-            const uint32_t list_pi = cc.pi;
-            while (cc.valid(a.nprobe) && cc.pi == list_pi) {
-                const uint32_t b = cc.b;
-                mbar_wait(bars_u32 + 8 * use_stage, use_phase);
-                const uint32_t blk = ring_u32 + use_stage * B;
-                uint32_t accu = accumulate_block<NCB, WIDE>(blk, T, ncb, lane);
-                if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
-                const uint32_t fac = blk + (uint32_t)D * 4u + 4u * (uint32_t)lane;
-                const float f_add = lds_f32(fac), f_rescale = lds_f32(fac + 128u), f_error = lds_f32(fac + 256u);
-                // the stage has been read: hand it back to the TMA engine for the block NST ahead
+        // refine + replay everything queued (reference order, live threshold)
+        auto flush = [&]() {
+            if (qn == 0) return;
+            float dist = 0.0f;
+            const bool mine = lane < qn;
+            float fae = 0.0f, fre = 0.0f;
+            unsigned long long q_vid = 0;
+            if (mine) {
+                fae = __ldg(ix.f_add_ex + q_gv);
+                fre = __ldg(ix.f_rescale_ex + q_gv);
+                q_vid = ix.ids[q_gv];
+            }
+            float exdot = 0.0f;
+            const int g = lane >> 3, j = lane & 7;
+            for (int r0 = 0; r0 < qn; r0 += kRefineSlots) {
+                const int c = r0 + g;  // candidate served by this 8-lane group
+                const unsigned long long gv_c = __shfl_sync(0xffffffffu, q_gv, c & 31);
+                const uint32_t stg = exst_u32 + (uint32_t)g * a.ex_stage_stride;
+                if (c < qn) stage_expand<EXK>(ix.ex + gv_c * ix.ex_stride, stg, D, j, ix.ex_bits);
                 __syncwarp();
+                float part = 0.0f;
+                if (c < qn) part = ex_dot_lane(stg, rq2_u32, D, j);
+                part = hsum8(part);
+                const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
+                if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
+                __syncwarp();
+            }
+            st_ref += qn;
+            if (mine) {
+                // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                float tt = s.bscale * q_ip;
+                tt = tt + exdot;
+                tt = tt + s.kbx;
+                const float mm2 = fre * tt;
+                const float aa = fae + q_gadd;
+                dist = aa + mm2;
+            }
+            for (int c = 0; c < qn; ++c) {
+                const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
+                const float d_s = __shfl_sync(0xffffffffu, dist, c);
+                const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
+                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                st_adm += 1;
+                if (!isfinite(d_s)) continue;
+                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+            }
+            qn = 0;
+        };
+        // append the lanes of `mask` to the queue in lane order (queue slot qn + r takes the r-th set lane)
+        auto enqueue = [&](unsigned mask, float lower, float ipv, unsigned long long gv, float gadd) {
+            const int n_new = __popc(mask);
+            if (qn + n_new > 32) flush();
+            const int r = lane - qn;
+            const int src = (r >= 0 && r < n_new) ? (int)__fns(mask, 0, r + 1) : 0;
+            const float nl = __shfl_sync(0xffffffffu, lower, src);
+            const float nip = __shfl_sync(0xffffffffu, ipv, src);
+            const unsigned long long ngv = __shfl_sync(0xffffffffu, gv, src);
+            const float nga = __shfl_sync(0xffffffffu, gadd, src);
+            if (r >= 0 && r < n_new) {
+                q_lower = nl;
+                q_ip = nip;
+                q_gv = ngv;
+                q_gadd = nga;
+                // warm L2 with the candidate's ex-code while the scan goes on
+                const uint8_t* ep = ix.ex + q_gv * ix.ex_stride;
+                for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+            }
+            qn += n_new;
+            if (qn >= 2 * kRefineSlots) flush();  // keeps rounds full and the threshold fresh
+        };
+        // 1-bit index (distance == estimate): replay the lanes of `mask` right away
+        auto replay_direct = [&](unsigned mask, float lower, float est, unsigned long long gv) {
+            unsigned long long vid = 0;
+            if ((mask >> lane) & 1u) vid = ix.ids[gv];
+            unsigned m = mask;
+            while (m) {
+                const int sl = __ffs(m) - 1;
+                m &= m - 1;
+                const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
+                const float d_s = __shfl_sync(0xffffffffu, est, sl);
+                const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
+                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                if (lb_s >= theta) continue;
+                st_adm += 1;
+                if (!isfinite(d_s)) continue;
+                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+            }
+        };
+
+        uint32_t next_pi = a.nprobe;  // head pass: first rank left to the tail stage
+        if (walk) {
+            Cursor cc;
+            cc.pi = start_pi;
+            cc.seek(ix, pr, a.nprobe);
+            while (cc.valid(a.nprobe)) {
+                const Probe p = pr[cc.pi];
+                const uint32_t nv = p.nv;
+                const unsigned long long vbase = p.vec_off;
+                st_blocks += cc.nb;
+                const uint32_t list_pi = cc.pi;
+                while (cc.valid(a.nprobe) && cc.pi == list_pi) {
+                    const uint32_t b = cc.b;
+                    mbar_wait(bars_u32 + 8 * use_stage, use_phase);
+                    const uint32_t blk = ring_u32 + use_stage * B;
+                    uint32_t accu = accumulate_block<NCB, WIDE>(blk, T, ncb, lane);
+                    if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
+                    const uint32_t fac = blk + (uint32_t)D * 4u + 4u * (uint32_t)lane;
+                    const float f_add = lds_f32(fac), f_rescale = lds_f32(fac + 128u), f_error = lds_f32(fac + 256u);
+                    // the stage has been read: hand it back to the TMA engine for the block NST ahead
+                    __syncwarp();
+                    if (++use_stage == NST) {
+                        use_stage = 0;
+                        use_phase ^= 1u;
+                    }
+                    --inflight;
+                    if (pc.valid(a.nprobe)) {
+                        if (lane == 0) {
+                            fence_proxy_async();
+                            mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
+                            tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
+                        }
+                        if (++iss_stage == NST) iss_stage = 0;
+                        ++inflight;
+                        pc.next(ix, pr, a.nprobe);
+                    }
+                    // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
+                    const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
+                    const float t1 = ip + s.k1x;
+                    const float t2 = f_rescale * t1;
+                    const float t3 = f_add + p.g_add;
+                    const float est = t3 + t2;
+                    const float t4 = f_error * p.g_error;
+                    float lower = est - t4;
+                    // K9
+                    const uint32_t li = b * kBatch + lane;
+                    bool valid = li < nv;
+                    if (a.filter != nullptr && valid) {
+                        const uint32_t id32 = (uint32_t)ix.ids[vbase + li];
+                        valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
+                    }
+                    if (!isfinite(lower)) lower = l2 ? 0.0f : -(p.dot_qc + s.qnorm);
+                    const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                    const bool cand = valid && (lower < theta0);
+                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                    st_cand += __popc(__ballot_sync(0xffffffffu, valid));
+                    if (mask != 0u) {
+                        if (EXK == 0) replay_direct(mask, lower, est, vbase + li);
+                        else enqueue(mask, lower, ip, vbase + li, p.g_add);
+                    }
+                    cc.next(ix, pr, a.nprobe);
+                }
+                if (EXK != 0) flush();
+                if (a.mode == kScanHead && cnt >= k) {  // heap full at a list boundary: the rest is the tail stage's
+                    next_pi = cc.pi;
+                    break;
+                }
+            }
+            // head pass stopped early: drain the blocks still in flight so the ring is free for the next query
+            while (inflight) {
+                mbar_wait(bars_u32 + 8 * use_stage, use_phase);
                 if (++use_stage == NST) {
                     use_stage = 0;
                     use_phase ^= 1u;
                 }
-                if (pc.valid(a.nprobe)) {
-                    if (lane == 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(bars_u32 + 8 * iss_stage, B);
-                        tma_load_1d(ring_u32 + iss_stage * B, pc.base + (size_t)pc.b * B, B, bars_u32 + 8 * iss_stage);
+                --inflight;
+            }
+        } else {
+            // replay pass: survivors of the tail kernel, visited in (rank, position) order -- the order the
+            // reference meets them -- against the live threshold.  Keys are unique, so ranking by counting sorts.
+            const Survivor* sv = a.surv + (size_t)q * a.surv_cap;
+            // sort key: rank (12 bits, nprobe <= 4096) | position (32) | slot in the buffer (10, cap <= 1024)
+            uint32_t npad = 32;
+            while (npad < n_surv) npad <<= 1;
+            for (uint32_t i = lane; i < npad; i += 32)
+                ord[i] = i < n_surv ? ((unsigned long long)sv[i].rank << 42) | ((unsigned long long)sv[i].pos << 10) | i : ~0ull;
+            __syncwarp();
+            for (uint32_t size = 2; size <= npad; size <<= 1) {  // bitonic sort, ascending
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t t = lane; t < npad / 2; t += 32) {
+                        const uint32_t i = 2 * t - (t & (stride - 1)), j2 = i + stride;
+                        const unsigned long long x = ord[i], y = ord[j2];
+                        if ((x > y) == ((i & size) == 0)) {
+                            ord[i] = y;
+                            ord[j2] = x;
+                        }
                     }
-                    if (++iss_stage == NST) iss_stage = 0;
-                    pc.next(ix, pr, a.nprobe);
+                    __syncwarp();
                 }
-                // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
-                const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
-                const float t1 = ip + s.k1x;
-                const float t2 = f_rescale * t1;
-                const float t3 = f_add + p.g_add;
-                const float est = t3 + t2;
-                const float t4 = f_error * p.g_error;
-                float lower = est - t4;
-                // K9
-                const uint32_t li = b * kBatch + lane;
-                bool valid = li < nv;
-                unsigned long long vid = 0;
-                if (a.filter != nullptr && valid) {
-                    vid = ix.ids[vbase + li];
-                    const uint32_t id32 = (uint32_t)vid;
-                    valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
-                }
-                if (!isfinite(lower)) lower = l2 ? 0.0f : -(p.dot_qc + s.qnorm);
-                const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
-                const bool cand = valid && (lower < theta0);
+            }
+            for (uint32_t base = 0; base < n_surv; base += 32) {
+                const uint32_t i = base + lane;
+                const bool have = i < n_surv;
+                Survivor rec = {0u, 0u, 0.0f, 0.0f};
+                if (have) rec = sv[(uint32_t)ord[i] & 1023u];
+                const Probe* pp = pr + (have ? rec.rank : 0u);
+                const unsigned long long gv = have ? pp->vec_off + rec.pos : 0ull;
+                const float gadd = have ? pp->g_add : 0.0f;
+                const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;
+                const bool cand = have && (rec.lower < theta0);
                 const unsigned mask = __ballot_sync(0xffffffffu, cand);
-                st_cand += __popc(__ballot_sync(0xffffffffu, valid));
                 if (mask != 0u) {
-                    if (EXK == 0) {
-                        // 1-bit index: distance == estimate, replay right away
-                        if (cand && a.filter == nullptr) vid = ix.ids[vbase + li];
-                        unsigned m = mask;
-                        while (m) {
-                            const int sl = __ffs(m) - 1;
-                            m &= m - 1;
-                            const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
-                            const float d_s = __shfl_sync(0xffffffffu, est, sl);
-                            const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
-                            const float theta = cnt >= k ? sd[k - 1] : INFINITY;
-                            if (lb_s >= theta) continue;
-                            st_adm += 1;
-                            if (!isfinite(d_s)) continue;
-                            topk_insert(sd, si, cnt, k, d_s, id_s, lane);
-                        }
-                    } else {
-                        const int n_new = __popc(mask);
-                        if (qn + n_new > 32) flush();
-                        // append in lane order: queue slot qn + r takes the r-th set lane of mask
-                        const int r = lane - qn;
-                        const int src = (r >= 0 && r < n_new) ? (int)__fns(mask, 0, r + 1) : 0;
-                        const float nl = __shfl_sync(0xffffffffu, lower, src);
-                        const float nip = __shfl_sync(0xffffffffu, ip, src);
-                        const unsigned long long nvid = __shfl_sync(0xffffffffu, vid, src);
-                        if (r >= 0 && r < n_new) {
-                            q_lower = nl;
-                            q_ip = nip;
-                            q_li = b * kBatch + (uint32_t)src;
-                            q_vid = nvid;
-                            // warm L2 with the candidate's ex-code while the list is still being scanned
-                            const uint8_t* ep = ix.ex + (vbase + q_li) * ix.ex_stride;
-                            for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
-                        }
-                        qn += n_new;
-                        if (qn >= 2 * kRefineSlots) flush();  // keeps rounds full and the threshold fresh
-                    }
+                    if (EXK == 0) replay_direct(mask, rec.lower, rec.x, gv);
+                    else enqueue(mask, rec.lower, rec.x, gv, gadd);
                 }
-                cc.next(ix, pr, a.nprobe);
             }
             if (EXK != 0) flush();
         }
@@ -568,7 +504,13 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
             a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
             a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
         }
-        if (lane == 0) a.out_counts[q] = (uint32_t)cnt;
+        if (lane == 0) {
+            a.out_counts[q] = (uint32_t)cnt;
+            if (a.mode == kScanHead) {
+                a.tail_start[q] = next_pi;
+                a.tau[q] = cnt >= k ? sd[k - 1] : INFINITY;
+            }
+        }
         __syncwarp();
     }
     if (lane == 0 && a.stats) {
@@ -576,6 +518,7 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
         atomicAdd(&a.stats->candidates, st_cand);
         atomicAdd(&a.stats->refined, st_ref);
         atomicAdd(&a.stats->admitted, st_adm);
+        if (st_ovf) atomicAdd(&a.stats->overflow_queries, st_ovf);
     }
 }
 
@@ -603,12 +546,13 @@ static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
     // ring depth: as many stages as fit 3 CTAs/SM, between 2 and 4
     const size_t per_sm = 227 * 1024;
     uint32_t nst = 4;
+    const uint32_t ord_cap = a.mode == kScanReplay ? a.surv_cap : 0;
     for (; nst > 2; --nst) {
-        const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex);
+        const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex, ord_cap);
         if ((size_t)w.total * kWarps * 3 + 3 * 1024 <= per_sm) break;
     }
     a.nst = nst;
-    const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex);
+    const WarpSmem w = warp_smem_layout(ix.block_stride, nst, a.ex_stage_stride, ix.D, a.top_k, has_ex, ord_cap);
     const size_t smem = (size_t)w.total * kWarps;
     if (smem > g_smem_optin) return fail(RBQ_INVALID_CONFIG, "scan kernel shared memory exceeds the device limit");
     const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (smem + 1024)));
@@ -631,8 +575,9 @@ static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
 int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
                 const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter,
                 size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
-                unsigned int* d_work_counter, cudaStream_t st) {
+                unsigned int* d_work_counter, int mode, const TailWs* tw, cudaStream_t st) {
     if (nq == 0) return RBQ_OK;
+    if (mode != kScanFull && tw == nullptr) return fail(RBQ_INVALID_CONFIG, "head/replay scan needs the tail workspace");
     if (top_k > (size_t)kMaxTopK) return fail(RBQ_INVALID_CONFIG, "top_k exceeds the device limit (1024)");
     if (ix.D > 2048) return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
     RBQ_CUDA(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned int), st));
@@ -653,6 +598,12 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     a.work_counter = d_work_counter;
     a.nst = 2;
     a.ex_stage_stride = 16;
+    a.mode = (uint32_t)mode;
+    a.tail_start = tw ? tw->tail_start : nullptr;
+    a.tau = tw ? tw->tau : nullptr;
+    a.surv = tw ? tw->surv : nullptr;
+    a.surv_cnt = tw ? tw->surv_cnt : nullptr;
+    a.surv_cap = tw ? tw->surv_cap : 0;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         if (ncb_lane <= 12) return launch_scan_ex<12, true>(ix, a, st);

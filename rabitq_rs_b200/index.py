@@ -294,6 +294,10 @@ class IvfRabitqIndex:
     def set_profiling(self, on):
         _check(_ffi.lib().rbq_set_profiling(self._need(), int(bool(on))))
 
+    def set_scan_mode(self, mode):
+        """0 auto, 1 sequential per-query walk, 2 list-major head/tail/replay (both exact)."""
+        _check(_ffi.lib().rbq_set_scan_mode(self._need(), int(mode)))
+
     def set_coarse_mode(self, mode):
         _check(_ffi.lib().rbq_set_coarse_mode(self._need(), int(mode)))
 

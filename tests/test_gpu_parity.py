@@ -137,7 +137,9 @@ def test_search_end_to_end(rbq, oracle, case):
     exact = assert_results_match(got, exp[:3], TOL, f"case {case}")
     assert exact == q.shape[0], f"only {exact}/{q.shape[0]} queries bit-identical"
     st = gix.stats()
-    assert st["blocks_scanned"] == int(exp[3][:, 3].sum())           # same lists, same blocks
+    want_blocks = int(exp[3][:, 3].sum())                                        # same lists, same blocks (auto schedule;
+    assert st["blocks_scanned"] + st["tail_blocks"] >= want_blocks              #  an overflowed tail is walked twice)
+    assert st["blocks_scanned"] + st["tail_blocks"] == want_blocks or st["overflow_queries"] > 0
     assert st["admitted"] == int(exp[3][:, 0].sum()) or bits > 1     # estimated (+ non-finite) in reference order
     assert st["refined"] >= int(exp[3][:, 2].sum()) or bits == 1     # refined set is a superset
 
@@ -309,3 +311,93 @@ def test_tensor_core_coarse_matches_exact_coarse(rbq, oracle, case):
     gix.set_coarse_mode(0)
     ref = gix.batch_search(q, rbq.SearchParams(10, min(16, nlist)))
     assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+
+
+# ---- list-major scan (head pass -> tail kernel over pairs grouped by list -> ordered replay) ----------------
+@pytest.mark.parametrize("case", SEARCH_CASES)
+def test_list_major_scan_end_to_end(rbq, oracle, case):
+    """Scan mode 2 must reproduce the reference's sequential decisions exactly: same ids, same score bits,
+    the same number of admitted candidates, and every (query, block) evaluated exactly once."""
+    n, dim, nlist, bits, metric, rot, kind, k, nprobe = case
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind=kind)
+    gix = _load(rbq, blob)
+    gix.set_scan_mode(2)
+    q = np.concatenate([data[:32], _queries(data, 480, 4)])
+    exp = oix.search_batch(q, k, nprobe, want_diag=True)
+    got = gix.batch_search(q, rbq.SearchParams(k, nprobe))
+    exact = assert_results_match(got, exp[:3], TOL, f"list-major case {case}")
+    assert exact == q.shape[0], f"only {exact}/{q.shape[0]} queries bit-identical"
+    st = gix.stats()
+    want_blocks = int(exp[3][:, 3].sum())
+    assert st["blocks_scanned"] + st["tail_blocks"] >= want_blocks  # an overflowed tail is walked twice
+    if kind == "clustered":  # prunable data: the survivor buffer must hold
+        assert st["overflow_queries"] == 0 and st["blocks_scanned"] + st["tail_blocks"] == want_blocks
+    assert st["tail_blocks"] > 0 or nprobe == 1
+    assert st["admitted"] == int(exp[3][:, 0].sum()) or bits > 1
+    seq = _load(rbq, blob)
+    seq.set_scan_mode(1)
+    ref = seq.batch_search(q, rbq.SearchParams(k, nprobe))
+    assert all(np.array_equal(x, y) for x, y in zip(_canon_all(got), _canon_all(ref)))
+
+
+def _canon_all(res):
+    from helpers import _canon
+
+    ids, sc, cnt = res
+    out = ids.copy()
+    for i in range(len(cnt)):
+        out[i, :cnt[i]] = _canon(ids[i, :cnt[i]], sc[i, :cnt[i]])
+    return out, sc, cnt
+
+
+def test_list_major_survivor_overflow_falls_back_exactly(rbq, oracle):
+    """With a 1-entry survivor buffer almost every query overflows; its tail is re-walked sequentially."""
+    from rabitq_rs_b200 import _ffi
+
+    data, oix, blob = oracle_index(6000, 128, 64, 7, 0, kind="clustered")
+    gix = _load(rbq, blob)
+    gix.set_scan_mode(2)
+    q = _queries(data, 300, 21)
+    exp = oix.search_batch(q, 20, 24)
+    assert _ffi.lib().rbq_debug_set_survivor_cap(1) == 0
+    try:
+        got = gix.batch_search(q, rbq.SearchParams(20, 24))
+        st = gix.stats()
+    finally:
+        _ffi.lib().rbq_debug_set_survivor_cap(0)
+    assert assert_results_match(got, exp, TOL, "overflow") == 300
+    assert st["overflow_queries"] > 0
+
+
+def test_list_major_filtered_edge_and_sharded(rbq, oracle):
+    data, oix, blob = oracle_index(3000, 64, 16, 7, 0, kind="uniform11")
+    gix = _load(rbq, blob)
+    gix.set_scan_mode(2)
+    q = _queries(data, 200, 9)
+    bits = rbq.ids_to_bitset(np.arange(0, 3000, 3), 3000)
+    got = gix.batch_search(q, rbq.SearchParams(10, 16), filter_bits=bits)
+    exp = oix.search_batch(q, 10, 16, filter_bits=bits)
+    assert assert_results_match(got, exp, TOL, "filtered") == 200
+    # heap never fills (top_k > vectors probed): everything stays in the head pass
+    assert_results_match(gix.batch_search(q, rbq.SearchParams(1000, 3)), oix.search_batch(q, 1000, 3), TOL, "k>n")
+    # single probe, and nprobe == nlist
+    assert_results_match(gix.batch_search(q, rbq.SearchParams(5, 1)), oix.search_batch(q, 5, 1), TOL, "nprobe1")
+    assert_results_match(gix.batch_search(q, rbq.SearchParams(5, 16)), oix.search_batch(q, 5, 16), TOL, "all lists")
+    # a shard owns a subset of the lists: pairs of foreign lists are skipped
+    sh = _load(rbq, blob, shard_rank=1, shard_count=3)
+    sh.set_scan_mode(2)
+    a = sh.batch_search(q, rbq.SearchParams(10, 16))
+    sh.set_scan_mode(1)
+    b = sh.batch_search(q, rbq.SearchParams(10, 16))
+    assert all(np.array_equal(x, y) for x, y in zip(_canon_all(a), _canon_all(b)))
+    # ragged / empty lists
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(3)
+    d2 = rng.standard_normal((777, 48)).astype(np.float32)
+    cents = rng.standard_normal((12, 48)).astype(np.float32)
+    assign = rng.integers(0, 9, 777).astype(np.uint32)
+    o2 = orc.Index.train_with_clusters(d2, cents, assign, 7, 0)
+    g2 = _load(rbq, o2.save_bytes())
+    g2.set_scan_mode(2)
+    assert assert_results_match(g2.batch_search(d2[:100], rbq.SearchParams(7, 12)), o2.search_batch(d2[:100], 7, 12)) == 100
