@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--nprobe", type=int, default=0, help="skip the recall sweep and use this nprobe")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-mode", type=int, default=int(os.environ.get("RBQ_SCAN_MODE", "0")), help="0 auto, 1 sequential, 2 list-major")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -315,6 +316,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    ix.set_scan_mode(args.scan_mode)
     ix.set_profiling(True)  # CUDA events around every stage on the launching stream
     sampler = ClockSampler(local)
     sampler.start()
@@ -324,6 +326,7 @@ def main():
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     scan_ms, scan_bytes, stage_ms, launches = 0.0, 0, np.zeros(4), 0
+    split_ms, split_bytes, tail_info = np.zeros(3), np.zeros(2), np.zeros(3)
     prune = np.zeros(4)
     barrier()
     wall0 = time.time()
@@ -335,7 +338,10 @@ def main():
         ev[s][1].synchronize()
         st = ix.stats()
         scan_ms += st["ms_scan"]
-        scan_bytes += st["bytes_scanned"]
+        scan_bytes += st["bytes_scanned"] + st["tail_bytes"]
+        split_ms += np.array([st["ms_scan_head"], st["ms_scan_tail"], st["ms_scan_replay"]])
+        split_bytes += np.array([st["bytes_scanned"], st["tail_bytes"]])
+        tail_info += np.array([st["tail_pairs"], st["survivors"], st["overflow_queries"]])
         stage_ms += np.array([st["ms_prep"], st["ms_coarse"], st["ms_select"], st["ms_scan"]])
         launches += st["kernel_launches"] + (1 if world > 1 else 0)
         prune += np.array([st["candidates"], st["refined"], st["admitted"], st["coarse_fallbacks"]])
@@ -420,6 +426,11 @@ def main():
                         "traffic": None, "bytes_per_launch": scan_bytes / max(args.steps, 1),
                         "ms_per_launch": scan_ms / max(args.steps, 1)},
            "stage_ms_per_step": {n: float(v) / args.steps for n, v in zip(("prep", "coarse", "select", "scan"), stage_ms)},
+           "scan_split": {"schedule": "list-major (head/tail/replay)" if split_bytes[1] > 0 else "sequential",
+                          "ms_head": split_ms[0] / args.steps, "ms_tail": split_ms[1] / args.steps, "ms_replay": split_ms[2] / args.steps,
+                          "bytes_head": split_bytes[0] / args.steps, "bytes_tail": split_bytes[1] / args.steps,
+                          "tail_pairs": tail_info[0] / args.steps, "survivors": tail_info[1] / args.steps,
+                          "overflow_queries": tail_info[2] / args.steps},
            "per_query": {"vectors_scanned": prune[0] / args.steps / nq, "refined": prune[1] / args.steps / nq,
                          "admitted": prune[2] / args.steps / nq, "coarse_fallbacks": prune[3] / args.steps / nq},
            "wall_s_timed_region": wall}

@@ -353,6 +353,172 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_tc_kernel(DevIndex i
     sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
 }
 
+// mode 1, fast path (nlist <= 256*KPT, small candidate sets): the query's approximate keys live in registers (KPT per
+// thread), the radix select skips the bit prefix all keys share (scores of one query span a narrow range, so a
+// fixed top-down digit order would pile every key on one histogram bin), the bin scan is a warp prefix sum, the
+// candidates' exact (l2, ip) are computed once and reused for K6, and the exact keys are ranked by counting.
+template <int KPT>
+__global__ void __launch_bounds__(kSelThreads) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
+                                                                       float* __restrict__ scores,
+                                                                       const QueryScalars* __restrict__ qs, int nprobe,
+                                                                       int sort_n, float eps_g, Probe* __restrict__ probes,
+                                                                       unsigned int* __restrict__ fallbacks) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
+    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
+    uint32_t* cand = reinterpret_cast<uint32_t*>(rq + ix.D);                    // sort_n candidate ids
+    float* cl2 = reinterpret_cast<float*>(cand + sort_n);                       // sort_n exact l2
+    float* cip = cl2 + sort_n;                                                  // sort_n exact ip
+    __shared__ SelShared sh;
+    __shared__ uint32_t s_min[kSelThreads / 32], s_max[kSelThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nl = (int)ix.nlist, D = ix.D;
+    const size_t q = blockIdx.x;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    float* sc = scores + q * (size_t)nl;
+    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+
+    uint32_t key[KPT];
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const int c = tid + kSelThreads * j;
+        key[j] = 0u;
+        if (c < nl) {
+            key[j] = order_key(sc[c], desc);
+            kmin = min(kmin, key[j]);
+            kmax = max(kmax, key[j]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) {
+        s_min[warp] = kmin;
+        s_max[warp] = kmax;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+        kmin = min(kmin, s_min[w]);
+        kmax = max(kmax, s_max[w]);
+    }
+    // radix select of the nprobe-th smallest key below the shared prefix
+    int hi = 32 - __clz(kmin ^ kmax);  // bits [hi, 32) are common to all keys (clz(0) == 32 -> hi = 0)
+    uint32_t prefix = hi >= 32 ? 0u : (kmin >> hi) << hi;
+    uint32_t remaining = (uint32_t)nprobe;
+    while (hi > 0) {
+        const int lo = hi > 8 ? hi - 8 : 0;
+        const uint32_t dmask = (1u << (hi - lo)) - 1u;
+        sh.hist[tid] = 0;  // kSelThreads == 256 bins
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            const int c = tid + kSelThreads * j;
+            if (c < nl && (((unsigned long long)(key[j] ^ prefix)) >> hi) == 0ull) atomicAdd(&sh.hist[(key[j] >> lo) & dmask], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {  // bins 8*lane .. 8*lane+7
+            uint32_t hcnt[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                hcnt[b] = sh.hist[8 * lane + b];
+                tot += hcnt[b];
+            }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            uint32_t before = inc - tot;
+            if (before < remaining && remaining <= inc) {  // exactly one lane
+                int b = 0;
+                for (; b < 7; ++b) {
+                    if (before + hcnt[b] >= remaining) break;
+                    before += hcnt[b];
+                }
+                sh.prefix = prefix | ((uint32_t)(8 * lane + b) << lo);
+                sh.remaining = remaining - before;
+            }
+        }
+        __syncthreads();
+        prefix = sh.prefix;
+        remaining = sh.remaining;
+        hi = lo;
+    }
+    const float T = key_to_float(prefix, desc);
+    const float qn = qs[q].qnorm, cm = ix.cmax_norm;
+    const float round_terms = (1.2f * (float)D + 20.0f) * 5.9604645e-8f;
+    float thr;
+    if (!desc) {
+        const float s2 = (qn + cm) * (qn + cm);
+        thr = T + 2.0f * (0.5f * eps_g + round_terms) * s2;
+    } else {
+        thr = T - 2.0f * (eps_g + round_terms) * qn * cm;
+    }
+    const uint32_t thr_key = order_key(thr, desc);
+    if (tid == 0) sh.count = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const int c = tid + kSelThreads * j;
+        if (c < nl && key[j] <= thr_key) {
+            const unsigned int slot = atomicAdd(&sh.count, 1u);
+            if (slot < (unsigned)sort_n) cand[slot] = (uint32_t)c;
+        }
+    }
+    __syncthreads();
+    const unsigned int m = sh.count;
+    const int lane8 = tid & 7, grp = tid >> 3;
+    const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
+    if (m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
+        for (unsigned int i = grp; i < m; i += kSelThreads / 8) {
+            const uint32_t cid = cand[i];
+            float l2, ip;
+            exact_pair(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            if (lane8 == 0) {
+                sel[i] = ((unsigned long long)order_key(desc ? ip : l2, desc) << 32) | cid;
+                cl2[i] = l2;
+                cip[i] = ip;
+            }
+        }
+        __syncthreads();
+        // exact keys are unique (cluster id in the low word): rank by counting, the nprobe smallest emit K6
+        for (unsigned int i = tid; i < m; i += kSelThreads) {
+            const unsigned long long mine = sel[i];
+            unsigned int rank = 0;
+            for (unsigned int j = 0; j < m; ++j) rank += sel[j] < mine;
+            if (rank < (unsigned)nprobe) {
+                const uint32_t cid = (uint32_t)(mine & 0xffffffffull);
+                const float l2 = cl2[i], ip = cip[i];
+                Probe pr;
+                pr.cid = cid;
+                pr.g_add = desc ? -ip : l2;
+                pr.g_error = sqrtf(l2);
+                pr.dot_qc = ip;
+                pr.nv = ix.list_n[cid];
+                pr.blk_off = ix.blk_off[cid];
+                pr.vec_off = ix.vec_off[cid];
+                probes[q * (size_t)nprobe + rank] = pr;
+            }
+        }
+        return;
+    }
+    // rare: exact scores for every centroid of this query, then the exact selection
+    if (tid == 0) atomicAdd(fallbacks, 1u);
+    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+    for (int c = grp; c < nl; c += kSelThreads / 8) {
+        float l2, ip;
+        exact_pair(rq, ix.centroids + (size_t)c * D, D, lane8, gmask, &l2, &ip);
+        if (lane8 == 0) sc[c] = desc ? ip : l2;
+    }
+    __syncthreads();
+    gather_exact(sc, nl, nprobe, desc, sh, sel);
+    sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
+}
+
 static int sort_size(size_t n) {
     int s = 32;
     while ((size_t)s < n) s <<= 1;
@@ -379,6 +545,17 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
     if (nprobe > (size_t)kMaxNprobe)
         return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
     const int sort_n = sort_size(std::min<size_t>(nprobe + 48, (size_t)kMaxNprobe));
+    if (ix.nlist <= 16u * kSelThreads && sort_n <= 256) {
+        const size_t smem_f = (size_t)sort_n * 20 + (size_t)ix.D * 4;
+        if (ix.nlist <= 4u * kSelThreads)
+            probe_select_fast_kernel<4><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
+                                                                                 d_probes, d_fallbacks);
+        else
+            probe_select_fast_kernel<16><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
+                                                                                  d_probes, d_fallbacks);
+        RBQ_CUDA(cudaGetLastError());
+        return RBQ_OK;
+    }
     const size_t smem = (size_t)sort_n * 12 + (size_t)ix.D * 4;
     if (smem > 48 * 1024)
         RBQ_CUDA(cudaFuncSetAttribute(probe_select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -122,9 +122,199 @@ __global__ void __launch_bounds__(256) query_prep_kernel(DevIndex ix, const floa
     }
 }
 
+// ---- warp-per-query variant (FhtKac rotator, trunc >= 64) -----------------------------------------------
+// One warp owns one query: no block barriers, the FHT window lives in registers (element r = e*32 + lane of
+// the window): strides 1..16 are lane exchanges (shfl.xor), strides >= 32 pair registers.  Stages run in the
+// reference's order (h = 1, 2, 4, ...) and every butterfly is the reference's (x + y, x - y), so the result is
+// bit-identical to fht() (reference src/rotation.rs:292-313).  x - y is evaluated as x + (-y) (same IEEE value).
+constexpr int kPrepWarps = 4;
+
+template <int E>
+__global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevIndex ix, const float* __restrict__ queries, uint32_t nq,
+                                                                         float* __restrict__ rot_out, uint8_t* __restrict__ lut_out,
+                                                                         QueryScalars* __restrict__ qs_out) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = ix.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kPrepWarps + warp;
+    if (q >= nq) return;  // warp-uniform; the kernel has no block-wide barrier
+    float* buf = smem + (size_t)warp * 2 * D;  // D rotated values
+    float* sq = buf + D;                       // D squares (second sequential fold)
+    const float* qin = queries + (size_t)q * ix.dim;
+    for (int i = lane; i < D; i += 32) buf[i] = i < ix.dim ? __ldg(qin + i) : 0.0f;
+    __syncwarp();
+
+    const bool pow2 = (ix.trunc == D);
+    const int start = D - ix.trunc, half = D / 2;
+    for (int round = 0; round < 4; ++round) {
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(ix.flip + round * (D / 8));  // bit i%32 of word i/32 (LSB first)
+        const int base = (pow2 || (round & 1) == 0) ? 0 : start;                            // multiple of 32
+        float v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int idx = base + e * 32 + lane;
+            const uint32_t sgn = ((__ldg(fw + (idx >> 5)) >> lane) & 1u) << 31;
+            v[e] = __uint_as_float(__float_as_uint(buf[idx]) ^ sgn);
+        }
+        if (!pow2) {  // the sign flip covers the whole padded vector, not only the FHT window
+            for (int i = lane; i < D; i += 32)
+                if (i < base || i >= base + ix.trunc) {
+                    const uint32_t sgn = ((__ldg(fw + (i >> 5)) >> lane) & 1u) << 31;
+                    buf[i] = __uint_as_float(__float_as_uint(buf[i]) ^ sgn);
+                }
+        }
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const uint32_t neg = (lane & m) ? 0x80000000u : 0u;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float other = __shfl_xor_sync(0xffffffffu, v[e], m);
+                v[e] = other + __uint_as_float(__float_as_uint(v[e]) ^ neg);
+            }
+        }
+#pragma unroll
+        for (int s = 1; s < E; s <<= 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if ((e & s) == 0) {
+                    const float x = v[e], y = v[e + s];
+                    v[e] = x + y;
+                    v[e + s] = x - y;
+                }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) buf[base + e * 32 + lane] = v[e] * ix.fac;
+        __syncwarp();
+        if (!pow2) {  // kacs_walk over the whole padded vector
+            for (int i = lane; i < half; i += 32) {
+                const float x = buf[i], y = buf[i + half];
+                buf[i] = x + y;
+                buf[i + half] = x - y;
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < D; i += 32) {
+        float x = buf[i];
+        if (!pow2) {
+            x = x * 0.25f;
+            buf[i] = x;
+        }
+        sq[i] = x * x;
+        rot_out[(size_t)q * D + i] = x;
+    }
+    __syncwarp();
+
+    // K3: the reference folds sum(q) and sum(q*q) sequentially (ivf.rs:863-864): lane 0 / lane 1 walk the arrays in order
+    float fold = 0.0f;
+    {
+        const float4* src = reinterpret_cast<const float4*>(lane == 1 ? sq : buf);
+        if (lane < 2) {
+#pragma unroll 4
+            for (int i = 0; i < D / 4; ++i) {
+                const float4 x = src[i];
+                fold = fold + x.x;
+                fold = fold + x.y;
+                fold = fold + x.z;
+                fold = fold + x.w;
+            }
+        }
+    }
+    const float s_sum = __shfl_sync(0xffffffffu, fold, 0), s_sumsq = __shfl_sync(0xffffffffu, fold, 1);
+
+    // K2: float LUT of codebook cb (dims 4cb..4cb+3): entry j = lut[j - lowbit(j)] + q[4cb + KPOS[j]]
+    const int ncb = D / 4;
+    auto table = [&](int cb, float (&t)[16]) {
+        const float4 qv = *reinterpret_cast<const float4*>(buf + 4 * cb);
+        t[0] = 0.0f;
+        t[1] = t[0] + qv.w;
+        t[2] = t[0] + qv.z;
+        t[3] = t[2] + qv.w;
+        t[4] = t[0] + qv.y;
+        t[5] = t[4] + qv.w;
+        t[6] = t[4] + qv.z;
+        t[7] = t[6] + qv.w;
+        t[8] = t[0] + qv.x;
+        t[9] = t[8] + qv.w;
+        t[10] = t[8] + qv.z;
+        t[11] = t[10] + qv.w;
+        t[12] = t[8] + qv.y;
+        t[13] = t[12] + qv.w;
+        t[14] = t[12] + qv.z;
+        t[15] = t[14] + qv.w;
+    };
+    float lmin = FLT_MAX, lmax = -FLT_MAX;
+    for (int cb = lane; cb < ncb; cb += 32) {
+        float t[16];
+        table(cb, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            lmin = fminf(lmin, t[j]);
+            lmax = fmaxf(lmax, t[j]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    const float vl = lmin, vr = lmax;
+    const float delta = (vr - vl) / 255.0f;
+    uint4* lut128 = reinterpret_cast<uint4*>(lut_out + (size_t)q * D * 4);
+    for (int cb = lane; cb < ncb; cb += 32) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (delta > 0.0f) {
+            float t[16];
+            table(cb, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = roundf((t[j] - vl) / delta);
+                x = fminf(fmaxf(x, 0.0f), 255.0f);  // clamp(0,255); NaN -> 0 like `as u8`
+                w[j >> 2] |= (uint32_t)(x == x ? (int)x : 0) << (8 * (j & 3));
+            }
+        }
+        lut128[cb] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (lane == 0) {
+        QueryScalars s;
+        const float bscale = (float)(1 << ix.ex_bits);
+        const float cbv = -(bscale - 0.5f);
+        s.delta = delta;
+        s.sum_vl = vl * (float)ncb;
+        s.k1x = -0.5f * s_sum;
+        s.kbx = cbv * s_sum;
+        s.qnorm = sqrtf(s_sumsq);
+        s.sum_q = s_sum;
+        s.bscale = bscale;
+        s.pad = 0.0f;
+        qs_out[q] = s;
+    }
+}
+
+template <int E>
+static int launch_prep_fht(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut, QueryScalars* d_qs,
+                           cudaStream_t st) {
+    const size_t smem = (size_t)kPrepWarps * 2 * ix.D * sizeof(float);
+    if (smem > 48 * 1024)
+        RBQ_CUDA(cudaFuncSetAttribute(query_prep_fht_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    query_prep_fht_kernel<E><<<(unsigned)((nq + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, smem, st>>>(ix, d_queries, (uint32_t)nq,
+                                                                                                            d_rot, d_lut, d_qs);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
                       QueryScalars* d_qs, cudaStream_t st) {
     if (nq == 0) return RBQ_OK;
+    if (ix.rot_type == RBQ_ROTATOR_FHT_KAC && ix.trunc >= 64 && ix.trunc <= 2048) {
+        switch (ix.trunc / 32) {
+            case 2: return launch_prep_fht<2>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            case 4: return launch_prep_fht<4>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            case 8: return launch_prep_fht<8>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            case 16: return launch_prep_fht<16>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            case 32: return launch_prep_fht<32>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            default: return launch_prep_fht<64>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+        }
+    }
     size_t smem = (size_t)ix.D * 5 * sizeof(float);
     if (smem > 48 * 1024)
         RBQ_CUDA(cudaFuncSetAttribute(query_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
