@@ -64,6 +64,8 @@ void fill_geometry(rbq_index* h) {
     d.fac = 1.0f / std::sqrt((float)d.trunc);
     d.nlist = (uint32_t)hi.nlist;
     d.block_stride = (uint32_t)hi.block_stride();
+    d.max_list_n = 0;
+    for (uint32_t n : hi.list_n) d.max_list_n = std::max(d.max_list_n, n);
     d.ex_stride = (uint32_t)hi.ex_stride();
 }
 
@@ -236,16 +238,22 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
             }
         } else {
             RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + 8) * 4, st));  // + list_cnt, list_fill, counters
-            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanHead, &tw, st)))
+            // head: FastScan of every query's first owned list + the reference's sequential loop over it
+            if ((rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches)))
                 return rc;
             if (h->profiling) cudaEventRecord(h->ev[4], st);
+            // tail: all remaining (query, list) pairs grouped by list -> survivors
             if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches))) return rc;
             if (h->profiling) cudaEventRecord(h->ev[5], st);
-            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanReplay, &tw, st)))
+            // bulk refine of the survivors, ordered replay, then the (normally empty) sequential fallback
+            if ((rc = launch_refine_replay(ix, d_rot, d_qs, d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
+                                           d_counts + q0, h->d_stats, tw, st, launches)))
                 return rc;
-            *launches += 9;
+            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallback, &tw, st)))
+                return rc;
+            *launches += 2;
             if (h->profiling) cudaEventRecord(h->ev[6], st);
         }
         if (h->profiling) {

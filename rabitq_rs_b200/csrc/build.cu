@@ -675,6 +675,8 @@ extern "C" int rbq_index_build(const float* data, size_t n, size_t dim, const fl
 
     dv.centroids = d_cent;
     dv.list_n = d_list_n;
+    dv.max_list_n = 0;
+    for (uint32_t c : hi.list_n) dv.max_list_n = std::max(dv.max_list_n, c);
     dv.blk_off = d_blk_off;
     dv.vec_off = d_vec_off;
     dv.blocks = d_blocks;

@@ -60,6 +60,7 @@ struct DevIndex {
     float fac;        // 1/sqrt(trunc)
     uint32_t nlist;
     uint32_t block_stride;  // 4D+384
+    uint32_t max_list_n;    // longest inverted list on this shard (vectors)
     uint32_t ex_stride;     // D*ex_bits/8
     const uint8_t* flip;    // 4*D/8
     const float* matrix_t;  // Matrix rotator, TRANSPOSED (k-major) for coalesced reads
@@ -105,7 +106,9 @@ struct Survivor {
 struct TailItem {  // work item of the tail kernel: a chunk of the (query, rank) pairs probing one list
     uint32_t cid, pair_begin, pair_count, pad;
 };
-enum ScanMode { kScanFull = 0, kScanHead = 1, kScanReplay = 2 };
+// kScanFallback: the queries listed in TailWs::fb_list (bit 31 clear: the whole probe sequence from scratch; bit 31 set:
+// resume from the head state at tail_start and walk the rest sequentially).
+enum ScanMode { kScanFull = 0, kScanHead = 1, kScanReplay = 2, kScanFallback = 3 };
 struct TailWs {  // device workspace of the head/tail/replay pipeline (per query tile)
     uint32_t* tail_start;  // [nq] first probe rank left to the tail stage (== nprobe: none)
     float* tau;            // [nq] k-th distance after the head stage (INF if the heap is not full)
@@ -120,7 +123,15 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     uint32_t* counters;    // [0] n_items, [1] item cursor
     uint32_t max_items;
     uint32_t pairs_per_item;
+    // head stage (resolve.cu): dense (lower bound, ip | estimate) of every vector of a query's first owned list
+    float2* head_buf;      // [nq * head_cap]
+    uint32_t head_cap;     // slots per query (multiple of 32); longer lists send the query to the fallback path
+    unsigned long long* surv_id;  // [nq * surv_cap] external ids of the survivors (written by the refine kernel)
+    uint32_t* fb_list;     // [nq] queries left to the sequential fallback (counters[2] = how many)
 };
+constexpr uint32_t kFbResume = 0x80000000u;
+// counters[]: [0] tail items, [1] tail item cursor, [2] fallback queries, [3] head-resolve cursor, [4] refine cursor,
+// [5] replay cursor, [6] fallback cursor
 
 // kernels (each .cu exposes a launcher)
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
@@ -139,6 +150,17 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
 int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                 size_t nprobe, const uint64_t* d_filter, size_t filter_nbits, DevStats* d_stats, const TailWs& tw,
                 cudaStream_t st, uint64_t* launches);
+// resolve.cu: the list-major pipeline around the tail kernel.
+//   head scan    FastScan of every query's first owned list -> tw.head_buf (dense)
+//   head resolve the reference's sequential prune/refine/top-k over that list -> heap state, tw.tau, tw.tail_start
+//   refine       ex-code distances of all tail survivors, in bulk
+//   replay       survivors in reference order against the live threshold (distances precomputed)
+int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
+                size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
+                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches);
+int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
+                         size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
+                         const TailWs& tw, cudaStream_t st, uint64_t* launches);
 void tail_debug_set_survivor_cap(uint32_t cap);  // 0 = default
 size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k);
 void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, char* base, TailWs& tw);

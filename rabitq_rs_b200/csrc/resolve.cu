@@ -1,0 +1,655 @@
+// resolve.cu -- the stages of the list-major pipeline that surround the tail kernel (scan_tail.cu).
+//
+//   head scan     K7+K8 (simd::accumulate_batch_avx2, compute_batch_distances_u16; reference src/simd.rs:972-1184,
+//                 2090-2140) over every query's first owned list, one warp per query, blocks read straight from
+//                 global memory; writes (lower bound, ip | estimate) of every vector to a dense per-query buffer.
+//   head resolve  K9-K11 over that buffer: the reference's sequential prune / refine / keep-k-smallest loop
+//                 (search_cluster_v2_batched, reference src/ivf.rs:2013-2127) with on-demand ex-code refinement.
+//                 Leaves the heap state in the output arrays, tau (the k-th distance) and tail_start.
+//   refine        K10 (ip_packed_ex2_f32 / ip_packed_ex6_f32, AVX2 lane order, src/simd.rs:1722-1825) for ALL tail
+//                 survivors in bulk: no dependency between candidates, so latency is hidden by occupancy.  Refining
+//                 a survivor the live threshold later rejects costs bandwidth, never correctness: the replay only
+//                 looks at the distances of candidates the reference would have refined.
+//   replay        survivors sorted into the reference's visit order (probe rank, position), then the reference's
+//                 decisions against the live threshold with the precomputed distances.
+//
+// The kernels are lean on purpose (no LUT registers, no block ring): 2-3x the resident warps of the sequential
+// scan kernel, which is what the latency-bound refine rounds need.  Queries the fast path cannot take (head list
+// longer than the dense buffer, heap not full after the head list, survivor overflow) are appended to a
+// fallback list and walked by the sequential kernel (scan.cu, kScanFallback) -- same results, bit for bit.
+#include <algorithm>
+
+#include "scan_common.cuh"
+
+namespace rbq {
+
+constexpr int kResWarps = 4;
+
+struct ResolveArgs {
+    const float* rot;
+    const uint8_t* lut;
+    const QueryScalars* qs;
+    const Probe* probes;
+    uint32_t nq, nprobe, top_k;
+    const unsigned long long* filter;
+    unsigned long long filter_nbits;
+    unsigned long long* out_ids;
+    float* out_scores;
+    uint32_t* out_counts;
+    DevStats* stats;
+    uint32_t* counters;  // TailWs::counters
+    float2* head_buf;
+    uint32_t head_cap;
+    uint32_t* tail_start;
+    float* tau;
+    uint32_t* fb_list;
+    Survivor* surv;
+    const uint32_t* surv_cnt;
+    uint32_t surv_cap;
+    unsigned long long* surv_id;
+    uint32_t ex_stage_stride;
+    uint32_t raw_stride;  // bytes per raw (packed) ex-code staging slot; 0: ex-codes are read straight from global memory
+    uint32_t has_ex;
+};
+
+// first probe rank >= from whose list has vectors on this shard (nprobe if none)
+__device__ __forceinline__ uint32_t first_owned_rank(const Probe* __restrict__ pr, uint32_t nprobe, uint32_t from, int lane) {
+    for (uint32_t base = from; base < nprobe; base += 32) {
+        const uint32_t r = base + (uint32_t)lane;
+        const unsigned m = __ballot_sync(0xffffffffu, r < nprobe && pr[r].nv != 0);
+        if (m) return base + (uint32_t)(__ffs(m) - 1);
+    }
+    return nprobe;
+}
+
+// ---- head scan ---------------------------------------------------------------------------------------------
+template <int NCB, bool WIDE>
+__global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (q >= a.nq) return;
+    const Probe* pr = a.probes + (size_t)q * a.nprobe;
+    const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
+    if (h >= a.nprobe) return;
+    const Probe p = pr[h];
+    if (p.nv > a.head_cap) return;  // fallback query (resolve_head_kernel files it)
+    const int D = ix.D, ncb = D / 4;
+    uint4 T[NCB];
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) {
+        const int cb = lane + 32 * i;
+        T[i] = (cb < ncb) ? ldg128(a.lut + (size_t)q * D * 4 + 16 * cb) : make_uint4(0, 0, 0, 0);
+    }
+    const QueryScalars s = a.qs[q];
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    const uint32_t nb = (p.nv + kBatch - 1) / kBatch;
+    const uint8_t* base = ix.blocks + (size_t)p.blk_off * ix.block_stride;
+    float2* out = a.head_buf + (size_t)q * a.head_cap;
+    for (uint32_t b = 0; b < nb; ++b) {
+        const uint8_t* blk = base + (size_t)b * ix.block_stride;
+        const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
+        const float f_add = __ldg(fac + lane), f_rescale = __ldg(fac + 32 + lane), f_error = __ldg(fac + 64 + lane);
+        uint32_t accu = accumulate_block_global<NCB, WIDE>(blk, T, ncb, lane);
+        if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
+        // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
+        const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
+        const float t1 = ip + s.k1x;
+        const float t2 = f_rescale * t1;
+        const float t3 = f_add + p.g_add;
+        const float est = t3 + t2;
+        const float t4 = f_error * p.g_error;
+        float lower = est - t4;
+        if (!isfinite(lower)) lower = l2 ? 0.0f : -(p.dot_qc + s.qnorm);
+        out[b * kBatch + lane] = make_float2(lower, a.has_ex ? ip : est);
+    }
+}
+
+// ---- per-warp shared memory of the resolve kernels ----------------------------------------------------------
+struct ResSmem {
+    uint32_t raw, exst, rq, si, sd, ord, total;
+};
+__host__ __device__ inline ResSmem res_smem_layout(uint32_t ex_stage_stride, uint32_t raw_stride, uint32_t D, uint32_t k, bool refine,
+                                                   bool topk, uint32_t surv_cap) {
+    ResSmem w;
+    uint32_t o = 0;
+    w.raw = o;
+    o += refine ? kRefineSlots * raw_stride : 0;
+    w.exst = o;
+    o += refine ? kRefineSlots * ex_stage_stride : 0;
+    w.rq = o;
+    o += refine ? ((D * 4 + 15) / 16) * 16 : 0;
+    w.si = o;
+    o += topk ? ((k * 8 + 15) / 16) * 16 : 0;
+    w.sd = o;
+    o += topk ? ((k * 4 + 15) / 16) * 16 : 0;
+    w.ord = o;
+    uint32_t cap2 = surv_cap ? 32 : 0;
+    while (cap2 < surv_cap) cap2 <<= 1;
+    o += cap2 * 8;
+    w.total = o;
+    return w;
+}
+
+// rotated query interleaved for ex_dot_lane: dim 16c + r -> float2 slot 8c + (r & 7), component r >> 3
+__device__ __forceinline__ void load_rq2(float* rq2, const float* __restrict__ rot, int D, int lane) {
+    for (int i = lane; i < D; i += 32) rq2[2 * (8 * (i >> 4) + (i & 7)) + ((i >> 3) & 1)] = __ldg(rot + i);
+}
+
+// K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's
+// ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes).  The packed
+// codes of round r+1 travel to shared memory (cp.async) while round r is expanded and multiplied, so only the first
+// round of a batch waits for memory.
+template <int EXK>
+__device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveArgs& a, unsigned long long gv, int nb, uint32_t raw_u32,
+                                              unsigned char* raw_ptr, uint32_t exst_u32, uint32_t rq2_u32, int lane) {
+    const int D = ix.D, g = lane >> 3, j = lane & 7;
+    const bool async = a.raw_stride != 0;
+    const uint32_t stg = exst_u32 + (uint32_t)g * a.ex_stage_stride;
+    const uint32_t pieces = ix.ex_stride / 16u;
+    auto issue = [&](int r0) {
+        const int c = r0 + g;
+        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
+        if (c < nb) {
+            const uint8_t* src = ix.ex + gv_c * ix.ex_stride;
+            const uint32_t dst = raw_u32 + (uint32_t)g * a.raw_stride;
+            for (uint32_t p = (uint32_t)j; p < pieces; p += 8) cp_async16(dst + 16u * p, src + 16u * p);
+        }
+    };
+    if (async) issue(0);
+    float exdot = 0.0f;
+    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
+        const int c = r0 + g;  // candidate served by this 8-lane group
+        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
+        if (async) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (c < nb) stage_expand<EXK, true>(raw_ptr + (size_t)g * a.raw_stride, stg, D, j, ix.ex_bits);
+            __syncwarp();
+            if (r0 + kRefineSlots < nb) issue(r0 + kRefineSlots);  // the raw slots are free again
+        } else {
+            if (c < nb) stage_expand<EXK, false>(ix.ex + gv_c * ix.ex_stride, stg, D, j, ix.ex_bits);
+            __syncwarp();
+        }
+        float part = 0.0f;
+        if (c < nb) part = ex_dot_lane(stg, rq2_u32, D, j);
+        part = hsum8(part);
+        const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
+        if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
+        __syncwarp();
+    }
+    return exdot;
+}
+
+// ---- head resolve ---------------------------------------------------------------------------------------------
+template <int EXK>
+__global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex ix, ResolveArgs a) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = ix.D, k = (int)a.top_k;
+    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, k, EXK != 0, true, 0);
+    unsigned char* wbase = res_smem + (size_t)warp * L.total;
+    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
+    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
+    float* sd = reinterpret_cast<float*>(wbase + L.sd);
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    unsigned long long st_blocks = 0, st_cand = 0, st_ref = 0, st_adm = 0;
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(&a.counters[3], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.nq) break;
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
+        int cnt = 0;
+        bool fallback = false;
+        uint32_t next_start = a.nprobe;
+        unsigned long long q_blocks = 0, q_cand = 0, q_ref = 0, q_adm = 0;
+        if (h < a.nprobe) {
+            const Probe p = pr[h];
+            if (p.nv > a.head_cap) {
+                fallback = true;
+            } else {
+                if (EXK != 0) load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+                const QueryScalars s = a.qs[q];
+                __syncwarp();
+                const uint32_t nv = p.nv, nb = (nv + kBatch - 1) / kBatch;
+                const unsigned long long vbase = p.vec_off;
+                const float2* hb = a.head_buf + (size_t)q * a.head_cap;
+                q_blocks = nb;
+
+                // candidate queue: slot i lives in lane i, in visit order
+                int qn = 0;
+                float q_lower = 0.0f, q_ip = 0.0f;
+                unsigned long long q_gv = 0;
+                // refine + replay everything queued (reference order, live threshold)
+                auto flush = [&]() {
+                    if (qn == 0) return;
+                    float dist = 0.0f;
+                    const bool mine = lane < qn;
+                    float fae = 0.0f, fre = 0.0f;
+                    unsigned long long q_vid = 0;
+                    if (mine) {
+                        fae = __ldg(ix.f_add_ex + q_gv);
+                        fre = __ldg(ix.f_rescale_ex + q_gv);
+                        q_vid = ix.ids[q_gv];
+                    }
+                    const float exdot = refine_batch<EXK>(ix, a, q_gv, qn, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+                    q_ref += qn;
+                    if (mine) {
+                        // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                        float tt = s.bscale * q_ip;
+                        tt = tt + exdot;
+                        tt = tt + s.kbx;
+                        const float mm2 = fre * tt;
+                        const float aa = fae + p.g_add;
+                        dist = aa + mm2;
+                    }
+                    for (int c = 0; c < qn; ++c) {
+                        const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
+                        const float d_s = __shfl_sync(0xffffffffu, dist, c);
+                        const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
+                        const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                        if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                        q_adm += 1;
+                        if (!isfinite(d_s)) continue;
+                        topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                    }
+                    qn = 0;
+                };
+                auto enqueue = [&](unsigned mask, float lower, float ipv, unsigned long long gv) {
+                    const int n_new = __popc(mask);
+                    if (qn + n_new > 32) flush();
+                    const int r = lane - qn;
+                    const int src = (r >= 0 && r < n_new) ? (int)__fns(mask, 0, r + 1) : 0;
+                    const float nl = __shfl_sync(0xffffffffu, lower, src);
+                    const float nip = __shfl_sync(0xffffffffu, ipv, src);
+                    const unsigned long long ngv = __shfl_sync(0xffffffffu, gv, src);
+                    if (r >= 0 && r < n_new) {
+                        q_lower = nl;
+                        q_ip = nip;
+                        q_gv = ngv;
+                        const uint8_t* ep = ix.ex + q_gv * ix.ex_stride;  // warm L2/L1 with the candidate's ex-code
+                        for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                    }
+                    qn += n_new;
+                    if (qn >= 2 * kRefineSlots) flush();  // keeps rounds full and the threshold fresh
+                };
+                // 1-bit index (distance == estimate): replay the lanes of `mask` right away
+                auto replay_direct = [&](unsigned mask, float lower, float est, unsigned long long gv) {
+                    unsigned long long vid = 0;
+                    if ((mask >> lane) & 1u) vid = ix.ids[gv];
+                    unsigned m = mask;
+                    while (m) {
+                        const int sl = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
+                        const float d_s = __shfl_sync(0xffffffffu, est, sl);
+                        const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
+                        const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                        if (lb_s >= theta) continue;
+                        q_adm += 1;
+                        if (!isfinite(d_s)) continue;
+                        topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                    }
+                };
+
+                float2 cur = hb[lane];
+                for (uint32_t b = 0; b < nb; ++b) {
+                    const float2 rec = cur;
+                    if (b + 1 < nb) cur = hb[(b + 1) * kBatch + lane];
+                    const uint32_t li = b * kBatch + lane;
+                    bool valid = li < nv;
+                    if (a.filter != nullptr && valid) {
+                        const uint32_t id32 = (uint32_t)ix.ids[vbase + li];
+                        valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
+                    }
+                    const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                    const bool cand = valid && (rec.x < theta0);
+                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                    q_cand += __popc(__ballot_sync(0xffffffffu, valid));
+                    if (mask != 0u) {
+                        if (EXK == 0) replay_direct(mask, rec.x, rec.y, vbase + li);
+                        else enqueue(mask, rec.x, rec.y, vbase + li);
+                    }
+                }
+                if (EXK != 0) flush();
+                const bool more = first_owned_rank(pr, a.nprobe, h + 1, lane) < a.nprobe;
+                if (cnt >= k) next_start = h + 1;
+                else if (more) fallback = true;  // the heap is not full yet: the sequential kernel walks on
+            }
+        }
+        if (fallback) {
+            if (lane == 0) {
+                a.fb_list[atomicAdd(&a.counters[2], 1u)] = q;  // from scratch
+                a.tail_start[q] = a.nprobe;
+                a.tau[q] = INFINITY;
+                a.out_counts[q] = 0u;
+            }
+            __syncwarp();
+            continue;
+        }
+        st_blocks += q_blocks;
+        st_cand += q_cand;
+        st_ref += q_ref;
+        st_adm += q_adm;
+        for (int i = lane; i < k; i += 32) {
+            const bool have = i < cnt;
+            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
+        }
+        if (lane == 0) {
+            a.out_counts[q] = (uint32_t)cnt;
+            a.tail_start[q] = next_start;
+            a.tau[q] = cnt >= k ? sd[k - 1] : INFINITY;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && a.stats) {
+        if (st_blocks) atomicAdd(&a.stats->blocks, st_blocks);
+        if (st_cand) atomicAdd(&a.stats->candidates, st_cand);
+        if (st_ref) atomicAdd(&a.stats->refined, st_ref);
+        if (st_adm) atomicAdd(&a.stats->admitted, st_adm);
+    }
+}
+
+// ---- bulk refine of the tail survivors ------------------------------------------------------------------------
+template <int EXK>
+__global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, ResolveArgs a) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = ix.D;
+    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, 0, true, false, 0);
+    unsigned char* wbase = res_smem + (size_t)warp * L.total;
+    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
+    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    unsigned long long st_ref = 0;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(&a.counters[4], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.nq) break;
+        const uint32_t n = a.surv_cnt[q];
+        if (n == 0 || n > a.surv_cap || a.tail_start[q] >= a.nprobe) continue;  // nothing to do / fallback query
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        __syncwarp();
+        load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+        const QueryScalars s = a.qs[q];
+        __syncwarp();
+        Survivor* sv = a.surv + (size_t)q * a.surv_cap;
+        unsigned long long* sid = a.surv_id + (size_t)q * a.surv_cap;
+        for (uint32_t b0 = 0; b0 < n; b0 += 32) {  // a batch: survivor b0 + i lives in lane i
+            const uint32_t i = b0 + (uint32_t)lane;
+            const int nb = (int)min(32u, n - b0);
+            Survivor rec = {0u, 0u, 0.0f, 0.0f};
+            unsigned long long gv = 0, vid = 0;
+            float g_add = 0.0f, fae = 0.0f, fre = 0.0f;
+            if (lane < nb) {
+                rec = sv[i];
+                const Probe* pp = pr + rec.rank;
+                gv = pp->vec_off + rec.pos;
+                g_add = pp->g_add;
+                const uint8_t* ep = ix.ex + gv * ix.ex_stride;  // start the candidate's ex-code towards L2
+                for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                fae = __ldg(ix.f_add_ex + gv);
+                fre = __ldg(ix.f_rescale_ex + gv);
+                vid = ix.ids[gv];
+            }
+            const float exdot = refine_batch<EXK>(ix, a, gv, nb, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+            if (lane < nb) {
+                // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                float tt = s.bscale * rec.x;
+                tt = tt + exdot;
+                tt = tt + s.kbx;
+                const float mm2 = fre * tt;
+                const float aa = fae + g_add;
+                sv[i].x = aa + mm2;
+                sid[i] = vid;
+            }
+        }
+        st_ref += n;
+    }
+    if (lane == 0 && a.stats && st_ref) atomicAdd(&a.stats->refined, st_ref);
+}
+
+// ---- replay ------------------------------------------------------------------------------------------------------
+template <int EXK>
+__global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex ix, ResolveArgs a) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = (int)a.top_k;
+    const ResSmem L = res_smem_layout(0, 0, 0, k, false, true, a.surv_cap);
+    unsigned char* wbase = res_smem + (size_t)warp * L.total;
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
+    float* sd = reinterpret_cast<float*>(wbase + L.sd);
+    unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    unsigned long long st_adm = 0, st_ovf = 0;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(&a.counters[5], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.nq) break;
+        const uint32_t start_pi = a.tail_start[q], n_surv = a.surv_cnt[q];
+        if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
+        if (n_surv > a.surv_cap) {                           // survivor buffer overflowed: the sequential kernel re-walks the tail
+            if (lane == 0) a.fb_list[atomicAdd(&a.counters[2], 1u)] = q | kFbResume;
+            st_ovf += 1;
+            continue;
+        }
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        __syncwarp();
+        int cnt = (int)a.out_counts[q];
+        for (int i = lane; i < cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
+            const float sc = a.out_scores[(size_t)q * k + i];
+            sd[i] = l2 ? sc : -sc;
+            si[i] = a.out_ids[(size_t)q * k + i];
+        }
+        const Survivor* sv = a.surv + (size_t)q * a.surv_cap;
+        // sort key: rank (12 bits, nprobe <= 4096) | position (32) | slot in the buffer (10, cap <= 1024)
+        uint32_t npad = 32;
+        while (npad < n_surv) npad <<= 1;
+        for (uint32_t i = lane; i < npad; i += 32)
+            ord[i] = i < n_surv ? ((unsigned long long)sv[i].rank << 42) | ((unsigned long long)sv[i].pos << 10) | i : ~0ull;
+        __syncwarp();
+        for (uint32_t size = 2; size <= npad; size <<= 1) {  // bitonic sort, ascending
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = lane; t < npad / 2; t += 32) {
+                    const uint32_t i = 2 * t - (t & (stride - 1)), j2 = i + stride;
+                    const unsigned long long x = ord[i], y = ord[j2];
+                    if ((x > y) == ((i & size) == 0)) {
+                        ord[i] = y;
+                        ord[j2] = x;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (uint32_t base = 0; base < n_surv; base += 32) {
+            const uint32_t i = base + lane;
+            const bool have = i < n_surv;
+            Survivor rec = {0u, 0u, 0.0f, 0.0f};
+            unsigned long long vid = 0;
+            if (have) {
+                const uint32_t slot = (uint32_t)ord[i] & 1023u;
+                rec = sv[slot];
+                if (EXK != 0) vid = a.surv_id[(size_t)q * a.surv_cap + slot];
+                else vid = ix.ids[pr[rec.rank].vec_off + rec.pos];
+            }
+            const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;
+            unsigned m = __ballot_sync(0xffffffffu, have && (rec.lower < theta0));
+            while (m) {
+                const int sl = __ffs(m) - 1;
+                m &= m - 1;
+                const float lb_s = __shfl_sync(0xffffffffu, rec.lower, sl);
+                const float d_s = __shfl_sync(0xffffffffu, rec.x, sl);
+                const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
+                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                st_adm += 1;
+                if (!isfinite(d_s)) continue;
+                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+            }
+        }
+        for (int i = lane; i < k; i += 32) {
+            const bool have = i < cnt;
+            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
+        }
+        if (lane == 0) a.out_counts[q] = (uint32_t)cnt;
+        __syncwarp();
+    }
+    if (lane == 0 && a.stats) {
+        if (st_adm) atomicAdd(&a.stats->admitted, st_adm);
+        if (st_ovf) atomicAdd(&a.stats->overflow_queries, st_ovf);
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------------
+static int g_res_sms = 0;
+static size_t g_res_smem_optin = 0;
+static int res_limits() {
+    if (g_res_sms) return RBQ_OK;
+    int dev = 0, v = 0;
+    RBQ_CUDA(cudaGetDevice(&dev));
+    RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    g_res_sms = v;
+    RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_res_smem_optin = (size_t)v;
+    return RBQ_OK;
+}
+
+static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
+                      const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits,
+                      uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw) {
+    a.rot = d_rot;
+    a.lut = d_lut;
+    a.qs = d_qs;
+    a.probes = d_probes;
+    a.nq = (uint32_t)nq;
+    a.nprobe = (uint32_t)nprobe;
+    a.top_k = (uint32_t)top_k;
+    a.filter = reinterpret_cast<const unsigned long long*>(d_filter);
+    a.filter_nbits = filter_nbits;
+    a.out_ids = reinterpret_cast<unsigned long long*>(d_ids);
+    a.out_scores = d_scores;
+    a.out_counts = d_counts;
+    a.stats = d_stats;
+    a.counters = tw.counters;
+    a.head_buf = tw.head_buf;
+    a.head_cap = tw.head_cap;
+    a.tail_start = tw.tail_start;
+    a.tau = tw.tau;
+    a.fb_list = tw.fb_list;
+    a.surv = tw.surv;
+    a.surv_cnt = tw.surv_cnt;
+    a.surv_cap = tw.surv_cap;
+    a.surv_id = tw.surv_id;
+    // refine staging: one byte per code (16 bytes per 16-dim chunk); stride = 32 (mod 128) so the four 8-lane groups
+    // hit disjoint shared-memory banks
+    a.ex_stage_stride = ((uint32_t)ix.D + 127u) / 128u * 128u + 32u;
+    // raw packed code staging (cp.async, 16-byte pieces); +16 keeps the generic unpacker's one-byte over-read in bounds
+    a.raw_stride = (ix.ex_bits != 0 && ix.ex_stride % 16u == 0) ? ix.ex_stride + 16u : 0u;
+    a.has_ex = ix.ex_bits != 0;
+}
+
+template <int NCB, bool WIDE>
+static int launch_head_scan_ex(const DevIndex& ix, const ResolveArgs& a, cudaStream_t st) {
+    head_scan_kernel<NCB, WIDE><<<(a.nq + 3) / 4, 128, 0, st>>>(ix, a);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+// grid of persistent CTAs for a kernel with `smem` bytes per CTA
+static unsigned res_grid(size_t nq, size_t smem) {
+    const size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
+    return (unsigned)std::min<size_t>((nq + kResWarps - 1) / kResWarps, (size_t)g_res_sms * per_sm);
+}
+
+#define RBQ_RES_LAUNCH(KERNEL, smem, grid)                                                                               \
+    do {                                                                                                                  \
+        if (ix.ex_bits == 0) {                                                                                            \
+            RBQ_CUDA(cudaFuncSetAttribute(KERNEL<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
+            KERNEL<0><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
+        } else if (ix.ex_bits == 2) {                                                                                     \
+            RBQ_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
+            KERNEL<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
+        } else if (ix.ex_bits == 6) {                                                                                     \
+            RBQ_CUDA(cudaFuncSetAttribute(KERNEL<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
+            KERNEL<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
+        } else {                                                                                                          \
+            RBQ_CUDA(cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
+            KERNEL<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
+        }                                                                                                                 \
+        RBQ_CUDA(cudaGetLastError());                                                                                     \
+    } while (0)
+
+int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
+                size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
+                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches) {
+    if (nq == 0) return RBQ_OK;
+    int rc = res_limits();
+    if (rc) return rc;
+    ResolveArgs a;
+    fill_args(a, ix, d_rot, d_lut, d_qs, d_probes, nq, nprobe, top_k, d_filter, filter_nbits, d_ids, d_scores, d_counts, d_stats, tw);
+    const int ncb_lane = (ix.D / 4 + 31) / 32;
+    if (ix.D > 1024) {
+        rc = ncb_lane <= 12 ? launch_head_scan_ex<12, true>(ix, a, st) : launch_head_scan_ex<16, true>(ix, a, st);
+    } else {
+        switch (ncb_lane) {
+            case 1: rc = launch_head_scan_ex<1, false>(ix, a, st); break;
+            case 2: rc = launch_head_scan_ex<2, false>(ix, a, st); break;
+            case 3: rc = launch_head_scan_ex<3, false>(ix, a, st); break;
+            case 4: rc = launch_head_scan_ex<4, false>(ix, a, st); break;
+            case 5:
+            case 6: rc = launch_head_scan_ex<6, false>(ix, a, st); break;
+            default: rc = launch_head_scan_ex<8, false>(ix, a, st); break;
+        }
+    }
+    if (rc) return rc;
+    const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, a.top_k, ix.ex_bits != 0, true, 0);
+    const size_t smem = (size_t)w.total * kResWarps;
+    if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
+    const unsigned grid = res_grid(nq, smem);
+    RBQ_RES_LAUNCH(resolve_head_kernel, smem, grid);
+    if (launches) *launches += 2;
+    return RBQ_OK;
+}
+
+int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
+                         size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
+                         const TailWs& tw, cudaStream_t st, uint64_t* launches) {
+    if (nq == 0) return RBQ_OK;
+    int rc = res_limits();
+    if (rc) return rc;
+    ResolveArgs a;
+    fill_args(a, ix, d_rot, nullptr, d_qs, d_probes, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, d_stats, tw);
+    if (ix.ex_bits != 0) {
+        const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, 0, true, false, 0);
+        const size_t smem = (size_t)w.total * kResWarps;
+        if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "refine kernel shared memory exceeds the device limit");
+        const unsigned grid = res_grid(nq, smem);
+        if (ix.ex_bits == 2) {
+            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            refine_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+        } else if (ix.ex_bits == 6) {
+            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            refine_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+        } else {
+            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            refine_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+        }
+        RBQ_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    const ResSmem w = res_smem_layout(0, 0, 0, a.top_k, false, true, a.surv_cap);
+    const size_t smem = (size_t)w.total * kResWarps;
+    if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
+    const unsigned grid = res_grid(nq, smem);
+    RBQ_RES_LAUNCH(resolve_replay_kernel, smem, grid);
+    if (launches) *launches += 1;
+    return RBQ_OK;
+}
+
+}  // namespace rbq

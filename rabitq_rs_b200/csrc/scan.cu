@@ -37,94 +37,6 @@ constexpr int kWarps = 4;
 constexpr int kMaxTopK = 1024;
 size_t scan_max_topk() { return kMaxTopK; }
 
-// ---- K7: lookups ---------------------------------------------------------------------------------
-// 32 nibble lookups of one codebook.  C = its 16 code bytes, T = its 16 LUT bytes.  acc[v] += lut[nibble(v)].
-// Byte j of C holds vector KPERM0[j] (low nibble) and KPERM0[j]+16 (high nibble); bytes 4k+2h, 4k+2h+1
-// form PRMT selector half h of register k and carry vectors m, m+16, m+8, m+24 with m = 2k+h.
-__device__ __forceinline__ void lookup_accumulate(const uint4& Cv, const uint4& T, uint32_t (&acc)[32]) {
-    const uint32_t C[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t c = C[k];
-        const uint32_t s = c & 0x77777777u;  // 3-bit byte selectors (bit 3 of a PRMT selector = sign-replicate mode)
-        const uint32_t sh = c << 4;          // brings the low nibbles' msb into byte-sign position
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t sel = h ? (s >> 16) : s;
-            const uint32_t lo = prmt(T.x, T.y, sel);                // entries 0..7
-            const uint32_t hi = prmt(T.z, T.w, sel);                // entries 8..15
-            const uint32_t m = prmt(c, sh, h ? 0xBFAEu : 0x9D8Cu);  // 0xFF where the nibble's msb is set
-            const uint32_t r = (lo & ~m) | (hi & m);                // 4 looked-up bytes
-            const int v = 2 * k + h;
-            acc[v] = __dp4a(r, 0x00000001u, acc[v]);
-            acc[v + 16] = __dp4a(r, 0x00000100u, acc[v + 16]);
-            acc[v + 8] = __dp4a(r, 0x00010000u, acc[v + 8]);
-            acc[v + 24] = __dp4a(r, 0x01000000u, acc[v + 24]);
-        }
-    }
-}
-
-// Cross-lane reduce-scatter: on return lane v holds the sum over lanes of acc[v].
-template <bool WIDE>
-__device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&acc)[32], int lane) {
-    const unsigned full = 0xffffffffu;
-    if (!WIDE) {
-        // totals fit 16 bits (padded_dim <= 1024): pack vector pairs (v, v+8) and halve the shuffles
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-        uint32_t X[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const uint32_t E = acc[m] + (acc[m + 8] << 16), O = acc[m + 16] + (acc[m + 24] << 16);
-            const uint32_t keep = b4 ? O : E, send = b4 ? E : O;
-            X[m] = keep + __shfl_xor_sync(full, send, 16);
-        }
-        uint32_t Y[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t keep = b2 ? X[i + 4] : X[i], send = b2 ? X[i] : X[i + 4];
-            Y[i] = keep + __shfl_xor_sync(full, send, 4);
-        }
-        uint32_t Z[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const uint32_t keep = b1 ? Y[i + 2] : Y[i], send = b1 ? Y[i] : Y[i + 2];
-            Z[i] = keep + __shfl_xor_sync(full, send, 2);
-        }
-        const uint32_t W = (b0 ? Z[1] : Z[0]) + __shfl_xor_sync(full, b0 ? Z[0] : Z[1], 1);
-        const uint32_t keep = b3 ? (W >> 16) : (W & 0xffffu), send = b3 ? (W & 0xffffu) : (W >> 16);
-        return keep + __shfl_xor_sync(full, send, 8);
-    } else {
-        // padded_dim > 1024: totals can exceed 16 bits, reduce in 32-bit (the caller applies the u16 wrap)
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-            const bool up = lane & w;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-                const uint32_t keep = up ? acc[i + w] : acc[i], send = up ? acc[i] : acc[i + w];
-                acc[i] = keep + __shfl_xor_sync(full, send, w);
-            }
-        }
-        return acc[0];
-    }
-}
-
-// K7 for one block resident in shared memory (blk = 32-bit shared address): returns accu[lane] (exact
-// integer sum, before the u16 wrap).  Branch-free: lanes past the last codebook hold an all-zero LUT row, so
-// whatever (clamped, valid) code bytes they read contribute nothing.
-template <int NCB, bool WIDE>
-__device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (&T)[NCB], int ncb, int lane) {
-    uint32_t acc[32];
-#pragma unroll
-    for (int v = 0; v < 32; ++v) acc[v] = 0u;
-#pragma unroll
-    for (int i = 0; i < NCB; ++i) {
-        const int cb = min(lane + 32 * i, ncb - 1);
-        const uint4 C = lds128(blk + 16u * (uint32_t)cb);
-        lookup_accumulate(C, T[i], acc);
-    }
-    return reduce_scatter<WIDE>(acc, lane);
-}
-
 struct ScanArgs {
     const float* rot;
     const uint8_t* lut;
@@ -147,6 +59,9 @@ struct ScanArgs {
     const Survivor* surv;
     const uint32_t* surv_cnt;
     uint32_t surv_cap;
+    // kScanFallback: the queries the list-major fast path handed back (see resolve.cu)
+    const uint32_t* fb_list;
+    const uint32_t* fb_count;
 };
 
 // Per-warp shared memory carve-up (bytes), all offsets 16-byte aligned.
@@ -232,6 +147,13 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
         uint32_t q = 0;
         if (lane == 0) q = atomicAdd(a.work_counter, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
+        bool resume = false;
+        if (a.mode == kScanFallback) {
+            if (q >= *a.fb_count) break;
+            const uint32_t entry = a.fb_list[q];
+            q = entry & ~kFbResume;
+            resume = (entry & kFbResume) != 0u;
+        }
         if (q >= a.nq) break;
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
 
@@ -245,6 +167,10 @@ __global__ void __launch_bounds__(kWarps * 32) scan_kernel(DevIndex ix, ScanArgs
             if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
             walk = n_surv > a.surv_cap;                          // survivor buffer overflowed: re-walk the tail
             if (walk) st_ovf += 1;
+        } else if (resume) {
+            start_pi = a.tail_start[q];
+        }
+        if (a.mode == kScanReplay || resume) {
             // resume from the head pass' top-k (stored best-first in the output arrays)
             cnt = (int)a.out_counts[q];
             for (int i = lane; i < cnt; i += 32) {
@@ -604,6 +530,9 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     a.surv = tw ? tw->surv : nullptr;
     a.surv_cnt = tw ? tw->surv_cnt : nullptr;
     a.surv_cap = tw ? tw->surv_cap : 0;
+    a.fb_list = tw ? tw->fb_list : nullptr;
+    a.fb_count = tw ? tw->counters + 2 : nullptr;
+    if (mode == kScanFallback) a.work_counter = tw->counters + 6;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         if (ncb_lane <= 12) return launch_scan_ex<12, true>(ix, a, st);

@@ -67,6 +67,113 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- K7: lookups ---------------------------------------------------------------------------------
+// 32 nibble lookups of one codebook.  C = its 16 code bytes, T = its 16 LUT bytes.  acc[v] += lut[nibble(v)].
+// Byte j of C holds vector KPERM0[j] (low nibble) and KPERM0[j]+16 (high nibble); bytes 4k+2h, 4k+2h+1
+// form PRMT selector half h of register k and carry vectors m, m+16, m+8, m+24 with m = 2k+h.
+__device__ __forceinline__ void lookup_accumulate(const uint4& Cv, const uint4& T, uint32_t (&acc)[32]) {
+    const uint32_t C[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = C[k];
+        const uint32_t s = c & 0x77777777u;  // 3-bit byte selectors (bit 3 of a PRMT selector = sign-replicate mode)
+        const uint32_t sh = c << 4;          // brings the low nibbles' msb into byte-sign position
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t sel = h ? (s >> 16) : s;
+            const uint32_t lo = prmt(T.x, T.y, sel);                // entries 0..7
+            const uint32_t hi = prmt(T.z, T.w, sel);                // entries 8..15
+            const uint32_t m = prmt(c, sh, h ? 0xBFAEu : 0x9D8Cu);  // 0xFF where the nibble's msb is set
+            const uint32_t r = (lo & ~m) | (hi & m);                // 4 looked-up bytes
+            const int v = 2 * k + h;
+            acc[v] = __dp4a(r, 0x00000001u, acc[v]);
+            acc[v + 16] = __dp4a(r, 0x00000100u, acc[v + 16]);
+            acc[v + 8] = __dp4a(r, 0x00010000u, acc[v + 8]);
+            acc[v + 24] = __dp4a(r, 0x01000000u, acc[v + 24]);
+        }
+    }
+}
+
+// Cross-lane reduce-scatter: on return lane v holds the sum over lanes of acc[v].
+template <bool WIDE>
+__device__ __forceinline__ uint32_t reduce_scatter(uint32_t (&acc)[32], int lane) {
+    const unsigned full = 0xffffffffu;
+    if (!WIDE) {
+        // totals fit 16 bits (padded_dim <= 1024): pack vector pairs (v, v+8) and halve the shuffles
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+        uint32_t X[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const uint32_t E = acc[m] + (acc[m + 8] << 16), O = acc[m + 16] + (acc[m + 24] << 16);
+            const uint32_t keep = b4 ? O : E, send = b4 ? E : O;
+            X[m] = keep + __shfl_xor_sync(full, send, 16);
+        }
+        uint32_t Y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t keep = b2 ? X[i + 4] : X[i], send = b2 ? X[i] : X[i + 4];
+            Y[i] = keep + __shfl_xor_sync(full, send, 4);
+        }
+        uint32_t Z[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t keep = b1 ? Y[i + 2] : Y[i], send = b1 ? Y[i] : Y[i + 2];
+            Z[i] = keep + __shfl_xor_sync(full, send, 2);
+        }
+        const uint32_t W = (b0 ? Z[1] : Z[0]) + __shfl_xor_sync(full, b0 ? Z[0] : Z[1], 1);
+        const uint32_t keep = b3 ? (W >> 16) : (W & 0xffffu), send = b3 ? (W & 0xffffu) : (W >> 16);
+        return keep + __shfl_xor_sync(full, send, 8);
+    } else {
+        // padded_dim > 1024: totals can exceed 16 bits, reduce in 32-bit (the caller applies the u16 wrap)
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+            const bool up = lane & w;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const uint32_t keep = up ? acc[i + w] : acc[i], send = up ? acc[i] : acc[i + w];
+                acc[i] = keep + __shfl_xor_sync(full, send, w);
+            }
+        }
+        return acc[0];
+    }
+}
+
+// K7 for one block resident in shared memory (blk = 32-bit shared address): returns accu[lane] (exact
+// integer sum, before the u16 wrap).  Branch-free: lanes past the last codebook hold an all-zero LUT row, so
+// whatever (clamped, valid) code bytes they read contribute nothing.
+template <int NCB, bool WIDE>
+__device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (&T)[NCB], int ncb, int lane) {
+    uint32_t acc[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) acc[v] = 0u;
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) {
+        const int cb = min(lane + 32 * i, ncb - 1);
+        const uint4 C = lds128(blk + 16u * (uint32_t)cb);
+        lookup_accumulate(C, T[i], acc);
+    }
+    return reduce_scatter<WIDE>(acc, lane);
+}
+
+// The same for a block read straight from global memory (head scan: every block is visited once per query, so
+// there is nothing to stage).
+template <int NCB, bool WIDE>
+__device__ __forceinline__ uint32_t accumulate_block_global(const uint8_t* __restrict__ blk, const uint4 (&T)[NCB], int ncb, int lane) {
+    uint32_t acc[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) acc[v] = 0u;
+    uint4 C[NCB];
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) C[i] = ldg128(blk + 16 * min(lane + 32 * i, ncb - 1));
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) lookup_accumulate(C[i], T[i], acc);
+    return reduce_scatter<WIDE>(acc, lane);
+}
 
 // ---- K10: packed ex-code dot, AVX2 lane order -------------------------------------------------------
 // Staging: the 8 lanes of a group expand one candidate's packed ex-code (global memory) into one byte per
@@ -74,19 +181,22 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // later reads its two codes of the chunk (dims 16c+j and 16c+8+j) as one 16-bit load.
 // EXK: 2 / 6 = the reference's C++-compatible layouts (src/simd.rs:2478-2695); 1 = generic LSB-first
 // bit stream (src/simd.rs:166-191), used for bit widths the reference cannot search (extension).
-template <int EXK>
+// SMEM: src is a generic pointer into shared memory (raw packed code copied there by cp.async) instead of global.
+template <int EXK, bool SMEM = false>
 __device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
+    auto ldw = [&](const uint8_t* p) -> uint32_t { return SMEM ? *reinterpret_cast<const uint32_t*>(p) : ldg32(p); };
+    auto ldb = [&](const uint8_t* p) -> uint32_t { return SMEM ? (uint32_t)*p : (uint32_t)__ldg(p); };
 #pragma unroll 4
     for (int c = j; c < D / 16; c += 8) {
         uint32_t A, Bq, Cq, Dq;  // codes 0-3, 4-7, 8-11, 12-15 of the chunk, one per byte
         if (EXK == 2) {
-            const uint32_t w = ldg32(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
+            const uint32_t w = ldw(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
             A = w & 0x03030303u;
             Bq = (w >> 2) & 0x03030303u;
             Cq = (w >> 4) & 0x03030303u;
             Dq = (w >> 6) & 0x03030303u;
         } else if (EXK == 6) {
-            const uint32_t w0 = ldg32(src + 12 * c), w1 = ldg32(src + 12 * c + 4), w2 = ldg32(src + 12 * c + 8);
+            const uint32_t w0 = ldw(src + 12 * c), w1 = ldw(src + 12 * c + 4), w2 = ldw(src + 12 * c + 8);
             // bytes 0-7: low nibble = low 4 bits of code b, high nibble = low 4 bits of code b+8; w2: the 2-bit layout
             A = (w0 & 0x0F0F0F0Fu) | ((w2 << 4) & 0x30303030u);
             Bq = (w1 & 0x0F0F0F0Fu) | ((w2 << 2) & 0x30303030u);
@@ -98,7 +208,7 @@ __device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, ui
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t pos = (uint32_t)(16 * c + k) * (uint32_t)ex_bits;
-                const uint32_t two = (uint32_t)__ldg(src + (pos >> 3)) | ((uint32_t)__ldg(src + (pos >> 3) + 1) << 8);
+                const uint32_t two = ldb(src + (pos >> 3)) | (ldb(src + (pos >> 3) + 1) << 8);
                 x[k >> 2] |= ((two >> (pos & 7u)) & mask) << (8 * (k & 3));
             }
             A = x[0];
@@ -118,8 +228,11 @@ __device__ __forceinline__ float ex_dot_lane(uint32_t stg, uint32_t rq2, int D, 
     for (int c = 0; c < D / 16; ++c) {
         const uint32_t pair = lds_u16(stg + 16u * (uint32_t)c + 2u * (uint32_t)j);
         const float2 qv = lds_f32x2(rq2 + 8u * (uint32_t)(8 * c + j));
-        acc = __fmaf_rn((float)(pair & 0xffu), qv.x, acc);
-        acc = __fmaf_rn((float)(pair >> 8), qv.y, acc);
+        // byte -> float without the conversion pipe: 0x4B0000xx is 2^23 + xx exactly, and the subtraction is exact
+        const float ca = __uint_as_float(prmt(pair, 0x4B000000u, 0x7540u)) - 8388608.0f;
+        const float cb = __uint_as_float(prmt(pair, 0x4B000000u, 0x7541u)) - 8388608.0f;
+        acc = __fmaf_rn(ca, qv.x, acc);
+        acc = __fmaf_rn(cb, qv.y, acc);
     }
     return acc;
 }

@@ -294,6 +294,13 @@ static uint32_t tail_surv_cap(size_t top_k) {
     return (uint32_t)std::min<size_t>(std::max<size_t>(c, 512), 1024);
 }
 
+// dense head buffer: room for the longest list, bounded so that a query tile's buffer stays below 512 MiB
+static uint32_t tail_head_cap(const DevIndex& ix, size_t nq) {
+    const size_t want = ((size_t)ix.max_list_n + 31) / 32 * 32;
+    const size_t afford = std::max<size_t>(256, (((size_t)512 << 20) / 8 / std::max<size_t>(nq, 1)) / 32 * 32);
+    return (uint32_t)std::max<size_t>(32, std::min(want, afford));
+}
+
 size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k) {
     const size_t cap = tail_surv_cap(top_k), max_items = nq * nprobe / kPairsPerItem + ix.nlist + 1;
     size_t n = 4096;
@@ -304,6 +311,9 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     n += nq * nprobe * 4 + 256;                      // pairs
     n += max_items * sizeof(TailItem) + 256;
     n += nq * cap * sizeof(Survivor) + 256;
+    n += nq * cap * 8 + 256;                             // surv_id
+    n += nq * (size_t)tail_head_cap(ix, nq) * 8 + 256;  // head_buf
+    n += nq * 4 + 256;                                   // fb_list
     return n;
 }
 
@@ -329,6 +339,10 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.pairs = reinterpret_cast<uint32_t*>(take(nq * nprobe * 4));
     tw.items = reinterpret_cast<TailItem*>(take((size_t)tw.max_items * sizeof(TailItem)));
     tw.surv = reinterpret_cast<Survivor*>(take(nq * (size_t)tw.surv_cap * sizeof(Survivor)));
+    tw.surv_id = reinterpret_cast<unsigned long long*>(take(nq * (size_t)tw.surv_cap * 8));
+    tw.head_cap = tail_head_cap(ix, nq);
+    tw.head_buf = reinterpret_cast<float2*>(take(nq * (size_t)tw.head_cap * 8));
+    tw.fb_list = reinterpret_cast<uint32_t*>(take(nq * 4));
 }
 
 template <int NCB, bool WIDE>
