@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <ctime>
+#include <cstdlib>
 #include <cstring>
 
 #include "rbq_internal.h"
@@ -186,10 +188,26 @@ size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_
     return n;
 }
 
+// Queries still in host memory: chunks are copied on a dedicated non-blocking stream, each followed by an event the
+// compute stream waits on before that chunk's front end.
+struct HostFeed {
+    static constexpr int kEvents = 16;
+    const float* h_q = nullptr;   // host queries (whole call)
+    float* d_q = nullptr;         // device staging for one tile
+    size_t dim = 0, chunk = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t* ev = nullptr;
+    int issue(size_t q_abs, size_t m, size_t off_in_tile) {
+        RBQ_CUDA(cudaMemcpyAsync(d_q + off_in_tile * dim, h_q + q_abs * dim, m * dim * 4, cudaMemcpyHostToDevice, copy));
+        RBQ_CUDA(cudaEventRecord(ev[(off_in_tile / chunk) % kEvents], copy));
+        return RBQ_OK;
+    }
+};
+
 // The pipeline on device buffers for one call (tiles internally).  d_filter may be null.
 int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t top_k, size_t nprobe,
                   const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts,
-                  char* ws_base, size_t qt, cudaStream_t st, uint64_t* launches) {
+                  char* ws_base, size_t qt, cudaStream_t st, uint64_t* launches, HostFeed* feed = nullptr) {
     const DevIndex& ix = h->dev;
     const size_t D = ix.D;
     Carver cv{ws_base};
@@ -207,19 +225,33 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         const size_t n = std::min(qt, nq - q0);
         int rc;
         if (h->profiling) cudaEventRecord(h->ev[0], st);
-        if ((rc = launch_query_prep(ix, d_queries + q0 * ix.dim, n, d_rot, d_lut, d_qs, st))) return rc;
-        if (h->profiling) cudaEventRecord(h->ev[1], st);
-        if (h->coarse_mode == 0) {
-            if ((rc = launch_coarse_exact(ix, d_rot, n, d_sc, st))) return rc;
-            if (h->profiling) cudaEventRecord(h->ev[2], st);
-            if ((rc = launch_probe_select(ix, d_rot, d_sc, n, nprobe, d_pr, st))) return rc;
-        } else {
-            if ((rc = launch_split_bf16(d_rot, n, (int)D, 0, d_qsplit, d_qn2, st))) return rc;
-            if ((rc = launch_coarse_tc(ix, d_qsplit, d_qn2, n, d_sc, st))) return rc;
-            if (h->profiling) cudaEventRecord(h->ev[2], st);
-            if ((rc = launch_probe_select_tc(ix, d_rot, d_sc, d_qs, n, nprobe, h->coarse_eps, d_pr, h->fallback_counter(), st)))
-                return rc;
-            *launches += 1;
+        // Front end (rotate + LUT, coarse scores, probe selection) is independent per query: when the queries are still
+        // arriving from the host (feed), it runs chunk by chunk behind the copy stream, so the H2D transfer of chunk
+        // c+1 overlaps the front end of chunk c and only the scan stage waits for the whole tile.
+        const size_t chunk = feed ? feed->chunk : n;
+        for (size_t c0 = 0; c0 < n; c0 += chunk) {
+            const size_t m = std::min(chunk, n - c0);
+            if (feed) {
+                if ((rc = feed->issue(q0 + c0, m, c0))) return rc;
+                RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[(c0 / chunk) % HostFeed::kEvents], 0));
+            }
+            const float* dq = feed ? feed->d_q + c0 * ix.dim : d_queries + (q0 + c0) * ix.dim;
+            if ((rc = launch_query_prep(ix, dq, m, d_rot + c0 * D, d_lut + c0 * D * 4, d_qs + c0, st))) return rc;
+            if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[1], st);
+            if (h->coarse_mode == 0) {
+                if ((rc = launch_coarse_exact(ix, d_rot + c0 * D, m, d_sc + c0 * ix.nlist, st))) return rc;
+                if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
+                if ((rc = launch_probe_select(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, m, nprobe, d_pr + c0 * nprobe, st))) return rc;
+            } else {
+                if ((rc = launch_split_bf16(d_rot + c0 * D, m, (int)D, 0, d_qsplit + c0 * 3 * D, d_qn2 + c0, st))) return rc;
+                if ((rc = launch_coarse_tc(ix, d_qsplit + c0 * 3 * D, d_qn2 + c0, m, d_sc + c0 * ix.nlist, st))) return rc;
+                if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
+                if ((rc = launch_probe_select_tc(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, d_qs + c0, m, nprobe, h->coarse_eps,
+                                                 d_pr + c0 * nprobe, h->fallback_counter(), st, false)))
+                    return rc;
+                *launches += 1;
+            }
+            *launches += 3;
         }
         if (h->profiling) cudaEventRecord(h->ev[3], st);
         // Scan stage.  Sequential: one warp walks one query's whole probe sequence.  List-major (large batches):
@@ -230,7 +262,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
             if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFull, nullptr, st)))
                 return rc;
-            *launches += 4;
+            *launches += 1;
             if (h->profiling) {
                 cudaEventRecord(h->ev[4], st);
                 cudaEventRecord(h->ev[5], st);
@@ -253,7 +285,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
             if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallback, &tw, st)))
                 return rc;
-            *launches += 2;
+            *launches += 1;
             if (h->profiling) cudaEventRecord(h->ev[6], st);
         }
         if (h->profiling) {
@@ -346,6 +378,10 @@ void rbq_index_free(rbq_index* h) {
         if (h->ws) cudaFree(h->ws);
         for (auto& e : h->ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : h->feed_ev)
+            if (e) cudaEventDestroy(e);
+        if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+        if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
     }
     delete h;
 }
@@ -502,19 +538,59 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     float* d_sc = cv.take<float>(qt * top_k);
     uint32_t* d_cn = cv.take<uint32_t>(qt);
     uint64_t* d_f = fwords ? cv.take<uint64_t>(fwords) : nullptr;
-    cudaStream_t st = nullptr;
+    if (!h->copy_stream) {
+        RBQ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        RBQ_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+        for (auto& e : h->feed_ev) RBQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the host entry point runs on the handle's own streams (the legacy default stream would serialise with every
+    // blocking stream of the process); the call is synchronous, so nothing outlives it
+    cudaStream_t st = getenv("RBQ_LEGACY_STREAM") ? nullptr : h->compute_stream;
     if (d_f) RBQ_CUDA(cudaMemcpyAsync(d_f, filter_bits, fwords * 8, cudaMemcpyHostToDevice, st));
     RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     uint64_t launches = 0;
+    HostFeed feed;
+    feed.h_q = queries;
+    feed.d_q = d_q;
+    feed.dim = dim;
+    feed.copy = getenv("RBQ_FEED_SAME_STREAM") ? st : h->copy_stream;
+    feed.ev = h->feed_ev;
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
-        RBQ_CUDA(cudaMemcpyAsync(d_q, queries + q0 * dim, n * dim * 4, cudaMemcpyHostToDevice, st));
-        rc = search_device(h, d_q, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, qt, st, &launches);
+        // chunk = the queries whose coarse GEMM fills one wave of the SMs (128-query row tiles x 256-centroid column tiles),
+        // at most 16 chunks per tile; RBQ_FEED_CHUNKS overrides the count (1 = no overlap)
+        static const long forced = [] {
+            const char* e = getenv("RBQ_FEED_CHUNKS");
+            return e ? std::min(16L, std::max(1L, atol(e))) : 0L;
+        }();
+        if (forced) {
+            feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
+        } else {
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            const size_t col_tiles = ((size_t)h->dev.nlist + 255) / 256;
+            const size_t row_tiles = std::max<size_t>(4, (size_t)sms / std::max<size_t>(col_tiles, 1));
+            feed.chunk = std::max(row_tiles * 128, ((n + 15) / 16 + 127) / 128 * 128);
+        }
+        if (n < 2048) feed.chunk = n;
+        // search_device copies queries [q0, q0+n) itself (feed) and indexes outputs from the tile start
+        static const bool trace = getenv("RBQ_TRACE") != nullptr;
+        timespec t0, t1, t2;
+        if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
+        rc = search_device(h, nullptr, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, qt, st, &launches, &feed);
         if (rc) return rc;
+        if (trace) clock_gettime(CLOCK_MONOTONIC, &t1);
+        feed.h_q += n * dim;
         RBQ_CUDA(cudaMemcpyAsync(ids + q0 * top_k, d_ids, n * top_k * 8, cudaMemcpyDeviceToHost, st));
         RBQ_CUDA(cudaMemcpyAsync(scores + q0 * top_k, d_sc, n * top_k * 4, cudaMemcpyDeviceToHost, st));
         RBQ_CUDA(cudaMemcpyAsync(counts + q0, d_cn, n * 4, cudaMemcpyDeviceToHost, st));
         RBQ_CUDA(cudaStreamSynchronize(st));
+        if (trace) {
+            clock_gettime(CLOCK_MONOTONIC, &t2);
+            fprintf(stderr, "[rbq trace] tile %zu queries: enqueue %.3f ms, total %.3f ms, chunk %zu\n", n,
+                    (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6,
+                    (t2.tv_sec - t0.tv_sec) * 1e3 + (t2.tv_nsec - t0.tv_nsec) * 1e-6, feed.chunk);
+        }
     }
     h->last_stats.kernel_launches = launches;
     return RBQ_OK;

@@ -205,22 +205,47 @@ __device__ __forceinline__ void gather_exact(const float* __restrict__ sc, int n
 
 // l2_distance_sqr and dot of the query against one centroid, AVX2 lane order; all 8 lanes of the
 // group return both values.
+template <bool NEED_L2 = true, bool NEED_IP = true>
 __device__ __forceinline__ void exact_pair(const float* __restrict__ rq, const float* __restrict__ ce, int D, int lane8,
                                            unsigned gmask, float* l2_out, float* ip_out) {
     float al2 = 0.0f, aip = 0.0f;
-    for (int i = lane8; i < D; i += 8) {
-        const float a = rq[i], b = ce[i];
-        const float d = a - b;
-        const float p = d * d;
-        al2 = al2 + p;
-        const float m = a * b;
-        aip = aip + m;
+    // 16 centroid elements in flight per lane (the row comes from L2): the adds stay in index order
+    int i = lane8;
+    for (; i + 8 * 15 < D; i += 8 * 16) {
+        float b[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) b[u] = __ldg(ce + i + 8 * u);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const float a = rq[i + 8 * u];
+            if (NEED_L2) {
+                const float d = a - b[u];
+                const float p = d * d;
+                al2 = al2 + p;
+            }
+            if (NEED_IP) {
+                const float m = a * b[u];
+                aip = aip + m;
+            }
+        }
+    }
+    for (; i < D; i += 8) {
+        const float a = rq[i], b = __ldg(ce + i);
+        if (NEED_L2) {
+            const float d = a - b;
+            const float p = d * d;
+            al2 = al2 + p;
+        }
+        if (NEED_IP) {
+            const float m = a * b;
+            aip = aip + m;
+        }
     }
     float l2 = 0.0f, ip = 0.0f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
-        l2 = l2 + __shfl_sync(gmask, al2, l, 8);
-        ip = ip + __shfl_sync(gmask, aip, l, 8);
+        if (NEED_L2) l2 = l2 + __shfl_sync(gmask, al2, l, 8);
+        if (NEED_IP) ip = ip + __shfl_sync(gmask, aip, l, 8);
     }
     *l2_out = l2;
     *ip_out = ip;
@@ -357,8 +382,8 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_tc_kernel(DevIndex i
 // thread), the radix select skips the bit prefix all keys share (scores of one query span a narrow range, so a
 // fixed top-down digit order would pile every key on one histogram bin), the bin scan is a warp prefix sum, the
 // candidates' exact (l2, ip) are computed once and reused for K6, and the exact keys are ranked by counting.
-template <int KPT>
-__global__ void __launch_bounds__(kSelThreads) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
+template <int KPT, bool NEED_IP>
+__global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
                                                                        float* __restrict__ scores,
                                                                        const QueryScalars* __restrict__ qs, int nprobe,
                                                                        int sort_n, float eps_g, Probe* __restrict__ probes,
@@ -441,12 +466,37 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_fast_kernel(DevIndex
                 }
                 sh.prefix = prefix | ((uint32_t)(8 * lane + b) << lo);
                 sh.remaining = remaining - before;
+                sh.nless = hcnt[b];  // keys left in the chosen bin
+                sh.count = 0;
             }
         }
         __syncthreads();
         prefix = sh.prefix;
         remaining = sh.remaining;
         hi = lo;
+        if (hi > 0 && sh.nless <= 64u) {
+            // few keys left: finish by ranking them directly (ties ordered by list position; only the value matters)
+            const unsigned nleft = sh.nless;
+            __syncthreads();  // everyone has read the scan results; the histogram becomes the key list
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                const int c = tid + kSelThreads * j;
+                if (c < nl && (((unsigned long long)(key[j] ^ prefix)) >> hi) == 0ull) sh.hist[atomicAdd(&sh.count, 1u)] = key[j];
+            }
+            __syncthreads();
+            if ((unsigned)tid < nleft) {
+                const uint32_t mine = sh.hist[tid];
+                unsigned rank = 0;
+                for (unsigned j = 0; j < nleft; ++j) {
+                    const uint32_t o = sh.hist[j];
+                    rank += (o < mine) || (o == mine && j < (unsigned)tid);
+                }
+                if (rank + 1 == remaining) sh.prefix = mine;
+            }
+            __syncthreads();
+            prefix = sh.prefix;
+            hi = 0;
+        }
     }
     const float T = key_to_float(prefix, desc);
     const float qn = qs[q].qnorm, cm = ix.cmax_norm;
@@ -476,8 +526,8 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_fast_kernel(DevIndex
     if (m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
         for (unsigned int i = grp; i < m; i += kSelThreads / 8) {
             const uint32_t cid = cand[i];
-            float l2, ip;
-            exact_pair(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            float l2, ip;  // L2 searches never read dot_query_centroid (src/ivf.rs:2031-2042 uses it for InnerProduct only)
+            exact_pair<true, NEED_IP>(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
             if (lane8 == 0) {
                 sel[i] = ((unsigned long long)order_key(desc ? ip : l2, desc) << 32) | cid;
                 cl2[i] = l2;
@@ -540,19 +590,25 @@ int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_s
 }
 
 int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scores, const QueryScalars* d_qs, size_t nq,
-                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st) {
+                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st, bool need_ip) {
     if (nq == 0) return RBQ_OK;
     if (nprobe > (size_t)kMaxNprobe)
         return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
     const int sort_n = sort_size(std::min<size_t>(nprobe + 48, (size_t)kMaxNprobe));
     if (ix.nlist <= 16u * kSelThreads && sort_n <= 256) {
         const size_t smem_f = (size_t)sort_n * 20 + (size_t)ix.D * 4;
-        if (ix.nlist <= 4u * kSelThreads)
-            probe_select_fast_kernel<4><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
-                                                                                 d_probes, d_fallbacks);
-        else
-            probe_select_fast_kernel<16><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
-                                                                                  d_probes, d_fallbacks);
+        const bool ipn = need_ip || ix.metric == RBQ_METRIC_INNER_PRODUCT;
+#define RBQ_SEL(KPT, IP)                                                                                              \
+    probe_select_fast_kernel<KPT, IP><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, \
+                                                                                eps_g, d_probes, d_fallbacks)
+        if (ix.nlist <= 4u * kSelThreads) {
+            if (ipn) RBQ_SEL(4, true);
+            else RBQ_SEL(4, false);
+        } else {
+            if (ipn) RBQ_SEL(16, true);
+            else RBQ_SEL(16, false);
+        }
+#undef RBQ_SEL
         RBQ_CUDA(cudaGetLastError());
         return RBQ_OK;
     }

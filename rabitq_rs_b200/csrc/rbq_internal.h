@@ -171,7 +171,8 @@ int launch_merge(int metric, int nshards, size_t nq, size_t top_k, const uint64_
                  const uint32_t* in_counts, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
                  cudaStream_t st);
 int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scores, const QueryScalars* d_qs, size_t nq,
-                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st);
+                           size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st,
+                           bool need_ip = true);
 int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
 int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st);
 int prepare_coarse_tc(rbq_index* h);  // builds cent_split / cent_n2 / cmax_norm from dev.centroids (api.cu)
@@ -208,6 +209,9 @@ struct rbq_index {
     unsigned int* fallback_counter() const { return work_counter() + 1; }
     mutable rbq_search_stats last_stats{};
     mutable cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    mutable cudaStream_t copy_stream = nullptr;  // H2D of host queries, overlapped with the front end (api.cu, HostFeed)
+    mutable cudaStream_t compute_stream = nullptr;  // the host entry points' compute stream
+    mutable cudaEvent_t feed_ev[16] = {};
     bool profiling = false;
     int scan_mode = 0;         // 0: auto, 1: sequential per-query walk, 2: list-major head/tail/replay
     int coarse_mode = 1;       // 0: exact FP32 all-pairs, 1: tensor-core candidates + exact re-score

@@ -18,6 +18,7 @@
 // longer than the dense buffer, heap not full after the head list, survivor overflow) are appended to a
 // fallback list and walked by the sequential kernel (scan.cu, kScanFallback) -- same results, bit for bit.
 #include <algorithm>
+#include <cstdlib>
 
 #include "scan_common.cuh"
 
@@ -50,6 +51,7 @@ struct ResolveArgs {
     uint32_t ex_stage_stride;
     uint32_t raw_stride;  // bytes per raw (packed) ex-code staging slot; 0: ex-codes are read straight from global memory
     uint32_t has_ex;
+    uint32_t flush_at;  // head resolve: refine as soon as this many candidates are queued
 };
 
 // first probe rank >= from whose list has vectors on this shard (nprobe if none)
@@ -85,11 +87,25 @@ __global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs
     const uint32_t nb = (p.nv + kBatch - 1) / kBatch;
     const uint8_t* base = ix.blocks + (size_t)p.blk_off * ix.block_stride;
     float2* out = a.head_buf + (size_t)q * a.head_cap;
+    // the next block's codes and factors are in flight while the current block is looked up
+    uint4 Cn[NCB];
+    load_block_codes<NCB>(base, Cn, ncb, lane);
+    const float* fac0 = reinterpret_cast<const float*>(base + (size_t)D * 4);
+    float fn_add = __ldg(fac0 + lane), fn_rescale = __ldg(fac0 + 32 + lane), fn_error = __ldg(fac0 + 64 + lane);
     for (uint32_t b = 0; b < nb; ++b) {
-        const uint8_t* blk = base + (size_t)b * ix.block_stride;
-        const float* fac = reinterpret_cast<const float*>(blk + (size_t)D * 4);
-        const float f_add = __ldg(fac + lane), f_rescale = __ldg(fac + 32 + lane), f_error = __ldg(fac + 64 + lane);
-        uint32_t accu = accumulate_block_global<NCB, WIDE>(blk, T, ncb, lane);
+        uint4 C[NCB];
+#pragma unroll
+        for (int i = 0; i < NCB; ++i) C[i] = Cn[i];
+        const float f_add = fn_add, f_rescale = fn_rescale, f_error = fn_error;
+        if (b + 1 < nb) {
+            const uint8_t* nblk = base + (size_t)(b + 1) * ix.block_stride;
+            load_block_codes<NCB>(nblk, Cn, ncb, lane);
+            const float* fac = reinterpret_cast<const float*>(nblk + (size_t)D * 4);
+            fn_add = __ldg(fac + lane);
+            fn_rescale = __ldg(fac + 32 + lane);
+            fn_error = __ldg(fac + 64 + lane);
+        }
+        uint32_t accu = accumulate_block_regs<NCB, WIDE>(C, T, lane);
         if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
         // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
         const float ip = __fmaf_rn(s.delta, (float)accu, s.sum_vl);
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
                     }
                     qn += n_new;
-                    if (qn >= 2 * kRefineSlots) flush();  // keeps rounds full and the threshold fresh
+                    if (qn >= (int)a.flush_at) flush();  // keeps rounds full and the threshold fresh
                 };
                 // 1-bit index (distance == estimate): replay the lanes of `mask` right away
                 auto replay_direct = [&](unsigned mask, float lower, float est, unsigned long long gv) {
@@ -552,6 +568,11 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     // raw packed code staging (cp.async, 16-byte pieces); +16 keeps the generic unpacker's one-byte over-read in bounds
     a.raw_stride = (ix.ex_bits != 0 && ix.ex_stride % 16u == 0) ? ix.ex_stride + 16u : 0u;
     a.has_ex = ix.ex_bits != 0;
+    static const uint32_t flush_at = [] {
+        const char* e = getenv("RBQ_FLUSH_AT");
+        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : 2 * kRefineSlots));
+    }();
+    a.flush_at = flush_at;
 }
 
 template <int NCB, bool WIDE>

@@ -162,14 +162,16 @@ __device__ __forceinline__ uint32_t accumulate_block(uint32_t blk, const uint4 (
 
 // The same for a block read straight from global memory (head scan: every block is visited once per query, so
 // there is nothing to stage).
+template <int NCB>
+__device__ __forceinline__ void load_block_codes(const uint8_t* __restrict__ blk, uint4 (&C)[NCB], int ncb, int lane) {
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) C[i] = ldg128(blk + 16 * min(lane + 32 * i, ncb - 1));
+}
 template <int NCB, bool WIDE>
-__device__ __forceinline__ uint32_t accumulate_block_global(const uint8_t* __restrict__ blk, const uint4 (&T)[NCB], int ncb, int lane) {
+__device__ __forceinline__ uint32_t accumulate_block_regs(const uint4 (&C)[NCB], const uint4 (&T)[NCB], int lane) {
     uint32_t acc[32];
 #pragma unroll
     for (int v = 0; v < 32; ++v) acc[v] = 0u;
-    uint4 C[NCB];
-#pragma unroll
-    for (int i = 0; i < NCB; ++i) C[i] = ldg128(blk + 16 * min(lane + 32 * i, ncb - 1));
 #pragma unroll
     for (int i = 0; i < NCB; ++i) lookup_accumulate(C[i], T[i], acc);
     return reduce_scatter<WIDE>(acc, lane);

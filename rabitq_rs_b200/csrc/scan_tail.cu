@@ -28,6 +28,7 @@ namespace rbq {
 constexpr int kTailWarps = 8;
 constexpr uint32_t kPairsPerItem = 64;
 constexpr uint32_t kMaxSegBlocks = 16;
+constexpr int kSurvBuf = 32;  // per-warp survivor staging (flushed with one atomic when a block could overflow it)
 
 // ---- grouping the (query, rank) pairs of the tail by list ------------------------------------------
 __global__ void tail_count_kernel(const Probe* __restrict__ probes, const uint32_t* __restrict__ tail_start, uint32_t nq,
@@ -131,7 +132,7 @@ __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a2, u
 __device__ __forceinline__ void lookup8(int (&acc)[4], const uint4& T, uint32_t s, uint32_t m0, uint32_t m1, uint32_t a0,
                                         uint32_t a2) {
     const uint32_t lo0 = prmt(T.x, T.y, s), hi0 = prmt(T.z, T.w, s);
-    const uint32_t s1 = s >> 16;
+    const uint32_t s1 = prmt(s, 0u, 0x4432u);  // s >> 16 on the byte-permute path (shifts issue at a quarter of its rate)
     const uint32_t lo1 = prmt(T.x, T.y, s1), hi1 = prmt(T.z, T.w, s1);
     const uint32_t r0 = (lo0 & ~m0) | (hi0 & m0), r1 = (lo1 & ~m1) | (hi1 & m1);
     imma_u8(acc, a0, a2, r0, r1);
@@ -141,6 +142,7 @@ template <int NCB, bool WIDE>
 __global__ void __launch_bounds__(kTailWarps * 32, 2) tail_kernel(DevIndex ix, TailArgs a) {
     extern __shared__ __align__(128) unsigned char tail_smem[];
     __shared__ uint32_t s_item;
+    __shared__ Survivor s_surv[kTailWarps][kSurvBuf];  // survivors of the pair a warp is working on
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = ix.D, ncb = D / 4;
     const uint32_t B = ix.block_stride;
@@ -155,6 +157,20 @@ __global__ void __launch_bounds__(kTailWarps * 32, 2) tail_kernel(DevIndex ix, T
     // after the reduction lane (g, t4) holds accu of vector vmap: register k = t4, half h = g >> 2, byte g & 3
     const int vmap = 2 * t4 + (g >> 2) + ((g & 1) ? 16 : 0) + ((g & 2) ? 8 : 0);
     unsigned long long st_surv = 0;
+    int nbuf = 0;  // entries waiting in s_surv[warp]
+    // one atomic per flush instead of one per block: the slot base is a global round trip
+    auto flush_survivors = [&](uint32_t q) {
+        if (nbuf == 0) return;
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&a.surv_cnt[q], (uint32_t)nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nbuf; i += 32)
+            if (base + (uint32_t)i < a.surv_cap) a.surv[(size_t)q * a.surv_cap + base + i] = s_surv[warp][i];
+        st_surv += (unsigned long long)nbuf;
+        nbuf = 0;
+        __syncwarp();
+    };
 
     for (;;) {
         __syncthreads();  // everyone is done with s_item and the staged segment
@@ -200,6 +216,11 @@ __global__ void __launch_bounds__(kTailWarps * 32, 2) tail_kernel(DevIndex ix, T
             for (uint32_t pi = warp; pi < it.pair_count; pi += kTailWarps) {
                 const uint32_t pid = a.pairs[it.pair_begin + pi];
                 const uint32_t q = pid / a.nprobe, rank = pid - q * a.nprobe;
+                if (pi + kTailWarps < it.pair_count) {  // pull the next pair's LUT towards L1 while this one is scanned
+                    const uint32_t qn = a.pairs[it.pair_begin + pi + kTailWarps] / a.nprobe;
+                    const uint8_t* nl = a.lut + (size_t)qn * D * 4;
+                    for (int o = lane * 128; o < D * 4; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(nl + o));
+                }
                 uint4 T[NCB];
 #pragma unroll
                 for (int i = 0; i < NCB; ++i) {
@@ -258,15 +279,12 @@ __global__ void __launch_bounds__(kTailWarps * 32, 2) tail_kernel(DevIndex ix, T
                     const bool cand = valid && (lower < tau);
                     const unsigned mask = __ballot_sync(0xffffffffu, cand);
                     if (mask != 0u) {
-                        uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&a.surv_cnt[q], (uint32_t)__popc(mask));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                        if (cand && slot < a.surv_cap)
-                            a.surv[(size_t)q * a.surv_cap + slot] = Survivor{rank, li, lower, a.has_ex ? ip : est};
-                        if (lane == 0) st_surv += __popc(mask);
+                        if (nbuf + __popc(mask) > kSurvBuf) flush_survivors(q);
+                        if (cand) s_surv[warp][nbuf + __popc(mask & ((1u << lane) - 1u))] = Survivor{rank, li, lower, a.has_ex ? ip : est};
+                        nbuf += __popc(mask);
                     }
                 }
+                flush_survivors(q);
             }
         }
     }
@@ -349,7 +367,7 @@ template <int NCB, bool WIDE>
 static int launch_tail_ex(const DevIndex& ix, TailArgs& a, cudaStream_t st) {
     const uint32_t EB = 12u * (uint32_t)ix.D + 384u;
     // two CTAs per SM: each may use half of the shared memory (minus the per-CTA reservation)
-    const size_t budget = std::min<size_t>(g_tail_smem_optin, (227 * 1024 - 2 * 1024) / 2 - 256);
+    const size_t budget = std::min<size_t>(g_tail_smem_optin, (227 * 1024 - 2 * 1024) / 2 - 256) - sizeof(Survivor) * kSurvBuf * kTailWarps;
     const uint32_t S = (uint32_t)std::min<size_t>(kMaxSegBlocks, std::max<size_t>(1, budget / EB));
     const size_t smem = (size_t)S * EB;
     if (smem > g_tail_smem_optin) return fail(RBQ_INVALID_CONFIG, "tail kernel shared memory exceeds the device limit");
