@@ -133,6 +133,28 @@ constexpr uint32_t kFbResume = 0x80000000u;
 // counters[]: [0] tail items, [1] tail item cursor, [2] fallback queries, [3] head-resolve cursor, [4] refine cursor,
 // [5] replay cursor, [6] fallback cursor
 
+// arguments of the tail kernels (scan_tail.cu: PRMT lookups; tail_tc.cu: one-hot GEMM on the tensor cores)
+struct TailArgs {
+    const uint8_t* lut;
+    const QueryScalars* qs;
+    const Probe* probes;
+    uint32_t nprobe;
+    const float* tau;
+    const uint32_t* pairs;
+    const TailItem* items;
+    uint32_t* counters;  // [0] number of items, [1] next item
+    Survivor* surv;
+    uint32_t* surv_cnt;
+    uint32_t surv_cap;
+    const unsigned long long* filter;
+    unsigned long long filter_nbits;
+    DevStats* stats;
+    uint32_t seg_blocks;  // blocks of a list staged at a time
+    uint32_t has_ex;
+};
+bool tail_tc_supported(const DevIndex& ix);
+int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st);
+
 // kernels (each .cu exposes a launcher)
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
                       QueryScalars* d_qs, cudaStream_t st);

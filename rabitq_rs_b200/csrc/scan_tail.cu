@@ -100,24 +100,6 @@ __global__ void tail_scatter_kernel(const Probe* __restrict__ probes, const uint
 }
 
 // ---- the tail kernel ----------------------------------------------------------------------------------
-struct TailArgs {
-    const uint8_t* lut;
-    const QueryScalars* qs;
-    const Probe* probes;
-    uint32_t nprobe;
-    const float* tau;
-    const uint32_t* pairs;
-    const TailItem* items;
-    uint32_t* counters;  // [0] number of items, [1] next item
-    Survivor* surv;
-    uint32_t* surv_cnt;
-    uint32_t surv_cap;
-    const unsigned long long* filter;
-    unsigned long long filter_nbits;
-    DevStats* stats;
-    uint32_t seg_blocks;  // blocks of a list staged at a time
-    uint32_t has_ex;
-};
 
 __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
     // C[16x8] += A[16x32] * B[32x8], u8 x u8 -> s32.  a1 = a3 = 0 (rows 8..15 unused).
@@ -410,6 +392,7 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
     a.seg_blocks = 1;
     a.has_ex = ix.ex_bits != 0;
     if (launches) *launches += 4;
+    if (tail_tc_supported(ix)) return launch_tail_tc(ix, a, st);
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         if (ncb_lane <= 12) return launch_tail_ex<12, true>(ix, a, st);

@@ -1,0 +1,342 @@
+// tail_tc.cu -- the list-major FastScan of the tail stage as an exact integer GEMM on the 5th-gen tensor cores.
+//
+// K7 (simd::accumulate_batch_avx2, reference src/simd.rs:972-1184; scalar ground truth :1462-1525) is
+//     accu[v][q] = sum over codebooks cb of lut_u8[q][16*cb + nibble(v, cb)]
+// i.e. a product of a one-hot matrix (vectors x 16*ncb, one 1 per codebook) with the queries' LUT bytes -- u8 x u8
+// with s32 accumulation, which is exact, so the tensor cores return the reference's integer bit for bit.  The PRMT
+// kernel (scan_tail.cu) spends ~3 ALU instructions per 4 lookups and is bound by the integer pipe; here a lookup
+// costs one 16-byte shared-memory store (the one-hot row) shared by all the queries that probe the list, and the
+// sums run on tcgen05.mma (kind::i8, M = 128 vectors, N = 64 queries, K = 32 bytes = 2 codebooks per instruction)
+// with the accumulators in TMEM.
+//
+// One CTA per SM, one work item (a list and <= 64 of the (query, rank) pairs probing it) at a time:
+//   * all 8 warps expand the list's packed codes of one K-chunk (8 codebooks = 128 bytes of one-hot per vector)
+//     into a 128B-swizzled K-major A tile per 128 vectors, and copy the 64 queries' LUT slice into the B tile
+//     (the LUT row of a query is already K-major: lut[16*cb + nibble], reference src/simd.rs:818-840);
+//   * one thread issues the MMAs of the chunk (4 per 128-vector tile); tcgen05.commit frees the stage, so the next
+//     chunk is expanded into the other stage while the tensor core works;
+//   * after the last chunk the 8 warps read the sums back (tcgen05.ld), evaluate K8 (compute_batch_distances_u16,
+//     src/simd.rs:2090-2140, AVX2 operation order) per (vector, query) and keep the candidates whose lower bound
+//     beats the query's head threshold -- the same survivors as the PRMT kernel, appended in any order (the replay
+//     sorts them).
+#include <algorithm>
+#include <cstdlib>
+
+#include "scan_common.cuh"
+
+namespace rbq {
+
+namespace tt {
+constexpr int MT_MAX = 4;                    // 128-vector tiles (4 blocks each) accumulated concurrently
+constexpr int NQ = 64;                       // queries per item = UMMA N
+constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
+constexpr int STAGES = 2;
+constexpr int THREADS = 256;
+constexpr int A_TILE = 128 * KCH;            // 16 KB
+constexpr int A_STAGE = MT_MAX * A_TILE;     // 64 KB
+constexpr int B_STAGE = NQ * KCH;            // 8 KB
+constexpr int SURV_CAP = 512;                // survivors staged in shared memory between flushes
+constexpr int TMEM_COLS = MT_MAX * NQ;       // 256 columns of s32 accumulators
+struct Misc {
+    float4 c0[NQ];   // delta, sum_vl, k1x, g_add
+    float4 c1[NQ];   // g_error, tau, non-finite fallback, unused
+    uint32_t q[NQ];  // query of pair slot n (0xffffffff: unused slot)
+    uint32_t rank[NQ];
+    uint32_t sq[SURV_CAP];
+    Survivor ss[SURV_CAP];
+    uint64_t bars[STAGES + 1];  // empty[stage], accumulators done
+    uint32_t tmem_base, item, surv_n, pad;
+};
+constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + sizeof(Misc) + 1024 /*alignment slack*/;
+}  // namespace tt
+
+// K-major operand, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) (unused) | SBO>>4 [32,46) = 8 rows * 128 B |
+// version 1 [46,48) | SWIZZLE_128B (2) [61,64)   (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t tt_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2) [4,6), A = B = unsigned 8-bit (0) [7,10) / [10,13),
+// both K-major, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t kTtIdesc = (2u << 4) | ((uint32_t)(tt::NQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void tt_bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra TT_DONE;\n"
+        "bra TT_WAIT;\n"
+        "TT_DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// 1 << pos for pos in [0, 32), 0 otherwise (pos is taken as unsigned, so "negative" positions give 0)
+__device__ __forceinline__ uint32_t onehot32(uint32_t pos) {
+    uint32_t d;
+    asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(d) : "r"(pos));
+    return d;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, TailArgs a) {
+    using namespace tt;
+    extern __shared__ unsigned char tt_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = sm;                                  // [STAGES][MT_MAX][128 rows][128 B]
+    unsigned char* sB = sm + (size_t)STAGES * A_STAGE;       // [STAGES][NQ rows][128 B]
+    Misc* mi = reinterpret_cast<Misc*>(sm + (size_t)STAGES * (A_STAGE + B_STAGE));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = ix.D, ncb = D / 4;
+    const uint32_t B = ix.block_stride;
+    const uint32_t nkc = ((uint32_t)ncb + 7u) / 8u;  // K-chunks of 8 codebooks
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    const uint32_t empty0 = smem_u32(&mi->bars[0]), accd = smem_u32(&mi->bars[STAGES]);
+
+    if (tid == 0) {
+        for (int s = 0; s <= STAGES; ++s) mbar_init(empty0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mi->surv_n = 0;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&mi->tmem_base)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = mi->tmem_base;
+
+    uint32_t prod[STAGES] = {0u, 0u};  // productions into each stage so far (uniform across the CTA)
+    uint32_t chunk_seq = 0;            // running chunk counter (stage = chunk_seq % STAGES)
+    uint32_t groups = 0;               // accumulator groups finished so far (phase of the `accd` barrier)
+
+    // A production role of this thread: byte quad qd of codebook row cbl of a block-chunk
+    const int qd = lane >> 3, cbl = lane & 7;
+    // epilogue role: TMEM lane quarter lq, tiles (warp >> 2) and (warp >> 2) + 2
+    const int lq = warp & 3;
+
+    // copies the staged survivors to the per-query buffers (one global atomic each, all in flight together)
+    auto flush_survivors = [&]() {
+        __syncthreads();
+        const uint32_t n = min(mi->surv_n, (uint32_t)SURV_CAP);
+        for (uint32_t i = tid; i < n; i += THREADS) {
+            const uint32_t q = mi->sq[i];
+            const uint32_t slot = atomicAdd(&a.surv_cnt[q], 1u);
+            if (slot < a.surv_cap) a.surv[(size_t)q * a.surv_cap + slot] = mi->ss[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (a.stats && n) atomicAdd(&a.stats->survivors, (unsigned long long)n);
+            mi->surv_n = 0;
+        }
+        __syncthreads();
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) mi->item = atomicAdd(&a.counters[1], 1u);
+        __syncthreads();
+        const uint32_t item = mi->item;
+        if (item >= a.counters[0]) break;
+        const TailItem it = a.items[item];
+        const uint32_t nv = ix.list_n[it.cid], nb = (nv + kBatch - 1) / kBatch;
+        const uint8_t* lbase = ix.blocks + (size_t)ix.blk_off[it.cid] * B;
+        const unsigned long long vbase = ix.vec_off[it.cid];
+        const uint32_t P = it.pair_count;
+        if (tid == 0 && a.stats) {
+            atomicAdd(&a.stats->tail_blocks, (unsigned long long)P * nb);
+            atomicAdd(&a.stats->tail_pairs, (unsigned long long)P);
+            atomicAdd(&a.stats->candidates, (unsigned long long)P * nv);
+        }
+        // per-pair constants of the item
+        if (tid < NQ) {
+            uint32_t q = 0xffffffffu, rank = 0;
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, -INFINITY, 0.f, 0.f);
+            if ((uint32_t)tid < P) {
+                const uint32_t pid = a.pairs[it.pair_begin + tid];
+                q = pid / a.nprobe;
+                rank = pid - q * a.nprobe;
+                const QueryScalars s = a.qs[q];
+                const Probe p = a.probes[pid];
+                c0 = make_float4(s.delta, s.sum_vl, s.k1x, p.g_add);
+                c1 = make_float4(p.g_error, a.tau[q], l2 ? 0.0f : -(p.dot_qc + s.qnorm), 0.f);
+            }
+            mi->q[tid] = q;
+            mi->rank[tid] = rank;
+            mi->c0[tid] = c0;
+            mi->c1[tid] = c1;
+        }
+        __syncthreads();
+
+        for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {  // accumulator group: up to 16 blocks = 4 tiles of 128 vectors
+            const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
+            for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
+                const uint32_t s = chunk_seq % STAGES;
+                if (prod[s] > 0) tt_bar_wait(empty0 + 8 * s, (prod[s] - 1) & 1u);  // the MMAs that read this stage are done
+                prod[s] += 1;
+                // ---- B: LUT slice [kc*128, kc*128+128) of the item's queries, row r = pair slot ----
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int piece = tid + THREADS * i, r = piece >> 3, j = piece & 7;
+                    const uint32_t q = mi->q[r];
+                    const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
+                    if (q != 0xffffffffu && koff < (uint32_t)D * 4u) {
+                        const uint4 v = ldg128(a.lut + (size_t)q * D * 4 + koff);
+                        sts128(sB_u32 + s * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4), v.x, v.y, v.z, v.w);
+                    }
+                }
+                // ---- A: one-hot rows of the group's blocks for codebooks 8*kc .. 8*kc+7 ----
+                for (uint32_t bg = warp; bg < nbg; bg += THREADS / 32) {
+                    const uint32_t cb = kc * 8u + (uint32_t)cbl;
+                    uint32_t word = 0;
+                    const bool live = cb < (uint32_t)ncb;
+                    if (live) word = ldg32(lbase + (size_t)(b0 + bg) * B + 16u * cb + 4u * (uint32_t)qd);
+                    const uint32_t tile = sA_u32 + s * A_STAGE + (bg >> 2) * A_TILE + (bg & 3u) * 32u * 128u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = 4 * qd + j;                       // byte position in the 16-byte codebook row
+                        const int v = (p >> 1) + ((p & 1) << 3);        // KPERM0[p]: vector of the low nibble (high: v + 16)
+                        const uint32_t byte = (word >> (8 * j)) & 0xffu;
+                        const uint32_t dst = tile + (uint32_t)v * 128u + (uint32_t)((cbl ^ (v & 7)) << 4);
+                        const uint32_t s_lo = (byte & 15u) * 8u, s_hi = (byte >> 4) * 8u;
+                        if (live) {
+                            sts128(dst, onehot32(s_lo), onehot32(s_lo - 32u), onehot32(s_lo - 64u), onehot32(s_lo - 96u));
+                            sts128(dst + 16u * 128u, onehot32(s_hi), onehot32(s_hi - 32u), onehot32(s_hi - 64u), onehot32(s_hi - 96u));
+                        } else {  // past the last codebook: the K padding of the chunk contributes nothing
+                            sts128(dst, 0u, 0u, 0u, 0u);
+                            sts128(dst + 16u * 128u, 0u, 0u, 0u, 0u);
+                        }
+                    }
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (uint32_t mt = 0; mt < mt_cnt; ++mt) {
+                        const uint64_t da = tt_desc(sA_u32 + s * A_STAGE + mt * A_TILE);
+                        const uint64_t db = tt_desc(sB_u32 + s * B_STAGE);
+#pragma unroll
+                        for (int k = 0; k < KCH / 32; ++k) {
+                            const uint32_t acc = (kc | (uint32_t)k) ? 1u : 0u;
+                            asm volatile(
+                                "{\n"
+                                ".reg .pred p;\n"
+                                "setp.ne.b32 p, %4, 0;\n"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+                                "}" ::"r"(tmem + mt * NQ),
+                                "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(kTtIdesc), "r"(acc)
+                                : "memory");
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
+                                 : "memory");
+                    if (kc + 1 == nkc)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accd) : "memory");
+                }
+            }
+            // ---- epilogue: sums -> K8 -> survivors ----
+            tt_bar_wait(accd, groups & 1u);
+            groups += 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (uint32_t mt = (uint32_t)(warp >> 2); mt < mt_cnt; mt += 2) {
+                const uint32_t bg = mt * 4u + (uint32_t)lq;  // this warp's block of the tile; TMEM lane = 32*lq + vector
+                const bool have_blk = bg < nbg;
+                const uint32_t li = (b0 + bg) * kBatch + (uint32_t)lane;
+                bool valid = have_blk && li < nv;
+                float f_add = 0.f, f_rescale = 0.f, f_error = 0.f;
+                if (have_blk) {
+                    const float* fac = reinterpret_cast<const float*>(lbase + (size_t)(b0 + bg) * B + (size_t)D * 4);
+                    f_add = __ldg(fac + lane);
+                    f_rescale = __ldg(fac + 32 + lane);
+                    f_error = __ldg(fac + 64 + lane);
+                }
+                if (a.filter != nullptr && valid) {
+                    const uint32_t id32 = (uint32_t)ix.ids[vbase + li];
+                    valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
+                }
+#pragma unroll 1
+                for (int c0i = 0; c0i < NQ; c0i += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + mt * NQ + (uint32_t)c0i;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t n = (uint32_t)(c0i + j);
+                        if (n >= P) break;  // uniform: unused pair slots hold garbage sums
+                        uint32_t accu = r[j];
+                        if (WIDE) accu &= 0xffffu;  // the reference accumulates in wrapping u16
+                        const float4 k0 = mi->c0[n], k1 = mi->c1[n];
+                        // K8 (AVX2 variant): ip = fmadd(delta, accu, sum_vl); est = (f_add+g_add) + f_rescale*(ip+k1x)
+                        const float ip = __fmaf_rn(k0.x, (float)accu, k0.y);
+                        const float t1 = ip + k0.z;
+                        const float t2 = f_rescale * t1;
+                        const float t3 = f_add + k0.w;
+                        const float est = t3 + t2;
+                        const float t4 = f_error * k1.x;
+                        float lower = est - t4;
+                        if (!isfinite(lower)) lower = k1.z;
+                        if (valid && lower < k1.y) {
+                            const Survivor sv = Survivor{mi->rank[n], li, lower, a.has_ex ? ip : est};
+                            const uint32_t q = mi->q[n];
+                            const uint32_t slot = atomicAdd(&mi->surv_n, 1u);
+                            if (slot < (uint32_t)SURV_CAP) {
+                                mi->sq[slot] = q;
+                                mi->ss[slot] = sv;
+                            } else {  // staging full: straight to the query's buffer
+                                const uint32_t gs = atomicAdd(&a.surv_cnt[q], 1u);
+                                if (gs < a.surv_cap) a.surv[(size_t)q * a.surv_cap + gs] = sv;
+                                if (a.stats) atomicAdd(&a.stats->survivors, 1ull);
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            flush_survivors();  // also the barrier that lets the next group overwrite the accumulators
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+bool tail_tc_supported(const DevIndex& ix) {
+    static const bool off = [] {
+        const char* e = getenv("RBQ_TAIL_PRMT");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return !off && ix.D % 16 == 0;
+}
+
+int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    RBQ_CUDA(cudaGetDevice(&dev));
+    RBQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (ix.D > 1024) {
+        RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
+        tail_tc_kernel<true><<<sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
+    } else {
+        RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
+        tail_tc_kernel<false><<<sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
+    }
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+}  // namespace rbq
