@@ -30,8 +30,11 @@ namespace tt {
 constexpr int MT_MAX = 4;                    // 128-vector tiles (4 blocks each) accumulated concurrently
 constexpr int NQ = 64;                       // queries per item = UMMA N
 constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
-constexpr int STAGES = 2;
-constexpr int THREADS = 256;
+constexpr int STAGES = 2;                    // A stages
+constexpr int BSTAGES = 4;                   // B stages: the LUT slices of chunks c+1, c+2 are in flight while chunk c is multiplied
+constexpr int APD = 4;                       // A prefetch distance (chunks): the packed codes come from HBM
+constexpr int PRODUCER_WARPS = 8;
+constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
 constexpr int A_TILE = 128 * KCH;            // 16 KB
 constexpr int A_STAGE = MT_MAX * A_TILE;     // 64 KB
 constexpr int B_STAGE = NQ * KCH;            // 8 KB
@@ -44,10 +47,10 @@ struct Misc {
     uint32_t rank[NQ];
     uint32_t sq[SURV_CAP];
     Survivor ss[SURV_CAP];
-    uint64_t bars[STAGES + 1];  // empty[stage], accumulators done
+    uint64_t bars[2 * STAGES + 1];  // full[stage], empty[stage], accumulators done
     uint32_t tmem_base, item, surv_n, pad;
 };
-constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + sizeof(Misc) + 1024 /*alignment slack*/;
+constexpr size_t SMEM = (size_t)STAGES * A_STAGE + (size_t)BSTAGES * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/;
 }  // namespace tt
 
 // K-major operand, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) (unused) | SBO>>4 [32,46) = 8 rows * 128 B |
@@ -58,7 +61,7 @@ __device__ __forceinline__ uint64_t tt_desc(uint32_t smem_addr) {
 }
 // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2) [4,6), A = B = unsigned 8-bit (0) [7,10) / [10,13),
 // both K-major, N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t kTtIdesc = (2u << 4) | ((uint32_t)(tt::NQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t tt_idesc(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 __device__ __forceinline__ void tt_bar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -80,24 +83,36 @@ __device__ __forceinline__ uint32_t onehot32(uint32_t pos) {
     return d;
 }
 
+__device__ __forceinline__ void tt_bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// barrier among the 8 producer warps only (the issuer warp never joins it)
+__device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <bool WIDE>
 __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, TailArgs a) {
     using namespace tt;
     extern __shared__ unsigned char tt_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = sm;                                  // [STAGES][MT_MAX][128 rows][128 B]
-    unsigned char* sB = sm + (size_t)STAGES * A_STAGE;       // [STAGES][NQ rows][128 B]
-    Misc* mi = reinterpret_cast<Misc*>(sm + (size_t)STAGES * (A_STAGE + B_STAGE));
+    unsigned char* sB = sm + (size_t)STAGES * A_STAGE;       // [BSTAGES][NQ rows][128 B]
+    Misc* mi = reinterpret_cast<Misc*>(sm + (size_t)STAGES * A_STAGE + (size_t)BSTAGES * B_STAGE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = ix.D, ncb = D / 4;
     const uint32_t B = ix.block_stride;
     const uint32_t nkc = ((uint32_t)ncb + 7u) / 8u;  // K-chunks of 8 codebooks
     const bool l2 = ix.metric == RBQ_METRIC_L2;
     const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
-    const uint32_t empty0 = smem_u32(&mi->bars[0]), accd = smem_u32(&mi->bars[STAGES]);
+    // barriers: full[stage] (256 producer arrivals), empty[stage] (tcgen05.commit), accumulators done (tcgen05.commit)
+    const uint32_t full0 = smem_u32(&mi->bars[0]), empty0 = smem_u32(&mi->bars[STAGES]), accd = smem_u32(&mi->bars[2 * STAGES]);
+    const bool issuer = warp == PRODUCER_WARPS;
 
     if (tid == 0) {
-        for (int s = 0; s <= STAGES; ++s) mbar_init(empty0 + 8 * s, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, PRODUCER_WARPS * 32);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accd, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mi->surv_n = 0;
     }
@@ -111,30 +126,29 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = mi->tmem_base;
 
-    uint32_t prod[STAGES] = {0u, 0u};  // productions into each stage so far (uniform across the CTA)
-    uint32_t chunk_seq = 0;            // running chunk counter (stage = chunk_seq % STAGES)
-    uint32_t groups = 0;               // accumulator groups finished so far (phase of the `accd` barrier)
+    uint32_t chunk_seq = 0;  // running chunk counter: A stage = chunk_seq % 2, B stage = chunk_seq % 4
+    uint32_t groups = 0;     // accumulator groups finished so far (phase of the `accd` barrier)
 
-    // A production role of this thread: byte quad qd of codebook row cbl of a block-chunk
+    // A production role of a producer thread: byte quad qd of codebook row cbl of a block-chunk
     const int qd = lane >> 3, cbl = lane & 7;
     // epilogue role: TMEM lane quarter lq, tiles (warp >> 2) and (warp >> 2) + 2
     const int lq = warp & 3;
 
     // copies the staged survivors to the per-query buffers (one global atomic each, all in flight together)
     auto flush_survivors = [&]() {
-        __syncthreads();
+        tt_sync_producers();
         const uint32_t n = min(mi->surv_n, (uint32_t)SURV_CAP);
-        for (uint32_t i = tid; i < n; i += THREADS) {
+        for (uint32_t i = tid; i < n; i += PRODUCER_WARPS * 32) {
             const uint32_t q = mi->sq[i];
             const uint32_t slot = atomicAdd(&a.surv_cnt[q], 1u);
             if (slot < a.surv_cap) a.surv[(size_t)q * a.surv_cap + slot] = mi->ss[i];
         }
-        __syncthreads();
+        tt_sync_producers();
         if (tid == 0) {
             if (a.stats && n) atomicAdd(&a.stats->survivors, (unsigned long long)n);
             mi->surv_n = 0;
         }
-        __syncthreads();
+        tt_sync_producers();
     };
 
     for (;;) {
@@ -145,9 +159,51 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
         if (item >= a.counters[0]) break;
         const TailItem it = a.items[item];
         const uint32_t nv = ix.list_n[it.cid], nb = (nv + kBatch - 1) / kBatch;
+        const uint32_t P = it.pair_count;
+        // UMMA N = the item's pairs rounded up to 16: the integer pipe's time is proportional to it
+        const uint32_t idesc = tt_idesc(min((uint32_t)NQ, (P + 15u) & ~15u));
+
+        if (issuer) {
+            // ===== MMA issuer: waits for a produced stage, issues its MMAs, commits the stage back =====
+            for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {
+                const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
+                for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
+                    const uint32_t s = chunk_seq % STAGES;
+                    tt_bar_wait(full0 + 8 * s, (chunk_seq / STAGES) & 1u);
+                    if (lane == 0) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t db = tt_desc(sB_u32 + (chunk_seq % BSTAGES) * B_STAGE);
+                        const uint64_t da0 = tt_desc(sA_u32 + s * A_STAGE);
+                        for (uint32_t mt = 0; mt < mt_cnt; ++mt) {
+                            const uint64_t da = da0 + (uint64_t)(mt * (A_TILE >> 4));
+#pragma unroll
+                            for (int k = 0; k < KCH / 32; ++k) {
+                                const uint32_t acc = (kc | (uint32_t)k) ? 1u : 0u;
+                                asm volatile(
+                                    "{\n"
+                                    ".reg .pred p;\n"
+                                    "setp.ne.b32 p, %4, 0;\n"
+                                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+                                    "}" ::"r"(tmem + mt * NQ),
+                                    "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
+                                    : "memory");
+                            }
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
+                                     : "memory");
+                        if (kc + 1 == nkc)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accd)
+                                         : "memory");
+                    }
+                    __syncwarp();
+                }
+            }
+            continue;
+        }
+
+        // ===== producers / epilogue (8 warps) =====
         const uint8_t* lbase = ix.blocks + (size_t)ix.blk_off[it.cid] * B;
         const unsigned long long vbase = ix.vec_off[it.cid];
-        const uint32_t P = it.pair_count;
         if (tid == 0 && a.stats) {
             atomicAdd(&a.stats->tail_blocks, (unsigned long long)P * nb);
             atomicAdd(&a.stats->tail_pairs, (unsigned long long)P);
@@ -171,31 +227,63 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
             mi->c0[tid] = c0;
             mi->c1[tid] = c1;
         }
-        __syncthreads();
+        tt_sync_producers();
 
         for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {  // accumulator group: up to 16 blocks = 4 tiles of 128 vectors
             const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
-            for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
-                const uint32_t s = chunk_seq % STAGES;
-                if (prod[s] > 0) tt_bar_wait(empty0 + 8 * s, (prod[s] - 1) & 1u);  // the MMAs that read this stage are done
-                prod[s] += 1;
-                // ---- B: LUT slice [kc*128, kc*128+128) of the item's queries, row r = pair slot ----
+            // B: LUT slice [kc*128, kc*128+128) of the item's queries (row r = pair slot), straight into shared memory
+            auto issue_b = [&](uint32_t kc, uint32_t seq) {
+                const uint32_t dstb = sB_u32 + (seq % BSTAGES) * B_STAGE;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int piece = tid + THREADS * i, r = piece >> 3, j = piece & 7;
+                    const int piece = tid + PRODUCER_WARPS * 32 * i, r = piece >> 3, j = piece & 7;
                     const uint32_t q = mi->q[r];
                     const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
-                    if (q != 0xffffffffu && koff < (uint32_t)D * 4u) {
-                        const uint4 v = ldg128(a.lut + (size_t)q * D * 4 + koff);
-                        sts128(sB_u32 + s * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4), v.x, v.y, v.z, v.w);
-                    }
+                    if (q != 0xffffffffu && koff < (uint32_t)D * 4u)
+                        cp_async16(dstb + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4), a.lut + (size_t)q * D * 4 + koff);
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            // A source: 4 code bytes (byte quad qd of codebook row 8*kc + cbl) of the warp's blocks bg = warp, warp + 8
+            auto load_a = [&](uint32_t kc, uint32_t (&w)[2]) {
+                const uint32_t cb = kc * 8u + (uint32_t)cbl;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t bg = (uint32_t)warp + 8u * i;
+                    w[i] = (bg < nbg && cb < (uint32_t)ncb) ? ldg32(lbase + (size_t)(b0 + bg) * B + 16u * cb + 4u * (uint32_t)qd) : 0u;
+                }
+            };
+            uint32_t wbuf[APD][2];  // packed codes of chunks kc .. kc+APD-1 (registers)
+            // every earlier MMA has completed (accumulator barrier), so all stages are free
+            issue_b(0, chunk_seq);
+            if (nkc > 1) issue_b(1, chunk_seq + 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+            for (int d = 0; d < APD; ++d) {
+                wbuf[d][0] = wbuf[d][1] = 0u;
+                if ((uint32_t)d < nkc) load_a((uint32_t)d, wbuf[d]);
+            }
+            for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
+                const uint32_t s = chunk_seq % STAGES, use = chunk_seq / STAGES;
+                // chunk_seq - 2 was the last reader of A stage s and of B stage (chunk_seq + 2) % 4
+                if (use > 0) tt_bar_wait(empty0 + 8 * s, (use - 1) & 1u);
+                if (kc + 2 < nkc) issue_b(kc + 2, chunk_seq + 2);
+                else asm volatile("cp.async.commit_group;" ::: "memory");
+                uint32_t wcur[2] = {wbuf[0][0], wbuf[0][1]};
+#pragma unroll
+                for (int d = 0; d + 1 < APD; ++d) {
+                    wbuf[d][0] = wbuf[d + 1][0];
+                    wbuf[d][1] = wbuf[d + 1][1];
+                }
+                wbuf[APD - 1][0] = wbuf[APD - 1][1] = 0u;
+                if (kc + APD < nkc) load_a(kc + APD, wbuf[APD - 1]);
                 // ---- A: one-hot rows of the group's blocks for codebooks 8*kc .. 8*kc+7 ----
-                for (uint32_t bg = warp; bg < nbg; bg += THREADS / 32) {
-                    const uint32_t cb = kc * 8u + (uint32_t)cbl;
-                    uint32_t word = 0;
-                    const bool live = cb < (uint32_t)ncb;
-                    if (live) word = ldg32(lbase + (size_t)(b0 + bg) * B + 16u * cb + 4u * (uint32_t)qd);
+                const bool live = kc * 8u + (uint32_t)cbl < (uint32_t)ncb;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t bg = (uint32_t)warp + 8u * i;
+                    if (bg >= nbg) break;
+                    const uint32_t word = wcur[i];
                     const uint32_t tile = sA_u32 + s * A_STAGE + (bg >> 2) * A_TILE + (bg & 3u) * 32u * 128u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -213,35 +301,12 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
                         }
                     }
                 }
+                asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's pieces of the chunk's LUT slice have landed
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-                __syncthreads();
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (uint32_t mt = 0; mt < mt_cnt; ++mt) {
-                        const uint64_t da = tt_desc(sA_u32 + s * A_STAGE + mt * A_TILE);
-                        const uint64_t db = tt_desc(sB_u32 + s * B_STAGE);
-#pragma unroll
-                        for (int k = 0; k < KCH / 32; ++k) {
-                            const uint32_t acc = (kc | (uint32_t)k) ? 1u : 0u;
-                            asm volatile(
-                                "{\n"
-                                ".reg .pred p;\n"
-                                "setp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-                                "}" ::"r"(tmem + mt * NQ),
-                                "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(kTtIdesc), "r"(acc)
-                                : "memory");
-                        }
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
-                                 : "memory");
-                    if (kc + 1 == nkc)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accd) : "memory");
-                }
+                tt_bar_arrive(full0 + 8 * s);
             }
             // ---- epilogue: sums -> K8 -> survivors ----
             tt_bar_wait(accd, groups & 1u);
-            groups += 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (uint32_t mt = (uint32_t)(warp >> 2); mt < mt_cnt; mt += 2) {
                 const uint32_t bg = mt * 4u + (uint32_t)lq;  // this warp's block of the tile; TMEM lane = 32*lq + vector
@@ -261,6 +326,7 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
                 }
 #pragma unroll 1
                 for (int c0i = 0; c0i < NQ; c0i += 32) {
+                    if ((uint32_t)c0i >= P) break;
                     uint32_t r[32];
                     const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + mt * NQ + (uint32_t)c0i;
                     asm volatile(
@@ -305,8 +371,10 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
                     }
                 }
             }
+            // TMEM reads done before this thread's next arrival on a `full` barrier lets the issuer overwrite the accumulators
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            flush_survivors();  // also the barrier that lets the next group overwrite the accumulators
+            groups += 1;
+            flush_survivors();
         }
     }
     __syncthreads();
