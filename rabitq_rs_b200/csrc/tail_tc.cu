@@ -31,9 +31,10 @@ constexpr int MT_MAX = 4;                    // 128-vector tiles (4 blocks each)
 constexpr int NQ = 64;                       // queries per item = UMMA N
 constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
 constexpr int STAGES = 2;                    // A stages
-constexpr int BSTAGES = 4;                   // B stages: the LUT slices of chunks c+1, c+2 are in flight while chunk c is multiplied
-constexpr int APD = 4;                       // A prefetch distance (chunks): the packed codes come from HBM
-constexpr int PRODUCER_WARPS = 8;
+constexpr int PD = 3;                        // prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
+constexpr int BSTAGES = PD + 2;              // B stages: chunk c+PD lands in the stage chunk c-2 has released
+constexpr int RSTAGES = PD + 1;              // raw packed-code ring (4 bytes per producer thread and chunk)
+constexpr int PRODUCER_WARPS = 16;           // one block of the group per warp
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
 constexpr int A_TILE = 128 * KCH;            // 16 KB
 constexpr int A_STAGE = MT_MAX * A_TILE;     // 64 KB
@@ -48,6 +49,8 @@ struct Misc {
     uint32_t sq[SURV_CAP];
     Survivor ss[SURV_CAP];
     uint64_t bars[2 * STAGES + 1];  // full[stage], empty[stage], accumulators done
+    uint4 onehot[16];               // row n: byte n = 1 (the 16-byte one-hot of a 4-bit code)
+    uint32_t raw[RSTAGES][PRODUCER_WARPS * 32];  // packed code bytes in flight (cp.async)
     uint32_t tmem_base, item, surv_n, pad;
 };
 constexpr size_t SMEM = (size_t)STAGES * A_STAGE + (size_t)BSTAGES * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/;
@@ -87,7 +90,7 @@ __device__ __forceinline__ void tt_bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // barrier among the 8 producer warps only (the issuer warp never joins it)
-__device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <bool WIDE>
 __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, TailArgs a) {
@@ -116,6 +119,10 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mi->surv_n = 0;
     }
+    if (tid < 16) {
+        const uint32_t w = 1u << (8 * (tid & 3));
+        mi->onehot[tid] = make_uint4((tid >> 2) == 0 ? w : 0u, (tid >> 2) == 1 ? w : 0u, (tid >> 2) == 2 ? w : 0u, (tid >> 2) == 3 ? w : 0u);
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&mi->tmem_base)), "r"(TMEM_COLS)
                      : "memory");
@@ -131,8 +138,9 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
 
     // A production role of a producer thread: byte quad qd of codebook row cbl of a block-chunk
     const int qd = lane >> 3, cbl = lane & 7;
-    // epilogue role: TMEM lane quarter lq, tiles (warp >> 2) and (warp >> 2) + 2
+    // epilogue role: TMEM lane quarter lq of tile warp >> 2
     const int lq = warp & 3;
+    const uint32_t onehot_u32 = smem_u32(&mi->onehot[0]);
 
     // copies the staged survivors to the per-query buffers (one global atomic each, all in flight together)
     auto flush_survivors = [&]() {
@@ -231,84 +239,61 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
 
         for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {  // accumulator group: up to 16 blocks = 4 tiles of 128 vectors
             const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
-            // B: LUT slice [kc*128, kc*128+128) of the item's queries (row r = pair slot), straight into shared memory
-            auto issue_b = [&](uint32_t kc, uint32_t seq) {
-                const uint32_t dstb = sB_u32 + (seq % BSTAGES) * B_STAGE;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int piece = tid + PRODUCER_WARPS * 32 * i, r = piece >> 3, j = piece & 7;
+            // chunk kc of the group: B = LUT slice [kc*128, kc*128+128) of the item's queries (row r = pair slot) straight into
+            // its swizzled stage, and this thread's 4 packed code bytes (byte quad qd of codebook row 8*kc + cbl of block
+            // bg = warp) into the raw ring -- both asynchronous, one commit group per chunk
+            auto prefetch = [&](uint32_t kc, uint32_t seq) {
+                if (kc < nkc) {
+                    const int r = tid >> 3, j = tid & 7;
                     const uint32_t q = mi->q[r];
                     const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
                     if (q != 0xffffffffu && koff < (uint32_t)D * 4u)
-                        cp_async16(dstb + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4), a.lut + (size_t)q * D * 4 + koff);
+                        cp_async16(sB_u32 + (seq % BSTAGES) * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4),
+                                   a.lut + (size_t)q * D * 4 + koff);
+                    const uint32_t cb = kc * 8u + (uint32_t)cbl;
+                    if ((uint32_t)warp < nbg && cb < (uint32_t)ncb)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&mi->raw[seq % RSTAGES][tid])),
+                                     "l"(lbase + (size_t)(b0 + warp) * B + 16u * cb + 4u * (uint32_t)qd)
+                                     : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            // A source: 4 code bytes (byte quad qd of codebook row 8*kc + cbl) of the warp's blocks bg = warp, warp + 8
-            auto load_a = [&](uint32_t kc, uint32_t (&w)[2]) {
-                const uint32_t cb = kc * 8u + (uint32_t)cbl;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t bg = (uint32_t)warp + 8u * i;
-                    w[i] = (bg < nbg && cb < (uint32_t)ncb) ? ldg32(lbase + (size_t)(b0 + bg) * B + 16u * cb + 4u * (uint32_t)qd) : 0u;
-                }
-            };
-            uint32_t wbuf[APD][2];  // packed codes of chunks kc .. kc+APD-1 (registers)
             // every earlier MMA has completed (accumulator barrier), so all stages are free
-            issue_b(0, chunk_seq);
-            if (nkc > 1) issue_b(1, chunk_seq + 1);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
-            for (int d = 0; d < APD; ++d) {
-                wbuf[d][0] = wbuf[d][1] = 0u;
-                if ((uint32_t)d < nkc) load_a((uint32_t)d, wbuf[d]);
-            }
+            for (int d = 0; d < PD; ++d) prefetch((uint32_t)d, chunk_seq + d);
+            const uint32_t tile = (uint32_t)(warp >> 2) * A_TILE + (uint32_t)(warp & 3) * 32u * 128u;
             for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
                 const uint32_t s = chunk_seq % STAGES, use = chunk_seq / STAGES;
-                // chunk_seq - 2 was the last reader of A stage s and of B stage (chunk_seq + 2) % 4
+                // chunk_seq - 2 was the last reader of A stage s and of B stage (chunk_seq + PD) % BSTAGES
                 if (use > 0) tt_bar_wait(empty0 + 8 * s, (use - 1) & 1u);
-                if (kc + 2 < nkc) issue_b(kc + 2, chunk_seq + 2);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                uint32_t wcur[2] = {wbuf[0][0], wbuf[0][1]};
-#pragma unroll
-                for (int d = 0; d + 1 < APD; ++d) {
-                    wbuf[d][0] = wbuf[d + 1][0];
-                    wbuf[d][1] = wbuf[d + 1][1];
-                }
-                wbuf[APD - 1][0] = wbuf[APD - 1][1] = 0u;
-                if (kc + APD < nkc) load_a(kc + APD, wbuf[APD - 1]);
-                // ---- A: one-hot rows of the group's blocks for codebooks 8*kc .. 8*kc+7 ----
-                const bool live = kc * 8u + (uint32_t)cbl < (uint32_t)ncb;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t bg = (uint32_t)warp + 8u * i;
-                    if (bg >= nbg) break;
-                    const uint32_t word = wcur[i];
-                    const uint32_t tile = sA_u32 + s * A_STAGE + (bg >> 2) * A_TILE + (bg & 3u) * 32u * 128u;
+                prefetch(kc + PD, chunk_seq + PD);
+                asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");  // this thread's pieces of chunk kc have landed
+                // ---- A: one-hot rows of the warp's block for codebooks 8*kc .. 8*kc+7 ----
+                if ((uint32_t)warp < nbg) {
+                    const bool live = kc * 8u + (uint32_t)cbl < (uint32_t)ncb;
+                    const uint32_t word = live ? mi->raw[chunk_seq % RSTAGES][tid] : 0u;
+                    const uint32_t base = sA_u32 + s * A_STAGE + tile;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int p = 4 * qd + j;                       // byte position in the 16-byte codebook row
-                        const int v = (p >> 1) + ((p & 1) << 3);        // KPERM0[p]: vector of the low nibble (high: v + 16)
-                        const uint32_t byte = (word >> (8 * j)) & 0xffu;
-                        const uint32_t dst = tile + (uint32_t)v * 128u + (uint32_t)((cbl ^ (v & 7)) << 4);
-                        const uint32_t s_lo = (byte & 15u) * 8u, s_hi = (byte >> 4) * 8u;
-                        if (live) {
-                            sts128(dst, onehot32(s_lo), onehot32(s_lo - 32u), onehot32(s_lo - 64u), onehot32(s_lo - 96u));
-                            sts128(dst + 16u * 128u, onehot32(s_hi), onehot32(s_hi - 32u), onehot32(s_hi - 64u), onehot32(s_hi - 96u));
-                        } else {  // past the last codebook: the K padding of the chunk contributes nothing
-                            sts128(dst, 0u, 0u, 0u, 0u);
-                            sts128(dst + 16u * 128u, 0u, 0u, 0u, 0u);
+                        const int p = 4 * qd + j;                 // byte position in the 16-byte codebook row
+                        const int v = (p >> 1) + ((p & 1) << 3);  // KPERM0[p]: vector of the low nibble (high: v + 16)
+                        const uint32_t dst = base + (uint32_t)v * 128u + (uint32_t)((cbl ^ (v & 7)) << 4);
+                        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+                        if (live) {  // past the last codebook the K padding of the chunk contributes nothing
+                            lo = lds128(onehot_u32 + ((word >> (8 * j)) & 15u) * 16u);
+                            hi = lds128(onehot_u32 + ((word >> (8 * j + 4)) & 15u) * 16u);
                         }
+                        sts128(dst, lo.x, lo.y, lo.z, lo.w);
+                        sts128(dst + 16u * 128u, hi.x, hi.y, hi.z, hi.w);
                     }
                 }
-                asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's pieces of the chunk's LUT slice have landed
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tt_bar_arrive(full0 + 8 * s);
             }
             // ---- epilogue: sums -> K8 -> survivors ----
             tt_bar_wait(accd, groups & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (uint32_t mt = (uint32_t)(warp >> 2); mt < mt_cnt; mt += 2) {
+            for (uint32_t mt = (uint32_t)(warp >> 2); mt < mt_cnt; mt += PRODUCER_WARPS / 4) {
                 const uint32_t bg = mt * 4u + (uint32_t)lq;  // this warp's block of the tile; TMEM lane = 32*lq + vector
                 const bool have_blk = bg < nbg;
                 const uint32_t li = (b0 + bg) * kBatch + (uint32_t)lane;
