@@ -27,19 +27,19 @@
 namespace rbq {
 
 namespace tt {
-constexpr int MT_MAX = 4;                    // 128-vector tiles (4 blocks each) accumulated concurrently
+constexpr int MT_MAX = 2;                    // 128-vector tiles (4 blocks each) accumulated concurrently
 constexpr int NQ = 64;                       // queries per item = UMMA N
 constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
 constexpr int STAGES = 2;                    // A stages
-constexpr int PD = 3;                        // prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
+constexpr int PD = 2;                        // prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
 constexpr int BSTAGES = PD + 2;              // B stages: chunk c+PD lands in the stage chunk c-2 has released
 constexpr int RSTAGES = PD + 1;              // raw packed-code ring (4 bytes per producer thread and chunk)
-constexpr int PRODUCER_WARPS = 16;           // one block of the group per warp
+constexpr int PRODUCER_WARPS = 4 * MT_MAX;   // one block of the group per warp
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
 constexpr int A_TILE = 128 * KCH;            // 16 KB
 constexpr int A_STAGE = MT_MAX * A_TILE;     // 64 KB
 constexpr int B_STAGE = NQ * KCH;            // 8 KB
-constexpr int SURV_CAP = 512;                // survivors staged in shared memory between flushes
+constexpr int SURV_CAP = 256;                // survivors staged in shared memory between flushes
 constexpr int TMEM_COLS = MT_MAX * NQ;       // 256 columns of s32 accumulators
 struct Misc {
     float4 c0[NQ];   // delta, sum_vl, k1x, g_add
@@ -90,10 +90,10 @@ __device__ __forceinline__ void tt_bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // barrier among the 8 producer warps only (the issuer warp never joins it)
-__device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(tt::PRODUCER_WARPS * 32) : "memory"); }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, TailArgs a) {
+__global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, TailArgs a) {
     using namespace tt;
     extern __shared__ unsigned char tt_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
         __syncthreads();
         const uint32_t item = mi->item;
         if (item >= a.counters[0]) break;
+        // the staged survivors go out when the buffer is half full (everyone reads the same count here: nobody appends
+        // between the barriers above and the first epilogue of the item)
+        if (!issuer && mi->surv_n > (uint32_t)SURV_CAP / 2) flush_survivors();
         const TailItem it = a.items[item];
         const uint32_t nv = ix.list_n[it.cid], nb = (nv + kBatch - 1) / kBatch;
         const uint32_t P = it.pair_count;
@@ -244,12 +247,15 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
             // bg = warp) into the raw ring -- both asynchronous, one commit group per chunk
             auto prefetch = [&](uint32_t kc, uint32_t seq) {
                 if (kc < nkc) {
-                    const int r = tid >> 3, j = tid & 7;
-                    const uint32_t q = mi->q[r];
-                    const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
-                    if (q != 0xffffffffu && koff < (uint32_t)D * 4u)
-                        cp_async16(sB_u32 + (seq % BSTAGES) * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4),
-                                   a.lut + (size_t)q * D * 4 + koff);
+#pragma unroll
+                    for (int i = 0; i < NQ * 8 / (PRODUCER_WARPS * 32); ++i) {
+                        const int piece = tid + PRODUCER_WARPS * 32 * i, r = piece >> 3, j = piece & 7;
+                        const uint32_t q = mi->q[r];
+                        const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
+                        if (q != 0xffffffffu && koff < (uint32_t)D * 4u)
+                            cp_async16(sB_u32 + (seq % BSTAGES) * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4),
+                                       a.lut + (size_t)q * D * 4 + koff);
+                    }
                     const uint32_t cb = kc * 8u + (uint32_t)cbl;
                     if ((uint32_t)warp < nbg && cb < (uint32_t)ncb)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&mi->raw[seq % RSTAGES][tid])),
@@ -359,9 +365,9 @@ __global__ void __launch_bounds__(tt::THREADS, 1) tail_tc_kernel(DevIndex ix, Ta
             // TMEM reads done before this thread's next arrival on a `full` barrier lets the issuer overwrite the accumulators
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             groups += 1;
-            flush_survivors();
         }
     }
+    if (!issuer) flush_survivors();
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -383,10 +389,10 @@ int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st) {
     RBQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (ix.D > 1024) {
         RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
-        tail_tc_kernel<true><<<sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
+        tail_tc_kernel<true><<<2 * sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
     } else {
         RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
-        tail_tc_kernel<false><<<sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
+        tail_tc_kernel<false><<<2 * sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
     }
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
