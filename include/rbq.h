@@ -125,6 +125,7 @@ typedef struct rbq_search_stats {
     uint64_t survivors;         /* tail vectors with lower bound < the head threshold (replayed in reference order) */
     uint64_t overflow_queries;  /* queries whose survivor buffer overflowed (their tail was re-walked sequentially) */
     float ms_scan_head, ms_scan_tail, ms_scan_replay; /* split of ms_scan (sequential mode: all in head) */
+    float ms_tail_kernel;       /* the tail FastScan kernel alone (events around that one launch; 0 in sequential mode) */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */

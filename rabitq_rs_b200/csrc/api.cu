@@ -220,7 +220,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
     float* d_qn2 = cv.take<float>(qt);
     TailWs tw;
     tail_ws_carve(ix, qt, nprobe, top_k, cv.take<char>(tail_ws_bytes(ix, qt, nprobe, top_k)), tw);
-    float ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    float ms[7] = {0, 0, 0, 0, 0, 0, 0};  // [6]: the tail FastScan kernel alone
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
         int rc;
@@ -276,7 +276,9 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 return rc;
             if (h->profiling) cudaEventRecord(h->ev[4], st);
             // tail: all remaining (query, list) pairs grouped by list -> survivors
-            if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches))) return rc;
+            if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches,
+                                  h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
+                return rc;
             if (h->profiling) cudaEventRecord(h->ev[5], st);
             // bulk refine of the survivors, ordered replay, then the (normally empty) sequential fallback
             if ((rc = launch_refine_replay(ix, d_rot, d_qs, d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
@@ -295,6 +297,11 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
                 ms[i] += t;
             }
+            if (list_major) {
+                float t = 0;
+                cudaEventElapsedTime(&t, h->ev[7], h->ev[8]);
+                ms[6] += t;
+            }
         }
     }
     if (h->profiling) {
@@ -305,6 +312,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         h->last_stats.ms_scan_head = ms[3];
         h->last_stats.ms_scan_tail = ms[4];
         h->last_stats.ms_scan_replay = ms[5];
+        h->last_stats.ms_tail_kernel = ms[6];
     }
     return RBQ_OK;
 }

@@ -171,7 +171,7 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
 // scan_tail.cu: group the tail (query, rank) pairs by list, then FastScan list-major; survivors -> tw.
 int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                 size_t nprobe, const uint64_t* d_filter, size_t filter_nbits, DevStats* d_stats, const TailWs& tw,
-                cudaStream_t st, uint64_t* launches);
+                cudaStream_t st, uint64_t* launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr);
 // resolve.cu: the list-major pipeline around the tail kernel.
 //   head scan    FastScan of every query's first owned list -> tw.head_buf (dense)
 //   head resolve the reference's sequential prune/refine/top-k over that list -> heap state, tw.tau, tw.tail_start
@@ -230,7 +230,7 @@ struct rbq_index {
     unsigned int* work_counter() const { return reinterpret_cast<unsigned int*>(d_stats + 1); }
     unsigned int* fallback_counter() const { return work_counter() + 1; }
     mutable rbq_search_stats last_stats{};
-    mutable cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    mutable cudaEvent_t ev[9] = {};  // stage boundaries 0..6, then begin/end of the tail FastScan kernel alone
     mutable cudaStream_t copy_stream = nullptr;  // H2D of host queries, overlapped with the front end (api.cu, HostFeed)
     mutable cudaStream_t compute_stream = nullptr;  // the host entry points' compute stream
     mutable cudaEvent_t feed_ev[16] = {};

@@ -360,9 +360,27 @@ static int launch_tail_ex(const DevIndex& ix, TailArgs& a, cudaStream_t st) {
     return RBQ_OK;
 }
 
+static int launch_tail_fastscan(const DevIndex& ix, TailArgs& a, cudaStream_t st) {
+    if (tail_tc_supported(ix)) return launch_tail_tc(ix, a, st);
+    const int ncb_lane = (ix.D / 4 + 31) / 32;
+    if (ix.D > 1024) {
+        if (ncb_lane <= 12) return launch_tail_ex<12, true>(ix, a, st);
+        return launch_tail_ex<16, true>(ix, a, st);
+    }
+    switch (ncb_lane) {
+        case 1: return launch_tail_ex<1, false>(ix, a, st);
+        case 2: return launch_tail_ex<2, false>(ix, a, st);
+        case 3: return launch_tail_ex<3, false>(ix, a, st);
+        case 4: return launch_tail_ex<4, false>(ix, a, st);
+        case 5:
+        case 6: return launch_tail_ex<6, false>(ix, a, st);
+        default: return launch_tail_ex<8, false>(ix, a, st);
+    }
+}
+
 int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                 size_t nprobe, const uint64_t* d_filter, size_t filter_nbits, DevStats* d_stats, const TailWs& tw,
-                cudaStream_t st, uint64_t* launches) {
+                cudaStream_t st, uint64_t* launches, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     if (nq == 0) return RBQ_OK;
     int rc = tail_limits();
     if (rc) return rc;
@@ -392,21 +410,10 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
     a.seg_blocks = 1;
     a.has_ex = ix.ex_bits != 0;
     if (launches) *launches += 4;
-    if (tail_tc_supported(ix)) return launch_tail_tc(ix, a, st);
-    const int ncb_lane = (ix.D / 4 + 31) / 32;
-    if (ix.D > 1024) {
-        if (ncb_lane <= 12) return launch_tail_ex<12, true>(ix, a, st);
-        return launch_tail_ex<16, true>(ix, a, st);
-    }
-    switch (ncb_lane) {
-        case 1: return launch_tail_ex<1, false>(ix, a, st);
-        case 2: return launch_tail_ex<2, false>(ix, a, st);
-        case 3: return launch_tail_ex<3, false>(ix, a, st);
-        case 4: return launch_tail_ex<4, false>(ix, a, st);
-        case 5:
-        case 6: return launch_tail_ex<6, false>(ix, a, st);
-        default: return launch_tail_ex<8, false>(ix, a, st);
-    }
+    if (ev_begin) cudaEventRecord(ev_begin, st);
+    rc = launch_tail_fastscan(ix, a, st);
+    if (ev_end) cudaEventRecord(ev_end, st);
+    return rc;
 }
 
 }  // namespace rbq
