@@ -52,6 +52,7 @@ struct ResolveArgs {
     uint32_t raw_stride;  // bytes per raw (packed) ex-code staging slot; 0: ex-codes are read straight from global memory
     uint32_t has_ex;
     uint32_t flush_at;  // head resolve: refine as soon as this many candidates are queued
+    uint32_t lazy_flush_at;  // lazy replay: queue length that triggers a refine round
 };
 
 // first probe rank >= from whose list has vectors on this shard (nprobe if none)
@@ -522,6 +523,175 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
     }
 }
 
+// ---- lazy replay: on-demand refinement of the sorted survivors ---------------------------------------------------
+// The bulk refine above evaluates K10 for EVERY survivor (lower bound < the head threshold tau), but the reference only
+// refines a candidate whose lower bound beats the LIVE k-th distance, which keeps falling while the tail is walked
+// (reference src/ivf.rs:2044-2052): at GIST/nprobe 16 that is ~15 of ~75 survivors per query.  This kernel sorts the
+// survivors into the reference's visit order first and then runs the head-resolve loop over them: candidates that beat
+// the current (stale => looser => superset) threshold are queued, a full queue is refined in one batch and replayed
+// against the live threshold.  Same decisions as the reference, a fraction of the ex-code traffic and FMA chains.
+template <int EXK>
+__global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex ix, ResolveArgs a) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = ix.D, k = (int)a.top_k;
+    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, k, true, true, a.surv_cap);
+    unsigned char* wbase = res_smem + (size_t)warp * L.total;
+    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
+    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
+    float* sd = reinterpret_cast<float*>(wbase + L.sd);
+    unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    unsigned long long st_adm = 0, st_ovf = 0, st_ref = 0;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(&a.counters[5], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.nq) break;
+        const uint32_t start_pi = a.tail_start[q], n_surv = a.surv_cnt[q];
+        if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
+        if (n_surv > a.surv_cap) {                           // survivor buffer overflowed: the sequential kernel re-walks the tail
+            if (lane == 0) a.fb_list[atomicAdd(&a.counters[2], 1u)] = q | kFbResume;
+            st_ovf += 1;
+            continue;
+        }
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        __syncwarp();
+        load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+        const QueryScalars s = a.qs[q];
+        int cnt = (int)a.out_counts[q];
+        for (int i = lane; i < cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
+            const float sc = a.out_scores[(size_t)q * k + i];
+            sd[i] = l2 ? sc : -sc;
+            si[i] = a.out_ids[(size_t)q * k + i];
+        }
+        const Survivor* sv = a.surv + (size_t)q * a.surv_cap;
+        // sort key: rank (12 bits, nprobe <= 4096) | position (32) | slot in the buffer (10, cap <= 1024)
+        uint32_t npad = 32;
+        while (npad < n_surv) npad <<= 1;
+        for (uint32_t i = lane; i < npad; i += 32)
+            ord[i] = i < n_surv ? ((unsigned long long)sv[i].rank << 42) | ((unsigned long long)sv[i].pos << 10) | i : ~0ull;
+        __syncwarp();
+        for (uint32_t size = 2; size <= npad; size <<= 1) {  // bitonic sort, ascending
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = lane; t < npad / 2; t += 32) {
+                    const uint32_t i = 2 * t - (t & (stride - 1)), j2 = i + stride;
+                    const unsigned long long x = ord[i], y = ord[j2];
+                    if ((x > y) == ((i & size) == 0)) {
+                        ord[i] = y;
+                        ord[j2] = x;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // candidate queue: slot i lives in lane i, in visit order
+        int qn = 0;
+        float q_lower = 0.0f, q_ip = 0.0f, q_gadd = 0.0f;
+        unsigned long long q_gv = 0;
+        unsigned long long q_ref = 0, q_adm = 0;
+        auto flush = [&]() {
+            if (qn == 0) return;
+            float dist = 0.0f;
+            const bool mine = lane < qn;
+            float fae = 0.0f, fre = 0.0f;
+            unsigned long long q_vid = 0;
+            if (mine) {
+                fae = __ldg(ix.f_add_ex + q_gv);
+                fre = __ldg(ix.f_rescale_ex + q_gv);
+                q_vid = ix.ids[q_gv];
+            }
+            const float exdot = refine_batch<EXK>(ix, a, q_gv, qn, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+            q_ref += qn;
+            if (mine) {
+                // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                float tt = s.bscale * q_ip;
+                tt = tt + exdot;
+                tt = tt + s.kbx;
+                const float mm2 = fre * tt;
+                const float aa = fae + q_gadd;
+                dist = aa + mm2;
+            }
+            for (int c = 0; c < qn; ++c) {
+                const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
+                const float d_s = __shfl_sync(0xffffffffu, dist, c);
+                const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
+                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                q_adm += 1;
+                if (!isfinite(d_s)) continue;
+                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+            }
+            qn = 0;
+        };
+        const int fl = (int)a.lazy_flush_at;
+        for (uint32_t base = 0; base < n_surv; base += 32) {
+            const uint32_t i = base + lane;
+            bool have = i < n_surv;
+            Survivor rec = {0u, 0u, 0.0f, 0.0f};
+            unsigned long long gv = 0;
+            float g_add = 0.0f;
+            if (have) {
+                rec = sv[(uint32_t)ord[i] & 1023u];
+                const Probe* pp = pr + rec.rank;
+                gv = pp->vec_off + rec.pos;
+                g_add = pp->g_add;
+            }
+            {   // the first few likely candidates of the batch: start their ex-codes towards L2 now
+                const float th = cnt >= k ? sd[k - 1] : INFINITY;
+                const bool likely = have && (rec.lower < th);
+                const unsigned m0 = __ballot_sync(0xffffffffu, likely);
+                if (likely && __popc(m0 & ((1u << lane) - 1u)) < 2 * fl) {
+                    const uint8_t* ep = ix.ex + gv * ix.ex_stride;
+                    for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                }
+            }
+            // the batch is consumed in visit order, a queue-full at a time, so that the threshold is refreshed between
+            // refine rounds; a lane that fails the test once is out for good (the threshold never rises)
+            for (;;) {
+                const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                have = have && (rec.lower < theta0);
+                unsigned mask = __ballot_sync(0xffffffffu, have);
+                if (mask == 0u) break;
+                const int room = fl - qn;  // >= 1: a full queue is flushed right away
+                if (__popc(mask) > room) mask &= (2u << __fns(mask, 0, room)) - 1u;  // the first `room` candidates
+                const int n_new = __popc(mask);
+                const int r = lane - qn;
+                const int src = (r >= 0 && r < n_new) ? (int)__fns(mask, 0, r + 1) : 0;
+                const float nl = __shfl_sync(0xffffffffu, rec.lower, src);
+                const float nip = __shfl_sync(0xffffffffu, rec.x, src);
+                const float nga = __shfl_sync(0xffffffffu, g_add, src);
+                const unsigned long long ngv = __shfl_sync(0xffffffffu, gv, src);
+                if (r >= 0 && r < n_new) {
+                    q_lower = nl;
+                    q_ip = nip;
+                    q_gadd = nga;
+                    q_gv = ngv;
+                }
+                if ((mask >> lane) & 1u) have = false;  // queued
+                qn += n_new;
+                if (qn >= fl) flush();
+            }
+        }
+        flush();
+        st_ref += q_ref;
+        st_adm += q_adm;
+        for (int i = lane; i < k; i += 32) {
+            const bool have = i < cnt;
+            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
+        }
+        if (lane == 0) a.out_counts[q] = (uint32_t)cnt;
+        __syncwarp();
+    }
+    if (lane == 0 && a.stats) {
+        if (st_adm) atomicAdd(&a.stats->admitted, st_adm);
+        if (st_ref) atomicAdd(&a.stats->refined, st_ref);
+        if (st_ovf) atomicAdd(&a.stats->overflow_queries, st_ovf);
+    }
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static int g_res_sms = 0;
 static size_t g_res_smem_optin = 0;
@@ -573,6 +743,11 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
         return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : 2 * kRefineSlots));
     }();
     a.flush_at = flush_at;
+    static const uint32_t lazy_flush_at = [] {
+        const char* e = getenv("RBQ_LAZY_FLUSH");
+        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : 2 * kRefineSlots));
+    }();
+    a.lazy_flush_at = lazy_flush_at;
 }
 
 template <int NCB, bool WIDE>
@@ -646,6 +821,31 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     if (rc) return rc;
     ResolveArgs a;
     fill_args(a, ix, d_rot, nullptr, d_qs, d_probes, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, d_stats, tw);
+    static const bool bulk = [] {
+        const char* e = getenv("RBQ_BULK_REFINE");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    if (ix.ex_bits != 0 && !bulk) {
+        // lazy: sorted survivors, refinement on demand against the live threshold (one kernel)
+        const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, a.top_k, true, true, a.surv_cap);
+        const size_t smem = (size_t)w.total * kResWarps;
+        if (smem <= g_res_smem_optin) {
+            const unsigned grid = res_grid(nq, smem);
+            if (ix.ex_bits == 2) {
+                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                resolve_lazy_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            } else if (ix.ex_bits == 6) {
+                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                resolve_lazy_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            } else {
+                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                resolve_lazy_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            }
+            RBQ_CUDA(cudaGetLastError());
+            if (launches) *launches += 1;
+            return RBQ_OK;
+        }
+    }
     if (ix.ex_bits != 0) {
         const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, 0, true, false, 0);
         const size_t smem = (size_t)w.total * kResWarps;
