@@ -98,6 +98,7 @@ int upload_index(rbq_index* h) {
     if ((rc = upload(h, hi.blocks.data(), hi.blocks.size(), &d.blocks))) return rc;
     if ((rc = upload(h, hi.ids.data(), hi.ids.size(), &d.ids))) return rc;
     if ((rc = upload(h, hi.ex.data(), hi.ex.size(), &d.ex, 16))) return rc;
+    if ((rc = prepare_ex_lanes(h))) return rc;
     if ((rc = upload(h, hi.f_add_ex.data(), hi.f_add_ex.size(), &d.f_add_ex))) return rc;
     if ((rc = upload(h, hi.f_rescale_ex.data(), hi.f_rescale_ex.size(), &d.f_rescale_ex))) return rc;
     std::vector<uint8_t>().swap(hi.blocks);

@@ -74,6 +74,9 @@ struct DevIndex {
     const uint8_t* blocks;
     const uint64_t* ids;
     const uint8_t* ex;
+    const uint8_t* exl;     // lane-major ex-codes (one byte per code, 8 rows of exl_lane bytes per vector; resolve.cu)
+    uint32_t exl_lane;      // bytes per row: D/8 rounded up to 16
+    uint32_t exl_stride;    // 8 * exl_lane
     const float* f_add_ex;
     const float* f_rescale_ex;
 };
@@ -177,6 +180,8 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
 //   head resolve the reference's sequential prune/refine/top-k over that list -> heap state, tw.tau, tw.tail_start
 //   refine       ex-code distances of all tail survivors, in bulk
 //   replay       survivors in reference order against the live threshold (distances precomputed)
+// resolve.cu: builds DevIndex::exl from the packed ex-codes already on the device (no-op for 1-bit indexes)
+int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
                 float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches);

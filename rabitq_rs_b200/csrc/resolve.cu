@@ -48,8 +48,8 @@ struct ResolveArgs {
     const uint32_t* surv_cnt;
     uint32_t surv_cap;
     unsigned long long* surv_id;
-    uint32_t ex_stage_stride;
-    uint32_t raw_stride;  // bytes per raw (packed) ex-code staging slot; 0: ex-codes are read straight from global memory
+    uint32_t exl_row;   // shared-memory stride of a lane's staged code row (exl_row_stride)
+    uint32_t rql_row;   // shared-memory stride of a lane's query row (rql_row_stride)
     uint32_t has_ex;
     uint32_t flush_at;  // head resolve: refine as soon as this many candidates are queued
     uint32_t lazy_flush_at;  // lazy replay: queue length that triggers a refine round
@@ -123,18 +123,15 @@ __global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs
 
 // ---- per-warp shared memory of the resolve kernels ----------------------------------------------------------
 struct ResSmem {
-    uint32_t raw, exst, rq, si, sd, ord, total;
+    uint32_t stage, rq, si, sd, ord, total;
 };
-__host__ __device__ inline ResSmem res_smem_layout(uint32_t ex_stage_stride, uint32_t raw_stride, uint32_t D, uint32_t k, bool refine,
-                                                   bool topk, uint32_t surv_cap) {
+__host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool topk, uint32_t surv_cap) {
     ResSmem w;
     uint32_t o = 0;
-    w.raw = o;
-    o += refine ? kRefineSlots * raw_stride : 0;
-    w.exst = o;
-    o += refine ? kRefineSlots * ex_stage_stride : 0;
+    w.stage = o;
+    o += refine ? 2u * 32u * exl_row : 0;  // two rounds of 4 candidates x 8 lane rows
     w.rq = o;
-    o += refine ? ((D * 4 + 15) / 16) * 16 : 0;
+    o += refine ? 8u * rql_row : 0;
     w.si = o;
     o += topk ? ((k * 8 + 15) / 16) * 16 : 0;
     w.sd = o;
@@ -147,54 +144,73 @@ __host__ __device__ inline ResSmem res_smem_layout(uint32_t ex_stage_stride, uin
     return w;
 }
 
-// rotated query interleaved for ex_dot_lane: dim 16c + r -> float2 slot 8c + (r & 7), component r >> 3
-__device__ __forceinline__ void load_rq2(float* rq2, const float* __restrict__ rot, int D, int lane) {
-    for (int i = lane; i < D; i += 32) rq2[2 * (8 * (i >> 4) + (i & 7)) + ((i >> 3) & 1)] = __ldg(rot + i);
+// rotated query in chain order: row j (stride rql_row bytes), position t = q[8t + j]; positions past D/8 are zero
+__device__ __forceinline__ void load_rql(unsigned char* rql, uint32_t rql_row, const float* __restrict__ rot, int D, uint32_t lane_bytes,
+                                         int lane) {
+    for (int i = lane; i < 8 * (int)lane_bytes; i += 32) {
+        const int j = i & 7, t = i >> 3;
+        reinterpret_cast<float*>(rql + (size_t)j * rql_row)[t] = i < D ? __ldg(rot + i) : 0.0f;
+    }
 }
 
 // K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's
-// ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes).  The packed
-// codes of round r+1 travel to shared memory (cp.async) while round r is expanded and multiplied, so only the first
-// round of a batch waits for memory.
-template <int EXK>
-__device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveArgs& a, unsigned long long gv, int nb, uint32_t raw_u32,
-                                              unsigned char* raw_ptr, uint32_t exst_u32, uint32_t rq2_u32, int lane) {
-    const int D = ix.D, g = lane >> 3, j = lane & 7;
-    const bool async = a.raw_stride != 0;
-    const uint32_t stg = exst_u32 + (uint32_t)g * a.ex_stage_stride;
-    const uint32_t pieces = ix.ex_stride / 16u;
-    auto issue = [&](int r0) {
+// ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes): every lane
+// copies ITS chain's code row (DevIndex::exl) into its own shared-memory row with cp.async and multiplies it against
+// its query row -- no unpacking and no exchange between lanes.  The rows of round r+1 travel while round r is
+// multiplied, so only the first round of a batch waits for memory.
+__device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveArgs& a, unsigned long long gv, int nb, uint32_t stage_u32,
+                                              uint32_t rql_u32, int lane) {
+    const int g = lane >> 3, j = lane & 7;
+    const uint32_t LB = ix.exl_lane;
+    const uint32_t my_row = (uint32_t)lane * a.exl_row, buf_bytes = 32u * a.exl_row;
+    const uint32_t qrow = rql_u32 + (uint32_t)j * a.rql_row;
+    auto issue = [&](int r0, uint32_t buf) {
         const int c = r0 + g;
         const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
         if (c < nb) {
-            const uint8_t* src = ix.ex + gv_c * ix.ex_stride;
-            const uint32_t dst = raw_u32 + (uint32_t)g * a.raw_stride;
-            for (uint32_t p = (uint32_t)j; p < pieces; p += 8) cp_async16(dst + 16u * p, src + 16u * p);
+            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
+            const uint32_t dst = stage_u32 + buf * buf_bytes + my_row;
+            for (uint32_t p = 0; p < LB; p += 16) cp_async16(dst + p, src + p);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (async) issue(0);
+    issue(0, 0u);
     float exdot = 0.0f;
-    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
+    uint32_t buf = 0;
+    for (int r0 = 0; r0 < nb; r0 += kRefineSlots, buf ^= 1u) {
         const int c = r0 + g;  // candidate served by this 8-lane group
-        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
-        if (async) {
-            cp_async_wait_all();
-            __syncwarp();
-            if (c < nb) stage_expand<EXK, true>(raw_ptr + (size_t)g * a.raw_stride, stg, D, j, ix.ex_bits);
-            __syncwarp();
-            if (r0 + kRefineSlots < nb) issue(r0 + kRefineSlots);  // the raw slots are free again
+        if (r0 + kRefineSlots < nb) {
+            issue(r0 + kRefineSlots, buf ^ 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
-            if (c < nb) stage_expand<EXK, false>(ix.ex + gv_c * ix.ex_stride, stg, D, j, ix.ex_bits);
-            __syncwarp();
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         float part = 0.0f;
-        if (c < nb) part = ex_dot_lane(stg, rq2_u32, D, j);
+        if (c < nb) part = ex_dot_chain(stage_u32 + buf * buf_bytes + my_row, qrow, LB);
         part = hsum8(part);
         const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
         if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
-        __syncwarp();
     }
     return exdot;
+}
+
+// ---- lane-major ex-codes (DevIndex::exl) ------------------------------------------------------------------------------
+// One thread per (vector, 16-dim chunk): decodes the chunk of the packed code (the reference's layouts, src/simd.rs:
+// 2478-2695, or the generic LSB-first stream) and scatters its 16 bytes to the 8 chain rows.  Runs once per index load.
+template <int EXK>
+__global__ void relayout_ex_kernel(const uint8_t* __restrict__ ex, uint32_t ex_stride, int ex_bits, int D, size_t nvec, uint32_t lane_bytes,
+                                   uint8_t* __restrict__ exl) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = D / 16;
+    if (idx >= nvec * (size_t)chunks) return;
+    const size_t v = idx / chunks;
+    const int c = (int)(idx % chunks);
+    uint32_t X[4];
+    decode_chunk<EXK, false>(ex + v * ex_stride, c, ex_bits, X[0], X[1], X[2], X[3]);
+    uint8_t* dst = exl + v * (size_t)(8u * lane_bytes);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)  // dim 16c + r = 8t + j with j = r & 7, t = 2c + (r >> 3)
+        dst[(size_t)(r & 7) * lane_bytes + 2 * c + (r >> 3)] = (uint8_t)(X[r >> 2] >> (8 * (r & 3)));
 }
 
 // ---- head resolve ---------------------------------------------------------------------------------------------
@@ -203,10 +219,10 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, k, EXK != 0, true, 0);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, EXK != 0, true, 0);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
-    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
-    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
+    unsigned char* rql = wbase + L.rq;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
     const bool l2 = ix.metric == RBQ_METRIC_L2;
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
             if (p.nv > a.head_cap) {
                 fallback = true;
             } else {
-                if (EXK != 0) load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+                if (EXK != 0) load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
                 const QueryScalars s = a.qs[q];
                 __syncwarp();
                 const uint32_t nv = p.nv, nb = (nv + kBatch - 1) / kBatch;
@@ -252,7 +268,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         fre = __ldg(ix.f_rescale_ex + q_gv);
                         q_vid = ix.ids[q_gv];
                     }
-                    const float exdot = refine_batch<EXK>(ix, a, q_gv, qn, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+                    const float exdot = refine_batch(ix, a, q_gv, qn, stage_u32, rql_u32, lane);
                     q_ref += qn;
                     if (mine) {
                         // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
@@ -287,8 +303,8 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         q_lower = nl;
                         q_ip = nip;
                         q_gv = ngv;
-                        const uint8_t* ep = ix.ex + q_gv * ix.ex_stride;  // warm L2/L1 with the candidate's ex-code
-                        for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                        const uint8_t* ep = ix.exl + q_gv * ix.exl_stride;  // warm L2 with the candidate's ex-code rows
+                        for (uint32_t o = 0; o < ix.exl_stride; o += 128) prefetch_l2(ep + o);
                     }
                     qn += n_new;
                     if (qn >= (int)a.flush_at) flush();  // keeps rounds full and the threshold fresh
@@ -377,10 +393,10 @@ __global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, Res
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D;
-    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, 0, true, false, 0);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
-    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
-    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
+    unsigned char* rql = wbase + L.rq;
     unsigned long long st_ref = 0;
     for (;;) {
         uint32_t q = 0;
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, Res
         if (n == 0 || n > a.surv_cap || a.tail_start[q] >= a.nprobe) continue;  // nothing to do / fallback query
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         __syncwarp();
-        load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         const QueryScalars s = a.qs[q];
         __syncwarp();
         Survivor* sv = a.surv + (size_t)q * a.surv_cap;
@@ -407,13 +423,13 @@ __global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, Res
                 const Probe* pp = pr + rec.rank;
                 gv = pp->vec_off + rec.pos;
                 g_add = pp->g_add;
-                const uint8_t* ep = ix.ex + gv * ix.ex_stride;  // start the candidate's ex-code towards L2
-                for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                const uint8_t* ep = ix.exl + gv * ix.exl_stride;  // start the candidate's ex-code rows towards L2
+                for (uint32_t o = 0; o < ix.exl_stride; o += 128) prefetch_l2(ep + o);
                 fae = __ldg(ix.f_add_ex + gv);
                 fre = __ldg(ix.f_rescale_ex + gv);
                 vid = ix.ids[gv];
             }
-            const float exdot = refine_batch<EXK>(ix, a, gv, nb, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+            const float exdot = refine_batch(ix, a, gv, nb, stage_u32, rql_u32, lane);
             if (lane < nb) {
                 // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
                 float tt = s.bscale * rec.x;
@@ -436,7 +452,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(0, 0, 0, k, false, true, a.surv_cap);
+    const ResSmem L = res_smem_layout(0, 0, k, false, true, a.surv_cap);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
@@ -535,10 +551,10 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.ex_stage_stride, a.raw_stride, D, k, true, true, a.surv_cap);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
-    const uint32_t exst_u32 = smem_u32(wbase + L.exst), rq2_u32 = smem_u32(wbase + L.rq), raw_u32 = smem_u32(wbase + L.raw);
-    float* rq2 = reinterpret_cast<float*>(wbase + L.rq);
+    const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
+    unsigned char* rql = wbase + L.rq;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
     unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);
@@ -558,7 +574,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         }
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         __syncwarp();
-        load_rq2(rq2, a.rot + (size_t)q * D, D, lane);
+        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         const QueryScalars s = a.qs[q];
         int cnt = (int)a.out_counts[q];
         for (int i = lane; i < cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
@@ -602,7 +618,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 fre = __ldg(ix.f_rescale_ex + q_gv);
                 q_vid = ix.ids[q_gv];
             }
-            const float exdot = refine_batch<EXK>(ix, a, q_gv, qn, raw_u32, wbase + L.raw, exst_u32, rq2_u32, lane);
+            const float exdot = refine_batch(ix, a, q_gv, qn, stage_u32, rql_u32, lane);
             q_ref += qn;
             if (mine) {
                 // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
@@ -643,8 +659,8 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 const bool likely = have && (rec.lower < th);
                 const unsigned m0 = __ballot_sync(0xffffffffu, likely);
                 if (likely && __popc(m0 & ((1u << lane) - 1u)) < 2 * fl) {
-                    const uint8_t* ep = ix.ex + gv * ix.ex_stride;
-                    for (uint32_t o = 0; o < ix.ex_stride; o += 128) prefetch_l2(ep + o);
+                    const uint8_t* ep = ix.exl + gv * ix.exl_stride;
+                    for (uint32_t o = 0; o < ix.exl_stride; o += 128) prefetch_l2(ep + o);
                 }
             }
             // the batch is consumed in visit order, a queue-full at a time, so that the threshold is refreshed between
@@ -692,6 +708,30 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     }
 }
 
+int prepare_ex_lanes(rbq_index* h) {
+    DevIndex& d = h->dev;
+    d.exl = nullptr;
+    d.exl_lane = exl_lane_bytes((uint32_t)d.D);
+    d.exl_stride = 8u * d.exl_lane;
+    const size_t nvec = h->host.vec_off.empty() ? 0 : (size_t)h->host.vec_off.back();
+    if (d.ex_bits == 0 || nvec == 0) return RBQ_OK;
+    uint8_t* out = nullptr;
+    const size_t bytes = nvec * (size_t)d.exl_stride;
+    RBQ_CUDA(cudaMalloc(&out, bytes + 16));
+    h->allocations.push_back(out);
+    RBQ_CUDA(cudaMemset(out, 0, bytes + 16));
+    const size_t work = nvec * (size_t)(d.D / 16);
+    const unsigned tb = 256;
+    const unsigned gb = (unsigned)((work + tb - 1) / tb);
+    if (d.ex_bits == 2) relayout_ex_kernel<2><<<gb, tb>>>(d.ex, d.ex_stride, d.ex_bits, d.D, nvec, d.exl_lane, out);
+    else if (d.ex_bits == 6) relayout_ex_kernel<6><<<gb, tb>>>(d.ex, d.ex_stride, d.ex_bits, d.D, nvec, d.exl_lane, out);
+    else relayout_ex_kernel<1><<<gb, tb>>>(d.ex, d.ex_stride, d.ex_bits, d.D, nvec, d.exl_lane, out);
+    RBQ_CUDA(cudaGetLastError());
+    RBQ_CUDA(cudaDeviceSynchronize());
+    d.exl = out;
+    return RBQ_OK;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static int g_res_sms = 0;
 static size_t g_res_smem_optin = 0;
@@ -732,11 +772,8 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.surv_cnt = tw.surv_cnt;
     a.surv_cap = tw.surv_cap;
     a.surv_id = tw.surv_id;
-    // refine staging: one byte per code (16 bytes per 16-dim chunk); stride = 32 (mod 128) so the four 8-lane groups
-    // hit disjoint shared-memory banks
-    a.ex_stage_stride = ((uint32_t)ix.D + 127u) / 128u * 128u + 32u;
-    // raw packed code staging (cp.async, 16-byte pieces); +16 keeps the generic unpacker's one-byte over-read in bounds
-    a.raw_stride = (ix.ex_bits != 0 && ix.ex_stride % 16u == 0) ? ix.ex_stride + 16u : 0u;
+    a.exl_row = exl_row_stride((uint32_t)ix.D);
+    a.rql_row = rql_row_stride((uint32_t)ix.D);
     a.has_ex = ix.ex_bits != 0;
     static const uint32_t flush_at = [] {
         const char* e = getenv("RBQ_FLUSH_AT");
@@ -804,7 +841,7 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
         }
     }
     if (rc) return rc;
-    const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, a.top_k, ix.ex_bits != 0, true, 0);
+    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
     const unsigned grid = res_grid(nq, smem);
@@ -827,7 +864,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     }();
     if (ix.ex_bits != 0 && !bulk) {
         // lazy: sorted survivors, refinement on demand against the live threshold (one kernel)
-        const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, a.top_k, true, true, a.surv_cap);
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap);
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem <= g_res_smem_optin) {
             const unsigned grid = res_grid(nq, smem);
@@ -847,7 +884,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
         }
     }
     if (ix.ex_bits != 0) {
-        const ResSmem w = res_smem_layout(a.ex_stage_stride, a.raw_stride, ix.D, 0, true, false, 0);
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0);
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "refine kernel shared memory exceeds the device limit");
         const unsigned grid = res_grid(nq, smem);
@@ -864,7 +901,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
         RBQ_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }
-    const ResSmem w = res_smem_layout(0, 0, 0, a.top_k, false, true, a.surv_cap);
+    const ResSmem w = res_smem_layout(0, 0, a.top_k, false, true, a.surv_cap);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
     const unsigned grid = res_grid(nq, smem);

@@ -184,40 +184,46 @@ __device__ __forceinline__ uint32_t accumulate_block_regs(const uint4 (&C)[NCB],
 // EXK: 2 / 6 = the reference's C++-compatible layouts (src/simd.rs:2478-2695); 1 = generic LSB-first
 // bit stream (src/simd.rs:166-191), used for bit widths the reference cannot search (extension).
 // SMEM: src is a generic pointer into shared memory (raw packed code copied there by cp.async) instead of global.
+// the 16 codes of chunk c of one packed ex-code, one per byte: A = codes 0-3, Bq = 4-7, Cq = 8-11, Dq = 12-15
 template <int EXK, bool SMEM = false>
-__device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
+__device__ __forceinline__ void decode_chunk(const uint8_t* __restrict__ src, int c, int ex_bits, uint32_t& A, uint32_t& Bq, uint32_t& Cq,
+                                             uint32_t& Dq) {
     auto ldw = [&](const uint8_t* p) -> uint32_t { return SMEM ? *reinterpret_cast<const uint32_t*>(p) : ldg32(p); };
     auto ldb = [&](const uint8_t* p) -> uint32_t { return SMEM ? (uint32_t)*p : (uint32_t)__ldg(p); };
+    if (EXK == 2) {
+        const uint32_t w = ldw(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
+        A = w & 0x03030303u;
+        Bq = (w >> 2) & 0x03030303u;
+        Cq = (w >> 4) & 0x03030303u;
+        Dq = (w >> 6) & 0x03030303u;
+    } else if (EXK == 6) {
+        const uint32_t w0 = ldw(src + 12 * c), w1 = ldw(src + 12 * c + 4), w2 = ldw(src + 12 * c + 8);
+        // bytes 0-7: low nibble = low 4 bits of code b, high nibble = low 4 bits of code b+8; w2: the 2-bit layout
+        A = (w0 & 0x0F0F0F0Fu) | ((w2 << 4) & 0x30303030u);
+        Bq = (w1 & 0x0F0F0F0Fu) | ((w2 << 2) & 0x30303030u);
+        Cq = ((w0 >> 4) & 0x0F0F0F0Fu) | (w2 & 0x30303030u);
+        Dq = ((w1 >> 4) & 0x0F0F0F0Fu) | ((w2 >> 2) & 0x30303030u);
+    } else {
+        const uint32_t mask = (1u << ex_bits) - 1u;
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t pos = (uint32_t)(16 * c + k) * (uint32_t)ex_bits;
+            const uint32_t two = ldb(src + (pos >> 3)) | (ldb(src + (pos >> 3) + 1) << 8);
+            x[k >> 2] |= ((two >> (pos & 7u)) & mask) << (8 * (k & 3));
+        }
+        A = x[0];
+        Bq = x[1];
+        Cq = x[2];
+        Dq = x[3];
+    }
+}
+template <int EXK, bool SMEM = false>
+__device__ __forceinline__ void stage_expand(const uint8_t* __restrict__ src, uint32_t stg, int D, int j, int ex_bits) {
 #pragma unroll 4
     for (int c = j; c < D / 16; c += 8) {
         uint32_t A, Bq, Cq, Dq;  // codes 0-3, 4-7, 8-11, 12-15 of the chunk, one per byte
-        if (EXK == 2) {
-            const uint32_t w = ldw(src + 4 * c);  // byte b: codes b, b+4, b+8, b+12 (2 bits each)
-            A = w & 0x03030303u;
-            Bq = (w >> 2) & 0x03030303u;
-            Cq = (w >> 4) & 0x03030303u;
-            Dq = (w >> 6) & 0x03030303u;
-        } else if (EXK == 6) {
-            const uint32_t w0 = ldw(src + 12 * c), w1 = ldw(src + 12 * c + 4), w2 = ldw(src + 12 * c + 8);
-            // bytes 0-7: low nibble = low 4 bits of code b, high nibble = low 4 bits of code b+8; w2: the 2-bit layout
-            A = (w0 & 0x0F0F0F0Fu) | ((w2 << 4) & 0x30303030u);
-            Bq = (w1 & 0x0F0F0F0Fu) | ((w2 << 2) & 0x30303030u);
-            Cq = ((w0 >> 4) & 0x0F0F0F0Fu) | (w2 & 0x30303030u);
-            Dq = ((w1 >> 4) & 0x0F0F0F0Fu) | ((w2 >> 2) & 0x30303030u);
-        } else {
-            const uint32_t mask = (1u << ex_bits) - 1u;
-            uint32_t x[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t pos = (uint32_t)(16 * c + k) * (uint32_t)ex_bits;
-                const uint32_t two = ldb(src + (pos >> 3)) | (ldb(src + (pos >> 3) + 1) << 8);
-                x[k >> 2] |= ((two >> (pos & 7u)) & mask) << (8 * (k & 3));
-            }
-            A = x[0];
-            Bq = x[1];
-            Cq = x[2];
-            Dq = x[3];
-        }
+        decode_chunk<EXK, SMEM>(src, c, ex_bits, A, Bq, Cq, Dq);
         sts128(stg + 16u * (uint32_t)c, prmt(A, Cq, 0x5140u), prmt(A, Cq, 0x7362u), prmt(Bq, Dq, 0x5140u), prmt(Bq, Dq, 0x7362u));
     }
 }
@@ -238,6 +244,41 @@ __device__ __forceinline__ float ex_dot_lane(uint32_t stg, uint32_t rq2, int D, 
     }
     return acc;
 }
+// ---- K10 on the device's lane-major ex-code layout (DevIndex::exl, built at load time by resolve.cu) ----------
+// The reference's ex-dot runs 8 independent FMA chains ("AVX lane" j owns dims j, j+8, j+16, ...; src/simd.rs:1749-1757,
+// 1804-1812).  exl stores every vector as 8 rows of one byte per code in exactly that order -- row j, position t =
+// code of dim 8t + j -- zero padded to `exl_lane` bytes, so a chain reads its own contiguous row and nothing has to be
+// unpacked or exchanged between lanes at search time.  The rotated query is staged the same way (row j, position t =
+// q[8t + j], zero padded): padding adds fma(0, 0, acc) = acc (acc is never -0: it starts at +0 and x + (-x) = +0).
+__host__ __device__ inline uint32_t exl_lane_bytes(uint32_t D) { return ((D / 8u) + 15u) / 16u * 16u; }
+// shared-memory row strides (bytes) that keep 128-bit loads of 8 consecutive rows on disjoint banks: 16 * odd
+__host__ __device__ inline uint32_t exl_row_stride(uint32_t D) { return ((exl_lane_bytes(D) / 16u) | 1u) * 16u; }
+__host__ __device__ inline uint32_t rql_row_stride(uint32_t D) { return ((exl_lane_bytes(D) * 4u / 16u) | 1u) * 16u; }
+
+// one chain: `row` = shared address of the lane's code bytes, `qrow` = shared address of its query floats
+__device__ __forceinline__ float ex_dot_chain(uint32_t row, uint32_t qrow, uint32_t lane_bytes) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (uint32_t t = 0; t < lane_bytes; t += 16) {
+        const uint4 w = lds128(row + t);
+        const uint32_t W[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 qv = lds128(qrow + 4u * t + 16u * (uint32_t)k);
+            // byte -> float without the conversion pipe: 0x4B0000xx is 2^23 + xx exactly, and the subtraction is exact
+            const float c0 = __uint_as_float(prmt(W[k], 0x4B000000u, 0x7540u)) - 8388608.0f;
+            const float c1 = __uint_as_float(prmt(W[k], 0x4B000000u, 0x7541u)) - 8388608.0f;
+            const float c2 = __uint_as_float(prmt(W[k], 0x4B000000u, 0x7542u)) - 8388608.0f;
+            const float c3 = __uint_as_float(prmt(W[k], 0x4B000000u, 0x7543u)) - 8388608.0f;
+            acc = __fmaf_rn(c0, __uint_as_float(qv.x), acc);
+            acc = __fmaf_rn(c1, __uint_as_float(qv.y), acc);
+            acc = __fmaf_rn(c2, __uint_as_float(qv.z), acc);
+            acc = __fmaf_rn(c3, __uint_as_float(qv.w), acc);
+        }
+    }
+    return acc;
+}
+
 // horizontal sum of the 8 lanes exactly as the AVX2 code: ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
 __device__ __forceinline__ float hsum8(float a) {
     a = a + __shfl_xor_sync(0xffffffffu, a, 4);
