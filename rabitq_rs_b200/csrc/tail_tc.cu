@@ -9,12 +9,15 @@
 // sums run on tcgen05.mma (kind::i8, M = 128 vectors, N = 64 queries, K = 32 bytes = 2 codebooks per instruction)
 // with the accumulators in TMEM.
 //
-// One CTA per SM, one work item (a list and <= 64 of the (query, rank) pairs probing it) at a time:
-//   * all 8 warps expand the list's packed codes of one K-chunk (8 codebooks = 128 bytes of one-hot per vector)
-//     into a 128B-swizzled K-major A tile per 128 vectors, and copy the 64 queries' LUT slice into the B tile
-//     (the LUT row of a query is already K-major: lut[16*cb + nibble], reference src/simd.rs:818-840);
-//   * one thread issues the MMAs of the chunk (4 per 128-vector tile); tcgen05.commit frees the stage, so the next
-//     chunk is expanded into the other stage while the tensor core works;
+// Two CTAs per SM, one work item (a list and <= 64 of the (query, rank) pairs probing it) at a time:
+//   * the A operand (one-hot rows) lives in TENSOR MEMORY, not shared memory: producer thread (warp w, lane v) owns
+//     vector v of block w of the group = TMEM lane 32*(w%4)+v of tile w/4, builds the 128 one-hot bytes of a K-chunk
+//     (8 codebooks) in 32 registers (one BMSK per word) and writes them with one tcgen05.st.32x32b.x32 -- the 32x
+//     expansion of the packed codes never touches the shared-memory pipe, which only carries the B operand;
+//   * the 64 queries' LUT slice of the chunk is copied into a 128B-swizzled K-major B tile with cp.async (the LUT row
+//     of a query is already K-major: lut[16*cb + nibble], reference src/simd.rs:818-840);
+//   * one thread issues the MMAs of the chunk (tcgen05.mma kind::i8, A from TMEM, B from shared memory; 4 per
+//     128-vector tile); tcgen05.commit frees the stage, so the next chunk is built while the tensor core works;
 //   * after the last chunk the 8 warps read the sums back (tcgen05.ld), evaluate K8 (compute_batch_distances_u16,
 //     src/simd.rs:2090-2140, AVX2 operation order) per (vector, query) and keep the candidates whose lower bound
 //     beats the query's head threshold -- the same survivors as the PRMT kernel, appended in any order (the replay
@@ -30,17 +33,18 @@ namespace tt {
 constexpr int MT_MAX = 2;                    // 128-vector tiles (4 blocks each) accumulated concurrently
 constexpr int NQ = 64;                       // queries per item = UMMA N
 constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
-constexpr int STAGES = 2;                    // A stages
+constexpr int STAGES = 2;                    // A stages (tensor memory)
 constexpr int PD = 2;                        // prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
 constexpr int BSTAGES = PD + 2;              // B stages: chunk c+PD lands in the stage chunk c-2 has released
 constexpr int RSTAGES = PD + 1;              // raw packed-code ring (4 bytes per producer thread and chunk)
 constexpr int PRODUCER_WARPS = 4 * MT_MAX;   // one block of the group per warp
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
-constexpr int A_TILE = 128 * KCH;            // 16 KB
-constexpr int A_STAGE = MT_MAX * A_TILE;     // 64 KB
+constexpr int A_COLS = KCH / 4;              // TMEM columns of one tile's K-chunk (4 one-hot bytes per 32-bit column)
 constexpr int B_STAGE = NQ * KCH;            // 8 KB
 constexpr int SURV_CAP = 256;                // survivors staged in shared memory between flushes
-constexpr int TMEM_COLS = MT_MAX * NQ;       // 256 columns of s32 accumulators
+constexpr int ACC_COLS = MT_MAX * NQ;        // s32 accumulators: tile mt at column mt * NQ
+constexpr int TMEM_COLS = 256;               // accumulators + STAGES x MT_MAX A chunks (power of two; two CTAs share the SM's 512)
+static_assert(ACC_COLS + STAGES * MT_MAX * A_COLS <= TMEM_COLS, "tensor memory budget");
 struct Misc {
     float4 c0[NQ];   // delta, sum_vl, k1x, g_add
     float4 c1[NQ];   // g_error, tau, non-finite fallback, unused
@@ -49,11 +53,10 @@ struct Misc {
     uint32_t sq[SURV_CAP];
     Survivor ss[SURV_CAP];
     uint64_t bars[2 * STAGES + 1];  // full[stage], empty[stage], accumulators done
-    uint4 onehot[16];               // row n: byte n = 1 (the 16-byte one-hot of a 4-bit code)
-    uint32_t raw[RSTAGES][PRODUCER_WARPS * 32];  // packed code bytes in flight (cp.async)
+    alignas(16) uint32_t raw[RSTAGES][PRODUCER_WARPS * 32];  // packed code bytes in flight (cp.async)
     uint32_t tmem_base, item, surv_n, pad;
 };
-constexpr size_t SMEM = (size_t)STAGES * A_STAGE + (size_t)BSTAGES * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/;
+constexpr size_t SMEM = (size_t)BSTAGES * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/;
 }  // namespace tt
 
 // K-major operand, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) (unused) | SBO>>4 [32,46) = 8 rows * 128 B |
@@ -97,15 +100,14 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
     using namespace tt;
     extern __shared__ unsigned char tt_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = sm;                                  // [STAGES][MT_MAX][128 rows][128 B]
-    unsigned char* sB = sm + (size_t)STAGES * A_STAGE;       // [BSTAGES][NQ rows][128 B]
-    Misc* mi = reinterpret_cast<Misc*>(sm + (size_t)STAGES * A_STAGE + (size_t)BSTAGES * B_STAGE);
+    unsigned char* sB = sm;                                  // [BSTAGES][NQ rows][128 B]
+    Misc* mi = reinterpret_cast<Misc*>(sm + (size_t)BSTAGES * B_STAGE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = ix.D, ncb = D / 4;
     const uint32_t B = ix.block_stride;
     const uint32_t nkc = ((uint32_t)ncb + 7u) / 8u;  // K-chunks of 8 codebooks
     const bool l2 = ix.metric == RBQ_METRIC_L2;
-    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    const uint32_t sB_u32 = smem_u32(sB);
     // barriers: full[stage] (256 producer arrivals), empty[stage] (tcgen05.commit), accumulators done (tcgen05.commit)
     const uint32_t full0 = smem_u32(&mi->bars[0]), empty0 = smem_u32(&mi->bars[STAGES]), accd = smem_u32(&mi->bars[2 * STAGES]);
     const bool issuer = warp == PRODUCER_WARPS;
@@ -118,10 +120,6 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
         mbar_init(accd, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mi->surv_n = 0;
-    }
-    if (tid < 16) {
-        const uint32_t w = 1u << (8 * (tid & 3));
-        mi->onehot[tid] = make_uint4((tid >> 2) == 0 ? w : 0u, (tid >> 2) == 1 ? w : 0u, (tid >> 2) == 2 ? w : 0u, (tid >> 2) == 3 ? w : 0u);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&mi->tmem_base)), "r"(TMEM_COLS)
@@ -136,11 +134,15 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
     uint32_t chunk_seq = 0;  // running chunk counter: A stage = chunk_seq % 2, B stage = chunk_seq % 4
     uint32_t groups = 0;     // accumulator groups finished so far (phase of the `accd` barrier)
 
-    // A production role of a producer thread: byte quad qd of codebook row cbl of a block-chunk
+    // fetch role of a producer thread: byte quad qd of codebook row cbl of its warp's block-chunk (cp.async into `raw`)
     const int qd = lane >> 3, cbl = lane & 7;
-    // epilogue role: TMEM lane quarter lq of tile warp >> 2
+    // A production role: vector `lane` of the block.  Its nibble of a codebook sits in byte vp of the codebook's 16 code
+    // bytes (KPERM0[vp] = lane & 15; reference src/simd.rs:774,876-902), high nibble for vectors 16..31; in `raw` that byte
+    // is byte (vp & 3) of word (vp >> 2) * 8 + codebook.
+    const int vp = ((lane & 7) << 1) | ((lane & 15) >> 3);
+    const uint32_t nib_shift = 8u * (uint32_t)(vp & 3) + 4u * (uint32_t)(lane >> 4);
+    // epilogue role (and the TMEM lanes this warp may touch): lane quarter lq of tile warp >> 2
     const int lq = warp & 3;
-    const uint32_t onehot_u32 = smem_u32(&mi->onehot[0]);
 
     // copies the staged survivors to the per-query buffers (one global atomic each, all in flight together)
     auto flush_survivors = [&]() {
@@ -184,9 +186,8 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
                     if (lane == 0) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t db = tt_desc(sB_u32 + (chunk_seq % BSTAGES) * B_STAGE);
-                        const uint64_t da0 = tt_desc(sA_u32 + s * A_STAGE);
                         for (uint32_t mt = 0; mt < mt_cnt; ++mt) {
-                            const uint64_t da = da0 + (uint64_t)(mt * (A_TILE >> 4));
+                            const uint32_t ta = tmem + (uint32_t)ACC_COLS + (s * MT_MAX + mt) * (uint32_t)A_COLS;
 #pragma unroll
                             for (int k = 0; k < KCH / 32; ++k) {
                                 const uint32_t acc = (kc | (uint32_t)k) ? 1u : 0u;
@@ -194,9 +195,9 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
                                     "{\n"
                                     ".reg .pred p;\n"
                                     "setp.ne.b32 p, %4, 0;\n"
-                                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+                                    "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
                                     "}" ::"r"(tmem + mt * NQ),
-                                    "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
+                                    "r"(ta + (uint32_t)(8 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
                                     : "memory");
                             }
                         }
@@ -267,33 +268,42 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
             // every earlier MMA has completed (accumulator barrier), so all stages are free
 #pragma unroll
             for (int d = 0; d < PD; ++d) prefetch((uint32_t)d, chunk_seq + d);
-            const uint32_t tile = (uint32_t)(warp >> 2) * A_TILE + (uint32_t)(warp & 3) * 32u * 128u;
             for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
                 const uint32_t s = chunk_seq % STAGES, use = chunk_seq / STAGES;
                 // chunk_seq - 2 was the last reader of A stage s and of B stage (chunk_seq + PD) % BSTAGES
                 if (use > 0) tt_bar_wait(empty0 + 8 * s, (use - 1) & 1u);
                 prefetch(kc + PD, chunk_seq + PD);
                 asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");  // this thread's pieces of chunk kc have landed
-                // ---- A: one-hot rows of the warp's block for codebooks 8*kc .. 8*kc+7 ----
+                __syncwarp();  // the other lanes' pieces of the warp's raw words have landed too
+                // ---- A: the one-hot row of this thread's vector for codebooks 8*kc .. 8*kc+7 -> tensor memory ----
                 if ((uint32_t)warp < nbg) {
-                    const bool live = kc * 8u + (uint32_t)cbl < (uint32_t)ncb;
-                    const uint32_t word = live ? mi->raw[chunk_seq % RSTAGES][tid] : 0u;
-                    const uint32_t base = sA_u32 + s * A_STAGE + tile;
+                    const uint32_t rw = smem_u32(&mi->raw[chunk_seq % RSTAGES][warp * 32 + (vp >> 2) * 8]);
+                    const uint4 w0 = lds128(rw), w1 = lds128(rw + 16u);
+                    const uint32_t W[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    uint32_t r[32];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int p = 4 * qd + j;                 // byte position in the 16-byte codebook row
-                        const int v = (p >> 1) + ((p & 1) << 3);  // KPERM0[p]: vector of the low nibble (high: v + 16)
-                        const uint32_t dst = base + (uint32_t)v * 128u + (uint32_t)((cbl ^ (v & 7)) << 4);
-                        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-                        if (live) {  // past the last codebook the K padding of the chunk contributes nothing
-                            lo = lds128(onehot_u32 + ((word >> (8 * j)) & 15u) * 16u);
-                            hi = lds128(onehot_u32 + ((word >> (8 * j + 4)) & 15u) * 16u);
-                        }
-                        sts128(dst, lo.x, lo.y, lo.z, lo.w);
-                        sts128(dst + 16u * 128u, hi.x, hi.y, hi.z, hi.w);
+                    for (int c = 0; c < 8; ++c) {
+                        // bit position of the 1 inside the codebook's 128-bit one-hot; past the last codebook: no bit at all
+                        const uint32_t pos = (kc * 8u + (uint32_t)c < (uint32_t)ncb) ? (((W[c] >> nib_shift) & 15u) << 3) : 0xffffff00u;
+                        r[4 * c + 0] = onehot32(pos);
+                        r[4 * c + 1] = onehot32(pos - 32u);
+                        r[4 * c + 2] = onehot32(pos - 64u);
+                        r[4 * c + 3] = onehot32(pos - 96u);
                     }
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)ACC_COLS + (s * MT_MAX + (uint32_t)(warp >> 2)) * (uint32_t)A_COLS;
+                    asm volatile(
+                        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+                        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+                        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+                        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                        : "memory");
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
-                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                fence_proxy_async();  // cp.async (generic proxy) writes of the B tile -> visible to the tensor core's async-proxy reads
                 tt_bar_arrive(full0 + 8 * s);
             }
             // ---- epilogue: sums -> K8 -> survivors ----
