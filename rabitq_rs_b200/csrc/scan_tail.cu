@@ -20,6 +20,7 @@
 //     end-of-block cross-lane reduction shrinks to 8 shuffles;
 //   * integer sums are exact, K8 is evaluated in the reference's (AVX2 variant) operation order.
 #include <algorithm>
+#include <cstdlib>
 
 #include "scan_common.cuh"
 

@@ -30,20 +30,26 @@
 namespace rbq {
 
 namespace tt {
-constexpr int MT_MAX = 2;                    // 128-vector tiles (4 blocks each) accumulated concurrently
+#ifndef RBQ_TT_MT
+#define RBQ_TT_MT 2
+#endif
+constexpr int MT_MAX = RBQ_TT_MT;                    // 128-vector tiles (4 blocks each) accumulated concurrently
 constexpr int NQ = 64;                       // queries per item = UMMA N
 constexpr int KCH = 128;                     // bytes of K per chunk = 8 codebooks = one swizzle row
 constexpr int STAGES = 2;                    // A stages (tensor memory)
-constexpr int PD = 2;                        // prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
-constexpr int BSTAGES = PD + 2;              // B stages: chunk c+PD lands in the stage chunk c-2 has released
-constexpr int RSTAGES = PD + 1;              // raw packed-code ring (4 bytes per producer thread and chunk)
+constexpr int PD_MAX = 6;                    // largest prefetch distance in chunks (LUT slices from L2, packed codes from HBM)
+// With prefetch distance PD the B ring has PD + STAGES stages: chunk c + PD lands in the stage chunk c - STAGES released, and
+// the producers prefetch right after they got A stage c % STAGES back, i.e. after that MMA has finished (the A ring lets the
+// tensor core lag the producers by at most STAGES chunks).  The raw packed-code ring (4 bytes per producer thread and chunk,
+// read by the producers only) has PD + 2 slots.
 constexpr int PRODUCER_WARPS = 4 * MT_MAX;   // one block of the group per warp
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
 constexpr int A_COLS = KCH / 4;              // TMEM columns of one tile's K-chunk (4 one-hot bytes per 32-bit column)
 constexpr int B_STAGE = NQ * KCH;            // 8 KB
 constexpr int SURV_CAP = 256;                // survivors staged in shared memory between flushes
 constexpr int ACC_COLS = MT_MAX * NQ;        // s32 accumulators: tile mt at column mt * NQ
-constexpr int TMEM_COLS = 256;               // accumulators + STAGES x MT_MAX A chunks (power of two; two CTAs share the SM's 512)
+constexpr int CTAS_PER_SM = MT_MAX == 1 ? 4 : 2;
+constexpr int TMEM_COLS = 512 / CTAS_PER_SM;               // accumulators + STAGES x MT_MAX A chunks (power of two; two CTAs share the SM's 512)
 static_assert(ACC_COLS + STAGES * MT_MAX * A_COLS <= TMEM_COLS, "tensor memory budget");
 struct Misc {
     float4 c0[NQ];   // delta, sum_vl, k1x, g_add
@@ -53,10 +59,10 @@ struct Misc {
     uint32_t sq[SURV_CAP];
     Survivor ss[SURV_CAP];
     uint64_t bars[2 * STAGES + 1];  // full[stage], empty[stage], accumulators done
-    alignas(16) uint32_t raw[RSTAGES][PRODUCER_WARPS * 32];  // packed code bytes in flight (cp.async)
+    alignas(16) uint32_t raw[PD_MAX + 2][PRODUCER_WARPS * 32];  // packed code bytes in flight (cp.async)
     uint32_t tmem_base, item, surv_n, pad;
 };
-constexpr size_t SMEM = (size_t)BSTAGES * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/;
+constexpr size_t smem_bytes(int pd) { return (size_t)(pd + STAGES) * B_STAGE + sizeof(Misc) + 1024 /*alignment slack*/; }
 }  // namespace tt
 
 // K-major operand, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) (unused) | SBO>>4 [32,46) = 8 rows * 128 B |
@@ -95,9 +101,10 @@ __device__ __forceinline__ void tt_bar_arrive(uint32_t bar) {
 // barrier among the 8 producer warps only (the issuer warp never joins it)
 __device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(tt::PRODUCER_WARPS * 32) : "memory"); }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, TailArgs a) {
+template <bool WIDE, int PD>
+__global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(DevIndex ix, TailArgs a) {
     using namespace tt;
+    constexpr int BSTAGES = PD + STAGES, RSTAGES = PD + 2;
     extern __shared__ unsigned char tt_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = sm;                                  // [BSTAGES][NQ rows][128 B]
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, PRODUCER_WARPS * 32);
+            mbar_init(full0 + 8 * s, PRODUCER_WARPS * 32);  // every producer thread arrives (measured faster than syncwarp + one lane)
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accd, 1);
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
     // bytes (KPERM0[vp] = lane & 15; reference src/simd.rs:774,876-902), high nibble for vectors 16..31; in `raw` that byte
     // is byte (vp & 3) of word (vp >> 2) * 8 + codebook.
     const int vp = ((lane & 7) << 1) | ((lane & 15) >> 3);
-    const uint32_t nib_shift = 8u * (uint32_t)(vp & 3) + 4u * (uint32_t)(lane >> 4);
+    const uint32_t nib_rot = (8u * (uint32_t)(vp & 3) + 4u * (uint32_t)(lane >> 4) + 29u) & 31u;  // rotate right by shift - 3
     // epilogue role (and the TMEM lanes this warp may touch): lane quarter lq of tile warp >> 2
     const int lq = warp & 3;
 
@@ -240,27 +247,36 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
             mi->c1[tid] = c1;
         }
         tt_sync_producers();
+        // this thread's two 16-byte pieces of every B chunk (row r = pair slot, piece j): source row, swizzled destination and
+        // the K range in which the piece exists -- fixed for the whole item
+        const uint8_t* bsrc[NQ * 8 / (PRODUCER_WARPS * 32)];
+        uint32_t bdst[NQ * 8 / (PRODUCER_WARPS * 32)], blim[NQ * 8 / (PRODUCER_WARPS * 32)];
+#pragma unroll
+        for (int i = 0; i < NQ * 8 / (PRODUCER_WARPS * 32); ++i) {
+            const int piece = tid + PRODUCER_WARPS * 32 * i, r = piece >> 3, j = piece & 7;
+            const uint32_t q = mi->q[r];
+            bsrc[i] = a.lut + (size_t)(q == 0xffffffffu ? 0u : q) * D * 4 + 16u * (uint32_t)j;
+            bdst[i] = sB_u32 + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            blim[i] = (q != 0xffffffffu && (uint32_t)D * 4u > 16u * (uint32_t)j) ? (uint32_t)D * 4u - 16u * (uint32_t)j : 0u;  // kc * KCH < blim
+        }
 
         for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {  // accumulator group: up to 16 blocks = 4 tiles of 128 vectors
             const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
             // chunk kc of the group: B = LUT slice [kc*128, kc*128+128) of the item's queries (row r = pair slot) straight into
             // its swizzled stage, and this thread's 4 packed code bytes (byte quad qd of codebook row 8*kc + cbl of block
             // bg = warp) into the raw ring -- both asynchronous, one commit group per chunk
+            const uint8_t* rsrc = lbase + (size_t)(b0 + min((uint32_t)warp, nbg - 1u)) * B + 16u * (uint32_t)cbl + 4u * (uint32_t)qd;
+            const uint32_t rlim = (uint32_t)warp < nbg && (uint32_t)cbl < (uint32_t)ncb ? ((uint32_t)ncb - (uint32_t)cbl + 7u) / 8u : 0u;  // kc < rlim
+            const uint32_t rdst = smem_u32(&mi->raw[0][tid]);
             auto prefetch = [&](uint32_t kc, uint32_t seq) {
                 if (kc < nkc) {
+                    const uint32_t koff = kc * KCH, bst = (seq % BSTAGES) * B_STAGE;
 #pragma unroll
-                    for (int i = 0; i < NQ * 8 / (PRODUCER_WARPS * 32); ++i) {
-                        const int piece = tid + PRODUCER_WARPS * 32 * i, r = piece >> 3, j = piece & 7;
-                        const uint32_t q = mi->q[r];
-                        const uint32_t koff = kc * KCH + 16u * (uint32_t)j;
-                        if (q != 0xffffffffu && koff < (uint32_t)D * 4u)
-                            cp_async16(sB_u32 + (seq % BSTAGES) * B_STAGE + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4),
-                                       a.lut + (size_t)q * D * 4 + koff);
-                    }
-                    const uint32_t cb = kc * 8u + (uint32_t)cbl;
-                    if ((uint32_t)warp < nbg && cb < (uint32_t)ncb)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&mi->raw[seq % RSTAGES][tid])),
-                                     "l"(lbase + (size_t)(b0 + warp) * B + 16u * cb + 4u * (uint32_t)qd)
+                    for (int i = 0; i < NQ * 8 / (PRODUCER_WARPS * 32); ++i)
+                        if (koff < blim[i]) cp_async16(bdst[i] + bst, bsrc[i] + koff);
+                    if (kc < rlim)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rdst + (seq % RSTAGES) * (uint32_t)(PRODUCER_WARPS * 32 * 4)),
+                                     "l"(rsrc + koff)
                                      : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -270,26 +286,33 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
             for (int d = 0; d < PD; ++d) prefetch((uint32_t)d, chunk_seq + d);
             for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
                 const uint32_t s = chunk_seq % STAGES, use = chunk_seq / STAGES;
-                // chunk_seq - 2 was the last reader of A stage s and of B stage (chunk_seq + PD) % BSTAGES
+                // chunk_seq - 2 was the last reader of A stage s.  (Building the row before this wait was measured slower:
+                // 0.65 vs 0.61 ms at GIST/10k -- the row would stay live in 32 registers across the wait.)
                 if (use > 0) tt_bar_wait(empty0 + 8 * s, (use - 1) & 1u);
-                prefetch(kc + PD, chunk_seq + PD);
+                prefetch(kc + PD, chunk_seq + PD);  // the operands of chunk kc + PD start travelling
                 asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");  // this thread's pieces of chunk kc have landed
                 __syncwarp();  // the other lanes' pieces of the warp's raw words have landed too
-                // ---- A: the one-hot row of this thread's vector for codebooks 8*kc .. 8*kc+7 -> tensor memory ----
+                // the one-hot row of this thread's vector for codebooks 8*kc .. 8*kc+7, built in registers
+                uint32_t r[32];
                 if ((uint32_t)warp < nbg) {
                     const uint32_t rw = smem_u32(&mi->raw[chunk_seq % RSTAGES][warp * 32 + (vp >> 2) * 8]);
                     const uint4 w0 = lds128(rw), w1 = lds128(rw + 16u);
                     const uint32_t W[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                    uint32_t r[32];
+                    const uint32_t live = min(8u, (uint32_t)ncb - kc * 8u);  // codebooks of this chunk that exist (uniform)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        // bit position of the 1 inside the codebook's 128-bit one-hot; past the last codebook: no bit at all
-                        const uint32_t pos = (kc * 8u + (uint32_t)c < (uint32_t)ncb) ? (((W[c] >> nib_shift) & 15u) << 3) : 0xffffff00u;
+                        // bit position of the 1 inside the codebook's 128-bit one-hot: 8 * nibble = (W ror (shift - 3)) & 0x78;
+                        // past the last codebook: no bit at all
+                        uint32_t pos = __funnelshift_r(W[c], W[c], nib_rot) & 0x78u;
+                        if ((uint32_t)c >= live) pos = 0xffffff00u;
                         r[4 * c + 0] = onehot32(pos);
                         r[4 * c + 1] = onehot32(pos - 32u);
                         r[4 * c + 2] = onehot32(pos - 64u);
                         r[4 * c + 3] = onehot32(pos - 96u);
                     }
+                }
+                if ((uint32_t)warp < nbg) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)ACC_COLS + (s * MT_MAX + (uint32_t)(warp >> 2)) * (uint32_t)A_COLS;
                     asm volatile(
                         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -303,7 +326,7 @@ __global__ void __launch_bounds__(tt::THREADS, 2) tail_tc_kernel(DevIndex ix, Ta
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                fence_proxy_async();  // cp.async (generic proxy) writes of the B tile -> visible to the tensor core's async-proxy reads
+                fence_proxy_async();  // its B pieces (generic-proxy writes) -> visible to the tensor core's async-proxy reads
                 tt_bar_arrive(full0 + 8 * s);
             }
             // ---- epilogue: sums -> K8 -> survivors ----
@@ -393,19 +416,29 @@ bool tail_tc_supported(const DevIndex& ix) {
     return !off && ix.D % 16 == 0;
 }
 
+template <bool WIDE, int PD>
+static int launch_tail_tc_ex(const DevIndex& ix, const TailArgs& a, int sms, cudaStream_t st) {
+    const size_t smem = tt::smem_bytes(PD);
+    RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<WIDE, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tail_tc_kernel<WIDE, PD><<<tt::CTAS_PER_SM * sms, tt::THREADS, smem, st>>>(ix, a);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
 int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st) {
     int dev = 0, sms = 0;
     RBQ_CUDA(cudaGetDevice(&dev));
     RBQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (ix.D > 1024) {
-        RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
-        tail_tc_kernel<true><<<2 * sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
-    } else {
-        RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt::SMEM));
-        tail_tc_kernel<false><<<2 * sms, tt::THREADS, tt::SMEM, st>>>(ix, a);
+    static const int pd = [] {
+        const char* e = getenv("RBQ_TAIL_PD");
+        return e ? atoi(e) : 2;
+    }();
+    if (ix.D > 1024) return launch_tail_tc_ex<true, 2>(ix, a, sms, st);
+    switch (pd) {
+        case 3: return launch_tail_tc_ex<false, 3>(ix, a, sms, st);
+        case 4: return launch_tail_tc_ex<false, 4>(ix, a, sms, st);
+        default: return launch_tail_tc_ex<false, 2>(ix, a, sms, st);
     }
-    RBQ_CUDA(cudaGetLastError());
-    return RBQ_OK;
 }
 
 }  // namespace rbq
