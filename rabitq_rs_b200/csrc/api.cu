@@ -226,11 +226,18 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         const size_t n = std::min(qt, nq - q0);
         int rc;
         if (h->profiling) cudaEventRecord(h->ev[0], st);
-        // Front end (rotate + LUT, coarse scores, probe selection) is independent per query: when the queries are still
-        // arriving from the host (feed), it runs chunk by chunk behind the copy stream, so the H2D transfer of chunk
-        // c+1 overlaps the front end of chunk c and only the scan stage waits for the whole tile.
+        // Scan-stage schedule.  Sequential: one warp walks one query's whole probe sequence.  List-major (large batches):
+        // head pass (the first owned list, sequential, fills the heap) -> tail kernel (all remaining pairs grouped by list)
+        // -> replay pass (survivors in reference order).  Both are exact.
+        const bool list_major = h->scan_mode == 2 || (h->scan_mode == 0 && nprobe >= 4 && n * nprobe >= 8 * (size_t)ix.nlist);
+        if (list_major)  // surv_cnt | list_cnt | list_fill | counters
+            RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
+        // Front end (rotate + LUT, coarse scores, probe selection) and the head pass are independent per query: when the
+        // queries are still arriving from the host (feed), they run chunk by chunk behind the copy stream, so the H2D
+        // transfer of chunk c+1 overlaps the work on chunk c and only the tail stage waits for the whole tile.
         const size_t chunk = feed ? feed->chunk : n;
-        for (size_t c0 = 0; c0 < n; c0 += chunk) {
+        int chunk_index = 0;
+        for (size_t c0 = 0; c0 < n; c0 += chunk, ++chunk_index) {
             const size_t m = std::min(chunk, n - c0);
             if (feed) {
                 if ((rc = feed->issue(q0 + c0, m, c0))) return rc;
@@ -253,12 +260,20 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 *launches += 1;
             }
             *launches += 3;
+            if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[3], st);
+            // head: FastScan of every query's first owned list + the reference's sequential loop over it
+            static const bool head_late = getenv("RBQ_HEAD_LATE") != nullptr;  // A/B knob: head pass once, after the last chunk
+            if (list_major && head_late) {
+                if (c0 + chunk >= n &&
+                    (rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                      d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, 0, n, 0)))
+                    return rc;
+            } else if (list_major &&
+                (rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, c0, m, chunk_index)))
+                return rc;
         }
-        if (h->profiling) cudaEventRecord(h->ev[3], st);
-        // Scan stage.  Sequential: one warp walks one query's whole probe sequence.  List-major (large batches):
-        // head pass (sequential, until the heap is full) -> tail kernel (all remaining pairs grouped by list)
-        // -> replay pass (survivors in reference order).  Both are exact.
-        const bool list_major = h->scan_mode == 2 || (h->scan_mode == 0 && nprobe >= 4 && n * nprobe >= 8 * (size_t)ix.nlist);
+        if (!list_major && h->profiling) cudaEventRecord(h->ev[3], st);
         if (!list_major) {
             if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFull, nullptr, st)))
@@ -270,11 +285,6 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 cudaEventRecord(h->ev[6], st);
             }
         } else {
-            RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + 8) * 4, st));  // + list_cnt, list_fill, counters
-            // head: FastScan of every query's first owned list + the reference's sequential loop over it
-            if ((rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches)))
-                return rc;
             if (h->profiling) cudaEventRecord(h->ev[4], st);
             // tail: all remaining (query, list) pairs grouped by list -> survivors
             if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches,
@@ -566,21 +576,14 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     feed.ev = h->feed_ev;
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
-        // chunk = the queries whose coarse GEMM fills one wave of the SMs (128-query row tiles x 256-centroid column tiles),
-        // at most 16 chunks per tile; RBQ_FEED_CHUNKS overrides the count (1 = no overlap)
+        // 4 chunks per tile: the H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks
+        // hide more of the copy but run the per-query kernels on grids too small to fill the GPU and cost 6 launches each
+        // (measured at GIST/10k, same box: 4 chunks 3.26M QPS, 8: 2.87M, 16: 2.23M); RBQ_FEED_CHUNKS overrides (1 = no overlap)
         static const long forced = [] {
             const char* e = getenv("RBQ_FEED_CHUNKS");
-            return e ? std::min(16L, std::max(1L, atol(e))) : 0L;
+            return e ? std::min(16L, std::max(1L, atol(e))) : 4L;
         }();
-        if (forced) {
-            feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
-        } else {
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            const size_t col_tiles = ((size_t)h->dev.nlist + 255) / 256;
-            const size_t row_tiles = std::max<size_t>(4, (size_t)sms / std::max<size_t>(col_tiles, 1));
-            feed.chunk = std::max(row_tiles * 128, ((n + 15) / 16 + 127) / 128 * 128);
-        }
+        feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
         if (n < 2048) feed.chunk = n;
         // search_device copies queries [q0, q0+n) itself (feed) and indexes outputs from the tile start
         static const bool trace = getenv("RBQ_TRACE") != nullptr;

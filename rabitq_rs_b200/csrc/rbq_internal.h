@@ -91,6 +91,8 @@ struct Probe {  // one per (query, probe rank), written by the probe kernel (32 
     uint32_t blk_off;   // first 32-vector block of the list
     uint64_t vec_off;   // first vector of the list
 };
+// TailWs::counters: slots 0..7 belong to the tail / replay kernels, then one work cursor per head-stage launch of a call
+constexpr uint32_t kTailCounters = 8, kHeadCursors = 32;
 struct DevStats {
     unsigned long long blocks, candidates, refined, admitted;
     // list-major tail stage (scan_tail.cu)
@@ -184,7 +186,8 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
 int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
-                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches);
+                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
+                size_t q_begin, size_t q_count, int chunk_index);
 int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                          size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
                          const TailWs& tw, cudaStream_t st, uint64_t* launches);

@@ -32,6 +32,7 @@ struct ResolveArgs {
     const QueryScalars* qs;
     const Probe* probes;
     uint32_t nq, nprobe, top_k;
+    uint32_t q_begin, q_count, cursor;  // head stage: the queries [q_begin, q_begin + q_count) of this launch; cursor = its work counter slot
     const unsigned long long* filter;
     unsigned long long filter_nbits;
     unsigned long long* out_ids;
@@ -69,8 +70,8 @@ __device__ __forceinline__ uint32_t first_owned_rank(const Probe* __restrict__ p
 template <int NCB, bool WIDE>
 __global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs a) {
     const int lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * 4u + (threadIdx.x >> 5);
-    if (q >= a.nq) return;
+    const uint32_t q = a.q_begin + blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (q >= a.q_begin + a.q_count) return;
     const Probe* pr = a.probes + (size_t)q * a.nprobe;
     const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
     if (h >= a.nprobe) return;
@@ -230,12 +231,14 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
 
     for (;;) {
         uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(&a.counters[3], 1u);
+        if (lane == 0) q = atomicAdd(&a.counters[a.cursor], 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= a.nq) break;
+        if (q >= a.q_count) break;
+        q += a.q_begin;
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
-        int cnt = 0;
+        TopK tk;
+        tk.init(sd, si, k);
         bool fallback = false;
         uint32_t next_start = a.nprobe;
         unsigned long long q_blocks = 0, q_cand = 0, q_ref = 0, q_adm = 0;
@@ -283,11 +286,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
                         const float d_s = __shfl_sync(0xffffffffu, dist, c);
                         const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
-                        const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                        const float theta = tk.theta();
                         if (lb_s >= theta) continue;  // skipped_by_lower_bound
                         q_adm += 1;
                         if (!isfinite(d_s)) continue;
-                        topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                        tk.insert(d_s, id_s, lane);
                     }
                     qn = 0;
                 };
@@ -320,11 +323,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         const float lb_s = __shfl_sync(0xffffffffu, lower, sl);
                         const float d_s = __shfl_sync(0xffffffffu, est, sl);
                         const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
-                        const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                        const float theta = tk.theta();
                         if (lb_s >= theta) continue;
                         q_adm += 1;
                         if (!isfinite(d_s)) continue;
-                        topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                        tk.insert(d_s, id_s, lane);
                     }
                 };
 
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                         const uint32_t id32 = (uint32_t)ix.ids[vbase + li];
                         valid = (unsigned long long)id32 < a.filter_nbits && ((a.filter[id32 >> 6] >> (id32 & 63u)) & 1ull);
                     }
-                    const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                    const float theta0 = tk.theta();  // stale w.r.t. queued candidates => superset
                     const bool cand = valid && (rec.x < theta0);
                     const unsigned mask = __ballot_sync(0xffffffffu, cand);
                     q_cand += __popc(__ballot_sync(0xffffffffu, valid));
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
                 }
                 if (EXK != 0) flush();
                 const bool more = first_owned_rank(pr, a.nprobe, h + 1, lane) < a.nprobe;
-                if (cnt >= k) next_start = h + 1;
+                if (tk.cnt >= k) next_start = h + 1;
                 else if (more) fallback = true;  // the heap is not full yet: the sequential kernel walks on
             }
         }
@@ -367,15 +370,18 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
         st_cand += q_cand;
         st_ref += q_ref;
         st_adm += q_adm;
+        const float tau_q = tk.theta();
+        __syncwarp();
         for (int i = lane; i < k; i += 32) {
-            const bool have = i < cnt;
-            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
-            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
+            const bool have = i < tk.cnt;
+            const float dv = tk.dist_at(i);
+            a.out_ids[(size_t)q * k + i] = have ? tk.id_at(i) : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? dv : -dv) : 0.0f;
         }
         if (lane == 0) {
-            a.out_counts[q] = (uint32_t)cnt;
+            a.out_counts[q] = (uint32_t)tk.cnt;
             a.tail_start[q] = next_start;
-            a.tau[q] = cnt >= k ? sd[k - 1] : INFINITY;
+            a.tau[q] = tau_q;
         }
         __syncwarp();
     }
@@ -576,11 +582,12 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         __syncwarp();
         load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         const QueryScalars s = a.qs[q];
-        int cnt = (int)a.out_counts[q];
-        for (int i = lane; i < cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
+        TopK tk;
+        tk.init(sd, si, k);
+        tk.cnt = (int)a.out_counts[q];
+        for (int i = lane; i < tk.cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
             const float sc = a.out_scores[(size_t)q * k + i];
-            sd[i] = l2 ? sc : -sc;
-            si[i] = a.out_ids[(size_t)q * k + i];
+            tk.set_at(i, l2 ? sc : -sc, a.out_ids[(size_t)q * k + i]);
         }
         const Survivor* sv = a.surv + (size_t)q * a.surv_cap;
         // sort key: rank (12 bits, nprobe <= 4096) | position (32) | slot in the buffer (10, cap <= 1024)
@@ -633,11 +640,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
                 const float d_s = __shfl_sync(0xffffffffu, dist, c);
                 const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
-                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                const float theta = tk.theta();
                 if (lb_s >= theta) continue;  // skipped_by_lower_bound
                 q_adm += 1;
                 if (!isfinite(d_s)) continue;
-                topk_insert(sd, si, cnt, k, d_s, id_s, lane);
+                tk.insert(d_s, id_s, lane);
             }
             qn = 0;
         };
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 g_add = pp->g_add;
             }
             {   // the first few likely candidates of the batch: start their ex-codes towards L2 now
-                const float th = cnt >= k ? sd[k - 1] : INFINITY;
+                const float th = tk.theta();
                 const bool likely = have && (rec.lower < th);
                 const unsigned m0 = __ballot_sync(0xffffffffu, likely);
                 if (likely && __popc(m0 & ((1u << lane) - 1u)) < 2 * fl) {
@@ -666,7 +673,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
             // the batch is consumed in visit order, a queue-full at a time, so that the threshold is refreshed between
             // refine rounds; a lane that fails the test once is out for good (the threshold never rises)
             for (;;) {
-                const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;  // stale w.r.t. queued candidates => superset
+                const float theta0 = tk.theta();  // stale w.r.t. queued candidates => superset
                 have = have && (rec.lower < theta0);
                 unsigned mask = __ballot_sync(0xffffffffu, have);
                 if (mask == 0u) break;
@@ -693,12 +700,14 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         flush();
         st_ref += q_ref;
         st_adm += q_adm;
+        __syncwarp();
         for (int i = lane; i < k; i += 32) {
-            const bool have = i < cnt;
-            a.out_ids[(size_t)q * k + i] = have ? si[i] : ~0ull;
-            a.out_scores[(size_t)q * k + i] = have ? (l2 ? sd[i] : -sd[i]) : 0.0f;
+            const bool have = i < tk.cnt;
+            const float dv = tk.dist_at(i);
+            a.out_ids[(size_t)q * k + i] = have ? tk.id_at(i) : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? dv : -dv) : 0.0f;
         }
-        if (lane == 0) a.out_counts[q] = (uint32_t)cnt;
+        if (lane == 0) a.out_counts[q] = (uint32_t)tk.cnt;
         __syncwarp();
     }
     if (lane == 0 && a.stats) {
@@ -754,6 +763,9 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.qs = d_qs;
     a.probes = d_probes;
     a.nq = (uint32_t)nq;
+    a.q_begin = 0;
+    a.q_count = (uint32_t)nq;
+    a.cursor = 3;
     a.nprobe = (uint32_t)nprobe;
     a.top_k = (uint32_t)top_k;
     a.filter = reinterpret_cast<const unsigned long long*>(d_filter);
@@ -789,7 +801,7 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
 
 template <int NCB, bool WIDE>
 static int launch_head_scan_ex(const DevIndex& ix, const ResolveArgs& a, cudaStream_t st) {
-    head_scan_kernel<NCB, WIDE><<<(a.nq + 3) / 4, 128, 0, st>>>(ix, a);
+    head_scan_kernel<NCB, WIDE><<<(a.q_count + 3) / 4, 128, 0, st>>>(ix, a);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
@@ -820,12 +832,16 @@ static unsigned res_grid(size_t nq, size_t smem) {
 
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
-                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches) {
-    if (nq == 0) return RBQ_OK;
+                float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
+                size_t q_begin, size_t q_count, int chunk_index) {
+    if (nq == 0 || q_count == 0) return RBQ_OK;
     int rc = res_limits();
     if (rc) return rc;
     ResolveArgs a;
     fill_args(a, ix, d_rot, d_lut, d_qs, d_probes, nq, nprobe, top_k, d_filter, filter_nbits, d_ids, d_scores, d_counts, d_stats, tw);
+    a.q_begin = (uint32_t)q_begin;
+    a.q_count = (uint32_t)q_count;
+    a.cursor = kTailCounters + (uint32_t)chunk_index % kHeadCursors;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         rc = ncb_lane <= 12 ? launch_head_scan_ex<12, true>(ix, a, st) : launch_head_scan_ex<16, true>(ix, a, st);
@@ -844,7 +860,7 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
-    const unsigned grid = res_grid(nq, smem);
+    const unsigned grid = res_grid(q_count, smem);
     RBQ_RES_LAUNCH(resolve_head_kernel, smem, grid);
     if (launches) *launches += 2;
     return RBQ_OK;

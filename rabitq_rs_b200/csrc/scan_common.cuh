@@ -322,4 +322,60 @@ __device__ __forceinline__ void topk_insert(float* sd, unsigned long long* si, i
     cnt = newcnt;
 }
 
+// The same list with a register fast path: for k <= 32 entry i lives in lane i (no shared-memory traffic, no
+// __syncwarp; insertion = one ballot and two shuffles), otherwise in the shared arrays sd / si.  Same order semantics.
+struct TopK {
+    float* sd;
+    unsigned long long* si;
+    int k, cnt;
+    bool reg;
+    float rd;
+    unsigned long long ri;
+    __device__ __forceinline__ void init(float* sd_, unsigned long long* si_, int k_) {
+        sd = sd_;
+        si = si_;
+        k = k_;
+        cnt = 0;
+        reg = k_ <= 32;
+        rd = 0.0f;
+        ri = 0ull;
+    }
+    // the k-th distance (the pruning threshold), +inf until the list is full
+    __device__ __forceinline__ float theta() const {
+        if (cnt < k) return INFINITY;
+        return reg ? __shfl_sync(0xffffffffu, rd, k - 1) : sd[k - 1];
+    }
+    __device__ __forceinline__ void insert(float d, unsigned long long id, int lane) {
+        if (!reg) {
+            topk_insert(sd, si, cnt, k, d, id, lane);
+            return;
+        }
+        const int pos = __popc(__ballot_sync(0xffffffffu, lane < cnt && rd <= d));
+        const float up_d = __shfl_up_sync(0xffffffffu, rd, 1);
+        const unsigned long long up_i = __shfl_up_sync(0xffffffffu, ri, 1);
+        if (pos >= k) return;
+        const int newcnt = cnt < k ? cnt + 1 : k;
+        if (lane == pos) {
+            rd = d;
+            ri = id;
+        } else if (lane > pos && lane < newcnt) {
+            rd = up_d;
+            ri = up_i;
+        }
+        cnt = newcnt;
+    }
+    // entry i (i == lane + 32 j): only valid for i < cnt
+    __device__ __forceinline__ float dist_at(int i) const { return reg ? rd : sd[i]; }
+    __device__ __forceinline__ unsigned long long id_at(int i) const { return reg ? ri : si[i]; }
+    __device__ __forceinline__ void set_at(int i, float d, unsigned long long id) {
+        if (reg) {
+            rd = d;
+            ri = id;
+        } else {
+            sd[i] = d;
+            si[i] = id;
+        }
+    }
+};
+
 }  // namespace rbq

@@ -307,7 +307,7 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     size_t n = 4096;
     n += nq * 4 + 256;                               // tail_start
     n += nq * 4 + 256;                               // tau
-    n += (nq + 2 * (size_t)ix.nlist + 8) * 4 + 256;  // surv_cnt | list_cnt | list_fill | counters (zeroed together)
+    n += (nq + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4 + 256;  // surv_cnt | list_cnt | list_fill | counters (zeroed together)
     n += ((size_t)ix.nlist + 1) * 4 + 256;           // list_off
     n += nq * nprobe * 4 + 256;                      // pairs
     n += max_items * sizeof(TailItem) + 256;
@@ -331,7 +331,7 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.pairs_per_item = kPairsPerItem;
     tw.tail_start = reinterpret_cast<uint32_t*>(take(nq * 4));
     tw.tau = reinterpret_cast<float*>(take(nq * 4));
-    uint32_t* z = reinterpret_cast<uint32_t*>(take((nq + 2 * (size_t)ix.nlist + 8) * 4));
+    uint32_t* z = reinterpret_cast<uint32_t*>(take((nq + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4));
     tw.surv_cnt = z;
     tw.list_cnt = z + nq;
     tw.list_fill = tw.list_cnt + ix.nlist;
