@@ -122,6 +122,8 @@ SEARCH_CASES = [  # (n, dim, nlist, bits, metric, rot, kind, k, nprobe)
     (3000, 960, 32, 7, 0, 1, "clustered", 100, 8),
     (2000, 32, 16, 7, 0, 0, "uniform11", 5, 16),       # MatrixRotator
     (2000, 1280, 16, 3, 0, 1, "clustered", 10, 4),     # wide path
+    (3000, 768, 32, 5, 1, 1, "clustered", 10, 8),      # BASELINE config 4 geometry (768-d, inner product, total_bits 5:
+                                                       # the reference panics on this width -- parity vs our oracle only)
 ]
 
 
@@ -401,3 +403,53 @@ def test_list_major_filtered_edge_and_sharded(rbq, oracle):
     g2 = _load(rbq, o2.save_bytes())
     g2.set_scan_mode(2)
     assert assert_results_match(g2.batch_search(d2[:100], rbq.SearchParams(7, 12)), o2.search_batch(d2[:100], 7, 12)) == 100
+
+
+def test_full_size_properties_sift1m_shape(rbq, oracle):
+    """BASELINE config 2 at full size (1M x 128, nlist 4096, total_bits 7, L2, 10k-query batch): too large for
+    the oracle to build in a CPU test, so parity is checked through size-independent properties -- the list-major
+    (tensor-core) schedule and the sequential per-query schedule are two independent implementations of the
+    reference loop and must agree on every query; results are sorted, idempotent, within the index, and the
+    host entry equals the device-resident entry; a sample of queries is checked against the oracle on the same
+    RBQ1 bytes."""
+    import torch
+    from oracle import oracle as orc
+    from rabitq_rs_b200.kmeans import kmeans_gpu
+
+    n, dim, nlist, nq, k, nprobe = 1_000_000, 128, 4096, 10_000, 10, 32
+    g = torch.Generator(device="cuda").manual_seed(7)
+    centers = torch.randn(1024, dim, generator=g, device="cuda")
+    base = (centers[torch.randint(0, 1024, (n,), generator=g, device="cuda")] + 0.35 * torch.randn(n, dim, generator=g, device="cuda")).cpu().numpy()
+    q = (centers[torch.randint(0, 1024, (nq,), generator=g, device="cuda")] + 0.35 * torch.randn(nq, dim, generator=g, device="cuda")).cpu().numpy()
+    cents, assign = kmeans_gpu(base, nlist, iters=4, seed=42, device=0)
+    ix = rbq.IvfRabitqIndex(dim, 0, device=0)
+    ix.fit_with_clusters(base, cents, assign, 7, "fht", seed=42, faster_config=True)
+    assert len(ix) == n and ix.cluster_count() == nlist
+    p = rbq.SearchParams(k, nprobe)
+    ix.set_scan_mode(2)
+    a = ix.batch_search(q, p)
+    st = ix.stats()
+    # a few queries of this tightly clustered data overflow their survivor buffer and are re-walked sequentially
+    assert st["tail_pairs"] > 0 and st["overflow_queries"] <= nq // 100, st
+    b = ix.batch_search(q, p)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)), "not idempotent"
+    ix.set_scan_mode(1)
+    c = ix.batch_search(q, p)
+    assert all(np.array_equal(x, y) for x, y in zip(_canon_all(a), _canon_all(c))), "list-major != sequential schedule"
+    ids, sc, cnt = a
+    assert (cnt == k).all() and (ids < n).all()
+    assert (np.diff(sc, axis=1) >= 0).all(), "L2 results must be sorted by ascending distance"
+    assert all(len(set(r.tolist())) == k for r in ids[:512]), "duplicate ids in a result"
+    # device-resident entry == host entry
+    dq = torch.from_numpy(q).cuda()
+    d_ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    d_sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    d_cn = torch.empty(nq, dtype=torch.int32, device="cuda")
+    ix.set_scan_mode(0)
+    ix.batch_search_device(dq, k, nprobe, d_ids, d_sc, d_cn)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ids.cpu().numpy().astype(np.uint64), ids) and np.array_equal(d_sc.cpu().numpy(), sc)
+    # a sample against the oracle on the same bytes
+    oix = orc.Index.load_bytes(ix.save_to_bytes())
+    exp = oix.search_batch(q[:256], k, nprobe)
+    assert assert_results_match((ids[:256], sc[:256], cnt[:256]), exp, TOL, "sift1m sample") == 256
