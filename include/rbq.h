@@ -101,6 +101,31 @@ int rbq_merge_topk_device(const rbq_index* ix, int nshards, size_t nq, size_t to
                           const uint64_t* in_ids, const float* in_scores, const uint32_t* in_counts,
                           uint64_t* out_ids, float* out_scores, uint32_t* out_counts, void* stream);
 
+/* ---- multi-GPU search in three phases (list shards, two small exchanges) ----
+ * No reference counterpart (src/ivf.rs is single-process).  All buffers are DEVICE pointers on the handle's
+ * device, everything is enqueued on `stream`, nothing synchronises with the host.  The three calls of one batch must
+ * be made in order on the same handle with the same (nq, top_k, nprobe) and no other search in between: the handle's
+ * workspace carries the rotated queries, LUTs and probe lists from phase to phase.
+ *  1. rbq_dist_front: rotate + LUT for ALL nq queries (every shard needs them), coarse scores + probe selection for
+ *     the slice [q_begin, q_begin + q_count) only; writes that slice's rows of `d_probes` (nq x nprobe records).
+ *     The caller all-gathers the rows (each rank contributes its slice).
+ *  2. rbq_dist_head: attaches this shard's list geometry to the gathered probe lists and runs the head pass for the
+ *     queries whose NEAREST probed list this shard owns; d_tau[q] = the k-th distance after it (+inf for the other
+ *     queries).  The caller all-reduces d_tau with MIN: a valid upper bound of every shard's final k-th distance.
+ *  3. rbq_dist_tail: all remaining (query, owned list) pairs pruned with the reduced d_tau, ordered replay; leaves the
+ *     shard's local top-k in d_ids / d_scores / d_counts (the buffers given to rbq_dist_head) for
+ *     rbq_merge_topk_device. */
+typedef struct rbq_probe_rec {
+    uint32_t cid;                   /* cluster id */
+    float g_add, g_error, dot_qc;   /* per-(query, list) constants (src/ivf.rs:1850-1857) */
+} rbq_probe_rec;
+int rbq_dist_front(const rbq_index* ix, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
+                   size_t q_begin, size_t q_count, rbq_probe_rec* d_probes, void* stream);
+int rbq_dist_head(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes,
+                  float* d_tau, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream);
+int rbq_dist_tail(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids,
+                  float* d_scores, uint32_t* d_counts, void* stream);
+
 /* Host-only: the shard every inverted list of an RBQ1 stream is assigned to for `shard_count` shards
  * (the same deterministic size-balanced map rbq_index_load uses; no GPU needed).  owner[i] in
  * [0, shard_count); list_sizes (optional) receives the vector count of every list. */

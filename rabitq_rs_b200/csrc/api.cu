@@ -93,6 +93,9 @@ int upload_index(rbq_index* h) {
     if ((rc = upload(h, hi.centroids.data(), hi.centroids.size(), &d.centroids))) return rc;
     if ((rc = prepare_coarse_tc(h))) return rc;
     if ((rc = upload(h, hi.list_n.data(), hi.list_n.size(), &d.list_n))) return rc;
+    d.list_owner = nullptr;
+    d.shard_rank = hi.shard_rank;
+    if (hi.shard_count > 1 && (rc = upload(h, hi.list_owner.data(), hi.list_owner.size(), &d.list_owner))) return rc;
     if ((rc = upload(h, hi.blk_off.data(), hi.blk_off.size(), &d.blk_off))) return rc;
     if ((rc = upload(h, hi.vec_off.data(), hi.vec_off.size(), &d.vec_off))) return rc;
     if ((rc = upload(h, hi.blocks.data(), hi.blocks.size(), &d.blocks))) return rc;
@@ -181,12 +184,45 @@ size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_
     n += qt * nprobe * sizeof(Probe) + 256;
     n += qt * 3 * D * 2 + qt * 4 + 512;    // bf16 split of the rotated queries + |q|^2 (tensor-core coarse stage)
     n += tail_ws_bytes(h->dev, qt, nprobe, top_k) + 256;  // head/tail/replay pipeline (scan_tail.cu)
+    n += qt + 256;                                       // head_owner flags (phased multi-GPU search)
     if (host_io) {
         n += qt * dim * 4 + 256;
         n += qt * top_k * 12 + qt * 4 + 768;
         n += filter_words * 8 + 256;
     }
     return n;
+}
+
+// One tile's device workspace.  The layout is a pure function of (qt, nprobe, top_k), so the phases of a multi-GPU search
+// find each other's data by carving again.
+struct WsLayout {
+    float* d_rot;
+    uint8_t* d_lut;
+    QueryScalars* d_qs;
+    float* d_sc;
+    Probe* d_pr;
+    uint16_t* d_qsplit;
+    float* d_qn2;
+    TailWs tw;
+    uint8_t* d_head_owner;
+    size_t end;
+};
+WsLayout carve_ws(const rbq_index* h, char* ws_base, size_t qt, size_t nprobe, size_t top_k) {
+    const DevIndex& ix = h->dev;
+    const size_t D = ix.D;
+    Carver cv{ws_base};
+    WsLayout L;
+    L.d_rot = cv.take<float>(qt * D);
+    L.d_lut = cv.take<uint8_t>(qt * D * 4);
+    L.d_qs = cv.take<QueryScalars>(qt);
+    L.d_sc = cv.take<float>(qt * (size_t)ix.nlist);
+    L.d_pr = cv.take<Probe>(qt * nprobe);
+    L.d_qsplit = cv.take<uint16_t>(qt * 3 * D);
+    L.d_qn2 = cv.take<float>(qt);
+    tail_ws_carve(ix, qt, nprobe, top_k, cv.take<char>(tail_ws_bytes(ix, qt, nprobe, top_k)), L.tw);
+    L.d_head_owner = cv.take<uint8_t>(qt);
+    L.end = cv.off;
+    return L;
 }
 
 // Queries still in host memory: chunks are copied on a dedicated non-blocking stream, each followed by an event the
@@ -211,16 +247,15 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                   char* ws_base, size_t qt, cudaStream_t st, uint64_t* launches, HostFeed* feed = nullptr) {
     const DevIndex& ix = h->dev;
     const size_t D = ix.D;
-    Carver cv{ws_base};
-    float* d_rot = cv.take<float>(qt * D);
-    uint8_t* d_lut = cv.take<uint8_t>(qt * D * 4);
-    QueryScalars* d_qs = cv.take<QueryScalars>(qt);
-    float* d_sc = cv.take<float>(qt * (size_t)ix.nlist);
-    Probe* d_pr = cv.take<Probe>(qt * nprobe);
-    uint16_t* d_qsplit = cv.take<uint16_t>(qt * 3 * D);
-    float* d_qn2 = cv.take<float>(qt);
-    TailWs tw;
-    tail_ws_carve(ix, qt, nprobe, top_k, cv.take<char>(tail_ws_bytes(ix, qt, nprobe, top_k)), tw);
+    const WsLayout L = carve_ws(h, ws_base, qt, nprobe, top_k);
+    float* d_rot = L.d_rot;
+    uint8_t* d_lut = L.d_lut;
+    QueryScalars* d_qs = L.d_qs;
+    float* d_sc = L.d_sc;
+    Probe* d_pr = L.d_pr;
+    uint16_t* d_qsplit = L.d_qsplit;
+    float* d_qn2 = L.d_qn2;
+    const TailWs& tw = L.tw;
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};  // [6]: the tail FastScan kernel alone
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
@@ -611,6 +646,105 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
 int rbq_search_batch(const rbq_index* h, const float* queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
                      uint64_t* ids, float* scores, uint32_t* counts) {
     return rbq_search_batch_filtered(h, queries, nq, dim, top_k, nprobe, nullptr, 0, ids, scores, counts);
+}
+
+// ---- multi-GPU search in three phases (include/rbq.h) ------------------------------------------------
+namespace {
+int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, size_t* nprobe, size_t* qt) {
+    int rc = check_search_args(h, dim_or_zero ? dim_or_zero : (size_t)h->dev.dim, top_k, nprobe);
+    if (rc) return rc;
+    if (top_k == 0 || nq == 0) return fail(RBQ_INVALID_CONFIG, "phased search needs nq > 0 and top_k > 0");
+    *qt = tile_queries(h, nq);
+    if (*qt < nq) return fail(RBQ_INVALID_CONFIG, "phased search handles one tile of queries per batch: split the batch");
+    if (*nprobe < 2) return fail(RBQ_INVALID_CONFIG, "phased search needs nprobe >= 2");
+    return RBQ_OK;
+}
+}  // namespace
+
+int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, size_t q_begin,
+                   size_t q_count, rbq_probe_rec* d_probes, void* stream) {
+    size_t qt = 0;
+    int rc = dist_args(h, nq, dim, top_k, &nprobe, &qt);
+    if (rc) return rc;
+    if (q_begin > nq || q_count > nq - q_begin) return fail(RBQ_INVALID_CONFIG, "query slice out of range");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    h->last_stats = rbq_search_stats{};
+    h->last_stats.queries = nq;
+    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, false, 0)))) return rc;
+    RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
+    const DevIndex& ix = h->dev;
+    const size_t D = ix.D;
+    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    // every shard scans its lists for ALL queries, so it needs every query's rotation, LUT and scalars ...
+    if ((rc = launch_query_prep(ix, d_queries, nq, L.d_rot, L.d_lut, L.d_qs, st))) return rc;
+    uint64_t launches = 1;
+    // ... but the probe lists are the same on every shard: each one computes a slice
+    if (q_count) {
+        const size_t c0 = q_begin, m = q_count;
+        if (h->coarse_mode == 0) {
+            if ((rc = launch_coarse_exact(ix, L.d_rot + c0 * D, m, L.d_sc + c0 * ix.nlist, st))) return rc;
+            if ((rc = launch_probe_select(ix, L.d_rot + c0 * D, L.d_sc + c0 * ix.nlist, m, nprobe, L.d_pr + c0 * nprobe, st))) return rc;
+            launches += 2;
+        } else {
+            if ((rc = launch_split_bf16(L.d_rot + c0 * D, m, (int)D, 0, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, st))) return rc;
+            if ((rc = launch_coarse_tc(ix, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, m, L.d_sc + c0 * ix.nlist, st))) return rc;
+            if ((rc = launch_probe_select_tc(ix, L.d_rot + c0 * D, L.d_sc + c0 * ix.nlist, L.d_qs + c0, m, nprobe, h->coarse_eps,
+                                             L.d_pr + c0 * nprobe, h->fallback_counter(), st, false)))
+                return rc;
+            launches += 3;
+        }
+        if ((rc = launch_probe_export(L.d_pr, q_begin, q_count, nprobe, d_probes, st))) return rc;
+        launches += 1;
+    }
+    h->last_stats.kernel_launches = launches;
+    return RBQ_OK;
+}
+
+int rbq_dist_head(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes, float* d_tau,
+                  uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream) {
+    size_t qt = 0;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &qt);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->ws_bytes < ws_need(h, qt, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
+    const DevIndex& ix = h->dev;
+    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    uint64_t launches = h->last_stats.kernel_launches;
+    if ((rc = launch_probe_import(ix, d_probes, nq, nprobe, L.d_pr, L.d_head_owner, st))) return rc;
+    RBQ_CUDA(cudaMemsetAsync(L.tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
+    if ((rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats, L.tw,
+                          st, &launches, 0, nq, 0, L.d_head_owner)))
+        return rc;
+    RBQ_CUDA(cudaMemcpyAsync(d_tau, L.tw.tau, nq * 4, cudaMemcpyDeviceToDevice, st));
+    h->last_stats.kernel_launches = launches + 1;
+    return RBQ_OK;
+}
+
+int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids, float* d_scores,
+                  uint32_t* d_counts, void* stream) {
+    size_t qt = 0;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &qt);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->ws_bytes < ws_need(h, qt, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
+    const DevIndex& ix = h->dev;
+    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    uint64_t launches = h->last_stats.kernel_launches;
+    RBQ_CUDA(cudaMemcpyAsync(L.tw.tau, d_tau, nq * 4, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, st, &launches))) return rc;
+    if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, nq, nprobe, top_k, d_ids, d_scores, d_counts, h->d_stats, L.tw, st, &launches)))
+        return rc;
+    if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats,
+                          h->work_counter(), kScanFallback, &L.tw, st)))
+        return rc;
+    h->last_stats.kernel_launches = launches + 2;
+    return RBQ_OK;
 }
 
 int rbq_merge_topk_device(const rbq_index* h, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids,

@@ -199,6 +199,8 @@ int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, Host
     }
     std::vector<int> owner;
     assign_shards(bytes, shard_count, owner);
+    ix.list_owner.resize(ncl);
+    for (uint64_t c = 0; c < ncl; ++c) ix.list_owner[c] = (uint8_t)owner[c];
 
     // pass 2
     ix.centroids.resize(ncl * (size_t)D);

@@ -36,6 +36,7 @@ struct HostIndex {
     int shard_rank = 0, shard_count = 1;
     std::vector<float> centroids;    // nlist*D (rotated space)
     std::vector<uint32_t> list_n_all;  // size of every list (owned or not)
+    std::vector<uint8_t> list_owner;   // shard that owns every list (empty: single shard)
     std::vector<uint32_t> list_n;      // size of every list on this shard (0 if not owned)
     std::vector<uint32_t> blk_off;     // nlist+1, in 32-vector blocks, owned lists only
     std::vector<uint64_t> vec_off;     // nlist+1
@@ -69,6 +70,8 @@ struct DevIndex {
     const float* cent_n2;   // |c|^2 per centroid
     float cmax_norm;        // max |c|
     const uint32_t* list_n; // nlist
+    const uint8_t* list_owner;  // nlist: owning shard of every list (nullptr: this handle owns all lists)
+    int shard_rank;
     const uint32_t* blk_off;
     const uint64_t* vec_off;
     const uint8_t* blocks;
@@ -182,12 +185,17 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
 //   head resolve the reference's sequential prune/refine/top-k over that list -> heap state, tw.tau, tw.tail_start
 //   refine       ex-code distances of all tail survivors, in bulk
 //   replay       survivors in reference order against the live threshold (distances precomputed)
+// resolve.cu: phased multi-GPU search helpers.  export: Probe rows [q_begin, q_begin+q_count) -> records; import: records of all
+// queries -> Probe with this shard's list geometry, head_owner[q] = this shard owns the query's nearest probed list
+int launch_probe_export(const Probe* d_probes, size_t q_begin, size_t q_count, size_t nprobe, rbq_probe_rec* d_out, cudaStream_t st);
+int launch_probe_import(const DevIndex& ix, const rbq_probe_rec* d_in, size_t nq, size_t nprobe, Probe* d_probes, uint8_t* d_head_owner,
+                        cudaStream_t st);
 // resolve.cu: builds DevIndex::exl from the packed ex-codes already on the device (no-op for 1-bit indexes)
 int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
                 float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
-                size_t q_begin, size_t q_count, int chunk_index);
+                size_t q_begin, size_t q_count, int chunk_index, const uint8_t* d_head_owner = nullptr);
 int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                          size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
                          const TailWs& tw, cudaStream_t st, uint64_t* launches);

@@ -32,6 +32,7 @@ struct ResolveArgs {
     const QueryScalars* qs;
     const Probe* probes;
     uint32_t nq, nprobe, top_k;
+    const uint8_t* head_owner;  // phased multi-GPU search: 0 = another shard runs this query's head pass (nullptr: all ours)
     uint32_t q_begin, q_count, cursor;  // head stage: the queries [q_begin, q_begin + q_count) of this launch; cursor = its work counter slot
     const unsigned long long* filter;
     unsigned long long filter_nbits;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs
     const int lane = threadIdx.x & 31;
     const uint32_t q = a.q_begin + blockIdx.x * 4u + (threadIdx.x >> 5);
     if (q >= a.q_begin + a.q_count) return;
+    if (a.head_owner != nullptr && !a.head_owner[q]) return;
     const Probe* pr = a.probes + (size_t)q * a.nprobe;
     const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
     if (h >= a.nprobe) return;
@@ -235,6 +237,14 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= a.q_count) break;
         q += a.q_begin;
+        if (a.head_owner != nullptr && !a.head_owner[q]) {  // another shard fills the heap first: all our pairs are tail pairs
+            if (lane == 0) {
+                a.out_counts[q] = 0u;
+                a.tail_start[q] = 0u;
+                a.tau[q] = INFINITY;
+            }
+            continue;
+        }
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
         TopK tk;
@@ -478,6 +488,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
             continue;
         }
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        const float tau_q = a.tau[q];  // caps the live threshold (see resolve_lazy_kernel)
         __syncwarp();
         int cnt = (int)a.out_counts[q];
         for (int i = lane; i < cnt; i += 32) {  // resume from the head pass' top-k (stored best-first)
@@ -516,7 +527,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
                 if (EXK != 0) vid = a.surv_id[(size_t)q * a.surv_cap + slot];
                 else vid = ix.ids[pr[rec.rank].vec_off + rec.pos];
             }
-            const float theta0 = cnt >= k ? sd[k - 1] : INFINITY;
+            const float theta0 = fminf(cnt >= k ? sd[k - 1] : INFINITY, tau_q);
             unsigned m = __ballot_sync(0xffffffffu, have && (rec.lower < theta0));
             while (m) {
                 const int sl = __ffs(m) - 1;
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
                 const float lb_s = __shfl_sync(0xffffffffu, rec.lower, sl);
                 const float d_s = __shfl_sync(0xffffffffu, rec.x, sl);
                 const unsigned long long id_s = __shfl_sync(0xffffffffu, vid, sl);
-                const float theta = cnt >= k ? sd[k - 1] : INFINITY;
+                const float theta = fminf(cnt >= k ? sd[k - 1] : INFINITY, tau_q);
                 if (lb_s >= theta) continue;  // skipped_by_lower_bound
                 st_adm += 1;
                 if (!isfinite(d_s)) continue;
@@ -582,6 +593,9 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         __syncwarp();
         load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         const QueryScalars s = a.qs[q];
+        // the head threshold caps the live one: a no-op on one GPU (the heap's k-th distance starts at tau and only falls), the
+        // bound another shard's head pass established in the phased multi-GPU search
+        const float tau_q = a.tau[q];
         TopK tk;
         tk.init(sd, si, k);
         tk.cnt = (int)a.out_counts[q];
@@ -640,7 +654,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 const float lb_s = __shfl_sync(0xffffffffu, q_lower, c);
                 const float d_s = __shfl_sync(0xffffffffu, dist, c);
                 const unsigned long long id_s = __shfl_sync(0xffffffffu, q_vid, c);
-                const float theta = tk.theta();
+                const float theta = fminf(tk.theta(), tau_q);
                 if (lb_s >= theta) continue;  // skipped_by_lower_bound
                 q_adm += 1;
                 if (!isfinite(d_s)) continue;
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 g_add = pp->g_add;
             }
             {   // the first few likely candidates of the batch: start their ex-codes towards L2 now
-                const float th = tk.theta();
+                const float th = fminf(tk.theta(), tau_q);
                 const bool likely = have && (rec.lower < th);
                 const unsigned m0 = __ballot_sync(0xffffffffu, likely);
                 if (likely && __popc(m0 & ((1u << lane) - 1u)) < 2 * fl) {
@@ -673,7 +687,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
             // the batch is consumed in visit order, a queue-full at a time, so that the threshold is refreshed between
             // refine rounds; a lane that fails the test once is out for good (the threshold never rises)
             for (;;) {
-                const float theta0 = tk.theta();  // stale w.r.t. queued candidates => superset
+                const float theta0 = fminf(tk.theta(), tau_q);  // stale w.r.t. queued candidates => superset
                 have = have && (rec.lower < theta0);
                 unsigned mask = __ballot_sync(0xffffffffu, have);
                 if (mask == 0u) break;
@@ -741,6 +755,45 @@ int prepare_ex_lanes(rbq_index* h) {
     return RBQ_OK;
 }
 
+// ---- phased multi-GPU search: probe lists travel between shards without the shard-local list geometry ------------------
+__global__ void probe_export_kernel(const Probe* __restrict__ probes, size_t first, size_t count, rbq_probe_rec* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Probe p = probes[first + i];
+    out[first + i] = rbq_probe_rec{p.cid, p.g_add, p.g_error, p.dot_qc};
+}
+__global__ void probe_import_kernel(DevIndex ix, const rbq_probe_rec* __restrict__ in, size_t nq, uint32_t nprobe, Probe* __restrict__ probes,
+                                    uint8_t* __restrict__ head_owner) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * nprobe) return;
+    const rbq_probe_rec r = in[i];
+    Probe p;
+    p.cid = r.cid;
+    p.g_add = r.g_add;
+    p.g_error = r.g_error;
+    p.dot_qc = r.dot_qc;
+    p.nv = ix.list_n[r.cid];
+    p.blk_off = ix.blk_off[r.cid];
+    p.vec_off = ix.vec_off[r.cid];
+    probes[i] = p;
+    if (i % nprobe == 0) head_owner[i / nprobe] = ix.list_owner == nullptr || ix.list_owner[r.cid] == (uint8_t)ix.shard_rank;
+}
+int launch_probe_export(const Probe* d_probes, size_t q_begin, size_t q_count, size_t nprobe, rbq_probe_rec* d_out, cudaStream_t st) {
+    const size_t count = q_count * nprobe;
+    if (count == 0) return RBQ_OK;
+    probe_export_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_probes, q_begin * nprobe, count, d_out);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+int launch_probe_import(const DevIndex& ix, const rbq_probe_rec* d_in, size_t nq, size_t nprobe, Probe* d_probes, uint8_t* d_head_owner,
+                        cudaStream_t st) {
+    const size_t count = nq * nprobe;
+    if (count == 0) return RBQ_OK;
+    probe_import_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(ix, d_in, nq, (uint32_t)nprobe, d_probes, d_head_owner);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static int g_res_sms = 0;
 static size_t g_res_smem_optin = 0;
@@ -766,6 +819,7 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.q_begin = 0;
     a.q_count = (uint32_t)nq;
     a.cursor = 3;
+    a.head_owner = nullptr;
     a.nprobe = (uint32_t)nprobe;
     a.top_k = (uint32_t)top_k;
     a.filter = reinterpret_cast<const unsigned long long*>(d_filter);
@@ -833,7 +887,7 @@ static unsigned res_grid(size_t nq, size_t smem) {
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
                 float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
-                size_t q_begin, size_t q_count, int chunk_index) {
+                size_t q_begin, size_t q_count, int chunk_index, const uint8_t* d_head_owner) {
     if (nq == 0 || q_count == 0) return RBQ_OK;
     int rc = res_limits();
     if (rc) return rc;
@@ -842,6 +896,7 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     a.q_begin = (uint32_t)q_begin;
     a.q_count = (uint32_t)q_count;
     a.cursor = kTailCounters + (uint32_t)chunk_index % kHeadCursors;
+    a.head_owner = d_head_owner;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         rc = ncb_lane <= 12 ? launch_head_scan_ex<12, true>(ix, a, st) : launch_head_scan_ex<16, true>(ix, a, st);

@@ -3,7 +3,16 @@
 Data path per query batch: every rank runs rotate/LUT/coarse/probe-select on the whole batch (centroids
 are replicated), scans only the probed lists it owns, and produces a local top-k; the local results are
 all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) and merged with the reference's result
-order.  The reference itself is single-process (src/ivf.rs has no communication)."""
+order.  The reference itself is single-process (src/ivf.rs has no communication).
+
+`ShardedSearcher` is the scalable form of that data path (three phases, two small exchanges):
+  1. every rank rotates all queries (its scan needs every LUT) but selects probe lists for its own SLICE of the
+     batch only; the slices (16 B per probe) are all-gathered;
+  2. the head pass of a query -- the sequential loop over its nearest list that fills the heap -- runs only on the
+     shard that owns that list; the resulting thresholds tau (4 B per query) are all-reduced with MIN;
+  3. every shard prunes its remaining (query, owned list) pairs with tau, keeps a local top-k, and the local
+     results are all-gathered and merged on the device.
+Per-rank work then shrinks with the number of shards in every stage but the query rotation."""
 import numpy as np
 
 
@@ -54,3 +63,56 @@ def merge_topk_host(ids, scores, counts, metric):
             out_s[q, t] = scores[s, q, j]
         out_c[q] = n
     return out_i, out_s, out_c
+
+
+def query_slices(nq, world, align=128):
+    """Contiguous query slices of equal padded length (a multiple of `align`, the coarse GEMM's row tile):
+    returns (per, [(begin, count)] * world); rank r writes rows [r*per, r*per+count) of the padded probe buffer."""
+    per = (((nq + world - 1) // world) + align - 1) // align * align
+    return per, [(min(r * per, nq), max(0, min((r + 1) * per, nq) - min(r * per, nq))) for r in range(world)]
+
+
+class ShardedSearcher:
+    """Phased multi-GPU search over one list shard per rank (rabitq_rs_b200.IvfRabitqIndex loaded with
+    shard_rank/shard_count).  Buffers are allocated once per (nq, top_k, nprobe)."""
+
+    def __init__(self, ix, rank, world, group=None):
+        self.ix, self.rank, self.world, self.group = ix, rank, world, group
+        self._key = None
+
+    def _buffers(self, nq, k, nprobe, dev):
+        import torch
+
+        key = (nq, k, nprobe)
+        if self._key != key:
+            self.per, self.slices = query_slices(nq, self.world)
+            self.probes = torch.zeros((self.per * self.world, nprobe, 4), dtype=torch.int32, device=dev)
+            self.tau = torch.empty(nq, dtype=torch.float32, device=dev)
+            self.l_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            self.l_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            self.l_cn = torch.empty(nq, dtype=torch.int32, device=dev)
+            self.g_ids = torch.empty((self.world, nq, k), dtype=torch.int64, device=dev)
+            self.g_sc = torch.empty((self.world, nq, k), dtype=torch.float32, device=dev)
+            self.g_cn = torch.empty((self.world, nq), dtype=torch.int32, device=dev)
+            self.m_ids, self.m_sc, self.m_cn = torch.empty_like(self.l_ids), torch.empty_like(self.l_sc), torch.empty_like(self.l_cn)
+            self._key = key
+        return self
+
+    def search(self, dq, k, nprobe):
+        """dq: [nq, dim] float32 CUDA tensor (the whole batch, on every rank) -> merged (ids, scores, counts) tensors."""
+        import torch.distributed as dist
+
+        nq = dq.shape[0]
+        b = self._buffers(nq, k, nprobe, dq.device)
+        q0, qc = b.slices[self.rank]
+        self.ix.dist_front(dq, k, nprobe, q0, qc, b.probes)
+        mine = b.probes[self.rank * b.per:(self.rank + 1) * b.per]
+        dist.all_gather_into_tensor(b.probes.view(-1), mine.reshape(-1), group=self.group)
+        self.ix.dist_head(nq, k, nprobe, b.probes, b.tau, b.l_ids, b.l_sc, b.l_cn)
+        dist.all_reduce(b.tau, op=dist.ReduceOp.MIN, group=self.group)
+        self.ix.dist_tail(nq, k, nprobe, b.tau, b.l_ids, b.l_sc, b.l_cn)
+        dist.all_gather_into_tensor(b.g_ids.view(-1), b.l_ids.view(-1), group=self.group)
+        dist.all_gather_into_tensor(b.g_sc.view(-1), b.l_sc.view(-1), group=self.group)
+        dist.all_gather_into_tensor(b.g_cn.view(-1), b.l_cn.view(-1), group=self.group)
+        self.ix.merge_topk_device(self.world, nq, k, b.g_ids, b.g_sc, b.g_cn, b.m_ids, b.m_sc, b.m_cn)
+        return b.m_ids, b.m_sc, b.m_cn

@@ -286,6 +286,38 @@ class IvfRabitqIndex:
                                                   int(nprobe), fb, fn, C.c_void_p(out_ids.data_ptr()),
                                                   C.c_void_p(out_scores.data_ptr()), C.c_void_p(out_counts.data_ptr()), st))
 
+    # ---- multi-GPU search in three phases (include/rbq.h: rbq_dist_front / _head / _tail) ----------------
+    def _stream(self, t, stream):
+        import torch
+
+        return C.c_void_p(stream) if stream else C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    def dist_front(self, queries, top_k, nprobe, q_begin, q_count, probes, stream=None):
+        """Phase 1: rotate + LUT for all queries, probe lists for the slice [q_begin, q_begin+q_count) -> rows of `probes`
+        (int32 CUDA tensor [>= nq, nprobe, 4] = rbq_probe_rec)."""
+        nq, dim = queries.shape
+        assert queries.is_cuda and queries.is_contiguous() and probes.is_cuda and probes.is_contiguous() and probes.numel() >= nq * nprobe * 4
+        _check(_ffi.lib().rbq_dist_front(self._need(), C.c_void_p(queries.data_ptr()), nq, dim, int(top_k), int(nprobe), int(q_begin),
+                                         int(q_count), C.c_void_p(probes.data_ptr()), self._stream(queries, stream)))
+
+    def dist_head(self, nq, top_k, nprobe, probes, tau, out_ids, out_scores, out_counts, stream=None):
+        """Phase 2: head pass for the queries whose nearest probed list this shard owns; tau[q] = k-th distance (+inf elsewhere)."""
+        _check(_ffi.lib().rbq_dist_head(self._need(), int(nq), int(top_k), int(nprobe), C.c_void_p(probes.data_ptr()),
+                                        C.c_void_p(tau.data_ptr()), C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
+                                        C.c_void_p(out_counts.data_ptr()), self._stream(tau, stream)))
+
+    def dist_tail(self, nq, top_k, nprobe, tau, out_ids, out_scores, out_counts, stream=None):
+        """Phase 3: remaining (query, owned list) pairs pruned with the MIN-reduced tau; leaves the shard's local top-k."""
+        _check(_ffi.lib().rbq_dist_tail(self._need(), int(nq), int(top_k), int(nprobe), C.c_void_p(tau.data_ptr()),
+                                        C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
+                                        C.c_void_p(out_counts.data_ptr()), self._stream(tau, stream)))
+
+    def merge_topk_device(self, nshards, nq, top_k, g_ids, g_scores, g_counts, out_ids, out_scores, out_counts, stream=None):
+        _check(_ffi.lib().rbq_merge_topk_device(self._need(), int(nshards), int(nq), int(top_k), C.c_void_p(g_ids.data_ptr()),
+                                                C.c_void_p(g_scores.data_ptr()), C.c_void_p(g_counts.data_ptr()),
+                                                C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
+                                                C.c_void_p(out_counts.data_ptr()), self._stream(g_ids, stream)))
+
     def stats(self):
         s = _ffi.SearchStats()
         _check(_ffi.lib().rbq_last_search_stats(self._need(), C.byref(s)))
