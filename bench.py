@@ -13,8 +13,10 @@ over one batch of queries.
 
 `--impl reference` times the CPU oracle alone (the Rust reference cannot be built here: no cargo).
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torch.distributed.run (one rank
-per GPU): inverted lists are sharded size-balanced across ranks, every rank searches the whole query
-batch on its lists, local top-k are all-gathered over NCCL and merged on the device.
+per GPU): inverted lists are sharded size-balanced across ranks and the batch runs the phased search of
+rabitq_rs_b200.distributed.ShardedSearcher: probe selection for a query slice per rank (all-gather), head pass on
+the shard that owns a query's nearest list (MIN all-reduce of the thresholds), tail + replay on every shard's
+lists, local top-k all-gathered over NCCL and merged on the device.
 """
 import argparse
 import json
@@ -294,6 +296,10 @@ def main():
     d_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
     d_cn = torch.empty(nq, dtype=torch.int32, device=dev)
     if world > 1:
+        from rabitq_rs_b200.distributed import ShardedSearcher
+
+        searcher = ShardedSearcher(ix, rank, world)
+        phased = os.environ.get("RBQ_BENCH_REPLICATED_FRONT") is None  # A/B knob: the earlier all-replicated front end
         g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
         g_sc = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
         g_cn = torch.empty((world, nq), dtype=torch.int32, device=dev)
@@ -302,6 +308,10 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
+        nonlocal m_ids, m_sc, m_cn
+        if world > 1 and phased:
+            m_ids, m_sc, m_cn = searcher.search(dq, k, nprobe)
+            return
         ix.batch_search_device(dq, k, nprobe, d_ids, d_sc, d_cn)
         if world > 1:
             dist.all_gather_into_tensor(g_ids.view(-1), d_ids.view(-1))
@@ -380,6 +390,14 @@ def main():
     L = _ffi.lib()
 
     def step_host():
+        if world > 1 and phased:  # host buffers in, merged result out: H2D of the batch, phased search, D2H of the merged top-k
+            dq.copy_(hq, non_blocking=True)
+            a, b, c = searcher.search(dq, k, nprobe)
+            h_ids.copy_(a, non_blocking=True)
+            h_sc.copy_(b, non_blocking=True)
+            h_cn.copy_(c, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            return
         rc = L.rbq_search_batch(ix.handle, C.c_void_p(hq.data_ptr()), nq, wl["dim"], k, nprobe, C.c_void_p(h_ids.data_ptr()),
                                 C.c_void_p(h_sc.data_ptr()), C.c_void_p(h_cn.data_ptr()))
         assert rc == 0, _ffi.last_error()
