@@ -126,6 +126,13 @@ int rbq_dist_head(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, c
 int rbq_dist_tail(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids,
                   float* d_scores, uint32_t* d_counts, void* stream);
 
+/* The same merge over ONE all-gathered buffer: shard s occupies bytes [s*chunk_bytes, (s+1)*chunk_bytes) holding
+ * ids[nq*top_k] (u64) | scores[nq*top_k] (f32) | counts[nq] (u32); chunk_bytes is a multiple of 8.  One collective
+ * instead of three. */
+int rbq_merge_topk_packed_device(const rbq_index* ix, int nshards, size_t nq, size_t top_k, const void* packed,
+                                 size_t chunk_bytes, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                                 void* stream);
+
 /* Host-only: the shard every inverted list of an RBQ1 stream is assigned to for `shard_count` shards
  * (the same deterministic size-balanced map rbq_index_load uses; no GPU needed).  owner[i] in
  * [0, shard_count); list_sizes (optional) receives the vector count of every list. */

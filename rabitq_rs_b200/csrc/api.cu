@@ -756,6 +756,18 @@ int rbq_merge_topk_device(const rbq_index* h, int nshards, size_t nq, size_t top
                         out_counts, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int rbq_merge_topk_packed_device(const rbq_index* h, int nshards, size_t nq, size_t top_k, const void* packed, size_t chunk_bytes,
+                                 uint64_t* out_ids, float* out_scores, uint32_t* out_counts, void* stream) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (chunk_bytes % 8 != 0 || chunk_bytes < nq * top_k * 12 + nq * 4) return fail(RBQ_INVALID_CONFIG, "packed top-k chunk too small or misaligned");
+    DeviceGuard g(h->device);
+    const char* base = static_cast<const char*>(packed);
+    return launch_merge(h->host.metric, nshards, nq, top_k, reinterpret_cast<const uint64_t*>(base),
+                        reinterpret_cast<const float*>(base + nq * top_k * 8), reinterpret_cast<const uint32_t*>(base + nq * top_k * 12),
+                        out_ids, out_scores, out_counts, reinterpret_cast<cudaStream_t>(stream), chunk_bytes / 8, chunk_bytes / 4,
+                        chunk_bytes / 4);
+}
+
 // ---- stage probes ------------------------------------------------------------------------------
 int rbq_debug_query_prep(const rbq_index* h, const float* queries, size_t nq, size_t dim, float* rotated, uint8_t* lut,
                          float* scalars) {

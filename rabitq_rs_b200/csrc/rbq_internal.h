@@ -207,7 +207,7 @@ int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScala
                       cudaStream_t st);
 int launch_merge(int metric, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids, const float* in_scores,
                  const uint32_t* in_counts, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
-                 cudaStream_t st);
+                 cudaStream_t st, size_t ids_stride = 0, size_t sc_stride = 0, size_t cn_stride = 0);
 int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scores, const QueryScalars* d_qs, size_t nq,
                            size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st,
                            bool need_ip = true);

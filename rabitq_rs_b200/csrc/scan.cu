@@ -599,20 +599,21 @@ int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScala
 __global__ void merge_kernel(int metric, int nshards, uint32_t nq, uint32_t k, const unsigned long long* __restrict__ in_ids,
                              const float* __restrict__ in_scores, const uint32_t* __restrict__ in_counts,
                              unsigned long long* __restrict__ out_ids, float* __restrict__ out_scores,
-                             uint32_t* __restrict__ out_counts) {
-    // Shards hold disjoint id sets, each list is sorted best-first; repeatedly take the best head.
+                             uint32_t* __restrict__ out_counts, size_t ids_stride, size_t sc_stride, size_t cn_stride) {
+    // in_*[shard] start ids_stride / sc_stride / cn_stride ELEMENTS apart (separate [nshards][nq][k] arrays, or one packed
+    // all-gather buffer holding ids | scores | counts per shard).  Shards hold disjoint id sets, each list is sorted best-first; repeatedly take the best head.
     // Order = the reference's result order: L2 ascending distance, IP descending score; ties -> lower shard.
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     uint32_t head = 0, cnt = 0;  // lane s (< nshards) tracks shard s; nshards <= 32
-    if (lane < nshards) cnt = in_counts[(size_t)lane * nq + q];
+    if (lane < nshards) cnt = in_counts[(size_t)lane * cn_stride + q];
     uint32_t n = 0;
     for (; n < k; ++n) {
         float key = INFINITY;
         bool have = lane < nshards && head < cnt;
         if (have) {
-            float sc = in_scores[((size_t)lane * nq + q) * k + head];
+            float sc = in_scores[(size_t)lane * sc_stride + (size_t)q * k + head];
             key = metric == RBQ_METRIC_L2 ? sc : -sc;
         }
         float best = key;
@@ -628,8 +629,8 @@ __global__ void merge_kernel(int metric, int nshards, uint32_t nq, uint32_t k, c
         }
         if (who >= 64) break;
         if (lane == who) {
-            out_ids[(size_t)q * k + n] = in_ids[((size_t)lane * nq + q) * k + head];
-            out_scores[(size_t)q * k + n] = in_scores[((size_t)lane * nq + q) * k + head];
+            out_ids[(size_t)q * k + n] = in_ids[(size_t)lane * ids_stride + (size_t)q * k + head];
+            out_scores[(size_t)q * k + n] = in_scores[(size_t)lane * sc_stride + (size_t)q * k + head];
             head++;
         }
     }
@@ -642,13 +643,14 @@ __global__ void merge_kernel(int metric, int nshards, uint32_t nq, uint32_t k, c
 
 int launch_merge(int metric, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids, const float* in_scores,
                  const uint32_t* in_counts, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
-                 cudaStream_t st) {
+                 cudaStream_t st, size_t ids_stride, size_t sc_stride, size_t cn_stride) {
     if (nq == 0 || top_k == 0) return RBQ_OK;
     if (nshards < 1 || nshards > 32) return fail(RBQ_INVALID_CONFIG, "merge supports 1..32 shards");
     const unsigned grid = (unsigned)((nq + 3) / 4);
     merge_kernel<<<grid, 128, 0, st>>>(metric, nshards, (uint32_t)nq, (uint32_t)top_k,
                                        reinterpret_cast<const unsigned long long*>(in_ids), in_scores, in_counts,
-                                       reinterpret_cast<unsigned long long*>(out_ids), out_scores, out_counts);
+                                       reinterpret_cast<unsigned long long*>(out_ids), out_scores, out_counts,
+                                       ids_stride ? ids_stride : nq * top_k, sc_stride ? sc_stride : nq * top_k, cn_stride ? cn_stride : nq);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

@@ -88,13 +88,17 @@ class ShardedSearcher:
             self.per, self.slices = query_slices(nq, self.world)
             self.probes = torch.zeros((self.per * self.world, nprobe, 4), dtype=torch.int32, device=dev)
             self.tau = torch.empty(nq, dtype=torch.float32, device=dev)
-            self.l_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-            self.l_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-            self.l_cn = torch.empty(nq, dtype=torch.int32, device=dev)
-            self.g_ids = torch.empty((self.world, nq, k), dtype=torch.int64, device=dev)
-            self.g_sc = torch.empty((self.world, nq, k), dtype=torch.float32, device=dev)
-            self.g_cn = torch.empty((self.world, nq), dtype=torch.int32, device=dev)
-            self.m_ids, self.m_sc, self.m_cn = torch.empty_like(self.l_ids), torch.empty_like(self.l_sc), torch.empty_like(self.l_cn)
+            # the shard's local top-k lives in one packed chunk (ids | scores | counts) so that ONE all-gather moves it
+            self.chunk = (nq * k * 12 + nq * 4 + 15) // 16 * 16
+            self.gathered = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=dev)
+            loc = self.gathered[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+            self.local = loc
+            self.l_ids = loc[:nq * k * 8].view(torch.int64).view(nq, k)
+            self.l_sc = loc[nq * k * 8:nq * k * 12].view(torch.float32).view(nq, k)
+            self.l_cn = loc[nq * k * 12:nq * k * 12 + nq * 4].view(torch.int32)
+            self.m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            self.m_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            self.m_cn = torch.empty(nq, dtype=torch.int32, device=dev)
             self._key = key
         return self
 
@@ -111,8 +115,6 @@ class ShardedSearcher:
         self.ix.dist_head(nq, k, nprobe, b.probes, b.tau, b.l_ids, b.l_sc, b.l_cn)
         dist.all_reduce(b.tau, op=dist.ReduceOp.MIN, group=self.group)
         self.ix.dist_tail(nq, k, nprobe, b.tau, b.l_ids, b.l_sc, b.l_cn)
-        dist.all_gather_into_tensor(b.g_ids.view(-1), b.l_ids.view(-1), group=self.group)
-        dist.all_gather_into_tensor(b.g_sc.view(-1), b.l_sc.view(-1), group=self.group)
-        dist.all_gather_into_tensor(b.g_cn.view(-1), b.l_cn.view(-1), group=self.group)
-        self.ix.merge_topk_device(self.world, nq, k, b.g_ids, b.g_sc, b.g_cn, b.m_ids, b.m_sc, b.m_cn)
+        dist.all_gather_into_tensor(b.gathered, b.local, group=self.group)  # in place: every rank owns one chunk
+        self.ix.merge_topk_packed_device(self.world, nq, k, b.gathered, b.chunk, b.m_ids, b.m_sc, b.m_cn)
         return b.m_ids, b.m_sc, b.m_cn

@@ -318,6 +318,11 @@ class IvfRabitqIndex:
                                                 C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
                                                 C.c_void_p(out_counts.data_ptr()), self._stream(g_ids, stream)))
 
+    def merge_topk_packed_device(self, nshards, nq, top_k, packed, chunk_bytes, out_ids, out_scores, out_counts, stream=None):
+        _check(_ffi.lib().rbq_merge_topk_packed_device(self._need(), int(nshards), int(nq), int(top_k), C.c_void_p(packed.data_ptr()),
+                                                       int(chunk_bytes), C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
+                                                       C.c_void_p(out_counts.data_ptr()), self._stream(packed, stream)))
+
     def stats(self):
         s = _ffi.SearchStats()
         _check(_ffi.lib().rbq_last_search_stats(self._need(), C.byref(s)))

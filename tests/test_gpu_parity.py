@@ -495,6 +495,18 @@ def test_phased_sharded_search_matches_single_shard(rbq, oracle, metric, bits):
     torch.cuda.synchronize()
     got = (m_ids.cpu().numpy().astype(np.uint64), m_sc.cpu().numpy(), m_cn.cpu().numpy().astype(np.uint32))
     assert np.array_equal(got[2], want[2])
+    # the one-collective form: every shard's ids | scores | counts in one packed chunk
+    chunk = (nq * k * 12 + nq * 4 + 15) // 16 * 16
+    packed = torch.zeros(world * chunk, dtype=torch.uint8, device="cuda")
+    for r in range(world):
+        c = packed[r * chunk:(r + 1) * chunk]
+        c[:nq * k * 8].view(torch.int64).copy_(l_ids[r].reshape(-1))
+        c[nq * k * 8:nq * k * 12].view(torch.float32).copy_(l_sc[r].reshape(-1))
+        c[nq * k * 12:nq * k * 12 + nq * 4].view(torch.int32).copy_(l_cn[r])
+    p_ids, p_sc, p_cn = torch.empty_like(m_ids), torch.empty_like(m_sc), torch.empty_like(m_cn)
+    shards[0].merge_topk_packed_device(world, nq, k, packed, chunk, p_ids, p_sc, p_cn)
+    torch.cuda.synchronize()
+    assert torch.equal(p_ids, m_ids) and torch.equal(p_sc, m_sc) and torch.equal(p_cn, m_cn)
     # Every shard's threshold sequence is min(tau, local k-th) >= the single sequence's threshold at the same point, so a shard
     # admits a superset of what the single search admits: the merged result can differ only by bound-violating candidates the
     # single sequence skipped (class D2) and is never worse.
