@@ -74,6 +74,11 @@ int rbq_index_ex_bits(const rbq_index* ix);
 int rbq_index_rotator_type(const rbq_index* ix);
 int rbq_index_device(const rbq_index* ix);
 
+/* ---- IvfRabitqIndex::fetch_embedding (src/ivf.rs:1247-1307): the vector reconstructed from its stored codes
+ * (centroid + delta*code + vl in rotated space, then the rotator's inverse).  out: dim floats (host).  *found = 0
+ * when no stored vector has this id (the reference returns None) -- on a list shard, when the id lives elsewhere. */
+int rbq_fetch_embedding(const rbq_index* ix, uint64_t vector_id, float* out, int* found);
+
 /* ---- search: IvfRabitqIndex::batch_search / search / search_filtered (src/ivf.rs:1705-1752) ----
  * queries: nq x dim row-major HOST memory.  Outputs (host): ids[nq*top_k], scores[nq*top_k] (L2:
  * estimated squared distance ascending; IP: score descending = -distance), counts[nq] = results per

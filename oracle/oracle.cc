@@ -214,6 +214,45 @@ static void rotate(const Rotator& r, const float* in, float* out) {
 
 // ---------------------------------------------------------------------------
 // simd.rs : FastScan LUT / pack / accumulate
+// src/rotation.rs:410-481 (FhtKac), 183-199 (Matrix: inverse = transpose)
+static void inverse_rotate(const Rotator& r, const float* rotated, float* out) {
+    size_t D = r.padded;
+    if (r.type == 0) {
+        for (size_t col = 0; col < r.dim; ++col) {
+            float acc = 0.0f;
+            for (size_t row = 0; row < D; ++row) {
+                float p = r.matrix[row * D + col] * rotated[row];
+                acc = acc + p;
+            }
+            out[col] = acc;
+        }
+        return;
+    }
+    std::vector<float> t(rotated, rotated + D);
+    size_t fo = D / 8;
+    if (r.trunc == D) {
+        for (int round = 3; round >= 0; --round) {
+            rescale(t.data(), D, 1.0f / r.fac);
+            fht(t.data(), D);
+            rescale(t.data(), D, 1.0f / (float)D);
+            flip_sign(t.data(), D, &r.flip[round * fo], fo);
+        }
+    } else {
+        size_t start = D - r.trunc;
+        rescale(t.data(), D, 4.0f);
+        for (int round = 3; round >= 0; --round) {
+            rescale(t.data(), D, 0.5f);
+            kacs_walk(t.data(), D);
+            float* win = (round % 2 == 0) ? t.data() : t.data() + start;
+            rescale(win, r.trunc, 1.0f / r.fac);
+            fht(win, r.trunc);
+            rescale(win, r.trunc, 1.0f / (float)r.trunc);
+            flip_sign(t.data(), D, &r.flip[round * fo], fo);
+        }
+    }
+    std::memcpy(out, t.data(), r.dim * 4);
+}
+
 // ---------------------------------------------------------------------------
 
 // src/simd.rs:818-840 pack_lut_f32 (lowbit DP)
@@ -1509,6 +1548,33 @@ int orc_index_load(void* h, const uint8_t* p, size_t n) {
     return rc;
 }
 void orc_index_rotate(void* h, const float* in, float* out) { rotate(((Index*)h)->rot, in, out); }
+void orc_index_inverse_rotate(void* h, const float* in, float* out) { inverse_rotate(((Index*)h)->rot, in, out); }
+// IvfRabitqIndex::fetch_embedding, src/ivf.rs:1247-1307: 1 = found (out[dim] filled), 0 = no such id
+int orc_fetch_embedding(void* hp, uint64_t id, float* out) {
+    Index* ix = (Index*)hp;
+    const size_t D = ix->D, db = D / 8, stride = batch_stride(D), exb = ex_bytes(D, ix->ex_bits);
+    for (auto& c : ix->clusters) {
+        size_t local = 0;
+        for (; local < c.ids.size(); ++local)
+            if (c.ids[local] == id) break;
+        if (local == c.ids.size()) continue;
+        std::vector<uint8_t> bits(D);
+        unpack_single_vector(c.batch_data.data() + (local / kBatch) * stride, (int)(local % kBatch), db, bits.data());
+        std::vector<uint16_t> ex(D, 0);
+        if (ix->ex_bits > 0) unpack_ex(c.ex_codes.data() + local * exb, D, ix->ex_bits, ex.data());
+        std::vector<float> rec(D);
+        const float delta = c.delta[local], vl = c.vl[local];
+        for (size_t i = 0; i < D; ++i) {
+            uint16_t code = (uint16_t)(ex[i] + ((uint16_t)bits[i] << ix->ex_bits));
+            float m = delta * (float)code;
+            float a = c.centroid[i] + m;
+            rec[i] = a + vl;
+        }
+        inverse_rotate(ix->rot, rec.data(), out);
+        return 1;
+    }
+    return 0;
+}
 
 // Batched search (OpenMP over queries == batch_search's rayon par_iter, src/ivf.rs:1743-1752).
 // ids/scores: nq*top_k, counts: nq.  score = distance (L2) or -distance (IP).

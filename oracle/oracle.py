@@ -342,6 +342,18 @@ class Index:
         lib().orc_index_rotate(self.h, _p(x), _p(out))
         return out
 
+    def inverse_rotate(self, x):
+        x = _f32(x)
+        out = np.empty(self.dim, np.float32)
+        lib().orc_index_inverse_rotate(self.h, _p(x), _p(out))
+        return out
+
+    def fetch_embedding(self, vector_id):
+        """IvfRabitqIndex::fetch_embedding (src/ivf.rs:1247-1307): the reconstructed vector or None."""
+        out = np.empty(self.dim, np.float32)
+        lib().orc_fetch_embedding.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        return out if lib().orc_fetch_embedding(self.h, int(vector_id), _p(out)) else None
+
     def search_batch(self, queries, top_k, nprobe, filter_bits=None, naive=False, want_diag=False):
         """Returns (ids[nq,k] u64, scores[nq,k] f32, counts[nq] u32[, diag[nq,4]])."""
         q = _f32(queries)

@@ -51,6 +51,7 @@ def lib():
     L.rbq_search_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
     L.rbq_merge_topk_device.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, vp, vp, vp]
     L.rbq_merge_topk_packed_device.argtypes = [vp, i32, sz, sz, vp, sz, vp, vp, vp, vp]
+    L.rbq_fetch_embedding.argtypes = [vp, u64, vp, C.POINTER(i32)]
     L.rbq_dist_front.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, vp, vp]
     L.rbq_dist_head.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp, vp]
     L.rbq_dist_tail.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp]

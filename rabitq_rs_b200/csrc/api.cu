@@ -747,6 +747,31 @@ int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, co
     return RBQ_OK;
 }
 
+int rbq_fetch_embedding(const rbq_index* h, uint64_t vector_id, float* out, int* found) {
+    if (!h || !out || !found) return fail(RBQ_INVALID_CONFIG, "null argument");
+    *found = 0;
+    const HostIndex& hi = h->host;
+    const size_t nvec = hi.vec_off.empty() ? 0 : (size_t)hi.vec_off.back();
+    if (nvec == 0) return RBQ_OK;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = ensure_ws(h, 4096 + (size_t)h->dev.dim * 4);
+    if (rc) return rc;
+    unsigned long long* d_pos = reinterpret_cast<unsigned long long*>(h->ws);
+    float* d_out = reinterpret_cast<float*>((char*)h->ws + 256);
+    if ((rc = launch_find_id(h->dev, nvec, vector_id, d_pos, nullptr))) return rc;
+    unsigned long long pos = ~0ull;
+    RBQ_CUDA(cudaMemcpy(&pos, d_pos, 8, cudaMemcpyDeviceToHost));
+    if (pos >= nvec) return RBQ_OK;  // None
+    // the list that holds the position, and the reconstruction scalars (kept on the host: search never reads them)
+    const size_t c = (size_t)(std::upper_bound(hi.vec_off.begin(), hi.vec_off.end(), (uint64_t)pos) - hi.vec_off.begin()) - 1;
+    if (hi.delta.size() != nvec || hi.vl.size() != nvec) return fail(RBQ_INVALID_CONFIG, "reconstruction factors are not resident");
+    if ((rc = launch_fetch_embedding(h->dev, (uint32_t)c, (uint32_t)(pos - hi.vec_off[c]), hi.delta[pos], hi.vl[pos], d_out, nullptr))) return rc;
+    RBQ_CUDA(cudaMemcpy(out, d_out, (size_t)h->dev.dim * 4, cudaMemcpyDeviceToHost));
+    *found = 1;
+    return RBQ_OK;
+}
+
 int rbq_merge_topk_device(const rbq_index* h, int nshards, size_t nq, size_t top_k, const uint64_t* in_ids,
                           const float* in_scores, const uint32_t* in_counts, uint64_t* out_ids, float* out_scores,
                           uint32_t* out_counts, void* stream) {

@@ -190,6 +190,9 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
 int launch_probe_export(const Probe* d_probes, size_t q_begin, size_t q_count, size_t nprobe, rbq_probe_rec* d_out, cudaStream_t st);
 int launch_probe_import(const DevIndex& ix, const rbq_probe_rec* d_in, size_t nq, size_t nprobe, Probe* d_probes, uint8_t* d_head_owner,
                         cudaStream_t st);
+// fetch.cu: fetch_embedding (position of an id; reconstruction of one stored vector)
+int launch_find_id(const DevIndex& ix, size_t nvec, uint64_t id, unsigned long long* d_pos, cudaStream_t st);
+int launch_fetch_embedding(const DevIndex& ix, uint32_t cid, uint32_t local, float delta, float vl, float* d_out, cudaStream_t st);
 // resolve.cu: builds DevIndex::exl from the packed ex-codes already on the device (no-op for 1-bit indexes)
 int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,

@@ -323,6 +323,13 @@ class IvfRabitqIndex:
                                                        int(chunk_bytes), C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
                                                        C.c_void_p(out_counts.data_ptr()), self._stream(packed, stream)))
 
+    def fetch_embedding(self, vector_id):
+        """IvfRabitqIndex::fetch_embedding (src/ivf.rs:1247-1307): the reconstructed vector, or None if the id is unknown."""
+        out = np.empty(int(_ffi.lib().rbq_index_dim(self._need())), np.float32)
+        found = C.c_int(0)
+        _check(_ffi.lib().rbq_fetch_embedding(self._need(), int(vector_id), _ptr(out), C.byref(found)))
+        return out if found.value else None
+
     def stats(self):
         s = _ffi.SearchStats()
         _check(_ffi.lib().rbq_last_search_stats(self._need(), C.byref(s)))

@@ -7,7 +7,8 @@ fn main() {
     let csrc = root.join("rabitq_rs_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["format.cc", "query_prep.cu", "coarse.cu", "coarse_tc.cu", "scan.cu", "build.cu", "api.cu"];
+    let sources = ["format.cc", "query_prep.cu", "coarse.cu", "coarse_tc.cu", "scan.cu", "scan_tail.cu", "tail_tc.cu", "resolve.cu",
+                   "fetch.cu", "build.cu", "api.cu"];  // keep in sync with rabitq_rs_b200/build.py::SOURCES
     let mut objs = Vec::new();
     for s in sources {
         let obj = out.join(format!("{s}.o"));

@@ -21,6 +21,17 @@ extern "C" {
     pub fn rbq_search_batch_device(ix: *const rbq_index, d_queries: *const f32, nq: usize, dim: usize, top_k: usize, nprobe: usize,
                                    d_filter: *const u64, filter_nbits: usize, d_ids: *mut u64, d_scores: *mut f32, d_counts: *mut u32,
                                    stream: *mut c_void) -> c_int;
+    pub fn rbq_fetch_embedding(ix: *const rbq_index, vector_id: u64, out: *mut f32, found: *mut c_int) -> c_int;
+    // multi-GPU, three phases (include/rbq.h): the caller runs the NCCL exchanges in between
+    pub fn rbq_dist_front(ix: *const rbq_index, d_queries: *const f32, nq: usize, dim: usize, top_k: usize, nprobe: usize,
+                          q_begin: usize, q_count: usize, d_probes: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rbq_dist_head(ix: *const rbq_index, nq: usize, top_k: usize, nprobe: usize, d_probes: *const c_void, d_tau: *mut f32,
+                         d_ids: *mut u64, d_scores: *mut f32, d_counts: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn rbq_dist_tail(ix: *const rbq_index, nq: usize, top_k: usize, nprobe: usize, d_tau: *const f32, d_ids: *mut u64,
+                         d_scores: *mut f32, d_counts: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn rbq_merge_topk_packed_device(ix: *const rbq_index, nshards: c_int, nq: usize, top_k: usize, packed: *const c_void,
+                                        chunk_bytes: usize, out_ids: *mut u64, out_scores: *mut f32, out_counts: *mut u32,
+                                        stream: *mut c_void) -> c_int;
 }
 
 /// Mirrors `rabitq_rs::RabitqError` (reference src/lib.rs:39-57); codes are `rbq_status`.
@@ -55,6 +66,14 @@ impl IvfRabitqIndex {
     pub fn len(&self) -> usize { unsafe { rbq_index_len(self.h) } }
     pub fn is_empty(&self) -> bool { self.len() == 0 }
     pub fn cluster_count(&self) -> usize { unsafe { rbq_index_cluster_count(self.h) } }
+
+    /// `IvfRabitqIndex::fetch_embedding` (reference src/ivf.rs:1247-1307).
+    pub fn fetch_embedding(&self, vector_id: usize) -> Option<Vec<f32>> {
+        let dim = unsafe { rbq_index_dim(self.h) };
+        let (mut out, mut found) = (vec![0.0f32; dim], 0 as c_int);
+        let rc = unsafe { rbq_fetch_embedding(self.h, vector_id as u64, out.as_mut_ptr(), &mut found) };
+        if rc == 0 && found != 0 { Some(out) } else { None }
+    }
 
     pub fn batch_search(&self, queries: &[&[f32]], params: SearchParams) -> Vec<Result<Vec<SearchResult>, RabitqError>> {
         let dim = unsafe { rbq_index_dim(self.h) };

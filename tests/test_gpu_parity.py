@@ -526,3 +526,23 @@ def _canon(ids, sc):
     from helpers import _canon as c
 
     return c(ids, sc)
+
+
+@pytest.mark.parametrize("geom", [(500, 64, 4, 7, 0, 0), (500, 128, 8, 7, 0, 1), (400, 96, 4, 3, 1, 1), (300, 960, 4, 7, 0, 1),
+                                  (300, 40, 4, 1, 0, 1), (300, 768, 4, 5, 1, 1)])
+def test_fetch_embedding_bit_exact(rbq, oracle, geom):
+    """rbq_fetch_embedding == the oracle's fetch_embedding bit for bit (every rotator / ex-code layout), None for an
+    unknown id, and only the owning shard finds an id."""
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    for i in list(range(0, n, 7)) + [n - 1]:
+        want = oix.fetch_embedding(i)
+        got = gix.fetch_embedding(i)
+        assert got is not None and np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"id {i}"
+    assert gix.fetch_embedding(n + 10) is None and oix.fetch_embedding(n + 10) is None
+    shards = [_load(rbq, blob, shard_rank=r, shard_count=2) for r in range(2)]
+    for i in (0, n // 2, n - 1):
+        found = [s.fetch_embedding(i) for s in shards]
+        assert sum(f is not None for f in found) == 1
+        assert np.array_equal(next(f for f in found if f is not None), oix.fetch_embedding(i))

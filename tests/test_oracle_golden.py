@@ -529,3 +529,20 @@ def test_matrix_rotator_index(oracle):
     assert np.all(ids[:, 0] == np.arange(8)) or (ids[:, :5] == np.arange(8)[:, None]).any(1).all()
     back = oracle.Index.load_bytes(ix.save_bytes())
     assert all(np.array_equal(x, y) for x, y in zip(ix.search_batch(data[:4], 5, 8), back.search_batch(data[:4], 5, 8)))
+
+
+# ---- fetch_embedding (src/tests.rs:1619-1737) -------------------------------------------------------------
+@pytest.mark.parametrize("dim,nlist,rot,n,seed", [(64, 4, 0, 100, 12345), (128, 8, 1, 50, 54321), (96, 4, 1, 60, 7)])
+def test_fetch_embedding_reconstruction(oracle, dim, nlist, rot, n, seed):
+    """The reference's own bar: relative reconstruction error < 2.0 for every stored vector, None for an unknown id
+    (MatrixRotator dim 64 / FhtKacRotator dim 128 as in src/tests.rs, plus a non-power-of-two FHT geometry); the
+    rotators' inverse really inverts."""
+    data = rust_like_uniform(n, dim, seed)
+    ix = oracle.Index.train(data, nlist, 7, 0, rot, seed, False, iters=6)
+    for i in range(n):
+        rec = ix.fetch_embedding(i)
+        assert rec is not None and rec.shape == (dim,)
+        assert np.linalg.norm(rec - data[i]) / max(np.linalg.norm(data[i]), 1e-12) < 2.0
+    assert ix.fetch_embedding(n + 10) is None
+    x = data[3]
+    assert np.abs(ix.inverse_rotate(ix.rotate(x)) - x).max() < 1e-5
