@@ -30,9 +30,12 @@ for i, h in enumerate(hdr):
         except ValueError:
             pass
 rows = list(csv.reader(open(src)))
-hdr = rows[1]
+# the page may hold several sections (one per source view): take the first SASS table
+heads = [i for i, r in enumerate(rows) if 'Source' in r and '# Samples' in r]
+hdr = rows[heads[0]]
 ci = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+end = heads[1] - 1 if len(heads) > 1 else len(rows)
+data = [r for r in rows[heads[0] + 1:end] if len(r) == len(hdr)]
 tot_s = sum(int(r[ci['# Samples']]) for r in data)
 tot_i = sum(int(r[ci['Instructions Executed']]) for r in data)
 print(f"SASS lines {len(data)}, warp-instructions {tot_i}, samples {tot_s}")
