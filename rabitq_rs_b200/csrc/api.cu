@@ -279,20 +279,26 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[(c0 / chunk) % HostFeed::kEvents], 0));
             }
             const float* dq = feed ? feed->d_q + c0 * ix.dim : d_queries + (q0 + c0) * ix.dim;
-            if ((rc = launch_query_prep(ix, dq, m, d_rot + c0 * D, d_lut + c0 * D * 4, d_qs + c0, st))) return rc;
+            bool split_done = false;
+            const bool tc = h->coarse_mode != 0;
+            if ((rc = launch_query_prep(ix, dq, m, d_rot + c0 * D, d_lut + c0 * D * 4, d_qs + c0, st, tc ? d_qsplit + c0 * 3 * D : nullptr,
+                                        tc ? d_qn2 + c0 : nullptr, &split_done)))
+                return rc;
             if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[1], st);
             if (h->coarse_mode == 0) {
                 if ((rc = launch_coarse_exact(ix, d_rot + c0 * D, m, d_sc + c0 * ix.nlist, st))) return rc;
                 if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
                 if ((rc = launch_probe_select(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, m, nprobe, d_pr + c0 * nprobe, st))) return rc;
             } else {
-                if ((rc = launch_split_bf16(d_rot + c0 * D, m, (int)D, 0, d_qsplit + c0 * 3 * D, d_qn2 + c0, st))) return rc;
+                if (!split_done) {
+                    if ((rc = launch_split_bf16(d_rot + c0 * D, m, (int)D, 0, d_qsplit + c0 * 3 * D, d_qn2 + c0, st))) return rc;
+                    *launches += 1;
+                }
                 if ((rc = launch_coarse_tc(ix, d_qsplit + c0 * 3 * D, d_qn2 + c0, m, d_sc + c0 * ix.nlist, st))) return rc;
                 if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
                 if ((rc = launch_probe_select_tc(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, d_qs + c0, m, nprobe, h->coarse_eps,
                                                  d_pr + c0 * nprobe, h->fallback_counter(), st, false)))
                     return rc;
-                *launches += 1;
             }
             *launches += 3;
             if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[3], st);

@@ -11,6 +11,8 @@
 #include <cfloat>
 
 #include "rbq_internal.h"
+#include <cuda_bf16.h>
+
 #include "rotate.cuh"
 
 namespace rbq {
@@ -132,7 +134,8 @@ constexpr int kPrepWarps = 4;
 template <int E>
 __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevIndex ix, const float* __restrict__ queries, uint32_t nq,
                                                                          float* __restrict__ rot_out, uint8_t* __restrict__ lut_out,
-                                                                         QueryScalars* __restrict__ qs_out) {
+                                                                         QueryScalars* __restrict__ qs_out,
+                                                                         __nv_bfloat16* __restrict__ split_out, float* __restrict__ n2_out) {
     extern __shared__ __align__(16) float smem[];
     const int D = ix.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * kPrepWarps + warp;
@@ -201,6 +204,14 @@ __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevInde
         }
         sq[i] = x * x;
         rot_out[(size_t)q * D + i] = x;
+        if (split_out != nullptr) {  // operand of the tensor-core coarse stage (coarse_tc.cu): [hi | hi | lo] bf16 split
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+            __nv_bfloat16* o = split_out + (size_t)q * 3 * D;
+            o[i] = hi;
+            o[D + i] = hi;
+            o[2 * D + i] = lo;
+        }
     }
     __syncwarp();
 
@@ -287,32 +298,37 @@ __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevInde
         s.bscale = bscale;
         s.pad = 0.0f;
         qs_out[q] = s;
+        if (n2_out != nullptr) n2_out[q] = s_sumsq;  // |q|^2 for the approximate scores (any summation order will do)
     }
 }
 
 template <int E>
 static int launch_prep_fht(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut, QueryScalars* d_qs,
-                           cudaStream_t st) {
+                           cudaStream_t st, void* d_split, float* d_n2) {
     const size_t smem = (size_t)kPrepWarps * 2 * ix.D * sizeof(float);
     if (smem > 48 * 1024)
         RBQ_CUDA(cudaFuncSetAttribute(query_prep_fht_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     query_prep_fht_kernel<E><<<(unsigned)((nq + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, smem, st>>>(ix, d_queries, (uint32_t)nq,
-                                                                                                            d_rot, d_lut, d_qs);
+                                                                                                            d_rot, d_lut, d_qs,
+                                                                                                            reinterpret_cast<__nv_bfloat16*>(d_split), d_n2);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
 
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
-                      QueryScalars* d_qs, cudaStream_t st) {
+                      QueryScalars* d_qs, cudaStream_t st, void* d_split, float* d_n2, bool* split_done) {
+    if (split_done) *split_done = false;
     if (nq == 0) return RBQ_OK;
     if (ix.rot_type == RBQ_ROTATOR_FHT_KAC && ix.trunc >= 64 && ix.trunc <= 2048) {
+        if (split_done) *split_done = d_split != nullptr && d_n2 != nullptr;
+        if (d_split == nullptr || d_n2 == nullptr) d_split = nullptr, d_n2 = nullptr;
         switch (ix.trunc / 32) {
-            case 2: return launch_prep_fht<2>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
-            case 4: return launch_prep_fht<4>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
-            case 8: return launch_prep_fht<8>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
-            case 16: return launch_prep_fht<16>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
-            case 32: return launch_prep_fht<32>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
-            default: return launch_prep_fht<64>(ix, d_queries, nq, d_rot, d_lut, d_qs, st);
+            case 2: return launch_prep_fht<2>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+            case 4: return launch_prep_fht<4>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+            case 8: return launch_prep_fht<8>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+            case 16: return launch_prep_fht<16>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+            case 32: return launch_prep_fht<32>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+            default: return launch_prep_fht<64>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
         }
     }
     size_t smem = (size_t)ix.D * 5 * sizeof(float);

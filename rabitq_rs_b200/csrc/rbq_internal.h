@@ -165,7 +165,8 @@ int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st);
 
 // kernels (each .cu exposes a launcher)
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
-                      QueryScalars* d_qs, cudaStream_t st);
+                      QueryScalars* d_qs, cudaStream_t st,
+                      void* d_split = nullptr, float* d_n2 = nullptr, bool* split_done = nullptr);  // optional: also writes the coarse GEMM's bf16 operand
 int launch_coarse_exact(const DevIndex& ix, const float* d_rot, size_t nq, float* d_scores, cudaStream_t st);
 int launch_probe_select(const DevIndex& ix, const float* d_rot, const float* d_scores, size_t nq, size_t nprobe,
                         Probe* d_probes, cudaStream_t st);
