@@ -52,6 +52,7 @@ struct ResolveArgs {
     unsigned long long* surv_id;
     uint32_t exl_row;   // shared-memory stride of a lane's staged code row (exl_row_stride)
     uint32_t rql_row;   // shared-memory stride of a lane's query row (rql_row_stride)
+    uint32_t stage_bufs;  // 2: the rows of round r+1 travel while round r is multiplied; 1: one round at a time, less shared memory
     uint32_t has_ex;
     uint32_t flush_at;  // head resolve: refine as soon as this many candidates are queued
     uint32_t lazy_flush_at;  // lazy replay: queue length that triggers a refine round
@@ -69,7 +70,7 @@ __device__ __forceinline__ uint32_t first_owned_rank(const Probe* __restrict__ p
 
 // ---- head scan ---------------------------------------------------------------------------------------------
 template <int NCB, bool WIDE>
-__global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs a) {
+__global__ void __launch_bounds__(128, 3) head_scan_kernel(DevIndex ix, ResolveArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = a.q_begin + blockIdx.x * 4u + (threadIdx.x >> 5);
     if (q >= a.q_begin + a.q_count) return;
@@ -128,11 +129,12 @@ __global__ void __launch_bounds__(128) head_scan_kernel(DevIndex ix, ResolveArgs
 struct ResSmem {
     uint32_t stage, rq, si, sd, ord, total;
 };
-__host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool topk, uint32_t surv_cap) {
+__host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool topk, uint32_t surv_cap,
+                                                   uint32_t stage_bufs = 2) {
     ResSmem w;
     uint32_t o = 0;
     w.stage = o;
-    o += refine ? 2u * 32u * exl_row : 0;  // two rounds of 4 candidates x 8 lane rows
+    o += refine ? stage_bufs * 32u * exl_row : 0;  // stage_bufs rounds of 4 candidates x 8 lane rows
     w.rq = o;
     o += refine ? 8u * rql_row : 0;
     w.si = o;
@@ -177,12 +179,13 @@ __device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveA
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const bool dbl = a.stage_bufs > 1u;
     issue(0, 0u);
     float exdot = 0.0f;
     uint32_t buf = 0;
-    for (int r0 = 0; r0 < nb; r0 += kRefineSlots, buf ^= 1u) {
+    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
         const int c = r0 + g;  // candidate served by this 8-lane group
-        if (r0 + kRefineSlots < nb) {
+        if (dbl && r0 + kRefineSlots < nb) {
             issue(r0 + kRefineSlots, buf ^ 1u);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
@@ -193,6 +196,8 @@ __device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveA
         part = hsum8(part);
         const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
         if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
+        if (dbl) buf ^= 1u;
+        else if (r0 + kRefineSlots < nb) issue(r0 + kRefineSlots, 0u);  // the lane's own row is free again (only it reads it)
     }
     return exdot;
 }
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, EXK != 0, true, 0);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, EXK != 0, true, 0, a.stage_bufs);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, Res
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0, a.stage_bufs);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap, a.stage_bufs);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -840,6 +845,11 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.surv_id = tw.surv_id;
     a.exl_row = exl_row_stride((uint32_t)ix.D);
     a.rql_row = rql_row_stride((uint32_t)ix.D);
+    static const uint32_t stage_bufs = [] {
+        const char* e = getenv("RBQ_STAGE_BUFS");
+        return (uint32_t)(e && atoi(e) == 2 ? 2 : 1);
+    }();
+    a.stage_bufs = stage_bufs;
     a.has_ex = ix.ex_bits != 0;
     static const uint32_t flush_at = [] {
         const char* e = getenv("RBQ_FLUSH_AT");
@@ -912,7 +922,7 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
         }
     }
     if (rc) return rc;
-    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0);
+    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0, a.stage_bufs);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
     const unsigned grid = res_grid(q_count, smem);
@@ -935,7 +945,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     }();
     if (ix.ex_bits != 0 && !bulk) {
         // lazy: sorted survivors, refinement on demand against the live threshold (one kernel)
-        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap);
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap, a.stage_bufs);
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem <= g_res_smem_optin) {
             const unsigned grid = res_grid(nq, smem);
@@ -955,7 +965,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
         }
     }
     if (ix.ex_bits != 0) {
-        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0);
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0, a.stage_bufs);
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "refine kernel shared memory exceeds the device limit");
         const unsigned grid = res_grid(nq, smem);
