@@ -223,7 +223,7 @@ __global__ void relayout_ex_kernel(const uint8_t* __restrict__ ex, uint32_t ex_s
 
 // ---- head resolve ---------------------------------------------------------------------------------------------
 template <int EXK>
-__global__ void __launch_bounds__(kResWarps * 32) resolve_head_kernel(DevIndex ix, ResolveArgs a) {
+__global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevIndex ix, ResolveArgs a) {
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
