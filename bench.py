@@ -201,6 +201,14 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version banner, ...) is sent to
+    # stderr by pointing fd 1 at fd 2 for the duration of the run; the result goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     import torch
     import torch.distributed as dist
@@ -279,7 +287,7 @@ def main():
                "cpu_baseline": {"value": v, "unit": "queries/s", "cores": info[0], "kind": "port",
                                 "sample": f"{info[1]} of the {nq} queries per step; CPU oracle (C++ restatement of rabitq-rs search; the Rust crate cannot be built: no cargo)"},
                "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(out)
         return
 
     # ---- our arm -------------------------------------------------------------------------------
@@ -493,7 +501,7 @@ def main():
                                "sample": f"first {sample} of the {nq} queries, same index bytes, nprobe={nprobe}; ids identical to the GPU result: {same:.4f}"}
     else:
         out["cpu_baseline"] = None
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
