@@ -332,7 +332,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                                   h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
                 return rc;
             if (h->profiling) cudaEventRecord(h->ev[5], st);
-            // bulk refine of the survivors, ordered replay, then the (normally empty) sequential fallback
+            // ordered replay of the survivors with refinement on demand, then the (normally empty) sequential fallback
             if ((rc = launch_refine_replay(ix, d_rot, d_qs, d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
                                            d_counts + q0, h->d_stats, tw, st, launches)))
                 return rc;

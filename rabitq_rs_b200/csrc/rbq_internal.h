@@ -134,7 +134,6 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     // head stage (resolve.cu): dense (lower bound, ip | estimate) of every vector of a query's first owned list
     float2* head_buf;      // [nq * head_cap]
     uint32_t head_cap;     // slots per query (multiple of 32); longer lists send the query to the fallback path
-    unsigned long long* surv_id;  // [nq * surv_cap] external ids of the survivors (written by the refine kernel)
     uint32_t* fb_list;     // [nq] queries left to the sequential fallback (counters[2] = how many)
 };
 constexpr uint32_t kFbResume = 0x80000000u;
@@ -184,7 +183,6 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
 // resolve.cu: the list-major pipeline around the tail kernel.
 //   head scan    FastScan of every query's first owned list -> tw.head_buf (dense)
 //   head resolve the reference's sequential prune/refine/top-k over that list -> heap state, tw.tau, tw.tail_start
-//   refine       ex-code distances of all tail survivors, in bulk
 //   replay       survivors in reference order against the live threshold (distances precomputed)
 // resolve.cu: phased multi-GPU search helpers.  export: Probe rows [q_begin, q_begin+q_count) -> records; import: records of all
 // queries -> Probe with this shard's list geometry, head_owner[q] = this shard owns the query's nearest probed list

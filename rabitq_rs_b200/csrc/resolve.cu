@@ -6,12 +6,10 @@
 //   head resolve  K9-K11 over that buffer: the reference's sequential prune / refine / keep-k-smallest loop
 //                 (search_cluster_v2_batched, reference src/ivf.rs:2013-2127) with on-demand ex-code refinement.
 //                 Leaves the heap state in the output arrays, tau (the k-th distance) and tail_start.
-//   refine        K10 (ip_packed_ex2_f32 / ip_packed_ex6_f32, AVX2 lane order, src/simd.rs:1722-1825) for ALL tail
-//                 survivors in bulk: no dependency between candidates, so latency is hidden by occupancy.  Refining
-//                 a survivor the live threshold later rejects costs bandwidth, never correctness: the replay only
-//                 looks at the distances of candidates the reference would have refined.
-//   replay        survivors sorted into the reference's visit order (probe rank, position), then the reference's
-//                 decisions against the live threshold with the precomputed distances.
+//   lazy replay   survivors sorted into the reference's visit order (probe rank, position), then the head-resolve loop over
+//                 them: K10 (ip_packed_ex2_f32 / ip_packed_ex6_f32, AVX2 lane order, src/simd.rs:1722-1825) only for the
+//                 candidates that beat the live threshold, the reference's decisions in order.
+//   replay        the same for 1-bit indexes (distance == estimate: nothing to refine).
 //
 // The kernels are lean on purpose (no LUT registers, no block ring): 2-3x the resident warps of the sequential
 // scan kernel, which is what the latency-bound refine rounds need.  Queries the fast path cannot take (head list
@@ -49,7 +47,6 @@ struct ResolveArgs {
     Survivor* surv;
     const uint32_t* surv_cnt;
     uint32_t surv_cap;
-    unsigned long long* surv_id;
     uint32_t exl_row;   // shared-memory stride of a lane's staged code row (exl_row_stride)
     uint32_t rql_row;   // shared-memory stride of a lane's query row (rql_row_stride)
     uint32_t stage_bufs;  // 2: the rows of round r+1 travel while round r is multiplied; 1: one round at a time, less shared memory
@@ -408,65 +405,6 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
     }
 }
 
-// ---- bulk refine of the tail survivors ------------------------------------------------------------------------
-template <int EXK>
-__global__ void __launch_bounds__(kResWarps * 32) refine_kernel(DevIndex ix, ResolveArgs a) {
-    extern __shared__ __align__(16) unsigned char res_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int D = ix.D;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0, a.stage_bufs);
-    unsigned char* wbase = res_smem + (size_t)warp * L.total;
-    const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
-    unsigned char* rql = wbase + L.rq;
-    unsigned long long st_ref = 0;
-    for (;;) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(&a.counters[4], 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= a.nq) break;
-        const uint32_t n = a.surv_cnt[q];
-        if (n == 0 || n > a.surv_cap || a.tail_start[q] >= a.nprobe) continue;  // nothing to do / fallback query
-        const Probe* pr = a.probes + (size_t)q * a.nprobe;
-        __syncwarp();
-        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
-        const QueryScalars s = a.qs[q];
-        __syncwarp();
-        Survivor* sv = a.surv + (size_t)q * a.surv_cap;
-        unsigned long long* sid = a.surv_id + (size_t)q * a.surv_cap;
-        for (uint32_t b0 = 0; b0 < n; b0 += 32) {  // a batch: survivor b0 + i lives in lane i
-            const uint32_t i = b0 + (uint32_t)lane;
-            const int nb = (int)min(32u, n - b0);
-            Survivor rec = {0u, 0u, 0.0f, 0.0f};
-            unsigned long long gv = 0, vid = 0;
-            float g_add = 0.0f, fae = 0.0f, fre = 0.0f;
-            if (lane < nb) {
-                rec = sv[i];
-                const Probe* pp = pr + rec.rank;
-                gv = pp->vec_off + rec.pos;
-                g_add = pp->g_add;
-                const uint8_t* ep = ix.exl + gv * ix.exl_stride;  // start the candidate's ex-code rows towards L2
-                for (uint32_t o = 0; o < ix.exl_stride; o += 128) prefetch_l2(ep + o);
-                fae = __ldg(ix.f_add_ex + gv);
-                fre = __ldg(ix.f_rescale_ex + gv);
-                vid = ix.ids[gv];
-            }
-            const float exdot = refine_batch(ix, a, gv, nb, stage_u32, rql_u32, lane);
-            if (lane < nb) {
-                // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
-                float tt = s.bscale * rec.x;
-                tt = tt + exdot;
-                tt = tt + s.kbx;
-                const float mm2 = fre * tt;
-                const float aa = fae + g_add;
-                sv[i].x = aa + mm2;
-                sid[i] = vid;
-            }
-        }
-        st_ref += n;
-    }
-    if (lane == 0 && a.stats && st_ref) atomicAdd(&a.stats->refined, st_ref);
-}
-
 // ---- replay ------------------------------------------------------------------------------------------------------
 template <int EXK>
 __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex ix, ResolveArgs a) {
@@ -529,8 +467,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
             if (have) {
                 const uint32_t slot = (uint32_t)ord[i] & 1023u;
                 rec = sv[slot];
-                if (EXK != 0) vid = a.surv_id[(size_t)q * a.surv_cap + slot];
-                else vid = ix.ids[pr[rec.rank].vec_off + rec.pos];
+                vid = ix.ids[pr[rec.rank].vec_off + rec.pos];
             }
             const float theta0 = fminf(cnt >= k ? sd[k - 1] : INFINITY, tau_q);
             unsigned m = __ballot_sync(0xffffffffu, have && (rec.lower < theta0));
@@ -562,7 +499,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
 }
 
 // ---- lazy replay: on-demand refinement of the sorted survivors ---------------------------------------------------
-// The bulk refine above evaluates K10 for EVERY survivor (lower bound < the head threshold tau), but the reference only
+// Every survivor has lower bound < the head threshold tau, but the reference only
 // refines a candidate whose lower bound beats the LIVE k-th distance, which keeps falling while the tail is walked
 // (reference src/ivf.rs:2044-2052): at GIST/nprobe 16 that is ~15 of ~75 survivors per query.  This kernel sorts the
 // survivors into the reference's visit order first and then runs the head-resolve loop over them: candidates that beat
@@ -842,7 +779,6 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.surv = tw.surv;
     a.surv_cnt = tw.surv_cnt;
     a.surv_cap = tw.surv_cap;
-    a.surv_id = tw.surv_id;
     a.exl_row = exl_row_stride((uint32_t)ix.D);
     a.rql_row = rql_row_stride((uint32_t)ix.D);
     static const uint32_t stage_bufs = [] {
@@ -939,48 +875,25 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     if (rc) return rc;
     ResolveArgs a;
     fill_args(a, ix, d_rot, nullptr, d_qs, d_probes, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, d_stats, tw);
-    static const bool bulk = [] {
-        const char* e = getenv("RBQ_BULK_REFINE");
-        return e != nullptr && atoi(e) != 0;
-    }();
-    if (ix.ex_bits != 0 && !bulk) {
-        // lazy: sorted survivors, refinement on demand against the live threshold (one kernel)
+    if (ix.ex_bits != 0) {
+        // sorted survivors, refinement on demand against the live threshold (one kernel)
         const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap, a.stage_bufs);
         const size_t smem = (size_t)w.total * kResWarps;
-        if (smem <= g_res_smem_optin) {
-            const unsigned grid = res_grid(nq, smem);
-            if (ix.ex_bits == 2) {
-                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                resolve_lazy_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
-            } else if (ix.ex_bits == 6) {
-                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                resolve_lazy_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
-            } else {
-                RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                resolve_lazy_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
-            }
-            RBQ_CUDA(cudaGetLastError());
-            if (launches) *launches += 1;
-            return RBQ_OK;
-        }
-    }
-    if (ix.ex_bits != 0) {
-        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 0, true, false, 0, a.stage_bufs);
-        const size_t smem = (size_t)w.total * kResWarps;
-        if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "refine kernel shared memory exceeds the device limit");
+        if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
         const unsigned grid = res_grid(nq, smem);
         if (ix.ex_bits == 2) {
-            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            refine_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            resolve_lazy_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
         } else if (ix.ex_bits == 6) {
-            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            refine_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            resolve_lazy_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
         } else {
-            RBQ_CUDA(cudaFuncSetAttribute(refine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            refine_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
+            RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            resolve_lazy_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
         }
         RBQ_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
+        return RBQ_OK;
     }
     const ResSmem w = res_smem_layout(0, 0, a.top_k, false, true, a.surv_cap);
     const size_t smem = (size_t)w.total * kResWarps;

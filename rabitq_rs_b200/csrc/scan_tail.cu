@@ -312,7 +312,6 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     n += nq * nprobe * 4 + 256;                      // pairs
     n += max_items * sizeof(TailItem) + 256;
     n += nq * cap * sizeof(Survivor) + 256;
-    n += nq * cap * 8 + 256;                             // surv_id
     n += nq * (size_t)tail_head_cap(ix, nq) * 8 + 256;  // head_buf
     n += nq * 4 + 256;                                   // fb_list
     return n;
@@ -340,7 +339,6 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.pairs = reinterpret_cast<uint32_t*>(take(nq * nprobe * 4));
     tw.items = reinterpret_cast<TailItem*>(take((size_t)tw.max_items * sizeof(TailItem)));
     tw.surv = reinterpret_cast<Survivor*>(take(nq * (size_t)tw.surv_cap * sizeof(Survivor)));
-    tw.surv_id = reinterpret_cast<unsigned long long*>(take(nq * (size_t)tw.surv_cap * 8));
     tw.head_cap = tail_head_cap(ix, nq);
     tw.head_buf = reinterpret_cast<float2*>(take(nq * (size_t)tw.head_cap * 8));
     tw.fb_list = reinterpret_cast<uint32_t*>(take(nq * 4));
