@@ -42,36 +42,46 @@ __global__ void tail_count_kernel(const Probe* __restrict__ probes, const uint32
     if (p.nv != 0) atomicAdd(&list_cnt[p.cid], 1u);
 }
 
-// One CTA: exclusive scan of the per-list pair counts and of the per-list item counts; writes the work items.
-__global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restrict__ list_cnt, uint32_t nlist,
-                                                         uint32_t per_item, uint32_t* __restrict__ list_off,
-                                                         TailItem* __restrict__ items, uint32_t max_items,
+// One CTA: exclusive scan of the per-list pair counts and of the per-list item counts; writes the work items.  Items of long
+// lists (more than one accumulator group of `big_blocks` blocks) come first: they take two or more passes over the K dimension
+// in the tensor-core kernel, and starting them early shortens the under-filled end of the persistent grid.
+__global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_n,
+                                                         uint32_t nlist, uint32_t per_item, uint32_t big_blocks,
+                                                         uint32_t* __restrict__ list_off, TailItem* __restrict__ items, uint32_t max_items,
                                                          uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_pairs[1024], s_items[1024];
+    __shared__ uint32_t s_pairs[1024], s_items[1024], s_big[1024];
     const uint32_t t = threadIdx.x, chunk = (nlist + 1023u) / 1024u;
     const uint32_t c0 = min(t * chunk, nlist), c1 = min(c0 + chunk, nlist);
-    uint32_t np = 0, ni = 0;
+    auto is_big = [&](uint32_t c) { return (list_n[c] + kBatch - 1) / kBatch > big_blocks; };
+    uint32_t np = 0, ni = 0, nbig = 0;
     for (uint32_t c = c0; c < c1; ++c) {
-        const uint32_t n = list_cnt[c];
+        const uint32_t n = list_cnt[c], k = (n + per_item - 1) / per_item;
         np += n;
-        ni += (n + per_item - 1) / per_item;
+        ni += k;
+        if (is_big(c)) nbig += k;
     }
     s_pairs[t] = np;
     s_items[t] = ni;
+    s_big[t] = nbig;
     __syncthreads();
     for (uint32_t o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan
-        const uint32_t ap = t >= o ? s_pairs[t - o] : 0u, ai = t >= o ? s_items[t - o] : 0u;
+        const uint32_t ap = t >= o ? s_pairs[t - o] : 0u, ai = t >= o ? s_items[t - o] : 0u, ab = t >= o ? s_big[t - o] : 0u;
         __syncthreads();
         s_pairs[t] += ap;
         s_items[t] += ai;
+        s_big[t] += ab;
         __syncthreads();
     }
-    uint32_t po = s_pairs[t] - np, io = s_items[t] - ni;
+    const uint32_t total_big = s_big[1023];
+    uint32_t po = s_pairs[t] - np;
+    uint32_t ib = s_big[t] - nbig;                                    // next slot among the big items
+    uint32_t is = total_big + (s_items[t] - ni) - (s_big[t] - nbig);  // next slot among the others
     for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t n = list_cnt[c];
         list_off[c] = po;
         if (n) {
             const uint32_t chunks = (n + per_item - 1) / per_item, sz = (n + chunks - 1) / chunks;  // balanced chunks
+            uint32_t& io = is_big(c) ? ib : is;
             for (uint32_t j = 0; j < chunks; ++j) {
                 const uint32_t b = j * sz, e = min(n, b + sz);
                 if (io < max_items && b < e) items[io] = TailItem{c, po + b, e - b, 0u};
@@ -386,7 +396,7 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
     const size_t npairs = nq * nprobe;
     const unsigned tb = 256, gb = (unsigned)((npairs + tb - 1) / tb);
     tail_count_kernel<<<gb, tb, 0, st>>>(d_probes, tw.tail_start, (uint32_t)nq, (uint32_t)nprobe, tw.list_cnt);
-    tail_plan_kernel<<<1, 1024, 0, st>>>(tw.list_cnt, ix.nlist, tw.pairs_per_item, tw.list_off, tw.items, tw.max_items,
+    tail_plan_kernel<<<1, 1024, 0, st>>>(tw.list_cnt, ix.list_n, ix.nlist, tw.pairs_per_item, 8u, tw.list_off, tw.items, tw.max_items,
                                          tw.counters);
     tail_scatter_kernel<<<gb, tb, 0, st>>>(d_probes, tw.tail_start, (uint32_t)nq, (uint32_t)nprobe, tw.list_off, tw.list_fill,
                                            tw.pairs);
