@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, 3) head_scan_kernel(DevIndex ix, ResolveA
 
 // ---- per-warp shared memory of the resolve kernels ----------------------------------------------------------
 struct ResSmem {
-    uint32_t stage, rq, si, sd, ord, total;
+    uint32_t stage, rq, si, sd, ord, slots, total;
 };
 __host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool topk, uint32_t surv_cap,
                                                    uint32_t stage_bufs = 2) {
@@ -138,10 +138,16 @@ __host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rq
     o += topk ? ((k * 8 + 15) / 16) * 16 : 0;
     w.sd = o;
     o += topk ? ((k * 4 + 15) / 16) * 16 : 0;
-    w.ord = o;
     uint32_t cap2 = surv_cap ? 32 : 0;
     while (cap2 < surv_cap) cap2 <<= 1;
-    o += cap2 * 8;
+    // Lazy replay (refine && surv_cap): the 64-bit sort keys are only needed until the survivors are sorted, which happens before
+    // the first refinement, so they live in the refine staging + query rows when those are large enough; what the replay loop
+    // reads afterwards is the sorted buffer slots, 2 bytes each.
+    const bool alias = refine && surv_cap != 0 && (w.si - w.stage) >= cap2 * 8;
+    w.slots = o;
+    o += (refine && surv_cap != 0) ? ((cap2 * 2 + 15) / 16) * 16 : 0;
+    w.ord = alias ? w.stage : o;
+    o += alias ? 0 : cap2 * 8;
     w.total = o;
     return w;
 }
@@ -516,7 +522,8 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     unsigned char* rql = wbase + L.rq;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
-    unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);
+    unsigned long long* ord = reinterpret_cast<unsigned long long*>(wbase + L.ord);  // may alias the staging + query rows
+    uint16_t* slots = reinterpret_cast<uint16_t*>(wbase + L.slots);
     const bool l2 = ix.metric == RBQ_METRIC_L2;
     unsigned long long st_adm = 0, st_ovf = 0, st_ref = 0;
     for (;;) {
@@ -533,7 +540,6 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         }
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         __syncwarp();
-        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         const QueryScalars s = a.qs[q];
         // the head threshold caps the live one: a no-op on one GPU (the heap's k-th distance starts at tau and only falls), the
         // bound another shard's head pass established in the phased multi-GPU search
@@ -565,6 +571,10 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 __syncwarp();
             }
         }
+        for (uint32_t i = lane; i < n_surv; i += 32) slots[i] = (uint16_t)((uint32_t)ord[i] & 1023u);
+        __syncwarp();  // the keys are dead: their memory becomes the query rows and the refine staging
+        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
+        __syncwarp();
         // candidate queue: slot i lives in lane i, in visit order
         int qn = 0;
         float q_lower = 0.0f, q_ip = 0.0f, q_gadd = 0.0f;
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
             unsigned long long gv = 0;
             float g_add = 0.0f;
             if (have) {
-                rec = sv[(uint32_t)ord[i] & 1023u];
+                rec = sv[slots[i]];
                 const Probe* pp = pr + rec.rank;
                 gv = pp->vec_off + rec.pos;
                 g_add = pp->g_add;
