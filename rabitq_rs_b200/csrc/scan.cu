@@ -482,7 +482,8 @@ static int launch_scan_ex(const DevIndex& ix, ScanArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)w.total * kWarps;
     if (smem > g_smem_optin) return fail(RBQ_INVALID_CONFIG, "scan kernel shared memory exceeds the device limit");
     const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (smem + 1024)));
-    const unsigned grid = (unsigned)std::min<size_t>(((size_t)a.nq + kWarps - 1) / kWarps, (size_t)g_num_sms * ctas_per_sm);
+    unsigned grid = (unsigned)std::min<size_t>(((size_t)a.nq + kWarps - 1) / kWarps, (size_t)g_num_sms * ctas_per_sm);
+    if (a.mode == kScanFallback) grid = std::min<unsigned>(grid, (unsigned)g_num_sms);  // normally nothing to do: keep the launch light
 #define RBQ_LAUNCH(EXK)                                                                                        \
     do {                                                                                                       \
         RBQ_CUDA(cudaFuncSetAttribute(scan_kernel<NCB, EXK, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

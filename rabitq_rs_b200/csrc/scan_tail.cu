@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restr
                                                          uint32_t nlist, uint32_t per_item, uint32_t big_blocks,
                                                          uint32_t* __restrict__ list_off, TailItem* __restrict__ items, uint32_t max_items,
                                                          uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_pairs[1024], s_items[1024], s_big[1024];
+    __shared__ uint32_t s_pairs[64], s_items[64], s_big[64];  // [0,32): warp totals, [32,64): their inclusive scan
     const uint32_t t = threadIdx.x, chunk = (nlist + 1023u) / 1024u;
     const uint32_t c0 = min(t * chunk, nlist), c1 = min(c0 + chunk, nlist);
     auto is_big = [&](uint32_t c) { return (list_n[c] + kBatch - 1) / kBatch > big_blocks; };
@@ -60,22 +60,47 @@ __global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restr
         ni += k;
         if (is_big(c)) nbig += k;
     }
-    s_pairs[t] = np;
-    s_items[t] = ni;
-    s_big[t] = nbig;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan
-        const uint32_t ap = t >= o ? s_pairs[t - o] : 0u, ai = t >= o ? s_items[t - o] : 0u, ab = t >= o ? s_big[t - o] : 0u;
-        __syncthreads();
-        s_pairs[t] += ap;
-        s_items[t] += ai;
-        s_big[t] += ab;
-        __syncthreads();
+    // inclusive scan over the 1024 threads: shuffles inside a warp, then the 32 warp totals
+    const uint32_t lane = t & 31u, wid = t >> 5;
+    uint32_t xp = np, xi = ni, xb = nbig;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+        const uint32_t ap = __shfl_up_sync(0xffffffffu, xp, o), ai = __shfl_up_sync(0xffffffffu, xi, o), ab = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) {
+            xp += ap;
+            xi += ai;
+            xb += ab;
+        }
     }
-    const uint32_t total_big = s_big[1023];
-    uint32_t po = s_pairs[t] - np;
-    uint32_t ib = s_big[t] - nbig;                                    // next slot among the big items
-    uint32_t is = total_big + (s_items[t] - ni) - (s_big[t] - nbig);  // next slot among the others
+    if (lane == 31) {
+        s_pairs[wid] = xp;
+        s_items[wid] = xi;
+        s_big[wid] = xb;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t yp = s_pairs[lane], yi = s_items[lane], yb = s_big[lane];
+#pragma unroll
+        for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t ap = __shfl_up_sync(0xffffffffu, yp, o), ai = __shfl_up_sync(0xffffffffu, yi, o), ab = __shfl_up_sync(0xffffffffu, yb, o);
+            if (lane >= o) {
+                yp += ap;
+                yi += ai;
+                yb += ab;
+            }
+        }
+        s_pairs[32 + lane] = yp;  // inclusive totals of warps 0..lane
+        s_items[32 + lane] = yi;
+        s_big[32 + lane] = yb;
+    }
+    __syncthreads();
+    const uint32_t bp = wid ? s_pairs[32 + wid - 1] : 0u, bi = wid ? s_items[32 + wid - 1] : 0u, bb = wid ? s_big[32 + wid - 1] : 0u;
+    const uint32_t inc_pairs = bp + xp, inc_items = bi + xi, inc_big = bb + xb;  // inclusive prefix of this thread
+    const uint32_t tot_pairs = s_pairs[63], tot_items = s_items[63];
+    const uint32_t total_big = s_big[63];
+    uint32_t po = inc_pairs - np;
+    uint32_t ib = inc_big - nbig;                                    // next slot among the big items
+    uint32_t is = total_big + (inc_items - ni) - (inc_big - nbig);  // next slot among the others
     for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t n = list_cnt[c];
         list_off[c] = po;
@@ -91,8 +116,8 @@ __global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restr
         po += n;
     }
     if (t == 1023) {
-        list_off[nlist] = s_pairs[1023];
-        counters[0] = min(s_items[1023], max_items);
+        list_off[nlist] = tot_pairs;
+        counters[0] = min(tot_items, max_items);
         counters[1] = 0u;
     }
 }
