@@ -799,12 +799,12 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.has_ex = ix.ex_bits != 0;
     static const uint32_t flush_at = [] {
         const char* e = getenv("RBQ_FLUSH_AT");
-        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : 2 * kRefineSlots));
+        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : kRefineSlots));  // one refine round per flush (measured best)
     }();
     a.flush_at = flush_at;
     static const uint32_t lazy_flush_at = [] {
         const char* e = getenv("RBQ_LAZY_FLUSH");
-        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : 2 * kRefineSlots));
+        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : kRefineSlots));
     }();
     a.lazy_flush_at = lazy_flush_at;
 }
