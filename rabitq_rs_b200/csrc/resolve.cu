@@ -164,8 +164,9 @@ __device__ __forceinline__ void load_rql(unsigned char* rql, uint32_t rql_row, c
 // K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's
 // ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes): every lane
 // copies ITS chain's code row (DevIndex::exl) into its own shared-memory row with cp.async and multiplies it against
-// its query row -- no unpacking and no exchange between lanes.  The rows of round r+1 travel while round r is
-// multiplied, so only the first round of a batch waits for memory.
+// its query row -- no unpacking and no exchange between lanes.  With two staging buffers (a.stage_bufs == 2) the rows of
+// round r+1 travel while round r is multiplied; the default is one buffer (the candidates' rows were already pulled into
+// L2 when they were queued, and the smaller footprint lets more warps be resident, which measured faster).
 __device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveArgs& a, unsigned long long gv, int nb, uint32_t stage_u32,
                                               uint32_t rql_u32, int lane) {
     const int g = lane >> 3, j = lane & 7;

@@ -5,8 +5,8 @@
 // i.e. a product of a one-hot matrix (vectors x 16*ncb, one 1 per codebook) with the queries' LUT bytes -- u8 x u8
 // with s32 accumulation, which is exact, so the tensor cores return the reference's integer bit for bit.  The PRMT
 // kernel (scan_tail.cu) spends ~3 ALU instructions per 4 lookups and is bound by the integer pipe; here a lookup
-// costs one 16-byte shared-memory store (the one-hot row) shared by all the queries that probe the list, and the
-// sums run on tcgen05.mma (kind::i8, M = 128 vectors, N = 64 queries, K = 32 bytes = 2 codebooks per instruction)
+// costs 16 bytes of a one-hot row written once to tensor memory and shared by all the queries that probe the list, and
+// the sums run on tcgen05.mma (kind::i8, M = 128 vectors, N = 64 queries, K = 32 bytes = 2 codebooks per instruction)
 // with the accumulators in TMEM.
 //
 // Two CTAs per SM, one work item (a list and <= 64 of the (query, rank) pairs probing it) at a time:
