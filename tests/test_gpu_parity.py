@@ -546,3 +546,18 @@ def test_fetch_embedding_bit_exact(rbq, oracle, geom):
         found = [s.fetch_embedding(i) for s in shards]
         assert sum(f is not None for f in found) == 1
         assert np.array_equal(next(f for f in found if f is not None), oix.fetch_embedding(i))
+
+
+@pytest.mark.parametrize("name", ["l2_b7_fht128", "ip_b3_fht96", "l2_b1_matrix32"])
+def test_committed_fixtures(rbq, name):
+    """The CUDA path against the committed golden fixtures (frozen RBQ1 bytes + the oracle's answers; see
+    tests/golden/make_fixtures.py): identical ids and score bits, both scan schedules, byte-identical re-serialisation."""
+    from test_oracle_golden import load_golden
+
+    blob, q, ids, scores, counts, (k, nprobe, metric) = load_golden(name)
+    gix = _load(rbq, blob)
+    assert gix.save_to_bytes() == blob
+    for mode in (1, 2):
+        gix.set_scan_mode(mode)
+        got = gix.batch_search(q, rbq.SearchParams(k, nprobe))
+        assert assert_results_match(got, (ids, scores, counts), TOL, f"golden {name} mode {mode}") == q.shape[0]

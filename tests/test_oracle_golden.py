@@ -546,3 +546,26 @@ def test_fetch_embedding_reconstruction(oracle, dim, nlist, rot, n, seed):
     assert ix.fetch_embedding(n + 10) is None
     x = data[3]
     assert np.abs(ix.inverse_rotate(ix.rotate(x)) - x).max() < 1e-5
+
+
+# ---- committed fixtures (tests/golden/*.npz, made by tests/golden/make_fixtures.py) ---------------------------
+GOLDEN = ["l2_b7_fht128", "ip_b3_fht96", "l2_b1_matrix32"]
+
+
+def load_golden(name):
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return z["blob"].tobytes(), z["queries"], z["ids"], z["scores"], z["counts"], [int(x) for x in z["params"]]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_reproduces_committed_fixtures(oracle, name):
+    """The oracle defines end-to-end parity for the CUDA path: its answers on the frozen RBQ1 bytes must not drift
+    (bit-identical ids and scores), and it must re-serialise the index byte for byte."""
+    blob, q, ids, scores, counts, (k, nprobe, metric) = load_golden(name)
+    ix = oracle.Index.load_bytes(blob)
+    assert ix.metric == metric and ix.save_bytes() == blob
+    got = ix.search_batch(q, k, nprobe)
+    assert np.array_equal(got[2], counts) and np.array_equal(got[0], ids)
+    assert np.array_equal(got[1].view(np.uint32), scores.view(np.uint32))
