@@ -399,8 +399,7 @@ def main():
 
     def step_host():
         if world > 1 and phased:  # host buffers in, merged result out: H2D of the batch, phased search, D2H of the merged top-k
-            dq.copy_(hq, non_blocking=True)
-            a, b, c = searcher.search(dq, k, nprobe)
+            a, b, c = searcher.search_host(hq, k, nprobe)  # each rank uploads 1/world of the batch, NVLink all-gather
             h_ids.copy_(a, non_blocking=True)
             h_sc.copy_(b, non_blocking=True)
             h_cn.copy_(c, non_blocking=True)

@@ -118,3 +118,26 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(b.gathered, b.local, group=self.group)  # in place: every rank owns one chunk
         self.ix.merge_topk_packed_device(self.world, nq, k, b.gathered, b.chunk, b.m_ids, b.m_sc, b.m_cn)
         return b.m_ids, b.m_sc, b.m_cn
+
+    def search_host(self, hq, k, nprobe):
+        """hq: [nq, dim] float32 PINNED host tensor holding the whole batch (every rank sees the same buffer, or at least
+        its own slice of it).  Each rank uploads only its 1/world slice over PCIe and the slices are all-gathered over
+        NVLink -- instead of every rank pulling the whole batch through its host link -- then the phased search runs."""
+        import torch
+        import torch.distributed as dist
+
+        nq, dim = hq.shape
+        per = (nq + self.world - 1) // self.world
+        if getattr(self, "_dq", None) is None or self._dq.shape != (per * self.world, dim):
+            self._dq = torch.empty((per * self.world, dim), dtype=torch.float32, device=self.ix_device())
+        lo, hi = min(self.rank * per, nq), min((self.rank + 1) * per, nq)
+        mine = self._dq[self.rank * per:(self.rank + 1) * per]
+        if hi > lo:
+            mine[:hi - lo].copy_(hq[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(self._dq.view(-1), mine.reshape(-1), group=self.group)
+        return self.search(self._dq[:nq], k, nprobe)
+
+    def ix_device(self):
+        import torch
+
+        return torch.device("cuda", self.ix.device)
