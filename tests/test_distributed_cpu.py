@@ -171,3 +171,19 @@ def test_phased_protocol_world_size_2_gloo(tmp_path):
     port = 29900 + (os.getpid() % 90)
     mp.spawn(_phased_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"phased{r}.npy") for r in range(2))
+
+
+def test_query_slices_cover_the_batch_exactly():
+    """Slices are contiguous, disjoint, aligned to the GEMM row tile, and cover [0, nq) for any world size."""
+    sys.path.insert(0, ROOT)
+    from rabitq_rs_b200.distributed import query_slices
+
+    for nq in (1, 7, 128, 129, 1000, 10000, 32768):
+        for world in (1, 2, 3, 4, 8):
+            per, slices = query_slices(nq, world)
+            assert per % 128 == 0 and per * world >= nq and len(slices) == world
+            covered = 0
+            for r, (b, c) in enumerate(slices):
+                assert b == min(r * per, nq) and 0 <= c <= per and b + c <= nq
+                covered += c
+            assert covered == nq
