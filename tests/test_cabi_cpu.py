@@ -98,3 +98,25 @@ def test_python_surface_mirrors_reference(rbq):
         assert callable(getattr(ix, name))
     bits = rbq.ids_to_bitset([0, 3, 64, 130])
     assert bits.tolist() == [9, 1, 4]
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of rbq_search_stats / rbq_probe_rec must have the size and field offsets the C header gives
+    them (a silent mismatch would scramble the diagnostics and the multi-GPU probe records)."""
+    import ctypes as C
+    import subprocess
+
+    from rabitq_rs_b200 import _ffi
+
+    fields = [f for f, _ in _ffi.SearchStats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rbq.h"\nint main(void) {\n'
+                   '  printf("%zu %zu\\n", sizeof(rbq_search_stats), sizeof(rbq_probe_rec));\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(rbq_search_stats, {f}));\n' for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(_ffi.SearchStats) and int(out[1]) == 16
+    for f, off in zip(fields, out[2:]):
+        assert getattr(_ffi.SearchStats, f).offset == int(off), f
