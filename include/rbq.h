@@ -163,6 +163,8 @@ typedef struct rbq_search_stats {
     uint64_t overflow_queries;  /* queries whose survivor buffer overflowed (their tail was re-walked sequentially) */
     float ms_scan_head, ms_scan_tail, ms_scan_replay; /* split of ms_scan (sequential mode: all in head) */
     float ms_tail_kernel;       /* the tail FastScan kernel alone (events around that one launch; 0 in sequential mode) */
+    uint32_t coarse_mode_used;  /* coarse stage the call ran: 0 exact, 1 dense tensor-core scores, 2 filtered in the GEMM epilogue */
+    uint32_t front_chunk;       /* queries per front-end chunk */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */
@@ -172,10 +174,20 @@ int rbq_set_profiling(rbq_index* ix, int on);
  * remaining (query, list) pairs grouped by list, then an ordered replay of the surviving candidates).
  * Both reproduce search_cluster_v2_batched's decisions exactly (src/ivf.rs:2013-2127). */
 int rbq_set_scan_mode(rbq_index* ix, int mode);
-/* Coarse-stage implementation: 0 = exact FP32 scoring of every centroid (CUDA cores),
- * 1 = tensor-core (tcgen05) candidate GEMM + exact FP32 re-score of the near-threshold centroids
- * (default).  Both produce the reference's probe list bit for bit. */
+/* Coarse-stage implementation (replaces the centroid loop of src/ivf.rs:1782-1835):
+ *  0 = exact FP32 scoring of every centroid (CUDA cores);
+ *  1 = tensor-core (tcgen05) GEMM writing the dense query x centroid score matrix, then an exact FP32 re-score of the
+ *      near-threshold centroids;
+ *  2 = the same GEMM with the selection fused into its epilogue: a per-query score threshold is estimated from a strided
+ *      centroid sample, the epilogue appends only the centroids that beat it to a short per-query candidate list, and the
+ *      selection kernel works on that list (queries whose list is provably incomplete take an exact fallback).  No
+ *      nq x nlist matrix is ever written; needs cluster_count >= 2048 and nprobe well below cluster_count;
+ * -1 = auto (default): 2 when available, else 1.
+ * All of them produce the reference's probe list bit for bit. */
 int rbq_set_coarse_mode(rbq_index* ix, int mode);
+/* bf16 terms of the coarse GEMM: 3 (default; operands split hi+lo, fp32-class scores, a handful of re-scored centroids)
+ * or 1 (a third of the tensor work, bf16-class scores, a wider band of centroids re-scored exactly).  Exact either way. */
+int rbq_set_coarse_terms(rbq_index* ix, int terms);
 
 /* ---- stage probes (parity tests call each device stage in isolation; host buffers) ----
  * rotated[nq*D], lut[nq*4D], scalars[nq*8] = delta,sum_vl,k1x,kbx,qnorm,sum_q,binary_scale,0

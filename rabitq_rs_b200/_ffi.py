@@ -16,7 +16,7 @@ class SearchStats(C.Structure):
                 ("ms_select", C.c_float), ("ms_scan", C.c_float),
                 ("tail_blocks", C.c_uint64), ("tail_bytes", C.c_uint64), ("tail_pairs", C.c_uint64),
                 ("survivors", C.c_uint64), ("overflow_queries", C.c_uint64),
-                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float)]
+                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32)]
 
 
 _lib = None
@@ -59,6 +59,7 @@ def lib():
     L.rbq_last_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.rbq_set_profiling.argtypes = [vp, i32]
     L.rbq_set_coarse_mode.argtypes = [vp, i32]
+    L.rbq_set_coarse_terms.argtypes = [vp, i32]
     L.rbq_set_scan_mode.argtypes = [vp, i32]
     L.rbq_debug_set_survivor_cap.argtypes = [C.c_uint32]
     L.rbq_debug_query_prep.argtypes = [vp, vp, sz, sz, vp, vp, vp]

@@ -92,6 +92,7 @@ int upload_index(rbq_index* h) {
     }
     if ((rc = upload(h, hi.centroids.data(), hi.centroids.size(), &d.centroids))) return rc;
     if ((rc = prepare_coarse_tc(h))) return rc;
+    if ((rc = prepare_coarse_sample(h))) return rc;
     if ((rc = upload(h, hi.list_n.data(), hi.list_n.size(), &d.list_n))) return rc;
     d.list_owner = nullptr;
     d.shard_rank = hi.shard_rank;
@@ -144,11 +145,54 @@ int rbq::prepare_coarse_tc(rbq_index* h) {
     return RBQ_OK;
 }
 
+// Centroid sample of the coarse filter mode: samp_n rows of cent_split, one per stride with a hashed offset inside the
+// stride (robust against centroid tables stored in a sorted order).  Tables below 2048 lists keep the dense path only.
+int rbq::prepare_coarse_sample(rbq_index* h) {
+    DevIndex& d = h->dev;
+    d.samp_split = nullptr;
+    d.samp_n2 = nullptr;
+    d.samp_n = 0;
+    const size_t nl = d.nlist, D = d.D;
+    if (nl < 2048) return RBQ_OK;
+    size_t S = std::min<size_t>(4096, std::max<size_t>(512, (nl / 16 + 255) / 256 * 256));
+    const size_t stride = nl / S;
+    std::vector<uint32_t> idx(S);
+    uint64_t st = 0x9e3779b97f4a7c15ull ^ (uint64_t)nl;
+    for (size_t j = 0; j < S; ++j) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        idx[j] = (uint32_t)(j * stride + (size_t)((st >> 33) % stride));
+    }
+    uint32_t* d_idx = nullptr;
+    void* sp = nullptr;
+    float* n2 = nullptr;
+    RBQ_CUDA(cudaMalloc(&d_idx, S * 4));
+    h->allocations.push_back(d_idx);
+    RBQ_CUDA(cudaMalloc(&sp, S * 3 * D * 2));
+    h->allocations.push_back(sp);
+    RBQ_CUDA(cudaMalloc(&n2, S * 4));
+    h->allocations.push_back(n2);
+    RBQ_CUDA(cudaMemcpy(d_idx, idx.data(), S * 4, cudaMemcpyHostToDevice));
+    int rc = launch_gather_rows(d.cent_split, 3 * D * 2, d_idx, S, sp, nullptr);
+    if (rc) return rc;
+    std::vector<float> hn2(nl), sn2(S);
+    RBQ_CUDA(cudaMemcpy(hn2.data(), d.cent_n2, nl * 4, cudaMemcpyDeviceToHost));
+    for (size_t j = 0; j < S; ++j) sn2[j] = hn2[idx[j]];
+    RBQ_CUDA(cudaMemcpy(n2, sn2.data(), S * 4, cudaMemcpyHostToDevice));
+    RBQ_CUDA(cudaDeviceSynchronize());
+    d.samp_split = sp;
+    d.samp_n2 = n2;
+    d.samp_n = (uint32_t)S;
+    return RBQ_OK;
+}
+
 namespace {
 
 int ensure_ws(const rbq_index* h, size_t bytes) {
     if (h->ws_bytes >= bytes) return RBQ_OK;
-    if (h->ws) cudaFree(h->ws);
+    if (h->ws) {
+        RBQ_CUDA(cudaDeviceSynchronize());  // earlier asynchronous calls may still be using the old workspace
+        cudaFree(h->ws);
+    }
     h->ws = nullptr;
     h->ws_bytes = 0;
     RBQ_CUDA(cudaMalloc(&h->ws, bytes));
@@ -168,61 +212,162 @@ struct Carver {
     }
 };
 
-size_t tile_queries(const rbq_index* h, size_t nq) {
-    size_t per_q = (size_t)h->dev.nlist * 4;
-    size_t cap = std::max<size_t>(1, ((size_t)1 << 30) / std::max<size_t>(per_q, 1));
-    return std::min<size_t>({nq, (size_t)32768, cap});
-}
+// How one call runs.  The SCAN works on tiles of `qt` queries (the list-major schedule wants as many (query, list) pairs per
+// list as it can get: the whole batch when it fits), the FRONT END on chunks of `cq` queries inside a tile (its per-query
+// scratch -- a dense score row or a candidate list -- is what limits a chunk, not the tile).
+struct Plan {
+    size_t qt = 0, cq = 0;
+    int coarse = 1;        // 0 exact FP32, 1 dense tensor-core scores, 2 tensor-core scores filtered in the GEMM epilogue
+    int terms = 3;         // bf16 split terms of the GEMM (3: fp32-class, 1: bf16-class with a wider re-score band)
+    float eps = 0.0f;      // bound on |gemm(q.c) - q.c| / (|q||c|)
+    uint32_t rank = 0, cap = 0, fb_ctas = 0;  // filter mode: sample rank of the threshold, candidate capacity, fallback CTAs
+};
 
-size_t ws_need(const rbq_index* h, size_t qt, size_t nprobe, size_t top_k, size_t dim, bool host_io, size_t filter_words) {
-    const size_t D = h->dev.D;
-    size_t n = 4096;
-    n += qt * D * 4 + 256;                 // rotated
-    n += qt * D * 4 + 256;                 // lut
-    n += qt * sizeof(QueryScalars) + 256;
-    n += qt * (size_t)h->dev.nlist * 4 + 256;  // scores
-    n += qt * nprobe * sizeof(Probe) + 256;
-    n += qt * 3 * D * 2 + qt * 4 + 512;    // bf16 split of the rotated queries + |q|^2 (tensor-core coarse stage)
-    n += tail_ws_bytes(h->dev, qt, nprobe, top_k) + 256;  // head/tail/replay pipeline (scan_tail.cu)
-    n += qt + 256;                                       // head_owner flags (phased multi-GPU search)
-    if (host_io) {
-        n += qt * dim * 4 + 256;
-        n += qt * top_k * 12 + qt * 4 + 768;
-        n += filter_words * 8 + 256;
+Plan make_plan(const rbq_index* h, size_t nq, size_t nprobe) {
+    const DevIndex& ix = h->dev;
+    Plan p;
+    const size_t pair_cap = std::max<size_t>(1, ((size_t)1 << 26) / std::max<size_t>(nprobe, 1));
+    p.qt = std::min<size_t>({nq, (size_t)131072, pair_cap});
+    p.terms = h->coarse_terms == 1 ? 1 : 3;
+    p.eps = p.terms == 1 ? 4.39453125e-3f /* 2^-8 + 2^-11: bf16 rounding of both operands */ : h->coarse_eps;
+    p.coarse = h->coarse_mode;
+    if (p.coarse < 0 || p.coarse == 2) {
+        p.rank = filter_sample_rank(ix.nlist, ix.samp_n, nprobe, p.terms);
+        p.cap = filter_cand_cap(ix.nlist, ix.samp_n, nprobe, p.terms);
+        const bool ok = p.rank != 0 && p.cap != 0;
+        p.coarse = ok ? 2 : 1;
     }
-    return n;
+    size_t per_q = (size_t)ix.nlist * 4;
+    if (p.coarse == 2) per_q = (size_t)p.cap * sizeof(CandRec) + (size_t)ix.samp_n * 4 + 16;
+    size_t cq = std::max<size_t>(128, (((size_t)1 << 30) / std::max<size_t>(per_q, 1)) / 128 * 128);
+    cq = std::min<size_t>(cq, 32768);
+    p.cq = std::min(cq, p.qt);
+    p.fb_ctas = 64;
+    return p;
 }
 
-// One tile's device workspace.  The layout is a pure function of (qt, nprobe, top_k), so the phases of a multi-GPU search
-// find each other's data by carving again.
 struct WsLayout {
     float* d_rot;
     uint8_t* d_lut;
     QueryScalars* d_qs;
-    float* d_sc;
     Probe* d_pr;
     uint16_t* d_qsplit;
     float* d_qn2;
     TailWs tw;
     uint8_t* d_head_owner;
+    float* d_sc;   // coarse 0/1: [cq][nlist]
+    FilterWs fw;   // coarse 2
     size_t end;
 };
-WsLayout carve_ws(const rbq_index* h, char* ws_base, size_t qt, size_t nprobe, size_t top_k) {
+// One tile's device workspace.  The layout is a pure function of (plan, nprobe, top_k), so the phases of a multi-GPU search
+// find each other's data by carving again.  base == nullptr only measures.
+WsLayout carve_ws(const rbq_index* h, char* ws_base, const Plan& pl, size_t nprobe, size_t top_k) {
     const DevIndex& ix = h->dev;
-    const size_t D = ix.D;
+    const size_t D = ix.D, qt = pl.qt, cq = pl.cq;
     Carver cv{ws_base};
     WsLayout L;
     L.d_rot = cv.take<float>(qt * D);
     L.d_lut = cv.take<uint8_t>(qt * D * 4);
     L.d_qs = cv.take<QueryScalars>(qt);
-    L.d_sc = cv.take<float>(qt * (size_t)ix.nlist);
     L.d_pr = cv.take<Probe>(qt * nprobe);
     L.d_qsplit = cv.take<uint16_t>(qt * 3 * D);
     L.d_qn2 = cv.take<float>(qt);
-    tail_ws_carve(ix, qt, nprobe, top_k, cv.take<char>(tail_ws_bytes(ix, qt, nprobe, top_k)), L.tw);
+    const size_t tb = tail_ws_bytes(ix, qt, nprobe, top_k);
+    char* tbase = cv.take<char>(tb);
+    if (ws_base) tail_ws_carve(ix, qt, nprobe, top_k, tbase, L.tw);
     L.d_head_owner = cv.take<uint8_t>(qt);
-    L.end = cv.off;
+    L.d_sc = nullptr;
+    L.fw = FilterWs{};
+    if (pl.coarse == 2) {
+        L.fw.cap = pl.cap;
+        L.fw.fb_ctas = pl.fb_ctas;
+        L.fw.samp_scores = cv.take<float>(cq * ix.samp_n);
+        L.fw.thr = cv.take<float>(cq);
+        L.fw.cand = cv.take<CandRec>(cq * pl.cap);
+        L.fw.cand_cnt = cv.take<uint32_t>(cq + 2);
+        L.fw.fb_count = L.fw.cand_cnt + cq;
+        L.fw.fb_list = cv.take<uint32_t>(cq);
+        L.fw.fb_scratch = cv.take<float>((size_t)pl.fb_ctas * ix.nlist);
+    } else {
+        L.d_sc = cv.take<float>(cq * (size_t)ix.nlist);
+    }
+    L.end = cv.off + 4096;
     return L;
+}
+
+size_t ws_need(const rbq_index* h, const Plan& pl, size_t nprobe, size_t top_k, size_t dim, bool host_io, size_t filter_words) {
+    size_t n = carve_ws(h, nullptr, pl, nprobe, top_k).end;
+    if (host_io) {
+        n += pl.qt * dim * 4 + 256;
+        n += pl.qt * top_k * 12 + pl.qt * 4 + 768;
+        n += filter_words * 8 + 256;
+    }
+    return n;
+}
+
+// Front end for the queries [c0, c0 + m) of a tile (rows c0.. of the tile buffers): rotation + LUT (+ bf16 operand split),
+// centroid scores, probe selection with the per-list constants.  m <= plan.cq.
+int run_front(const rbq_index* h, const WsLayout& L, const Plan& pl, const float* dq, size_t c0, size_t m, size_t nprobe, cudaStream_t st,
+              uint64_t* launches, bool prep, cudaEvent_t ev_prep, cudaEvent_t ev_coarse, bool need_ip = false) {
+    const DevIndex& ix = h->dev;
+    const size_t D = ix.D;
+    int rc;
+    const bool tc = pl.coarse != 0;
+    bool split_done = false;
+    if (prep) {
+        if ((rc = launch_query_prep(ix, dq, m, L.d_rot + c0 * D, L.d_lut + c0 * D * 4, L.d_qs + c0, st, tc ? L.d_qsplit + c0 * 3 * D : nullptr,
+                                    tc ? L.d_qn2 + c0 : nullptr, &split_done)))
+            return rc;
+        *launches += 1;
+    }
+    if (ev_prep) cudaEventRecord(ev_prep, st);
+    if (pl.coarse == 0) {
+        if ((rc = launch_coarse_exact(ix, L.d_rot + c0 * D, m, L.d_sc, st))) return rc;
+        if (ev_coarse) cudaEventRecord(ev_coarse, st);
+        if ((rc = launch_probe_select(ix, L.d_rot + c0 * D, L.d_sc, m, nprobe, L.d_pr + c0 * nprobe, st))) return rc;
+        *launches += 2;
+        return RBQ_OK;
+    }
+    if (!split_done) {
+        if ((rc = launch_split_bf16(L.d_rot + c0 * D, m, (int)D, 0, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, st))) return rc;
+        *launches += 1;
+    }
+    if (pl.coarse == 1) {
+        if ((rc = launch_coarse_tc(ix, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, m, L.d_sc, st, pl.terms))) return rc;
+        if (ev_coarse) cudaEventRecord(ev_coarse, st);
+        if ((rc = launch_probe_select_tc(ix, L.d_rot + c0 * D, L.d_sc, L.d_qs + c0, m, nprobe, pl.eps, L.d_pr + c0 * nprobe,
+                                         h->fallback_counter(), st, need_ip)))
+            return rc;
+        *launches += 2;
+        return RBQ_OK;
+    }
+    // filter mode: sample scores -> per-query threshold -> full GEMM keeping the centroids that beat it -> selection
+    const FilterWs& fw = L.fw;
+    RBQ_CUDA(cudaMemsetAsync(fw.cand_cnt, 0, (pl.cq + 2) * 4, st));  // candidate counters | fallback count | fallback cursor
+    GemmEpi e;
+    e.nq = (int)m;
+    e.metric = ix.metric;
+    e.qn2 = L.d_qn2 + c0;
+    e.ncols = (int)ix.samp_n;
+    e.cn2 = ix.samp_n2;
+    e.scores = fw.samp_scores;
+    if ((rc = launch_coarse_gemm(kGemmScores, L.d_qsplit + c0 * 3 * D, m, ix.samp_split, ix.samp_n, (int)D, pl.terms, e, st))) return rc;
+    if ((rc = launch_sample_threshold(fw.samp_scores, m, ix.samp_n, pl.rank, ix.metric, fw.thr, st))) return rc;
+    e.ncols = (int)ix.nlist;
+    e.cn2 = ix.cent_n2;
+    e.scores = nullptr;
+    e.thr = fw.thr;
+    e.cand = fw.cand;
+    e.cand_cnt = fw.cand_cnt;
+    e.cap = fw.cap;
+    if ((rc = launch_coarse_gemm(kGemmFilter, L.d_qsplit + c0 * 3 * D, m, ix.cent_split, ix.nlist, (int)D, pl.terms, e, st))) return rc;
+    if (ev_coarse) cudaEventRecord(ev_coarse, st);
+    // rows of rot / qs / probes are tile rows c0.. ; the candidate lists are chunk rows 0..
+    if ((rc = launch_probe_select_cand(ix, L.d_rot + c0 * D, L.d_qs + c0, m, nprobe, pl.eps, fw, L.d_pr + c0 * nprobe, h->fallback_counter(), st,
+                                       need_ip)))
+        return rc;
+    *launches += 5;
+    return RBQ_OK;
 }
 
 // Queries still in host memory: chunks are copied on a dedicated non-blocking stream, each followed by an event the
@@ -234,9 +379,9 @@ struct HostFeed {
     size_t dim = 0, chunk = 0;
     cudaStream_t copy = nullptr;
     cudaEvent_t* ev = nullptr;
-    int issue(size_t q_abs, size_t m, size_t off_in_tile) {
+    int issue(size_t q_abs, size_t m, size_t off_in_tile, int slot) {
         RBQ_CUDA(cudaMemcpyAsync(d_q + off_in_tile * dim, h_q + q_abs * dim, m * dim * 4, cudaMemcpyHostToDevice, copy));
-        RBQ_CUDA(cudaEventRecord(ev[(off_in_tile / chunk) % kEvents], copy));
+        RBQ_CUDA(cudaEventRecord(ev[slot % kEvents], copy));
         return RBQ_OK;
     }
 };
@@ -244,17 +389,10 @@ struct HostFeed {
 // The pipeline on device buffers for one call (tiles internally).  d_filter may be null.
 int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t top_k, size_t nprobe,
                   const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts,
-                  char* ws_base, size_t qt, cudaStream_t st, uint64_t* launches, HostFeed* feed = nullptr) {
+                  char* ws_base, const Plan& pl, cudaStream_t st, uint64_t* launches, HostFeed* feed = nullptr) {
     const DevIndex& ix = h->dev;
-    const size_t D = ix.D;
-    const WsLayout L = carve_ws(h, ws_base, qt, nprobe, top_k);
-    float* d_rot = L.d_rot;
-    uint8_t* d_lut = L.d_lut;
-    QueryScalars* d_qs = L.d_qs;
-    float* d_sc = L.d_sc;
-    Probe* d_pr = L.d_pr;
-    uint16_t* d_qsplit = L.d_qsplit;
-    float* d_qn2 = L.d_qn2;
+    const size_t qt = pl.qt;
+    const WsLayout L = carve_ws(h, ws_base, pl, nprobe, top_k);
     const TailWs& tw = L.tw;
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};  // [6]: the tail FastScan kernel alone
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
@@ -267,56 +405,31 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         const bool list_major = h->scan_mode == 2 || (h->scan_mode == 0 && nprobe >= 4 && n * nprobe >= 8 * (size_t)ix.nlist);
         if (list_major)  // surv_cnt | list_cnt | list_fill | counters
             RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
-        // Front end (rotate + LUT, coarse scores, probe selection) and the head pass are independent per query: when the
-        // queries are still arriving from the host (feed), they run chunk by chunk behind the copy stream, so the H2D
-        // transfer of chunk c+1 overlaps the work on chunk c and only the tail stage waits for the whole tile.
-        const size_t chunk = feed ? feed->chunk : n;
-        int chunk_index = 0;
-        for (size_t c0 = 0; c0 < n; c0 += chunk, ++chunk_index) {
+        // Front end (rotate + LUT, coarse scores, probe selection) and the head pass are independent per query: they run chunk
+        // by chunk (a chunk = what the front end's scratch holds; smaller when the queries are still arriving from the host, so
+        // that the H2D transfer of chunk c+1 overlaps the work on chunk c) and only the tail stage waits for the whole tile.
+        size_t chunk = std::min(pl.cq, n);
+        if (feed) chunk = std::max<size_t>(128, std::min(chunk, feed->chunk));
+        int head_launch = 0, ci = 0;
+        for (size_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
             const size_t m = std::min(chunk, n - c0);
+            const bool last = c0 + chunk >= n;
             if (feed) {
-                if ((rc = feed->issue(q0 + c0, m, c0))) return rc;
-                RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[(c0 / chunk) % HostFeed::kEvents], 0));
+                if ((rc = feed->issue(q0 + c0, m, c0, ci))) return rc;
+                RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[ci % HostFeed::kEvents], 0));
             }
             const float* dq = feed ? feed->d_q + c0 * ix.dim : d_queries + (q0 + c0) * ix.dim;
-            bool split_done = false;
-            const bool tc = h->coarse_mode != 0;
-            if ((rc = launch_query_prep(ix, dq, m, d_rot + c0 * D, d_lut + c0 * D * 4, d_qs + c0, st, tc ? d_qsplit + c0 * 3 * D : nullptr,
-                                        tc ? d_qn2 + c0 : nullptr, &split_done)))
+            if ((rc = run_front(h, L, pl, dq, c0, m, nprobe, st, launches, true, h->profiling && last ? h->ev[1] : nullptr,
+                                h->profiling && last ? h->ev[2] : nullptr)))
                 return rc;
-            if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[1], st);
-            if (h->coarse_mode == 0) {
-                if ((rc = launch_coarse_exact(ix, d_rot + c0 * D, m, d_sc + c0 * ix.nlist, st))) return rc;
-                if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
-                if ((rc = launch_probe_select(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, m, nprobe, d_pr + c0 * nprobe, st))) return rc;
-            } else {
-                if (!split_done) {
-                    if ((rc = launch_split_bf16(d_rot + c0 * D, m, (int)D, 0, d_qsplit + c0 * 3 * D, d_qn2 + c0, st))) return rc;
-                    *launches += 1;
-                }
-                if ((rc = launch_coarse_tc(ix, d_qsplit + c0 * 3 * D, d_qn2 + c0, m, d_sc + c0 * ix.nlist, st))) return rc;
-                if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[2], st);
-                if ((rc = launch_probe_select_tc(ix, d_rot + c0 * D, d_sc + c0 * ix.nlist, d_qs + c0, m, nprobe, h->coarse_eps,
-                                                 d_pr + c0 * nprobe, h->fallback_counter(), st, false)))
-                    return rc;
-            }
-            *launches += 3;
-            if (h->profiling && c0 + chunk >= n) cudaEventRecord(h->ev[3], st);
+            if (h->profiling && last) cudaEventRecord(h->ev[3], st);
             // head: FastScan of every query's first owned list + the reference's sequential loop over it
-            static const bool head_late = getenv("RBQ_HEAD_LATE") != nullptr;  // A/B knob: head pass once, after the last chunk
-            if (list_major && head_late) {
-                if (c0 + chunk >= n &&
-                    (rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                      d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, 0, n, 0)))
-                    return rc;
-            } else if (list_major &&
-                (rc = launch_head(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, c0, m, chunk_index)))
+            if (list_major && (rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                                d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, c0, m, &head_launch)))
                 return rc;
         }
-        if (!list_major && h->profiling) cudaEventRecord(h->ev[3], st);
         if (!list_major) {
-            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+            if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFull, nullptr, st)))
                 return rc;
             *launches += 1;
@@ -328,15 +441,15 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         } else {
             if (h->profiling) cudaEventRecord(h->ev[4], st);
             // tail: all remaining (query, list) pairs grouped by list -> survivors
-            if ((rc = launch_tail(ix, d_lut, d_qs, d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches,
+            if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches,
                                   h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
                 return rc;
             if (h->profiling) cudaEventRecord(h->ev[5], st);
             // ordered replay of the survivors with refinement on demand, then the (normally empty) sequential fallback
-            if ((rc = launch_refine_replay(ix, d_rot, d_qs, d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
+            if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
                                            d_counts + q0, h->d_stats, tw, st, launches)))
                 return rc;
-            if ((rc = launch_scan(ix, d_rot, d_lut, d_qs, d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+            if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallback, &tw, st)))
                 return rc;
             *launches += 1;
@@ -344,6 +457,8 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         }
         if (h->profiling) {
             RBQ_CUDA(cudaEventSynchronize(h->ev[6]));
+            // with several front-end chunks the stage events bracket the LAST chunk only: prep/coarse/select then cover that
+            // chunk, and everything before it is charged to the prep stage (ev[0] -> ev[1])
             for (int i = 0; i < 6; ++i) {
                 float t = 0;
                 cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
@@ -368,6 +483,19 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
     }
     return RBQ_OK;
 }
+
+// Calls on one handle share its workspace: every entry point that enqueues work first makes its stream wait for the
+// previous call's last kernel (busy event) and records the event again when it is done enqueuing, so calls from other
+// threads or on other streams are ordered on the device, not only on the host.
+struct Serial {
+    const rbq_index* h;
+    cudaStream_t st;
+    Serial(const rbq_index* h_, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->busy_ev) cudaEventCreateWithFlags(&h->busy_ev, cudaEventDisableTiming);
+        else cudaStreamWaitEvent(st, h->busy_ev, 0);
+    }
+    ~Serial() { cudaEventRecord(h->busy_ev, st); }
+};
 
 int check_search_args(const rbq_index* ix, size_t dim, size_t top_k, size_t* nprobe) {
     if (!ix) return fail(RBQ_INVALID_CONFIG, "null index handle");
@@ -440,6 +568,7 @@ void rbq_index_free(rbq_index* h) {
             if (e) cudaEventDestroy(e);
         for (auto& e : h->feed_ev)
             if (e) cudaEventDestroy(e);
+        if (h->busy_ev) cudaEventDestroy(h->busy_ev);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
     }
@@ -506,8 +635,17 @@ int rbq_set_profiling(rbq_index* h, int on) {
 }
 int rbq_set_coarse_mode(rbq_index* h, int mode) {
     if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
-    if (mode != 0 && mode != 1) return fail(RBQ_INVALID_CONFIG, "coarse mode must be 0 (exact) or 1 (tensor-core candidates)");
+    if (mode < -1 || mode > 2)
+        return fail(RBQ_INVALID_CONFIG, "coarse mode must be -1 (auto), 0 (exact), 1 (dense tensor-core scores) or 2 (filtered in the GEMM epilogue)");
+    std::lock_guard<std::mutex> lk(h->mu);
     h->coarse_mode = mode;
+    return RBQ_OK;
+}
+int rbq_set_coarse_terms(rbq_index* h, int terms) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (terms != 1 && terms != 3) return fail(RBQ_INVALID_CONFIG, "coarse terms must be 1 or 3");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->coarse_terms = terms;
     return RBQ_OK;
 }
 
@@ -529,6 +667,7 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     DevStats ds;
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));  // asynchronous entry points may still be running
     RBQ_CUDA(cudaMemcpy(&ds, h->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
     h->last_stats.blocks_scanned = ds.blocks;
     h->last_stats.bytes_scanned = ds.blocks * (uint64_t)h->dev.block_stride;
@@ -555,6 +694,7 @@ int rbq_search_batch_device(const rbq_index* h, const float* d_queries, size_t n
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
     h->last_stats = rbq_search_stats{};
     h->last_stats.queries = nq;
     if (nq == 0) return RBQ_OK;
@@ -562,13 +702,15 @@ int rbq_search_batch_device(const rbq_index* h, const float* d_queries, size_t n
         RBQ_CUDA(cudaMemsetAsync(d_counts, 0, nq * 4, st));
         return RBQ_OK;
     }
-    const size_t qt = tile_queries(h, nq);
-    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, false, 0)))) return rc;
+    const Plan pl = make_plan(h, nq, nprobe);
+    if ((rc = ensure_ws(h, ws_need(h, pl, nprobe, top_k, dim, false, 0)))) return rc;
     RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     uint64_t launches = 0;
     rc = search_device(h, d_queries, nq, top_k, nprobe, d_filter_bits, filter_nbits, d_ids, d_scores, d_counts,
-                       (char*)h->ws, qt, st, &launches);
+                       (char*)h->ws, pl, st, &launches);
     h->last_stats.kernel_launches = launches;
+    h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.front_chunk = (uint32_t)pl.cq;
     return rc;
 }
 
@@ -587,12 +729,15 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         std::memset(counts, 0, nq * 4);
         return RBQ_OK;
     }
-    const size_t qt = tile_queries(h, nq);
-    const size_t fwords = filter_bits ? (filter_nbits + 63) / 64 : 0;
-    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, true, fwords)))) return rc;
+    const Plan pl = make_plan(h, nq, nprobe);
+    const size_t qt = pl.qt;
+    // a filter that is present but empty (RoaringBitmap::new()) admits nothing (reference src/tests.rs
+    // filtered_search_with_empty_filter): keep one zero word so the kernels see a non-null filter
+    const size_t fwords = filter_bits ? std::max<size_t>((filter_nbits + 63) / 64, 1) : 0;
+    if ((rc = ensure_ws(h, ws_need(h, pl, nprobe, top_k, dim, true, fwords)))) return rc;
     // host-io buffers live behind the pipeline buffers
     Carver cv{(char*)h->ws};
-    cv.off = ws_need(h, qt, nprobe, top_k, dim, false, 0);
+    cv.off = ws_need(h, pl, nprobe, top_k, dim, false, 0);
     float* d_q = cv.take<float>(qt * dim);
     uint64_t* d_ids = cv.take<uint64_t>(qt * top_k);
     float* d_sc = cv.take<float>(qt * top_k);
@@ -606,7 +751,12 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     // the host entry point runs on the handle's own streams (the legacy default stream would serialise with every
     // blocking stream of the process); the call is synchronous, so nothing outlives it
     cudaStream_t st = getenv("RBQ_LEGACY_STREAM") ? nullptr : h->compute_stream;
-    if (d_f) RBQ_CUDA(cudaMemcpyAsync(d_f, filter_bits, fwords * 8, cudaMemcpyHostToDevice, st));
+    Serial serial(h, st);
+    if (d_f) {
+        const size_t src_words = (filter_nbits + 63) / 64;
+        if (src_words) RBQ_CUDA(cudaMemcpyAsync(d_f, filter_bits, src_words * 8, cudaMemcpyHostToDevice, st));
+        else RBQ_CUDA(cudaMemsetAsync(d_f, 0, 8, st));
+    }
     RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     uint64_t launches = 0;
     HostFeed feed;
@@ -615,6 +765,8 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     feed.dim = dim;
     feed.copy = getenv("RBQ_FEED_SAME_STREAM") ? st : h->copy_stream;
     feed.ev = h->feed_ev;
+    // the copy stream reuses the staging buffer of the previous call: it must not run ahead of that call's kernels
+    if (feed.copy != st) RBQ_CUDA(cudaStreamWaitEvent(feed.copy, h->busy_ev, 0));
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
         // 4 chunks per tile: the H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks
@@ -630,7 +782,7 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         static const bool trace = getenv("RBQ_TRACE") != nullptr;
         timespec t0, t1, t2;
         if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
-        rc = search_device(h, nullptr, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, qt, st, &launches, &feed);
+        rc = search_device(h, nullptr, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, pl, st, &launches, &feed);
         if (rc) return rc;
         if (trace) clock_gettime(CLOCK_MONOTONIC, &t1);
         feed.h_q += n * dim;
@@ -646,6 +798,8 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         }
     }
     h->last_stats.kernel_launches = launches;
+    h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.front_chunk = (uint32_t)pl.cq;
     return RBQ_OK;
 }
 
@@ -656,12 +810,12 @@ int rbq_search_batch(const rbq_index* h, const float* queries, size_t nq, size_t
 
 // ---- multi-GPU search in three phases (include/rbq.h) ------------------------------------------------
 namespace {
-int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, size_t* nprobe, size_t* qt) {
+int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, size_t* nprobe, Plan* pl) {
     int rc = check_search_args(h, dim_or_zero ? dim_or_zero : (size_t)h->dev.dim, top_k, nprobe);
     if (rc) return rc;
     if (top_k == 0 || nq == 0) return fail(RBQ_INVALID_CONFIG, "phased search needs nq > 0 and top_k > 0");
-    *qt = tile_queries(h, nq);
-    if (*qt < nq) return fail(RBQ_INVALID_CONFIG, "phased search handles one tile of queries per batch: split the batch");
+    *pl = make_plan(h, nq, *nprobe);
+    if (pl->qt < nq) return fail(RBQ_INVALID_CONFIG, "phased search handles one tile of queries per batch (131072 queries, 2^26 probes): split the batch");
     if (*nprobe < 2) return fail(RBQ_INVALID_CONFIG, "phased search needs nprobe >= 2");
     return RBQ_OK;
 }
@@ -669,86 +823,91 @@ int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, s
 
 int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, size_t q_begin,
                    size_t q_count, rbq_probe_rec* d_probes, void* stream) {
-    size_t qt = 0;
-    int rc = dist_args(h, nq, dim, top_k, &nprobe, &qt);
+    Plan pl;
+    int rc = dist_args(h, nq, dim, top_k, &nprobe, &pl);
     if (rc) return rc;
     if (q_begin > nq || q_count > nq - q_begin) return fail(RBQ_INVALID_CONFIG, "query slice out of range");
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
     h->last_stats = rbq_search_stats{};
     h->last_stats.queries = nq;
-    if ((rc = ensure_ws(h, ws_need(h, qt, nprobe, top_k, dim, false, 0)))) return rc;
+    h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.front_chunk = (uint32_t)pl.cq;
+    if ((rc = ensure_ws(h, ws_need(h, pl, nprobe, top_k, dim, false, 0)))) return rc;
     RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
     const DevIndex& ix = h->dev;
-    const size_t D = ix.D;
-    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
+    if (h->profiling) cudaEventRecord(h->ev[0], st);
     // every shard scans its lists for ALL queries, so it needs every query's rotation, LUT and scalars ...
     if ((rc = launch_query_prep(ix, d_queries, nq, L.d_rot, L.d_lut, L.d_qs, st))) return rc;
+    if (h->profiling) cudaEventRecord(h->ev[1], st);
     uint64_t launches = 1;
-    // ... but the probe lists are the same on every shard: each one computes a slice
+    // ... but the probe lists are the same on every shard: each one computes a slice (in front-end chunks)
+    for (size_t c0 = q_begin; c0 < q_begin + q_count; c0 += pl.cq) {
+        const size_t m = std::min(pl.cq, q_begin + q_count - c0);
+        if ((rc = run_front(h, L, pl, nullptr, c0, m, nprobe, st, &launches, false, nullptr, nullptr))) return rc;
+    }
     if (q_count) {
-        const size_t c0 = q_begin, m = q_count;
-        if (h->coarse_mode == 0) {
-            if ((rc = launch_coarse_exact(ix, L.d_rot + c0 * D, m, L.d_sc + c0 * ix.nlist, st))) return rc;
-            if ((rc = launch_probe_select(ix, L.d_rot + c0 * D, L.d_sc + c0 * ix.nlist, m, nprobe, L.d_pr + c0 * nprobe, st))) return rc;
-            launches += 2;
-        } else {
-            if ((rc = launch_split_bf16(L.d_rot + c0 * D, m, (int)D, 0, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, st))) return rc;
-            if ((rc = launch_coarse_tc(ix, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, m, L.d_sc + c0 * ix.nlist, st))) return rc;
-            if ((rc = launch_probe_select_tc(ix, L.d_rot + c0 * D, L.d_sc + c0 * ix.nlist, L.d_qs + c0, m, nprobe, h->coarse_eps,
-                                             L.d_pr + c0 * nprobe, h->fallback_counter(), st, false)))
-                return rc;
-            launches += 3;
-        }
         if ((rc = launch_probe_export(L.d_pr, q_begin, q_count, nprobe, d_probes, st))) return rc;
         launches += 1;
     }
+    if (h->profiling) cudaEventRecord(h->ev[2], st);
     h->last_stats.kernel_launches = launches;
     return RBQ_OK;
 }
 
 int rbq_dist_head(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes, float* d_tau,
                   uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream) {
-    size_t qt = 0;
-    int rc = dist_args(h, nq, 0, top_k, &nprobe, &qt);
+    Plan pl;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
     if (rc) return rc;
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (h->ws_bytes < ws_need(h, qt, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
+    Serial serial(h, st);
+    if (h->ws_bytes < ws_need(h, pl, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
     const DevIndex& ix = h->dev;
-    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
     uint64_t launches = h->last_stats.kernel_launches;
+    if (h->profiling) cudaEventRecord(h->ev[3], st);
     if ((rc = launch_probe_import(ix, d_probes, nq, nprobe, L.d_pr, L.d_head_owner, st))) return rc;
-    RBQ_CUDA(cudaMemsetAsync(L.tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
+    RBQ_CUDA(cudaMemsetAsync(L.tw.surv_cnt, 0, (pl.qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
+    int head_launch = 0;
     if ((rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats, L.tw,
-                          st, &launches, 0, nq, 0, L.d_head_owner)))
+                          st, &launches, 0, nq, &head_launch, L.d_head_owner)))
         return rc;
     RBQ_CUDA(cudaMemcpyAsync(d_tau, L.tw.tau, nq * 4, cudaMemcpyDeviceToDevice, st));
+    if (h->profiling) cudaEventRecord(h->ev[4], st);
     h->last_stats.kernel_launches = launches + 1;
     return RBQ_OK;
 }
 
 int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids, float* d_scores,
                   uint32_t* d_counts, void* stream) {
-    size_t qt = 0;
-    int rc = dist_args(h, nq, 0, top_k, &nprobe, &qt);
+    Plan pl;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
     if (rc) return rc;
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (h->ws_bytes < ws_need(h, qt, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
+    Serial serial(h, st);
+    if (h->ws_bytes < ws_need(h, pl, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
     const DevIndex& ix = h->dev;
-    const WsLayout L = carve_ws(h, (char*)h->ws, qt, nprobe, top_k);
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
     uint64_t launches = h->last_stats.kernel_launches;
+    if (h->profiling) cudaEventRecord(h->ev[5], st);
     RBQ_CUDA(cudaMemcpyAsync(L.tw.tau, d_tau, nq * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, st, &launches))) return rc;
+    if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, st, &launches,
+                          h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
+        return rc;
     if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, nq, nprobe, top_k, d_ids, d_scores, d_counts, h->d_stats, L.tw, st, &launches)))
         return rc;
     if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats,
                           h->work_counter(), kScanFallback, &L.tw, st)))
         return rc;
+    if (h->profiling) cudaEventRecord(h->ev[6], st);
     h->last_stats.kernel_launches = launches + 2;
     return RBQ_OK;
 }
@@ -761,6 +920,7 @@ int rbq_fetch_embedding(const rbq_index* h, uint64_t vector_id, float* out, int*
     if (nvec == 0) return RBQ_OK;
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));  // the workspace may still be in use by an asynchronous search
     int rc = ensure_ws(h, 4096 + (size_t)h->dev.dim * 4);
     if (rc) return rc;
     unsigned long long* d_pos = reinterpret_cast<unsigned long long*>(h->ws);
@@ -827,39 +987,41 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
                     float* probe_consts) {
     int rc = check_search_args(h, dim, 1, &nprobe);
     if (rc) return rc;
+    if (nq == 0) return RBQ_OK;
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
-    const size_t D = h->dev.D, nl = h->dev.nlist;
-    if ((rc = ensure_ws(h, nq * (dim * 4 + D * 8 + 32 + nl * 4 + nprobe * sizeof(Probe) + D * 6 + 4) + 16384))) return rc;
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));
+    // the product's own front end (run_front), whatever coarse mode the handle is in
+    const Plan pl = make_plan(h, nq, nprobe);
+    const size_t base = ws_need(h, pl, nprobe, 1, dim, false, 0);
+    if ((rc = ensure_ws(h, base + pl.qt * dim * 4 + 4096))) return rc;
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, 1);
     Carver cv{(char*)h->ws};
-    float* d_q = cv.take<float>(nq * dim);
-    float* d_rot = cv.take<float>(nq * D);
-    uint8_t* d_lut = cv.take<uint8_t>(nq * D * 4);
-    QueryScalars* d_qs = cv.take<QueryScalars>(nq);
-    float* d_sc = cv.take<float>(nq * nl);
-    Probe* d_pr = cv.take<Probe>(nq * nprobe);
-    RBQ_CUDA(cudaMemcpy(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice));
-    if ((rc = launch_query_prep(h->dev, d_q, nq, d_rot, d_lut, d_qs, nullptr))) return rc;
-    if (h->coarse_mode == 0) {
-        if ((rc = launch_coarse_exact(h->dev, d_rot, nq, d_sc, nullptr))) return rc;
-        if ((rc = launch_probe_select(h->dev, d_rot, d_sc, nq, nprobe, d_pr, nullptr))) return rc;
-    } else {
-        uint16_t* d_qsplit = cv.take<uint16_t>(nq * 3 * D);
-        float* d_qn2 = cv.take<float>(nq);
-        RBQ_CUDA(cudaMemset(h->fallback_counter(), 0, 4));
-        if ((rc = launch_split_bf16(d_rot, nq, (int)D, 0, d_qsplit, d_qn2, nullptr))) return rc;
-        if ((rc = launch_coarse_tc(h->dev, d_qsplit, d_qn2, nq, d_sc, nullptr))) return rc;
-        if ((rc = launch_probe_select_tc(h->dev, d_rot, d_sc, d_qs, nq, nprobe, h->coarse_eps, d_pr, h->fallback_counter(), nullptr)))
-            return rc;
+    cv.off = base;
+    float* d_q = cv.take<float>(pl.qt * dim);
+    RBQ_CUDA(cudaMemset(h->fallback_counter(), 0, 4));
+    std::vector<Probe> pr(pl.qt * nprobe);
+    uint64_t launches = 0;
+    for (size_t q0 = 0; q0 < nq; q0 += pl.qt) {
+        const size_t n = std::min(pl.qt, nq - q0);
+        RBQ_CUDA(cudaMemcpy(d_q, queries + q0 * dim, n * dim * 4, cudaMemcpyHostToDevice));
+        for (size_t c0 = 0; c0 < n; c0 += pl.cq) {
+            const size_t m = std::min(pl.cq, n - c0);
+            if ((rc = run_front(h, L, pl, d_q + c0 * dim, c0, m, nprobe, nullptr, &launches, true, nullptr, nullptr, true))) return rc;
+        }
+        RBQ_CUDA(cudaMemcpy(pr.data(), L.d_pr, n * nprobe * sizeof(Probe), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n * nprobe; ++i) {
+            const size_t o = q0 * nprobe + i;
+            probe_cids[o] = pr[i].cid;
+            probe_consts[3 * o] = pr[i].g_add;
+            probe_consts[3 * o + 1] = pr[i].g_error;
+            probe_consts[3 * o + 2] = pr[i].dot_qc;
+        }
     }
-    std::vector<Probe> pr(nq * nprobe);
-    RBQ_CUDA(cudaMemcpy(pr.data(), d_pr, pr.size() * sizeof(Probe), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < pr.size(); ++i) {
-        probe_cids[i] = pr[i].cid;
-        probe_consts[3 * i] = pr[i].g_add;
-        probe_consts[3 * i + 1] = pr[i].g_error;
-        probe_consts[3 * i + 2] = pr[i].dot_qc;
-    }
+    h->last_stats = rbq_search_stats{};
+    h->last_stats.queries = nq;
+    h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.front_chunk = (uint32_t)pl.cq;
     return RBQ_OK;
 }
 

@@ -685,6 +685,7 @@ extern "C" int rbq_index_build(const float* data, size_t n, size_t dim, const fl
     dv.f_add_ex = d_fae;
     dv.f_rescale_ex = d_fre;
     if ((rc = prepare_coarse_tc(h))) return rc;
+    if ((rc = prepare_coarse_sample(h))) return rc;
     if ((rc = prepare_ex_lanes(h))) return rc;
     void* stp = nullptr;
     RBQ_CUDA(cudaMalloc(&stp, sizeof(DevStats) + 64));

@@ -13,6 +13,7 @@
 // total_cmp-ordered key (ties broken by cluster id like the reference), sorts them, and re-derives
 // the K6 constants with the same lane order.
 #include <algorithm>
+#include <cmath>
 
 #include "rbq_internal.h"
 
@@ -382,12 +383,25 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_tc_kernel(DevIndex i
 // thread), the radix select skips the bit prefix all keys share (scores of one query span a narrow range, so a
 // fixed top-down digit order would pile every key on one histogram bin), the bin scan is a warp prefix sum, the
 // candidates' exact (l2, ip) are computed once and reused for K6, and the exact keys are ranked by counting.
-template <int KPT, bool NEED_IP>
+// LIST: the keys come from the query's candidate list (coarse filter mode: the GEMM epilogue kept only the centroids whose
+// approximate score beat a per-query threshold `fthr` estimated from a centroid sample) instead of a dense score row.  The
+// list provably holds every centroid with approximate score <= fthr, so the selection below is exact whenever the 2*delta
+// band around the nprobe-th best candidate stays inside fthr; otherwise (or when the list overflowed / is too short) the
+// query goes to the exact fallback kernel.
+struct SelList {
+    const CandRec* cand;
+    const uint32_t* cand_cnt;
+    const float* fthr;
+    uint32_t cap;
+    uint32_t* fb_list;
+    uint32_t* fb_count;
+};
+template <int KPT, bool NEED_IP, bool LIST>
 __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
                                                                        float* __restrict__ scores,
                                                                        const QueryScalars* __restrict__ qs, int nprobe,
                                                                        int sort_n, float eps_g, Probe* __restrict__ probes,
-                                                                       unsigned int* __restrict__ fallbacks) {
+                                                                       unsigned int* __restrict__ fallbacks, SelList sl) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
     float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
@@ -396,20 +410,40 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     float* cip = cl2 + sort_n;                                                  // sort_n exact ip
     __shared__ SelShared sh;
     __shared__ uint32_t s_min[kSelThreads / 32], s_max[kSelThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nl = (int)ix.nlist, D = ix.D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, D = ix.D;
     const size_t q = blockIdx.x;
     const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
-    float* sc = scores + q * (size_t)nl;
+    int nl = (int)ix.nlist;
+    float* sc = nullptr;
+    const CandRec* cl = nullptr;
+    if (LIST) {
+        const uint32_t cnt = sl.cand_cnt[q];
+        if (cnt > sl.cap || cnt < (uint32_t)nprobe) {  // overflowed or too short: exact fallback (uniform branch)
+            if (tid == 0) sl.fb_list[atomicAdd(sl.fb_count, 1u)] = (uint32_t)q;
+            return;
+        }
+        nl = (int)cnt;
+        cl = sl.cand + q * (size_t)sl.cap;
+    } else {
+        sc = scores + q * (size_t)nl;
+    }
     for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
 
-    uint32_t key[KPT];
+    uint32_t key[KPT], col[LIST ? KPT : 1];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
         const int c = tid + kSelThreads * j;
         key[j] = 0u;
+        if (LIST) col[j] = 0u;
         if (c < nl) {
-            key[j] = order_key(sc[c], desc);
+            if (LIST) {
+                const CandRec rec = cl[c];
+                key[j] = order_key(rec.score, desc);
+                col[j] = rec.cid;
+            } else {
+                key[j] = order_key(sc[c], desc);
+            }
             kmin = min(kmin, key[j]);
             kmax = max(kmax, key[j]);
         }
@@ -509,6 +543,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
         thr = T - 2.0f * (eps_g + round_terms) * qn * cm;
     }
     const uint32_t thr_key = order_key(thr, desc);
+    // LIST: the candidate list is complete only up to the filter threshold
+    const bool covered = !LIST || thr_key <= order_key(sl.fthr[q], desc);
     if (tid == 0) sh.count = 0;
     __syncthreads();
 #pragma unroll
@@ -516,14 +552,14 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
         const int c = tid + kSelThreads * j;
         if (c < nl && key[j] <= thr_key) {
             const unsigned int slot = atomicAdd(&sh.count, 1u);
-            if (slot < (unsigned)sort_n) cand[slot] = (uint32_t)c;
+            if (slot < (unsigned)sort_n) cand[slot] = LIST ? col[j] : (uint32_t)c;
         }
     }
     __syncthreads();
     const unsigned int m = sh.count;
     const int lane8 = tid & 7, grp = tid >> 3;
     const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
-    if (m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
+    if (covered && m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
         for (unsigned int i = grp; i < m; i += kSelThreads / 8) {
             const uint32_t cid = cand[i];
             float l2, ip;  // L2 searches never read dot_query_centroid (src/ivf.rs:2031-2042 uses it for InnerProduct only)
@@ -556,6 +592,10 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
         }
         return;
     }
+    if (LIST) {  // rare: the exact fallback kernel scores every centroid of this query
+        if (tid == 0) sl.fb_list[atomicAdd(sl.fb_count, 1u)] = (uint32_t)q;
+        return;
+    }
     // rare: exact scores for every centroid of this query, then the exact selection
     if (tid == 0) atomicAdd(fallbacks, 1u);
     for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
@@ -569,7 +609,107 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
 }
 
-static int sort_size(size_t n) {
+// Exact fallback of the filter mode: the queries listed in fb_list get exact scores for every centroid (into a per-CTA scratch
+// row) and the exact selection, like the dense kernels' rare path.  Persistent: fb_count[0] = how many, fb_count[1] = cursor.
+__global__ void __launch_bounds__(kSelThreads) probe_select_exact_kernel(DevIndex ix, const float* __restrict__ rot, int nprobe, int sort_n,
+                                                                        Probe* __restrict__ probes, const uint32_t* __restrict__ fb_list,
+                                                                        uint32_t* __restrict__ fb_count, float* __restrict__ scratch,
+                                                                        unsigned int* __restrict__ fallbacks) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
+    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
+    __shared__ SelShared sh;
+    __shared__ uint32_t s_idx;
+    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    float* sc = scratch + (size_t)blockIdx.x * nl;
+    const int lane8 = tid & 7, grp = tid >> 3;
+    const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
+    const uint32_t total = fb_count[0];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_idx = atomicAdd(&fb_count[1], 1u);
+        __syncthreads();
+        const uint32_t idx = s_idx;
+        if (idx >= total) break;
+        const size_t q = fb_list[idx];
+        if (tid == 0) atomicAdd(fallbacks, 1u);
+        for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+        for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+        __syncthreads();
+        for (int c = grp; c < nl; c += kSelThreads / 8) {
+            float l2, ip;
+            exact_pair(rq, ix.centroids + (size_t)c * D, D, lane8, gmask, &l2, &ip);
+            if (lane8 == 0) sc[c] = desc ? ip : l2;
+        }
+        __syncthreads();
+        gather_exact(sc, nl, nprobe, desc, sh, sel);
+        sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
+    }
+}
+
+// Filter mode, step 2: the rank-th best of a query's sample scores = the filter threshold.  One CTA of 128 threads per query,
+// the sample (<= 4096 scores) in registers, bisection on the 32-bit order key.
+constexpr int kThrThreads = 128, kThrVpt = 32;
+__global__ void __launch_bounds__(kThrThreads) sample_threshold_kernel(const float* __restrict__ ss, uint32_t samp_n, uint32_t rank, int desc,
+                                                                      float* __restrict__ thr) {
+    __shared__ uint32_t s_cnt[2][kThrThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = ss + (size_t)blockIdx.x * samp_n;
+    uint32_t key[kThrVpt];
+#pragma unroll
+    for (int j = 0; j < kThrVpt; ++j) {
+        const uint32_t c = (uint32_t)tid + kThrThreads * j;
+        key[j] = c < samp_n ? order_key(row[c], desc != 0) : 0xffffffffu;
+    }
+    uint32_t lo = 0u, hi = 0xffffffffu;  // smallest K with #(key <= K) >= rank lies in [lo, hi]
+    for (int it = 0; it < 32; ++it) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < kThrVpt; ++j) c += key[j] <= mid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) s_cnt[it & 1][warp] = c;
+        __syncthreads();
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThrThreads / 32; ++w) tot += s_cnt[it & 1][w];
+        if (tot >= rank) hi = mid;
+        else lo = mid + 1u;
+    }
+    if (tid == 0) thr[blockIdx.x] = key_to_float(hi, desc != 0);
+}
+int launch_sample_threshold(const float* d_samp_scores, size_t nq, uint32_t samp_n, uint32_t rank, int metric, float* d_thr, cudaStream_t st) {
+    if (nq == 0) return RBQ_OK;
+    if (samp_n > (uint32_t)(kThrThreads * kThrVpt) || rank == 0 || rank > samp_n) return fail(RBQ_INVALID_CONFIG, "sample threshold: bad sample size or rank");
+    sample_threshold_kernel<<<(unsigned)nq, kThrThreads, 0, st>>>(d_samp_scores, samp_n, rank, metric == RBQ_METRIC_INNER_PRODUCT, d_thr);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+// Sample rank whose score, used as the filter threshold, leaves about rank * nlist / samp_n candidates per query and
+// falls below the needed population rank (nprobe plus the re-score band) with probability < ~1e-3 (3 sigma of the
+// order statistic).  0: the filter mode does not pay (nprobe too large for this centroid table).
+uint32_t filter_sample_rank(uint32_t nlist, uint32_t samp_n, size_t nprobe, int terms) {
+    if (samp_n == 0 || nlist == 0) return 0;
+    const double f = (double)samp_n / (double)nlist;
+    const double need = ((terms == 1 ? 2.5 : 1.25) * (double)nprobe + 8.0) * f;
+    uint32_t r = 4;
+    while ((double)r - 3.0 * std::sqrt((double)r) < need) ++r;
+    return r <= samp_n / 4 ? r : 0;
+}
+uint32_t filter_cand_cap(uint32_t nlist, uint32_t samp_n, size_t nprobe, int terms) {
+    const uint32_t r = filter_sample_rank(nlist, samp_n, nprobe, terms);
+    if (r == 0) return 0;
+    const double expect = (double)r * (double)nlist / (double)samp_n;
+    uint32_t cap = 512;
+    while ((double)cap < 2.0 * expect + 64.0) cap <<= 1;
+    return cap <= 4096 ? cap : 0;
+}
+
+static int sort_size
+(size_t n) {
     int s = 32;
     while ((size_t)s < n) s <<= 1;
     return s;
@@ -598,9 +738,9 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
     if (ix.nlist <= 16u * kSelThreads && sort_n <= 256) {
         const size_t smem_f = (size_t)sort_n * 20 + (size_t)ix.D * 4;
         const bool ipn = need_ip || ix.metric == RBQ_METRIC_INNER_PRODUCT;
-#define RBQ_SEL(KPT, IP)                                                                                              \
-    probe_select_fast_kernel<KPT, IP><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, \
-                                                                                eps_g, d_probes, d_fallbacks)
+#define RBQ_SEL(KPT, IP)                                                                                                     \
+    probe_select_fast_kernel<KPT, IP, false><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, \
+                                                                                       eps_g, d_probes, d_fallbacks, SelList{})
         if (ix.nlist <= 4u * kSelThreads) {
             if (ipn) RBQ_SEL(4, true);
             else RBQ_SEL(4, false);
@@ -617,6 +757,51 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
         RBQ_CUDA(cudaFuncSetAttribute(probe_select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_select_tc_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ix, d_rot, d_scores, d_qs, (int)nprobe, sort_n, eps_g,
                                                                    d_probes, d_fallbacks);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
+// Filter mode, steps 4-5: selection from the candidate lists, then the exact fallback for the queries it could not settle.
+int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, size_t nq, size_t nprobe, float eps_g,
+                             const FilterWs& fw, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st, bool need_ip) {
+    if (nq == 0) return RBQ_OK;
+    if (nprobe > (size_t)kMaxNprobe)
+        return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
+    const int sort_n = sort_size(std::min<size_t>(2 * nprobe + 64, (size_t)kMaxNprobe));
+    const size_t smem_f = (size_t)sort_n * 20 + (size_t)ix.D * 4;
+    const bool ipn = need_ip || ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    SelList sl{fw.cand, fw.cand_cnt, fw.thr, fw.cap, fw.fb_list, fw.fb_count};
+#define RBQ_SELL(KPT, IP)                                                                                                              \
+    do {                                                                                                                              \
+        if (smem_f > 48 * 1024)                                                                                                       \
+            RBQ_CUDA(cudaFuncSetAttribute(probe_select_fast_kernel<KPT, IP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
+        probe_select_fast_kernel<KPT, IP, true><<<(unsigned)nq, kSelThreads, smem_f, st>>>(ix, d_rot, nullptr, d_qs, (int)nprobe, sort_n, eps_g, \
+                                                                                          d_probes, d_fallbacks, sl);                \
+    } while (0)
+    const uint32_t kpt = (fw.cap + kSelThreads - 1) / kSelThreads;
+    if (kpt <= 2) {
+        if (ipn) RBQ_SELL(2, true);
+        else RBQ_SELL(2, false);
+    } else if (kpt <= 4) {
+        if (ipn) RBQ_SELL(4, true);
+        else RBQ_SELL(4, false);
+    } else if (kpt <= 8) {
+        if (ipn) RBQ_SELL(8, true);
+        else RBQ_SELL(8, false);
+    } else if (kpt <= 16) {
+        if (ipn) RBQ_SELL(16, true);
+        else RBQ_SELL(16, false);
+    } else {
+        return fail(RBQ_INVALID_CONFIG, "candidate capacity exceeds the selection kernel's limit (4096)");
+    }
+#undef RBQ_SELL
+    RBQ_CUDA(cudaGetLastError());
+    const int sort_x = sort_size(nprobe);
+    const size_t smem_x = (size_t)sort_x * 8 + (size_t)ix.D * 4;
+    if (smem_x > 48 * 1024)
+        RBQ_CUDA(cudaFuncSetAttribute(probe_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+    probe_select_exact_kernel<<<fw.fb_ctas, kSelThreads, smem_x, st>>>(ix, d_rot, (int)nprobe, sort_x, d_probes, fw.fb_list, fw.fb_count,
+                                                                       fw.fb_scratch, d_fallbacks);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "rbq_internal.h"
 
 namespace rbq {
@@ -27,6 +29,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int THREADS = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int ACC_BUFS = 2;           // accumulator buffers in tensor memory: the epilogue of tile i overlaps the MMAs of tile i+1
+constexpr int TMEM_COLS = ACC_BUFS * BN;  // 512 = the whole tensor memory of the SM (one CTA per SM: 193 KB of shared memory)
 constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 }  // namespace tc
 
@@ -37,6 +41,7 @@ __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -68,22 +73,57 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// monotone map of f32::total_cmp onto u32 (same as coarse.cu::order_key, ascending)
+__device__ __forceinline__ uint32_t tc_order_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
 
+// Persistent GEMM: every CTA walks a sequence of 128 x 256 output tiles.  Three roles: one thread feeds the 4-stage
+// shared-memory ring with TMA, one thread issues tcgen05.mma into one of the two 256-column accumulator buffers, four warps
+// drain the other buffer.  MODE picks what the drain does with a score:
+//   kGemmScores  store it (dense nq x ncols matrix: small centroid tables, the centroid sample of the filter mode)
+//   kGemmFilter  compare with the row's threshold and append the few that pass to the row's candidate list
+//   kGemmArgmin  keep the row's best (k-means assignment); tiles of one row block are consecutive so it lives in registers
+template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
-    coarse_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nq, int nlist,
-                       int num_kb, int metric, const float* __restrict__ qn2, const float* __restrict__ cn2,
-                       float* __restrict__ scores) {
+    coarse_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmEpi e, int num_kb,
+                       int mtiles, int ntiles) {
     using namespace tc;
     extern __shared__ unsigned char gsm_raw[];
     unsigned char* gsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = gsm;
     unsigned char* sB = gsm + (size_t)STAGES * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES));
-    // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-    const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull = s_u32(bars + 2 * STAGES);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) accumulator buffer full, [2S+2..2S+4) accumulator buffer drained; then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_BUFS);
+    const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull0 = s_u32(bars + 2 * STAGES),
+                   tempty0 = s_u32(bars + 2 * STAGES + ACC_BUFS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+
+    // this CTA's tiles: strided over the grid, row blocks fastest (CTAs running together share a centroid tile); for the
+    // arg-min drain a contiguous range of the column-fastest order (a row block's tiles follow each other)
+    const int total = mtiles * ntiles;
+    int t_begin, t_end, t_step;
+    if (MODE == kGemmArgmin) {
+        const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+        t_begin = min(total, (int)blockIdx.x * per);
+        t_end = min(total, t_begin + per);
+        t_step = 1;
+    } else {
+        t_begin = (int)blockIdx.x;
+        t_end = total;
+        t_step = (int)gridDim.x;
+    }
+    auto tile_mn = [&](int t, int& m, int& n) {
+        if (MODE == kGemmArgmin) {
+            m = t / ntiles;
+            n = t - m * ntiles;
+        } else {
+            n = t / mtiles;
+            m = t - n * mtiles;
+        }
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -92,11 +132,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             bar_init(full0 + 8 * s, 1);
             bar_init(empty0 + 8 * s, 1);
         }
-        bar_init(tfull, 1);
+        for (int b = 0; b < ACC_BUFS; ++b) {
+            bar_init(tfull0 + 8 * b, 1);
+            bar_init(tempty0 + 8 * b, 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 256 columns x 128 lanes of fp32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(BN) : "memory");
+    if (warp == 1) {  // TMEM: 2 x 256 columns x 128 lanes of fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -106,92 +149,167 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-                bar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-                tma_load_2d(s_u32(sA + (size_t)s * A_BYTES), &map_a, full0 + 8 * s, kb * BK, m_blk * BM);
-                tma_load_2d(s_u32(sB + (size_t)s * B_BYTES), &map_b, full0 + 8 * s, kb * BK, n_blk * BN);
+            uint32_t it = 0;
+            for (int t = t_begin; t < t_end; t += t_step) {
+                int m_blk, n_blk;
+                tile_mn(t, m_blk, n_blk);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    bar_wait(empty0 + 8 * s, ((it / STAGES) & 1u) ^ 1u);
+                    bar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+                    tma_load_2d(s_u32(sA + (size_t)s * A_BYTES), &map_a, full0 + 8 * s, kb * BK, m_blk * BM);
+                    tma_load_2d(s_u32(sB + (size_t)s * B_BYTES), &map_b, full0 + 8 * s, kb * BK, n_blk * BN);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer (one thread) =====
             constexpr uint32_t idesc = umma_idesc(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                bar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+            uint32_t it = 0, ti = 0;
+            for (int t = t_begin; t < t_end; t += t_step, ++ti) {
+                const uint32_t buf = ti & 1u;
+                bar_wait(tempty0 + 8 * buf, ((ti >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer (free at first use)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = umma_desc(s_u32(sA + (size_t)s * A_BYTES));
-                const uint64_t db = umma_desc(s_u32(sB + (size_t)s * B_BYTES));
+                const uint32_t acc_addr = tmem + buf * (uint32_t)BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    bar_wait(full0 + 8 * s, (it / STAGES) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc(s_u32(sA + (size_t)s * A_BYTES));
+                    const uint64_t db = umma_desc(s_u32(sB + (size_t)s * B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / UK; ++k) {
-                    const uint32_t acc = (kb | k) ? 1u : 0u;
-                    // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-                    asm volatile(
-                        "{\n"
-                        ".reg .pred p;\n"
-                        "setp.ne.b32 p, %4, 0;\n"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-                        "}" ::"r"(tmem),
-                        "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
-                        : "memory");
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint32_t acc = (kb | k) ? 1u : 0u;
+                        // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                        asm volatile(
+                            "{\n"
+                            ".reg .pred p;\n"
+                            "setp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+                            "}" ::"r"(acc_addr),
+                            "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
+                            : "memory");
+                    }
+                    // frees the smem stage once the MMAs above have read it (implies fence::before_thread_sync)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
+                                 : "memory");
                 }
-                // frees the smem stage once the MMAs above have read it (implies fence::before_thread_sync)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull0 + 8 * buf)
                              : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> scores =====
+        // ===== epilogue: TMEM -> registers -> (scores | candidate lists | running arg-min) =====
         const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-        bar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m_blk * BM + quarter * 32 + lane;
-        const float qq = (row < nq && metric == RBQ_METRIC_L2) ? qn2[row] : 0.0f;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int n0 = n_blk * BN + c0;
-            if (row < nq) {
-                float* out = scores + (size_t)row * nlist + n0;
-                if (n0 + 32 <= nlist && (nlist & 3) == 0) {
+        const bool l2 = e.metric == RBQ_METRIC_L2;
+        uint32_t ti = 0;
+        int best_m = -1;  // kGemmArgmin: row block the running best belongs to
+        unsigned long long best = ~0ull;
+        auto flush_best = [&]() {
+            const int row = best_m * BM + quarter * 32 + lane;
+            if (best_m >= 0 && row < e.nq && best != ~0ull) atomicMin(e.best + row, best);
+        };
+        for (int t = t_begin; t < t_end; t += t_step, ++ti) {
+            int m_blk, n_blk;
+            tile_mn(t, m_blk, n_blk);
+            const uint32_t buf = ti & 1u;
+            const int row = m_blk * BM + quarter * 32 + lane;
+            const bool row_ok = row < e.nq;
+            const float qq = (row_ok && l2) ? __ldg(e.qn2 + row) : 0.0f;
+            float thr = 0.0f;
+            if (MODE == kGemmFilter) thr = row_ok ? __ldg(e.thr + row) : (l2 ? -INFINITY : INFINITY);
+            if (MODE == kGemmArgmin && m_blk != best_m) {
+                flush_best();
+                best_m = m_blk;
+                best = ~0ull;
+            }
+            bar_wait(tfull0 + 8 * buf, (ti >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int ncols_tile = min(BN, e.ncols - n_blk * BN);  // columns of this tile that exist
+            for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int n0 = n_blk * BN + c0;
+                const bool full32 = n0 + 32 <= e.ncols && (e.ncols & 3) == 0;
+                if (MODE == kGemmScores) {
+                    if (row_ok) {
+                        float* out = e.scores + (size_t)row * e.ncols + n0;
+                        if (full32) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v;
-                        float* pv = &v.x;
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 v;
+                                float* pv = &v.x;
+                                float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (l2) cc = __ldg(reinterpret_cast<const float4*>(e.cn2 + n0 + j));
+                                const float* pc = &cc.x;
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float g = __uint_as_float(r[j + t]);
-                            pv[t] = metric == RBQ_METRIC_L2 ? (qq + cn2[n0 + j + t]) - 2.0f * g : g;
+                                for (int u = 0; u < 4; ++u) {
+                                    const float g = __uint_as_float(r[j + u]);
+                                    pv[u] = l2 ? (qq + pc[u]) - 2.0f * g : g;
+                                }
+                                *reinterpret_cast<float4*>(out + j) = v;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < e.ncols) {
+                                    const float g = __uint_as_float(r[j]);
+                                    out[j] = l2 ? (qq + e.cn2[n0 + j]) - 2.0f * g : g;
+                                }
                         }
-                        *reinterpret_cast<float4*>(out + j) = v;
                     }
                 } else {
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + j < nlist) {
-                            const float g = __uint_as_float(r[j]);
-                            out[j] = metric == RBQ_METRIC_L2 ? (qq + cn2[n0 + j]) - 2.0f * g : g;
+                    const int lim = min(32, e.ncols - n0);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (l2) {
+                            if (full32) cc = __ldg(reinterpret_cast<const float4*>(e.cn2 + n0 + j));
+                            else {
+                                float* pc = &cc.x;
+                                for (int u = 0; u < 4; ++u) pc[u] = n0 + j + u < e.ncols ? e.cn2[n0 + j + u] : 0.0f;
+                            }
                         }
+                        const float* pc = &cc.x;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float g = __uint_as_float(r[j + u]);
+                            const float sc = l2 ? (qq + pc[u]) - 2.0f * g : g;
+                            if (MODE == kGemmFilter) {
+                                const bool pass = (l2 ? sc <= thr : sc >= thr) && (j + u < lim);
+                                if (pass) {
+                                    const uint32_t slot = atomicAdd(e.cand_cnt + row, 1u);
+                                    if (slot < e.cap) e.cand[(size_t)row * e.cap + slot] = CandRec{sc, (uint32_t)(n0 + j + u)};
+                                }
+                            } else {  // arg-min over max(score, 0), ties to the lower column (reference src/kmeans.rs:505-516)
+                                const unsigned long long key =
+                                    ((unsigned long long)tc_order_key(fmaxf(sc, 0.0f)) << 32) | (uint32_t)(n0 + j + u);
+                                if (j + u < lim && key < best) best = key;
+                            }
+                        }
+                    }
                 }
             }
+            // this warp's TMEM reads are complete: hand the buffer back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(tempty0 + 8 * buf);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (MODE == kGemmArgmin) flush_best();
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -232,6 +350,20 @@ int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, v
     return RBQ_OK;
 }
 
+// rows idx[0..n) of a row-major byte matrix -> dst (16-byte granules); builds the centroid sample of the filter mode
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, size_t row_u4, const uint32_t* __restrict__ idx, uint4* __restrict__ dst) {
+    const uint4* s = src + (size_t)idx[blockIdx.x] * row_u4;
+    uint4* d = dst + (size_t)blockIdx.x * row_u4;
+    for (size_t i = threadIdx.x; i < row_u4; i += blockDim.x) d[i] = s[i];
+}
+int launch_gather_rows(const void* d_src, size_t row_bytes, const uint32_t* d_idx, size_t n, void* d_dst, cudaStream_t st) {
+    if (n == 0) return RBQ_OK;
+    if (row_bytes % 16 != 0) return fail(RBQ_INVALID_CONFIG, "gather_rows: row size must be a multiple of 16 bytes");
+    gather_rows_kernel<<<(unsigned)n, 128, 0, st>>>(reinterpret_cast<const uint4*>(d_src), row_bytes / 16, d_idx, reinterpret_cast<uint4*>(d_dst));
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
 // ---- tensor maps + launch ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -248,12 +380,12 @@ static int get_encode() {
     return RBQ_OK;
 }
 
-// 2-D bf16 tensor [rows][cols] (cols contiguous), box = [box_rows][64 cols], 128-byte swizzle, OOB -> 0
-static int make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols, int box_rows) {
+// 2-D bf16 tensor [rows][k_cols] with row pitch `pitch_elems`: the terms = 1 view reads only the leading D columns of a 3D-wide split
+static int make_map_pitch(CUtensorMap* map, const void* base, size_t rows, size_t k_cols, size_t pitch_elems, int box_rows) {
     int rc = get_encode();
     if (rc) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)k_cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -263,25 +395,50 @@ static int make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols
     return RBQ_OK;
 }
 
-// scores[nq][nlist] (approximate).  d_qsplit: nq x 3D bf16, d_csplit: nlist x 3D bf16.
-int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st) {
-    if (nq == 0) return RBQ_OK;
-    const size_t K3 = (size_t)3 * ix.D;
-    CUtensorMap ma, mb;
-    int rc;
-    if ((rc = make_map(&ma, d_qsplit, nq, K3, tc::BM))) return rc;
-    if ((rc = make_map(&mb, ix.cent_split, ix.nlist, K3, tc::BN))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
-        attr_set = true;
-    }
-    const int num_kb = (int)((K3 + tc::BK - 1) / tc::BK);
-    dim3 grid((ix.nlist + tc::BN - 1) / tc::BN, (unsigned)((nq + tc::BM - 1) / tc::BM));
-    coarse_gemm_kernel<<<grid, tc::THREADS, tc::SMEM, st>>>(ma, mb, (int)nq, (int)ix.nlist, num_kb, ix.metric, d_qn2, ix.cent_n2,
-                                                           d_scores);
+static int gemm_sms() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return sms > 0 ? sms : 148;
+}
+
+template <int MODE>
+static int launch_gemm_mode(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, int num_kb, int mtiles, int ntiles, cudaStream_t st) {
+    RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+    const long long total = (long long)mtiles * ntiles;
+    const int grid = (int)std::min<long long>(total, gemm_sms());
+    coarse_gemm_kernel<MODE><<<grid, tc::THREADS, tc::SMEM, st>>>(ma, mb, epi, num_kb, mtiles, ntiles);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
+}
+
+int launch_coarse_gemm(int mode, const void* d_a, size_t rows, const void* d_b, size_t cols, int D, int terms, const GemmEpi& epi,
+                       cudaStream_t st) {
+    if (rows == 0 || cols == 0) return RBQ_OK;
+    const size_t pitch = (size_t)3 * D, K = terms == 1 ? (size_t)D : pitch;
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map_pitch(&ma, d_a, rows, K, pitch, tc::BM))) return rc;
+    if ((rc = make_map_pitch(&mb, d_b, cols, K, pitch, tc::BN))) return rc;
+    const int num_kb = (int)((K + tc::BK - 1) / tc::BK);
+    const size_t mt = (rows + tc::BM - 1) / tc::BM, nt = (cols + tc::BN - 1) / tc::BN;
+    if (mt * nt > 0x7fffffffull) return fail(RBQ_INVALID_CONFIG, "coarse GEMM: too many tiles in one launch");
+    switch (mode) {
+        case kGemmScores: return launch_gemm_mode<kGemmScores>(ma, mb, epi, num_kb, (int)mt, (int)nt, st);
+        case kGemmFilter: return launch_gemm_mode<kGemmFilter>(ma, mb, epi, num_kb, (int)mt, (int)nt, st);
+        default: return launch_gemm_mode<kGemmArgmin>(ma, mb, epi, num_kb, (int)mt, (int)nt, st);
+    }
+}
+
+// scores[nq][nlist] (approximate).  d_qsplit: nq x 3D bf16, d_csplit: nlist x 3D bf16.
+int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st, int terms) {
+    GemmEpi e;
+    e.nq = (int)nq;
+    e.ncols = (int)ix.nlist;
+    e.metric = ix.metric;
+    e.qn2 = d_qn2;
+    e.cn2 = ix.cent_n2;
+    e.scores = d_scores;
+    return launch_coarse_gemm(kGemmScores, d_qsplit, nq, ix.cent_split, ix.nlist, ix.D, terms, e, st);
 }
 
 }  // namespace rbq

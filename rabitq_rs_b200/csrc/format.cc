@@ -5,6 +5,7 @@
 // between the version word and the trailer; same validation order and error strings.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "rbq_internal.h"
 
@@ -23,7 +24,7 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 
 // ---- CRC-32/IEEE, slice-by-8 ---------------------------------------------------------------
 static uint32_t g_crc[8][256];
-static bool g_crc_ready = false;
+static std::once_flag g_crc_once;  // loads run outside any lock (one thread per GPU shard)
 static void crc_init() {
     for (uint32_t i = 0; i < 256; ++i) {
         uint32_t c = i;
@@ -32,10 +33,9 @@ static void crc_init() {
     }
     for (uint32_t i = 0; i < 256; ++i)
         for (int t = 1; t < 8; ++t) g_crc[t][i] = (g_crc[t - 1][i] >> 8) ^ g_crc[0][g_crc[t - 1][i] & 0xff];
-    g_crc_ready = true;
 }
 uint32_t crc32_ieee(uint32_t crc, const uint8_t* p, size_t n) {
-    if (!g_crc_ready) crc_init();
+    std::call_once(g_crc_once, crc_init);
     crc = ~crc;
     while (n >= 8) {
         uint32_t a, b;
@@ -103,6 +103,8 @@ int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, Host
     const char* kEof = "failed to fill whole buffer";
     if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
         return fail(RBQ_INVALID_CONFIG, "shard_rank/shard_count out of range");
+    if (shard_count > kMaxShards)  // list_owner is a byte per list and the device merge walks <= kMaxShards sorted lists
+        return fail(RBQ_INVALID_CONFIG, "shard_count exceeds the supported maximum (32)");
     Reader r{p, n};
     char magic[4];
     if (!r.get(magic, 4)) return fail(RBQ_IO, kEof);

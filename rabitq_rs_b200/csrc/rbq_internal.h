@@ -14,6 +14,7 @@ struct rbq_index;
 namespace rbq {
 
 constexpr int kBatch = 32;  // FASTSCAN_BATCH_SIZE (reference src/simd.rs:768)
+constexpr int kMaxShards = 32;  // list_owner is one byte per list; the device merge walks one sorted list per lane
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const std::string& msg);
@@ -69,6 +70,11 @@ struct DevIndex {
     const void* cent_split; // nlist*3D bf16: [hi | lo | hi] split of the centroids (tensor-core coarse stage)
     const float* cent_n2;   // |c|^2 per centroid
     float cmax_norm;        // max |c|
+    // strided sample of the centroids (coarse filter mode: a per-query score threshold is estimated from the sample, the
+    // full GEMM's epilogue then keeps only the centroids that beat it)
+    const void* samp_split; // samp_n*3D bf16, rows gathered from cent_split
+    const float* samp_n2;   // |c|^2 of the sampled centroids
+    uint32_t samp_n;        // 0: filter mode unavailable (small nlist)
     const uint32_t* list_n; // nlist
     const uint8_t* list_owner;  // nlist: owning shard of every list (nullptr: this handle owns all lists)
     int shard_rank;
@@ -132,8 +138,9 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     uint32_t max_items;
     uint32_t pairs_per_item;
     // head stage (resolve.cu): dense (lower bound, ip | estimate) of every vector of a query's first owned list
-    float2* head_buf;      // [nq * head_cap]
+    float2* head_buf;      // [head_rows * head_cap]: row (q - first query of the head sub-chunk)
     uint32_t head_cap;     // slots per query (multiple of 32); longer lists send the query to the fallback path
+    uint32_t head_rows;    // queries per head sub-chunk
     uint32_t* fb_list;     // [nq] queries left to the sequential fallback (counters[2] = how many)
 };
 constexpr uint32_t kFbResume = 0x80000000u;
@@ -197,7 +204,7 @@ int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
                 float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
-                size_t q_begin, size_t q_count, int chunk_index, const uint8_t* d_head_owner = nullptr);
+                size_t q_begin, size_t q_count, int* launch_index, const uint8_t* d_head_owner = nullptr);
 int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                          size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
                          const TailWs& tw, cudaStream_t st, uint64_t* launches);
@@ -214,7 +221,45 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
                            size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st,
                            bool need_ip = true);
 int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
-int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st);
+int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st, int terms = 3);
+// coarse_tc.cu: the persistent tcgen05 GEMM behind every dense contraction of the engine.  A: rows x (3D bf16, pitch 3D), B: cols x
+// (3D bf16); terms = 3 uses the whole split (fp32-class dot products), terms = 1 only the leading hi x hi block (bf16-class).
+enum GemmMode { kGemmScores = 0, kGemmFilter = 1, kGemmArgmin = 2 };
+struct CandRec {  // a centroid that passed the filter: its approximate score and id
+    float score;
+    uint32_t cid;
+};
+struct GemmEpi {
+    int nq = 0, ncols = 0, metric = 0;
+    const float* qn2 = nullptr;      // |a|^2 per row (L2)
+    const float* cn2 = nullptr;      // |b|^2 per column (L2)
+    float* scores = nullptr;         // kGemmScores: [nq][ncols]
+    const float* thr = nullptr;      // kGemmFilter: per-row threshold (L2: keep score <= thr; IP: keep score >= thr)
+    CandRec* cand = nullptr;         // kGemmFilter: [nq][cap]
+    uint32_t* cand_cnt = nullptr;    //              [nq], zeroed by the caller; may exceed cap (overflow)
+    uint32_t cap = 0;
+    unsigned long long* best = nullptr;  // kGemmArgmin: [nq], (order key of max(score, 0)) << 32 | column, initialised to ~0
+};
+int launch_coarse_gemm(int mode, const void* d_a, size_t rows, const void* d_b, size_t cols, int D, int terms, const GemmEpi& epi,
+                       cudaStream_t st);
+// coarse.cu, filter mode: threshold from the sample scores, selection from the candidate lists, exact fallback
+struct FilterWs {
+    float* samp_scores;   // [cq][samp_n]
+    float* thr;           // [cq]
+    CandRec* cand;        // [cq][cap]
+    uint32_t* cand_cnt;   // [cq]  } zeroed together per chunk
+    uint32_t* fb_count;   // [2]   } [0] queries sent to the exact fallback, [1] its work cursor
+    uint32_t* fb_list;    // [cq]
+    float* fb_scratch;    // [fb_ctas][nlist]
+    uint32_t cap, fb_ctas;
+};
+int launch_sample_threshold(const float* d_samp_scores, size_t nq, uint32_t samp_n, uint32_t rank, int metric, float* d_thr, cudaStream_t st);
+int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, size_t nq, size_t nprobe, float eps_g,
+                             const FilterWs& fw, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st, bool need_ip);
+uint32_t filter_sample_rank(uint32_t nlist, uint32_t samp_n, size_t nprobe, int terms);
+uint32_t filter_cand_cap(uint32_t nlist, uint32_t samp_n, size_t nprobe, int terms);
+int prepare_coarse_sample(rbq_index* h);
+int launch_gather_rows(const void* d_src, size_t row_bytes, const uint32_t* d_idx, size_t n, void* d_dst, cudaStream_t st);
 int prepare_coarse_tc(rbq_index* h);  // builds cent_split / cent_n2 / cmax_norm from dev.centroids (api.cu)
 size_t probe_select_max_nprobe();
 size_t scan_max_topk();
@@ -254,6 +299,9 @@ struct rbq_index {
     mutable cudaEvent_t feed_ev[16] = {};
     bool profiling = false;
     int scan_mode = 0;         // 0: auto, 1: sequential per-query walk, 2: list-major head/tail/replay
-    int coarse_mode = 1;       // 0: exact FP32 all-pairs, 1: tensor-core candidates + exact re-score
-    float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|)
+    int coarse_mode = -1;      // -1: auto (2 when the centroid table and nprobe allow it, else 1), 0: exact FP32 all-pairs,
+                               // 1: dense tensor-core scores + exact re-score, 2: tensor-core scores filtered in the GEMM epilogue
+    int coarse_terms = 3;      // bf16 split terms multiplied by the coarse GEMM: 3 (fp32-class scores) or 1 (bf16-class, wider re-score band)
+    float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|) with 3 terms
+    mutable cudaEvent_t busy_ev = nullptr;  // recorded after the last kernel of every call: the next call's stream waits on it
 };

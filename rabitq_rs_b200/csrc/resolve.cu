@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128, 3) head_scan_kernel(DevIndex ix, ResolveA
     const bool l2 = ix.metric == RBQ_METRIC_L2;
     const uint32_t nb = (p.nv + kBatch - 1) / kBatch;
     const uint8_t* base = ix.blocks + (size_t)p.blk_off * ix.block_stride;
-    float2* out = a.head_buf + (size_t)q * a.head_cap;
+    float2* out = a.head_buf + (size_t)(q - a.q_begin) * a.head_cap;
     // the next block's codes and factors are in flight while the current block is looked up
     uint4 Cn[NCB];
     load_block_codes<NCB>(base, Cn, ncb, lane);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
                 __syncwarp();
                 const uint32_t nv = p.nv, nb = (nv + kBatch - 1) / kBatch;
                 const unsigned long long vbase = p.vec_off;
-                const float2* hb = a.head_buf + (size_t)q * a.head_cap;
+                const float2* hb = a.head_buf + (size_t)(q - a.q_begin) * a.head_cap;
                 q_blocks = nb;
 
                 // candidate queue: slot i lives in lane i, in visit order
@@ -748,10 +748,10 @@ int launch_probe_import(const DevIndex& ix, const rbq_probe_rec* d_in, size_t nq
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-static int g_res_sms = 0;
-static size_t g_res_smem_optin = 0;
+// limits of the CURRENT device, refreshed by every launcher (a process may drive several GPUs from several threads)
+static thread_local int g_res_sms = 0;
+static thread_local size_t g_res_smem_optin = 0;
 static int res_limits() {
-    if (g_res_sms) return RBQ_OK;
     int dev = 0, v = 0;
     RBQ_CUDA(cudaGetDevice(&dev));
     RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
@@ -844,37 +844,43 @@ static unsigned res_grid(size_t nq, size_t smem) {
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
                 size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids,
                 float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw, cudaStream_t st, uint64_t* launches,
-                size_t q_begin, size_t q_count, int chunk_index, const uint8_t* d_head_owner) {
+                size_t q_begin, size_t q_count, int* launch_index, const uint8_t* d_head_owner) {
     if (nq == 0 || q_count == 0) return RBQ_OK;
     int rc = res_limits();
     if (rc) return rc;
     ResolveArgs a;
     fill_args(a, ix, d_rot, d_lut, d_qs, d_probes, nq, nprobe, top_k, d_filter, filter_nbits, d_ids, d_scores, d_counts, d_stats, tw);
-    a.q_begin = (uint32_t)q_begin;
-    a.q_count = (uint32_t)q_count;
-    a.cursor = kTailCounters + (uint32_t)chunk_index % kHeadCursors;
     a.head_owner = d_head_owner;
     const int ncb_lane = (ix.D / 4 + 31) / 32;
-    if (ix.D > 1024) {
-        rc = ncb_lane <= 12 ? launch_head_scan_ex<12, true>(ix, a, st) : launch_head_scan_ex<16, true>(ix, a, st);
-    } else {
-        switch (ncb_lane) {
-            case 1: rc = launch_head_scan_ex<1, false>(ix, a, st); break;
-            case 2: rc = launch_head_scan_ex<2, false>(ix, a, st); break;
-            case 3: rc = launch_head_scan_ex<3, false>(ix, a, st); break;
-            case 4: rc = launch_head_scan_ex<4, false>(ix, a, st); break;
-            case 5:
-            case 6: rc = launch_head_scan_ex<6, false>(ix, a, st); break;
-            default: rc = launch_head_scan_ex<8, false>(ix, a, st); break;
-        }
-    }
-    if (rc) return rc;
     const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0, a.stage_bufs);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
-    const unsigned grid = res_grid(q_count, smem);
-    RBQ_RES_LAUNCH(resolve_head_kernel, smem, grid);
-    if (launches) *launches += 2;
+    // the dense head buffer holds tw.head_rows queries: the slice is walked in sub-chunks that reuse it (same stream)
+    for (size_t s0 = q_begin; s0 < q_begin + q_count; s0 += tw.head_rows) {
+        a.q_begin = (uint32_t)s0;
+        a.q_count = (uint32_t)std::min<size_t>(tw.head_rows, q_begin + q_count - s0);
+        // work cursor of this launch: the first kHeadCursors launches of a tile use pre-zeroed slots, later ones recycle
+        const int li = launch_index ? (*launch_index)++ : 0;
+        a.cursor = kTailCounters + (uint32_t)li % kHeadCursors;
+        if (li >= (int)kHeadCursors) RBQ_CUDA(cudaMemsetAsync(tw.counters + a.cursor, 0, 4, st));
+        if (ix.D > 1024) {
+            rc = ncb_lane <= 12 ? launch_head_scan_ex<12, true>(ix, a, st) : launch_head_scan_ex<16, true>(ix, a, st);
+        } else {
+            switch (ncb_lane) {
+                case 1: rc = launch_head_scan_ex<1, false>(ix, a, st); break;
+                case 2: rc = launch_head_scan_ex<2, false>(ix, a, st); break;
+                case 3: rc = launch_head_scan_ex<3, false>(ix, a, st); break;
+                case 4: rc = launch_head_scan_ex<4, false>(ix, a, st); break;
+                case 5:
+                case 6: rc = launch_head_scan_ex<6, false>(ix, a, st); break;
+                default: rc = launch_head_scan_ex<8, false>(ix, a, st); break;
+            }
+        }
+        if (rc) return rc;
+        const unsigned grid = res_grid(a.q_count, smem);
+        RBQ_RES_LAUNCH(resolve_head_kernel, smem, grid);
+        if (launches) *launches += 2;
+    }
     return RBQ_OK;
 }
 

@@ -309,10 +309,10 @@ __global__ void __launch_bounds__(kTailWarps * 32, 2) tail_kernel(DevIndex ix, T
     if (lane == 0 && a.stats && st_surv) atomicAdd(&a.stats->survivors, st_surv);
 }
 
-static int g_tail_sms = 0;
-static size_t g_tail_smem_optin = 0;
+// limits of the CURRENT device, refreshed by every launcher (a process may drive several GPUs from several threads)
+static thread_local int g_tail_sms = 0;
+static thread_local size_t g_tail_smem_optin = 0;
 static int tail_limits() {
-    if (g_tail_sms) return RBQ_OK;
     int dev = 0, v = 0;
     RBQ_CUDA(cudaGetDevice(&dev));
     RBQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
@@ -330,11 +330,15 @@ static uint32_t tail_surv_cap(size_t top_k) {
     return (uint32_t)std::min<size_t>(std::max<size_t>(c, 512), 1024);
 }
 
-// dense head buffer: room for the longest list, bounded so that a query tile's buffer stays below 512 MiB
-static uint32_t tail_head_cap(const DevIndex& ix, size_t nq) {
+// dense head buffer: room for the longest list of the shard (lists beyond 64Ki vectors send their queries to the sequential
+// fallback), and as many query rows as fit 512 MiB -- the head pass runs over row-sized sub-chunks of the batch
+static uint32_t tail_head_cap(const DevIndex& ix) {
     const size_t want = ((size_t)ix.max_list_n + 31) / 32 * 32;
-    const size_t afford = std::max<size_t>(256, (((size_t)512 << 20) / 8 / std::max<size_t>(nq, 1)) / 32 * 32);
-    return (uint32_t)std::max<size_t>(32, std::min(want, afford));
+    return (uint32_t)std::max<size_t>(32, std::min<size_t>(want, 65536));
+}
+static uint32_t tail_head_rows(const DevIndex& ix, size_t nq) {
+    const size_t afford = ((size_t)512 << 20) / 8 / tail_head_cap(ix);
+    return (uint32_t)std::max<size_t>(1, std::min<size_t>(nq, std::max<size_t>(afford, 1024)));
 }
 
 size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k) {
@@ -347,7 +351,7 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     n += nq * nprobe * 4 + 256;                      // pairs
     n += max_items * sizeof(TailItem) + 256;
     n += nq * cap * sizeof(Survivor) + 256;
-    n += nq * (size_t)tail_head_cap(ix, nq) * 8 + 256;  // head_buf
+    n += (size_t)tail_head_rows(ix, nq) * tail_head_cap(ix) * 8 + 256;  // head_buf
     n += nq * 4 + 256;                                   // fb_list
     return n;
 }
@@ -374,8 +378,9 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.pairs = reinterpret_cast<uint32_t*>(take(nq * nprobe * 4));
     tw.items = reinterpret_cast<TailItem*>(take((size_t)tw.max_items * sizeof(TailItem)));
     tw.surv = reinterpret_cast<Survivor*>(take(nq * (size_t)tw.surv_cap * sizeof(Survivor)));
-    tw.head_cap = tail_head_cap(ix, nq);
-    tw.head_buf = reinterpret_cast<float2*>(take(nq * (size_t)tw.head_cap * 8));
+    tw.head_cap = tail_head_cap(ix);
+    tw.head_rows = tail_head_rows(ix, nq);
+    tw.head_buf = reinterpret_cast<float2*>(take((size_t)tw.head_rows * tw.head_cap * 8));
     tw.fb_list = reinterpret_cast<uint32_t*>(take(nq * 4));
 }
 

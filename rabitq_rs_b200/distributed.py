@@ -107,6 +107,9 @@ class ShardedSearcher:
         import torch.distributed as dist
 
         nq = dq.shape[0]
+        # the C side clamps nprobe to [1, cluster_count] and strides the probe rows by the clamped value: size and slice
+        # the exchange buffers with the same number
+        nprobe = min(max(int(nprobe), 1), self.ix.cluster_count())
         b = self._buffers(nq, k, nprobe, dq.device)
         q0, qc = b.slices[self.rank]
         self.ix.dist_front(dq, k, nprobe, q0, qc, b.probes)

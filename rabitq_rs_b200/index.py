@@ -237,8 +237,11 @@ class IvfRabitqIndex:
                                     _ptr(counts))
         else:
             fb = np.ascontiguousarray(filter_bits, np.uint64)
+            nbits = fb.size * 64
+            if fb.size == 0:  # an empty filter is still a filter (admits nothing): the ABI tells "absent" by a NULL pointer
+                fb = np.zeros(1, np.uint64)
             rc = L.rbq_search_batch_filtered(self._need(), _ptr(q), nq, dim, k, int(params.nprobe), _ptr(fb),
-                                             fb.size * 64, _ptr(ids), _ptr(scores), _ptr(counts))
+                                             nbits, _ptr(ids), _ptr(scores), _ptr(counts))
         _check(rc)
         return ids[:, :k], scores[:, :k], counts
 
@@ -343,7 +346,11 @@ class IvfRabitqIndex:
         _check(_ffi.lib().rbq_set_scan_mode(self._need(), int(mode)))
 
     def set_coarse_mode(self, mode):
+        """-1 auto, 0 exact FP32, 1 dense tensor-core scores, 2 scores filtered in the GEMM epilogue (all exact)."""
         _check(_ffi.lib().rbq_set_coarse_mode(self._need(), int(mode)))
+
+    def set_coarse_terms(self, terms):
+        _check(_ffi.lib().rbq_set_coarse_terms(self._need(), int(terms)))
 
     # ---- stage probes (tests) ---------------------------------------------------------------------
     def debug_query_prep(self, queries):

@@ -561,3 +561,76 @@ def test_committed_fixtures(rbq, name):
         gix.set_scan_mode(mode)
         got = gix.batch_search(q, rbq.SearchParams(k, nprobe))
         assert assert_results_match(got, (ids, scores, counts), TOL, f"golden {name} mode {mode}") == q.shape[0]
+
+
+# ---- coarse filter mode: probe selection fused into the GEMM epilogue (no nq x nlist score matrix) ----------------
+def _random_cluster_index(orc, n, dim, nlist, metric, seed, bits=1, sort_centroids=False, dup=False):
+    rng = np.random.default_rng(seed)
+    cents = rng.standard_normal((nlist, dim)).astype(np.float32)
+    if dup:  # runs of identical centroids: equal scores, the reference orders them by cluster id
+        cents[1::2] = cents[0::2][: len(cents[1::2])]
+    if sort_centroids:  # adversarial for a strided sample: the table is ordered along one coordinate
+        cents = cents[np.argsort(cents[:, 0])]
+    data = (cents[rng.integers(0, nlist, n)] + 0.3 * rng.standard_normal((n, dim))).astype(np.float32)
+    if metric == 1:
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    d2 = (data * data).sum(1)[:, None] - 2.0 * data @ cents.T + (cents * cents).sum(1)[None, :]
+    assign = d2.argmin(1).astype(np.uint32)
+    return data, orc.Index.train_with_clusters(data, cents, assign, bits, metric)
+
+
+FILTER_CASES = [  # (n, dim, nlist, metric, sorted centroid table, duplicated centroids)
+    (30000, 64, 2560, 0, False, False),
+    (30000, 128, 4096, 1, False, False),
+    (20000, 96, 2100, 0, True, False),    # nlist not a multiple of the GEMM tile; sorted table
+    (20000, 64, 2048, 0, False, True),    # ties between centroids
+]
+
+
+@pytest.mark.parametrize("case", FILTER_CASES)
+def test_coarse_filter_mode_matches_exact_coarse(rbq, oracle, case):
+    """Mode 2 (threshold from a centroid sample, candidates appended by the GEMM epilogue, selection on the lists,
+    exact fallback) must give the reference's probe list bit for bit, like mode 0 and the oracle."""
+    from oracle import oracle as orc
+
+    n, dim, nlist, metric, srt, dup = case
+    data, oix = _random_cluster_index(orc, n, dim, nlist, metric, 11, sort_centroids=srt, dup=dup)
+    gix = _load(rbq, oix.save_bytes())
+    q = np.concatenate([data[:200], _queries(data, 824, 31)])
+    q[5] = 0.0
+    for nprobe in (1, 8, 40, 200):
+        gix.set_coarse_mode(0)
+        c0, f0 = gix.debug_probe(q, nprobe)
+        for terms in (3, 1):
+            gix.set_coarse_mode(2)
+            gix.set_coarse_terms(terms)
+            c2, f2 = gix.debug_probe(q, nprobe)
+            st = gix.stats()
+            if nprobe <= 40:  # a larger nprobe may make the filter ineligible (then the dense path runs)
+                assert st["coarse_mode_used"] == 2, (nprobe, terms, st)
+            assert np.array_equal(c0, c2), f"filter mode changed the probe list (nprobe {nprobe}, terms {terms})"
+            assert np.array_equal(f0.view(np.uint32), f2.view(np.uint32))
+        gix.set_coarse_terms(3)
+        for i in range(0, q.shape[0], 97):
+            assert np.array_equal(c0[i], oix.search_dump(q[i], 1, nprobe)["probe"])
+    # end to end through the auto mode (= filter here), few fallbacks
+    gix.set_coarse_mode(-1)
+    got = gix.batch_search(q, rbq.SearchParams(10, 16))
+    st = gix.stats()
+    assert st["coarse_mode_used"] == 2 and st["coarse_fallbacks"] <= q.shape[0] // 20, st
+    gix.set_coarse_mode(0)
+    ref = gix.batch_search(q, rbq.SearchParams(10, 16))
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    # nprobe too large for the filter to pay: auto falls back to the dense tensor-core path
+    gix.set_coarse_mode(-1)
+    gix.batch_search(q[:64], rbq.SearchParams(10, nlist // 2))
+    assert gix.stats()["coarse_mode_used"] == 1
+
+
+def test_empty_filter_admits_nothing(rbq, oracle):
+    """RoaringBitmap::new() as the filter: no results (reference src/tests.rs filtered_search_with_empty_filter)."""
+    data, oix, blob = oracle_index(2000, 64, 16, 7, 0, kind="uniform11")
+    gix = _load(rbq, blob)
+    assert gix.search_filtered(data[3], rbq.SearchParams(10, 8), []) == []
+    ids, sc, cnt = gix.batch_search(data[:300], rbq.SearchParams(10, 8), np.zeros(0, np.uint64))
+    assert (cnt == 0).all()
