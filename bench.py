@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--nprobe", type=int, default=0, help="skip the recall sweep and use this nprobe")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-mode", type=int, default=int(os.environ.get("RBQ_SCAN_MODE", "0")), help="0 auto, 1 sequential, 2 list-major")
+    ap.add_argument("--coarse-mode", type=int, default=int(os.environ.get("RBQ_COARSE_MODE", "-1")), help="-1 auto, 0 exact, 1 dense TC, 2 filtered TC")
+    ap.add_argument("--coarse-terms", type=int, default=int(os.environ.get("RBQ_COARSE_TERMS", "3")), help="bf16 terms of the coarse GEMM (3 or 1)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -336,6 +338,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     ix.set_scan_mode(args.scan_mode)
+    ix.set_coarse_mode(args.coarse_mode)
+    ix.set_coarse_terms(args.coarse_terms)
     ix.set_profiling(True)  # CUDA events around every stage on the launching stream
     sampler = ClockSampler(local)
     sampler.start()

@@ -50,6 +50,10 @@ int rbq_index_load_mem(const uint8_t* bytes, size_t len, int device, int shard_r
  * rbq_index_save_mem: pass out==NULL to query the size. */
 int rbq_index_save(const rbq_index* ix, const char* path);
 int rbq_index_save_mem(const rbq_index* ix, uint8_t* out, size_t cap, size_t* written);
+/* The same stream with only the lists flagged in keep_list[cluster_count] (the other lists are written empty, their
+ * centroids stay): probe selection on the result equals probe selection on the full index, so queries whose probed lists
+ * are all kept get the full index's answers -- parity checks against a CPU implementation on a 100M-vector index. */
+int rbq_index_save_lists_mem(const rbq_index* ix, const uint8_t* keep_list, size_t nlist, uint8_t* out, size_t cap, size_t* written);
 void rbq_index_free(rbq_index* ix);
 
 /* ---- build: IvfRabitqIndex::train_with_clusters (src/ivf.rs:1025-1103) on the GPU ----
@@ -62,6 +66,32 @@ int rbq_index_build(const float* data, size_t n, size_t dim, const float* centro
                     const uint32_t* assignments, int total_bits, int metric, int rotator_type,
                     uint64_t seed, int faster_config, const uint8_t* rotator_state, int device,
                     rbq_index** out);
+
+/* ---- streaming build on device-resident data (the same train_with_clusters, for data sets too large to pass as one host
+ * array: BASELINE config 5 is 100M x 128).  The caller clusters first (rbq_kmeans_* below, or its own k-means) and announces
+ * how many vectors every list will receive (list_sizes, host, nlist entries, WHOLE data set); chunks of vectors that already
+ * live on the device are then added in ascending id order (vector i of a chunk gets id id_base + i; inside a list, ids keep
+ * their order of arrival, like the forward scan of src/ivf.rs:1141-1149).  RabitqConfig::faster semantics (constant rescale
+ * factor).  shard_rank/shard_count as rbq_index_load: only the lists of this shard are kept, the others' vectors are skipped.
+ * max_chunk bounds the vectors per rbq_builder_add_device call.  rbq_builder_finish checks the announced sizes, releases the
+ * build scratch and turns the builder into a searchable index (it consumes the builder, also on failure). */
+typedef struct rbq_builder rbq_builder;
+int rbq_builder_create(size_t dim, const float* centroids, size_t nlist, const uint32_t* list_sizes, int total_bits, int metric,
+                       int rotator_type, uint64_t seed, const uint8_t* rotator_state, int device, int shard_rank, int shard_count,
+                       size_t max_chunk, rbq_builder** out);
+int rbq_builder_add_device(rbq_builder* b, const float* d_data, const uint32_t* d_assign, size_t m, uint64_t id_base, void* stream);
+int rbq_builder_finish(rbq_builder* b, rbq_index** out);
+void rbq_builder_free(rbq_builder* b);
+
+/* ---- k-means for `train` on the device (src/kmeans.rs:71-186, 291-326, 439-643): training subset of at most
+ * max_points_per_centroid * k points (0 = the reference's 256), Forgy initialisation, niter Lloyd iterations; the assignment
+ * step is the engine's tcgen05 GEMM with the arg-min fused into its epilogue, the centroid update a deterministic segmented
+ * mean.  d_data: n x dim (device), d_centroids: k x dim (device, out).  rbq_kmeans_assign_device = assign_full_dataset
+ * (nearest centroid by |x|^2 + |c|^2 - 2 x.c clamped at 0, ties to the lower cluster id). */
+int rbq_kmeans_device(const float* d_data, size_t n, size_t dim, size_t k, int niter, uint64_t seed, size_t max_points_per_centroid,
+                      float* d_centroids, int device, void* stream);
+int rbq_kmeans_assign_device(const float* d_data, size_t n, size_t dim, const float* d_centroids, size_t k, uint32_t* d_assign,
+                             int device, void* stream);
 
 /* ---- accessors: len / cluster_count (src/ivf.rs:1218-1230) and index fields ---- */
 size_t rbq_index_len(const rbq_index* ix);           /* all vectors of the index (all shards) */

@@ -6,9 +6,9 @@ raises if it is missing -- there is no CPU fallback.
 """
 from . import _ffi
 from .index import (CudaError, DimensionMismatch, EmptyIndex, InvalidConfig, InvalidPersistence, IoError,
-                    IvfRabitqIndex, Metric, RabitqError, RotatorType, SearchParams, ids_to_bitset, shard_assignment)
+                    IndexBuilder, IvfRabitqIndex, Metric, RabitqError, RotatorType, SearchParams, ids_to_bitset, shard_assignment)
 
 _ffi.lib()  # fail loudly at import time if the CUDA library is not built
 
-__all__ = ["IvfRabitqIndex", "SearchParams", "Metric", "RotatorType", "RabitqError", "DimensionMismatch",
+__all__ = ["IvfRabitqIndex", "IndexBuilder", "SearchParams", "Metric", "RotatorType", "RabitqError", "DimensionMismatch",
            "InvalidConfig", "EmptyIndex", "IoError", "InvalidPersistence", "CudaError", "ids_to_bitset", "shard_assignment"]

@@ -36,10 +36,18 @@ def lib():
     L.rbq_index_load_mem.argtypes = [vp, sz, i32, i32, i32, C.POINTER(vp)]
     L.rbq_index_save.argtypes = [vp, C.c_char_p]
     L.rbq_index_save_mem.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.rbq_index_save_lists_mem.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
     L.rbq_index_free.argtypes = [vp]
     L.rbq_index_free.restype = None
     if hasattr(L, "rbq_index_build"):
         L.rbq_index_build.argtypes = [vp, sz, sz, vp, sz, vp, i32, i32, i32, u64, i32, vp, i32, C.POINTER(vp)]
+    L.rbq_builder_create.argtypes = [sz, vp, sz, vp, i32, i32, i32, u64, vp, i32, i32, i32, sz, C.POINTER(vp)]
+    L.rbq_builder_add_device.argtypes = [vp, vp, vp, sz, u64, vp]
+    L.rbq_builder_finish.argtypes = [vp, C.POINTER(vp)]
+    L.rbq_builder_free.argtypes = [vp]
+    L.rbq_builder_free.restype = None
+    L.rbq_kmeans_device.argtypes = [vp, sz, sz, sz, i32, u64, sz, vp, i32, vp]
+    L.rbq_kmeans_assign_device.argtypes = [vp, sz, sz, vp, sz, vp, i32, vp]
     for name in ("len", "local_len", "dim", "padded_dim", "cluster_count"):
         f = getattr(L, "rbq_index_" + name)
         f.argtypes, f.restype = [vp], sz

@@ -575,24 +575,72 @@ void rbq_index_free(rbq_index* h) {
     delete h;
 }
 
-int rbq_index_save_mem(const rbq_index* h, uint8_t* out, size_t cap, size_t* written) {
+// keep (optional): nlist flags; lists with keep[c] == 0 are written empty (their centroid stays)
+static int save_impl(const rbq_index* h, const uint8_t* keep, uint8_t* out, size_t cap, size_t* written) {
     if (!h || !written) return fail(RBQ_INVALID_CONFIG, "null argument");
     if (h->host.shard_count != 1) return fail(RBQ_INVALID_CONFIG, "only a complete (unsharded) index can be saved");
     DeviceGuard g(h->device);
     std::lock_guard<std::mutex> lk(h->mu);
-    HostIndex tmp = h->host;  // metadata + centroids/delta/vl; bulk arrays come back from the device
-    const size_t nb = tmp.blk_off[tmp.nlist], nv = tmp.vec_off[tmp.nlist];
-    tmp.blocks.resize(nb * tmp.block_stride());
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));
+    const HostIndex& src = h->host;
+    const size_t nlist = src.nlist, stride = src.block_stride(), exs = src.ex_stride();
+    HostIndex tmp;  // metadata + centroids; bulk arrays come back from the device
+    tmp.dim = src.dim;
+    tmp.D = src.D;
+    tmp.metric = src.metric;
+    tmp.rot_type = src.rot_type;
+    tmp.ex_bits = src.ex_bits;
+    tmp.rot_bytes = src.rot_bytes;
+    tmp.nlist = nlist;
+    tmp.centroids = src.centroids;
+    tmp.list_n.assign(nlist, 0);
+    tmp.blk_off.assign(nlist + 1, 0);
+    tmp.vec_off.assign(nlist + 1, 0);
+    uint64_t nv = 0, nb = 0;
+    for (size_t c = 0; c < nlist; ++c) {
+        tmp.blk_off[c] = (uint32_t)nb;
+        tmp.vec_off[c] = nv;
+        if (!keep || keep[c]) {
+            tmp.list_n[c] = src.list_n[c];
+            nv += src.list_n[c];
+            nb += (src.list_n[c] + kBatch - 1) / kBatch;
+        }
+    }
+    tmp.blk_off[nlist] = (uint32_t)nb;
+    tmp.vec_off[nlist] = nv;
+    tmp.list_n_all = tmp.list_n;
+    tmp.nvec_total = nv;
+    tmp.blocks.resize(nb * stride);
     tmp.ids.resize(nv);
-    tmp.ex.resize(nv * tmp.ex_stride());
+    tmp.ex.resize(nv * exs);
     tmp.f_add_ex.resize(nv);
     tmp.f_rescale_ex.resize(nv);
-    if (!tmp.blocks.empty()) RBQ_CUDA(cudaMemcpy(tmp.blocks.data(), h->dev.blocks, tmp.blocks.size(), cudaMemcpyDeviceToHost));
-    if (nv) {
-        RBQ_CUDA(cudaMemcpy(tmp.ids.data(), h->dev.ids, nv * 8, cudaMemcpyDeviceToHost));
-        if (!tmp.ex.empty()) RBQ_CUDA(cudaMemcpy(tmp.ex.data(), h->dev.ex, tmp.ex.size(), cudaMemcpyDeviceToHost));
-        RBQ_CUDA(cudaMemcpy(tmp.f_add_ex.data(), h->dev.f_add_ex, nv * 4, cudaMemcpyDeviceToHost));
-        RBQ_CUDA(cudaMemcpy(tmp.f_rescale_ex.data(), h->dev.f_rescale_ex, nv * 4, cudaMemcpyDeviceToHost));
+    tmp.delta.resize(nv);
+    tmp.vl.resize(nv);
+    if (!keep) {
+        if (!tmp.blocks.empty()) RBQ_CUDA(cudaMemcpy(tmp.blocks.data(), h->dev.blocks, tmp.blocks.size(), cudaMemcpyDeviceToHost));
+        if (nv) {
+            RBQ_CUDA(cudaMemcpy(tmp.ids.data(), h->dev.ids, nv * 8, cudaMemcpyDeviceToHost));
+            if (!tmp.ex.empty()) RBQ_CUDA(cudaMemcpy(tmp.ex.data(), h->dev.ex, tmp.ex.size(), cudaMemcpyDeviceToHost));
+            RBQ_CUDA(cudaMemcpy(tmp.f_add_ex.data(), h->dev.f_add_ex, nv * 4, cudaMemcpyDeviceToHost));
+            RBQ_CUDA(cudaMemcpy(tmp.f_rescale_ex.data(), h->dev.f_rescale_ex, nv * 4, cudaMemcpyDeviceToHost));
+        }
+        tmp.delta = src.delta;
+        tmp.vl = src.vl;
+    } else {
+        for (size_t c = 0; c < nlist; ++c) {
+            const size_t n = tmp.list_n[c];
+            if (!n) continue;
+            const size_t so = src.vec_off[c], to = tmp.vec_off[c], nbl = (n + kBatch - 1) / kBatch;
+            RBQ_CUDA(cudaMemcpy(tmp.blocks.data() + (size_t)tmp.blk_off[c] * stride, h->dev.blocks + (size_t)src.blk_off[c] * stride, nbl * stride,
+                                cudaMemcpyDeviceToHost));
+            RBQ_CUDA(cudaMemcpy(tmp.ids.data() + to, h->dev.ids + so, n * 8, cudaMemcpyDeviceToHost));
+            if (exs) RBQ_CUDA(cudaMemcpy(tmp.ex.data() + to * exs, h->dev.ex + so * exs, n * exs, cudaMemcpyDeviceToHost));
+            RBQ_CUDA(cudaMemcpy(tmp.f_add_ex.data() + to, h->dev.f_add_ex + so, n * 4, cudaMemcpyDeviceToHost));
+            RBQ_CUDA(cudaMemcpy(tmp.f_rescale_ex.data() + to, h->dev.f_rescale_ex + so, n * 4, cudaMemcpyDeviceToHost));
+            std::memcpy(tmp.delta.data() + to, src.delta.data() + so, n * 4);
+            std::memcpy(tmp.vl.data() + to, src.vl.data() + so, n * 4);
+        }
     }
     std::vector<uint8_t> buf;
     write_rbq1(tmp, buf);
@@ -602,6 +650,14 @@ int rbq_index_save_mem(const rbq_index* h, uint8_t* out, size_t cap, size_t* wri
         std::memcpy(out, buf.data(), buf.size());
     }
     return RBQ_OK;
+}
+
+int rbq_index_save_mem(const rbq_index* h, uint8_t* out, size_t cap, size_t* written) { return save_impl(h, nullptr, out, cap, written); }
+
+int rbq_index_save_lists_mem(const rbq_index* h, const uint8_t* keep_list, size_t nlist, uint8_t* out, size_t cap, size_t* written) {
+    if (!h || !keep_list) return fail(RBQ_INVALID_CONFIG, "null argument");
+    if (nlist != h->host.nlist) return fail(RBQ_INVALID_CONFIG, "keep_list must hold one flag per cluster");
+    return save_impl(h, keep_list, out, cap, written);
 }
 
 int rbq_index_save(const rbq_index* h, const char* path) {

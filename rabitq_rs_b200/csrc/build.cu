@@ -98,22 +98,29 @@ float const_scaling_factor_host(size_t D, int ex_bits, uint64_t seed) {
 }
 
 // ---- device kernels --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rotate_only_kernel(DevIndex ix, const float* __restrict__ in,
+// src (optional): input row of output row v (streaming build: the chunk's vectors in list order); rows with src == ~0 are skipped
+__global__ void __launch_bounds__(256) rotate_only_kernel(DevIndex ix, const float* __restrict__ in, const uint32_t* __restrict__ src,
                                                           float* __restrict__ out) {
     extern __shared__ float rsm[];
     const int D = ix.D, tid = threadIdx.x, nt = blockDim.x;
     float* buf = rsm;
     float* tmp = rsm + D;
     const size_t v = blockIdx.x;
-    rotate_block(ix, in + v * ix.dim, buf, tmp, tid, nt);
+    size_t row = v;
+    if (src != nullptr) {
+        const uint32_t r = src[v];
+        if (r == 0xffffffffu) return;
+        row = r;
+    }
+    rotate_block(ix, in + row * ix.dim, buf, tmp, tid, nt);
     for (int i = tid; i < D; i += nt) out[v * D + i] = buf[i];
 }
 
-int launch_rotate_only(const DevIndex& ix, const float* d_in, size_t n, float* d_out, cudaStream_t st) {
+int launch_rotate_only(const DevIndex& ix, const float* d_in, size_t n, float* d_out, cudaStream_t st, const uint32_t* d_src) {
     if (n == 0) return RBQ_OK;
     const size_t smem = (size_t)ix.D * 2 * sizeof(float);
     const int threads = ix.D >= 512 ? 256 : 128;
-    rotate_only_kernel<<<(unsigned)n, threads, smem, st>>>(ix, d_in, d_out);
+    rotate_only_kernel<<<(unsigned)n, threads, smem, st>>>(ix, d_in, d_src, d_out);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
@@ -140,11 +147,17 @@ __global__ void __launch_bounds__(kQWarps * 32) quantize_kernel(DevIndex ix, con
                                                                const uint32_t* __restrict__ list_of,
                                                                const float* __restrict__ cents, unsigned n,
                                                                float t_const, const double* __restrict__ t_per_vec,
-                                                               BuildOut out) {
+                                                               BuildOut out, const unsigned long long* __restrict__ dst_pos) {
     extern __shared__ __align__(16) unsigned char qsm[];
     const int D = ix.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ex = ix.ex_bits;
     const unsigned v = blockIdx.x * kQWarps + warp;
     if (v >= n) return;
+    // o: where the vector's outputs go (streaming build: its final position inside its list; ~0 = not on this shard)
+    unsigned long long o = v;
+    if (dst_pos != nullptr) {
+        o = dst_pos[v];
+        if (o == ~0ull) return;
+    }
     float* r = reinterpret_cast<float*>(qsm) + (size_t)warp * 2 * D;  // residual
     float* oa = r + D;                                               // |r| / norm
     unsigned short* code = reinterpret_cast<unsigned short*>(qsm + (size_t)kQWarps * 2 * D * 4) + (size_t)warp * D;
@@ -256,16 +269,16 @@ __global__ void __launch_bounds__(kQWarps * 32) quantize_kernel(DevIndex ix, con
         }
     }
     if (lane == 0) {
-        out.f_add[v] = f_add;
-        out.f_rescale[v] = f_rescale;
-        out.f_error[v] = f_error;
-        out.f_add_ex[v] = f_add_ex;
-        out.f_rescale_ex[v] = f_rescale_ex;
-        out.delta[v] = delta;
-        out.vl[v] = vl;
+        out.f_add[o] = f_add;
+        out.f_rescale[o] = f_rescale;
+        out.f_error[o] = f_error;
+        out.f_add_ex[o] = f_add_ex;
+        out.f_rescale_ex[o] = f_rescale_ex;
+        out.delta[o] = delta;
+        out.vl[o] = vl;
     }
     // sign codes, MSB-first (simd.rs:141-150)
-    uint8_t* brow = out.bin_rows + (size_t)v * (D / 8);
+    uint8_t* brow = out.bin_rows + (size_t)o * (D / 8);
     for (int b = lane; b < D / 8; b += 32) {
         unsigned byte = 0;
 #pragma unroll
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kQWarps * 32) quantize_kernel(DevIndex ix, con
     }
     // ex codes (quantizer.rs:212-243 -> simd.rs:2406-2695 for 1/2/6 bits, generic LSB-first otherwise)
     if (ex > 0) {
-        uint8_t* erow = out.ex + (size_t)v * ix.ex_stride;
+        uint8_t* erow = out.ex + (size_t)o * ix.ex_stride;
         for (int ch = lane; ch < D / 16; ch += 32) {
             const unsigned short* c = code + 16 * ch;
             if (ex == 2) {
@@ -316,13 +329,13 @@ __global__ void __launch_bounds__(kQWarps * 32) quantize_kernel(DevIndex ix, con
 
 int launch_build_quantize(const DevIndex& ix, const float* d_rot, const uint32_t* d_list_of, size_t n,
                           const float* d_cents, float t_const, const double* d_t_per_vec, BuildOut out,
-                          cudaStream_t st) {
+                          cudaStream_t st, const unsigned long long* d_dst_pos) {
     if (n == 0) return RBQ_OK;
     const size_t smem = (size_t)kQWarps * ix.D * (2 * 4 + 2);
     if (smem > 48 * 1024)
         RBQ_CUDA(cudaFuncSetAttribute(quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     quantize_kernel<<<(unsigned)((n + kQWarps - 1) / kQWarps), kQWarps * 32, smem, st>>>(ix, d_rot, d_list_of, d_cents,
-                                                                                      (unsigned)n, t_const, d_t_per_vec, out);
+                                                                                      (unsigned)n, t_const, d_t_per_vec, out, d_dst_pos);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
@@ -373,6 +386,17 @@ __global__ void pack_blocks_kernel(int D, uint32_t block_stride, const uint8_t* 
 using namespace rbq;
 
 namespace {
+struct DeviceGuardLite {
+    int prev = -1;
+    explicit DeviceGuardLite(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuardLite() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 struct Scratch {  // frees temporary device buffers on every exit path
     std::vector<void*> ptrs;
     ~Scratch() {
@@ -695,5 +719,387 @@ extern "C" int rbq_index_build(const float* data, size_t n, size_t dim, const fl
     for (auto& e : h->ev) cudaEventCreate(&e);
     guard.ok = true;
     *out = h;
+    return RBQ_OK;
+}
+
+// ---- streaming build: device-resident data, chunk by chunk -----------------------------------------------------------
+// For indexes too large to hand over as one host array (BASELINE config 5: 100M x 128).  The caller clusters the data first
+// (any k-means: rbq_kmeans_* below or its own), tells the builder how many vectors every list will receive, and then feeds
+// chunks of (vectors, assignments) that already live on the device, in ascending id order.  Every chunk is sorted by list
+// (stable), rotated, quantised and scattered to its final place inside the list-concatenated arrays -- the same kernels and
+// the same bytes as rbq_index_build; with shard_count > 1 only the lists of shard_rank are kept (the same shard a load of the
+// complete file would keep).
+#include <cub/device/device_radix_sort.cuh>
+
+struct rbq_builder {
+    rbq_index* h = nullptr;
+    float t_const = -1.0f;
+    size_t n_local = 0, nblk = 0, chunk_cap = 0;
+    uint64_t added = 0;  // vectors offered so far (all shards)
+    // persistent outputs (owned by h->allocations) and temporaries (freed at finish)
+    float *d_cent = nullptr, *d_fae = nullptr, *d_fre = nullptr;
+    uint32_t *d_list_n = nullptr, *d_blk_off = nullptr;
+    uint64_t *d_vec_off = nullptr, *d_ids = nullptr;
+    uint8_t *d_blocks = nullptr, *d_ex = nullptr, *d_owner = nullptr;
+    std::vector<void*> tmp;
+    uint8_t* d_bin = nullptr;
+    float *d_fa = nullptr, *d_fr = nullptr, *d_fe = nullptr, *d_delta = nullptr, *d_vl = nullptr, *d_rot = nullptr;
+    uint32_t *d_cursor = nullptr, *d_keys_in = nullptr, *d_keys = nullptr, *d_idx_in = nullptr, *d_idx = nullptr, *d_blk_list = nullptr;
+    unsigned long long* d_dst = nullptr;
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int key_bits = 32;
+    ~rbq_builder() {
+        for (void* p : tmp) cudaFree(p);
+    }
+};
+
+namespace {
+// key = list id for vectors this shard keeps, ~0 otherwise (sorts last); idx = position in the chunk
+__global__ void builder_keys_kernel(const uint32_t* __restrict__ assign, const uint8_t* __restrict__ owner, int shard_rank, uint32_t nlist,
+                                    uint32_t m, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, unsigned int* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t c = assign[i];
+    uint32_t k = 0xffffffffu;
+    if (c >= nlist) atomicAdd(bad, 1u);
+    else if (owner == nullptr || owner[c] == (uint8_t)shard_rank) k = c;
+    keys[i] = k;
+    idx[i] = i;
+}
+// sorted (key, idx): final position of every kept vector = list start + vectors of the list that arrived earlier + rank inside
+// the chunk's run of that list; the head of every run bumps the list's cursor by the run length
+__global__ void builder_place_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t m, const uint64_t* __restrict__ vec_off,
+                                     const uint32_t* __restrict__ list_n, uint32_t* __restrict__ cursor, unsigned long long id_base,
+                                     unsigned long long* __restrict__ dst, uint64_t* __restrict__ ids, unsigned int* __restrict__ bad) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t c = keys[j];
+    if (c == 0xffffffffu) {
+        dst[j] = ~0ull;
+        idx[j] = 0xffffffffu;
+        return;
+    }
+    uint32_t lo = 0, hi = j;  // first position holding key c
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < c) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t within = cursor[c] + (j - lo);  // cursor is only advanced by the next kernel
+    if (within >= list_n[c]) {
+        atomicAdd(bad, 1u);
+        dst[j] = ~0ull;
+        idx[j] = 0xffffffffu;
+        return;
+    }
+    const unsigned long long p = vec_off[c] + within;
+    dst[j] = p;
+    ids[p] = id_base + idx[j];
+}
+__global__ void builder_advance_kernel(const uint32_t* __restrict__ keys, uint32_t m, uint32_t* __restrict__ cursor) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t c = keys[j];
+    if (c == 0xffffffffu || (j > 0 && keys[j - 1] == c)) return;  // heads of runs only
+    uint32_t lo = j, hi = m;  // first position past the run
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] <= c) lo = mid + 1;
+        else hi = mid;
+    }
+    cursor[c] += lo - j;
+}
+template <class T>
+int btmp(rbq_builder* b, T** out, size_t count) {
+    void* d = nullptr;
+    RBQ_CUDA(cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16)));
+    b->tmp.push_back(d);
+    *out = reinterpret_cast<T*>(d);
+    return RBQ_OK;
+}
+}  // namespace
+
+extern "C" void rbq_builder_free(rbq_builder* b) {
+    if (!b) return;
+    if (b->h) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(b->h->device);
+        for (void* p : b->tmp) cudaFree(p);
+        b->tmp.clear();
+        rbq_index_free(b->h);
+        cudaSetDevice(prev);
+    }
+    delete b;
+}
+
+extern "C" int rbq_builder_create(size_t dim, const float* centroids, size_t nlist, const uint32_t* list_sizes, int total_bits, int metric,
+                                  int rotator_type, uint64_t seed, const uint8_t* rotator_state, int device, int shard_rank, int shard_count,
+                                  size_t max_chunk, rbq_builder** out) {
+    if (!out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    *out = nullptr;
+    if (nlist == 0 || !centroids || !list_sizes) return fail(RBQ_INVALID_CONFIG, "centroids must be non-empty");
+    if (total_bits < 1 || total_bits > 16) return fail(RBQ_INVALID_CONFIG, "total_bits must be between 1 and 16");
+    if (total_bits > 9) return fail(RBQ_INVALID_CONFIG, "total_bits above 9 (ex_bits > 8) is not supported");
+    if (dim == 0) return fail(RBQ_INVALID_CONFIG, "input vectors must share the same dimension");
+    if (metric != RBQ_METRIC_L2 && metric != RBQ_METRIC_INNER_PRODUCT) return fail(RBQ_INVALID_CONFIG, "unknown metric");
+    if (rotator_type != RBQ_ROTATOR_MATRIX && rotator_type != RBQ_ROTATOR_FHT_KAC) return fail(RBQ_INVALID_CONFIG, "unknown rotator type");
+    if (shard_count < 1 || shard_count > kMaxShards || shard_rank < 0 || shard_rank >= shard_count)
+        return fail(RBQ_INVALID_CONFIG, "shard_rank/shard_count out of range");
+    if (max_chunk == 0 || max_chunk > 0x7fffffffull) return fail(RBQ_INVALID_CONFIG, "max_chunk must be in [1, 2^31)");
+    uint64_t n_total = 0;
+    for (size_t c = 0; c < nlist; ++c) {
+        if (list_sizes[c] > 1000000)
+            return fail(RBQ_INVALID_CONFIG, "a list holds more than 1,000,000 vectors (the RBQ1 loader's per-cluster limit)");
+        n_total += list_sizes[c];
+    }
+    if (n_total == 0) return fail(RBQ_INVALID_CONFIG, "training data must be non-empty");
+    if (nlist > n_total) return fail(RBQ_INVALID_CONFIG, "nlist cannot exceed number of vectors");
+
+    rbq_builder* b = new rbq_builder();
+    rbq_index* h = new rbq_index();
+    b->h = h;
+    struct Guard {
+        rbq_builder* b;
+        bool ok = false;
+        ~Guard() {
+            if (!ok) rbq_builder_free(b);
+        }
+    } guard{b};
+    h->device = device;
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    RBQ_CUDA(cudaSetDevice(device));
+    struct Restore {
+        int d;
+        ~Restore() { cudaSetDevice(d); }
+    } restore{prev_dev};
+
+    HostIndex& hi = h->host;
+    hi.dim = (uint32_t)dim;
+    hi.D = (uint32_t)(rotator_type == RBQ_ROTATOR_FHT_KAC ? (dim + 63) / 64 * 64 : dim);
+    hi.metric = metric;
+    hi.rot_type = rotator_type;
+    hi.ex_bits = total_bits - 1;
+    hi.nlist = nlist;
+    hi.nvec_total = n_total;
+    hi.shard_rank = shard_rank;
+    hi.shard_count = shard_count;
+    const size_t D = hi.D, exs = hi.ex_stride(), stride = hi.block_stride();
+    if (D % 16 != 0)
+        return fail(RBQ_INVALID_CONFIG, "padded_dim must be a multiple of 16 (FastScan requirement, reference src/simd.rs:978-981)");
+    if (D > 2048) return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
+    if (rotator_type == RBQ_ROTATOR_FHT_KAC) {
+        hi.rot_bytes.resize(4 * D / 8);
+        if (rotator_state) std::memcpy(hi.rot_bytes.data(), rotator_state, hi.rot_bytes.size());
+        else {
+            uint64_t st = seed;
+            for (auto& x : hi.rot_bytes) x = (uint8_t)(splitmix64(st) >> 56);
+        }
+    } else if (rotator_state) {
+        hi.rot_bytes.assign(rotator_state, rotator_state + D * D * 4);
+    } else {
+        make_matrix(D, seed, hi.rot_bytes);
+    }
+    b->t_const = hi.ex_bits > 0 ? const_scaling_factor_host(D, hi.ex_bits, seed) : -1.0f;  // RabitqConfig::faster
+    hi.list_n_all.assign(list_sizes, list_sizes + nlist);
+    int rc;
+    if ((rc = shard_layout(hi))) return rc;
+    if (shard_count == 1) hi.list_owner.clear();
+    const size_t n_local = hi.vec_off[nlist], nblk = hi.blk_off[nlist];
+    b->n_local = n_local;
+    b->nblk = nblk;
+    b->chunk_cap = max_chunk;
+
+    DevIndex& dv = h->dev;
+    dv.dim = (int)dim;
+    dv.D = (int)D;
+    dv.metric = metric;
+    dv.ex_bits = hi.ex_bits;
+    dv.rot_type = rotator_type;
+    int lg = 0;
+    while ((2u << lg) <= dim) ++lg;
+    dv.trunc = 1 << lg;
+    dv.fac = 1.0f / std::sqrt((float)dv.trunc);
+    dv.nlist = (uint32_t)nlist;
+    dv.block_stride = (uint32_t)stride;
+    dv.ex_stride = (uint32_t)exs;
+    dv.shard_rank = shard_rank;
+    {
+        uint8_t* d_flip = nullptr;
+        float* d_mt = nullptr;
+        if (rotator_type == RBQ_ROTATOR_FHT_KAC) {
+            if ((rc = persist(h, &d_flip, hi.rot_bytes.size()))) return rc;
+            RBQ_CUDA(cudaMemcpy(d_flip, hi.rot_bytes.data(), hi.rot_bytes.size(), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> mt(D * D);
+            const float* m = reinterpret_cast<const float*>(hi.rot_bytes.data());
+            for (size_t r = 0; r < D; ++r)
+                for (size_t k = 0; k < D; ++k) mt[k * D + r] = m[r * D + k];
+            if ((rc = persist(h, &d_mt, D * D))) return rc;
+            RBQ_CUDA(cudaMemcpy(d_mt, mt.data(), D * D * 4, cudaMemcpyHostToDevice));
+        }
+        dv.flip = d_flip;
+        dv.matrix_t = d_mt;
+    }
+    if ((rc = persist(h, &b->d_cent, nlist * D))) return rc;
+    if ((rc = persist(h, &b->d_list_n, nlist))) return rc;
+    if ((rc = persist(h, &b->d_blk_off, nlist + 1))) return rc;
+    if ((rc = persist(h, &b->d_vec_off, nlist + 1))) return rc;
+    if ((rc = persist(h, &b->d_blocks, nblk * stride))) return rc;
+    if ((rc = persist(h, &b->d_ids, n_local))) return rc;
+    if ((rc = persist(h, &b->d_ex, n_local * exs, 16))) return rc;
+    if ((rc = persist(h, &b->d_fae, n_local))) return rc;
+    if ((rc = persist(h, &b->d_fre, n_local))) return rc;
+    if (shard_count > 1) {
+        if ((rc = persist(h, &b->d_owner, nlist))) return rc;
+        RBQ_CUDA(cudaMemcpy(b->d_owner, hi.list_owner.data(), nlist, cudaMemcpyHostToDevice));
+    }
+    RBQ_CUDA(cudaMemcpy(b->d_list_n, hi.list_n.data(), nlist * 4, cudaMemcpyHostToDevice));
+    RBQ_CUDA(cudaMemcpy(b->d_blk_off, hi.blk_off.data(), (nlist + 1) * 4, cudaMemcpyHostToDevice));
+    RBQ_CUDA(cudaMemcpy(b->d_vec_off, hi.vec_off.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice));
+    // rotate the centroids (ivf.rs:1088-1089)
+    {
+        float* d_in = nullptr;
+        const size_t CH = std::min<size_t>(nlist, 65536);
+        RBQ_CUDA(cudaMalloc(&d_in, CH * dim * 4));
+        for (size_t c0 = 0; c0 < nlist; c0 += CH) {
+            const size_t m = std::min(CH, nlist - c0);
+            cudaError_t e = cudaMemcpy(d_in, centroids + c0 * dim, m * dim * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) rc = launch_rotate_only(dv, d_in, m, b->d_cent + c0 * D, nullptr);
+            if (e != cudaSuccess || rc) {
+                cudaFree(d_in);
+                return rc ? rc : fail(RBQ_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e));
+            }
+        }
+        RBQ_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_in);
+    }
+    hi.centroids.resize(nlist * D);
+    RBQ_CUDA(cudaMemcpy(hi.centroids.data(), b->d_cent, nlist * D * 4, cudaMemcpyDeviceToHost));
+    // temporaries
+    if ((rc = btmp(b, &b->d_bin, n_local * (D / 8)))) return rc;
+    if ((rc = btmp(b, &b->d_fa, n_local))) return rc;
+    if ((rc = btmp(b, &b->d_fr, n_local))) return rc;
+    if ((rc = btmp(b, &b->d_fe, n_local))) return rc;
+    if ((rc = btmp(b, &b->d_delta, n_local))) return rc;
+    if ((rc = btmp(b, &b->d_vl, n_local))) return rc;
+    if ((rc = btmp(b, &b->d_rot, max_chunk * D))) return rc;
+    if ((rc = btmp(b, &b->d_cursor, nlist + 1))) return rc;
+    RBQ_CUDA(cudaMemset(b->d_cursor, 0, (nlist + 1) * 4));
+    if ((rc = btmp(b, &b->d_keys_in, max_chunk))) return rc;
+    if ((rc = btmp(b, &b->d_keys, max_chunk))) return rc;
+    if ((rc = btmp(b, &b->d_idx_in, max_chunk))) return rc;
+    if ((rc = btmp(b, &b->d_idx, max_chunk))) return rc;
+    if ((rc = btmp(b, &b->d_dst, max_chunk))) return rc;
+    if ((rc = btmp(b, &b->d_blk_list, std::max<size_t>(nblk, 1)))) return rc;
+    {
+        std::vector<uint32_t> blk_list(nblk);
+        for (size_t c = 0; c < nlist; ++c)
+            for (uint32_t x = hi.blk_off[c]; x < hi.blk_off[c + 1]; ++x) blk_list[x] = (uint32_t)c;
+        if (nblk) RBQ_CUDA(cudaMemcpy(b->d_blk_list, blk_list.data(), nblk * 4, cudaMemcpyHostToDevice));
+    }
+    RBQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b->sort_tmp_bytes, b->d_keys_in, b->d_keys, b->d_idx_in, b->d_idx, (int)max_chunk, 0, 32,
+                                             (cudaStream_t) nullptr));
+    {
+        char* p = nullptr;
+        if ((rc = btmp(b, &p, b->sort_tmp_bytes + 16))) return rc;
+        b->d_sort_tmp = p;
+    }
+    dv.centroids = b->d_cent;
+    dv.list_n = b->d_list_n;
+    dv.blk_off = b->d_blk_off;
+    dv.vec_off = b->d_vec_off;
+    guard.ok = true;
+    *out = b;
+    return RBQ_OK;
+}
+
+extern "C" int rbq_builder_add_device(rbq_builder* b, const float* d_data, const uint32_t* d_assign, size_t m, uint64_t id_base, void* stream) {
+    if (!b || !b->h) return fail(RBQ_INVALID_CONFIG, "null builder");
+    if (m == 0) return RBQ_OK;
+    if (!d_data || !d_assign) return fail(RBQ_INVALID_CONFIG, "null argument");
+    if (m > b->chunk_cap) return fail(RBQ_INVALID_CONFIG, "chunk larger than the builder's max_chunk");
+    rbq_index* h = b->h;
+    DeviceGuardLite g(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const DevIndex& dv = h->dev;
+    const unsigned tb = 256, gb = (unsigned)((m + tb - 1) / tb);
+    unsigned int* d_bad = reinterpret_cast<unsigned int*>(b->d_cursor + dv.nlist);  // error counter behind the cursors
+    builder_keys_kernel<<<gb, tb, 0, st>>>(d_assign, b->d_owner, dv.shard_rank, dv.nlist, (uint32_t)m, b->d_keys_in, b->d_idx_in, d_bad);
+    size_t tmp_bytes = b->sort_tmp_bytes;
+    RBQ_CUDA(cub::DeviceRadixSort::SortPairs(b->d_sort_tmp, tmp_bytes, b->d_keys_in, b->d_keys, b->d_idx_in, b->d_idx, (int)m, 0, 32, st));
+    builder_place_kernel<<<gb, tb, 0, st>>>(b->d_keys, b->d_idx, (uint32_t)m, b->d_vec_off, b->d_list_n, b->d_cursor, id_base, b->d_dst, b->d_ids,
+                                            d_bad);
+    builder_advance_kernel<<<gb, tb, 0, st>>>(b->d_keys, (uint32_t)m, b->d_cursor);
+    RBQ_CUDA(cudaGetLastError());
+    int rc;
+    if ((rc = launch_rotate_only(dv, d_data, m, b->d_rot, st, b->d_idx))) return rc;
+    BuildOut bo;
+    bo.bin_rows = b->d_bin;
+    bo.ex = b->d_ex;
+    bo.f_add = b->d_fa;
+    bo.f_rescale = b->d_fr;
+    bo.f_error = b->d_fe;
+    bo.f_add_ex = b->d_fae;
+    bo.f_rescale_ex = b->d_fre;
+    bo.delta = b->d_delta;
+    bo.vl = b->d_vl;
+    if ((rc = launch_build_quantize(dv, b->d_rot, b->d_keys, m, b->d_cent, b->t_const, nullptr, bo, st, b->d_dst))) return rc;
+    b->added += m;
+    return RBQ_OK;
+}
+
+extern "C" int rbq_builder_finish(rbq_builder* b, rbq_index** out) {
+    if (!b || !b->h || !out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    *out = nullptr;
+    rbq_index* h = b->h;
+    DeviceGuardLite g(h->device);
+    HostIndex& hi = h->host;
+    DevIndex& dv = h->dev;
+    const size_t nlist = hi.nlist, D = hi.D;
+    RBQ_CUDA(cudaDeviceSynchronize());
+    // every list must have received exactly the announced number of vectors, and no chunk may have carried a bad list id
+    std::vector<uint32_t> cur(nlist + 1);
+    RBQ_CUDA(cudaMemcpy(cur.data(), b->d_cursor, (nlist + 1) * 4, cudaMemcpyDeviceToHost));
+    if (cur[nlist] != 0) return fail(RBQ_INVALID_CONFIG, "assignments reference invalid cluster ids or overflow the announced list sizes");
+    for (size_t c = 0; c < nlist; ++c)
+        if (cur[c] != hi.list_n[c]) return fail(RBQ_INVALID_CONFIG, "the vectors added do not match the announced list sizes");
+    if (b->nblk) {
+        pack_blocks_kernel<<<(unsigned)b->nblk, 128>>>((int)D, dv.block_stride, b->d_bin, b->d_fa, b->d_fr, b->d_fe, b->d_blk_list, b->d_list_n,
+                                                       b->d_blk_off, b->d_vec_off, b->d_blocks);
+        RBQ_CUDA(cudaGetLastError());
+    }
+    hi.delta.resize(b->n_local);
+    hi.vl.resize(b->n_local);
+    if (b->n_local) {
+        RBQ_CUDA(cudaMemcpy(hi.delta.data(), b->d_delta, b->n_local * 4, cudaMemcpyDeviceToHost));
+        RBQ_CUDA(cudaMemcpy(hi.vl.data(), b->d_vl, b->n_local * 4, cudaMemcpyDeviceToHost));
+    }
+    RBQ_CUDA(cudaDeviceSynchronize());
+    for (void* p : b->tmp) cudaFree(p);
+    b->tmp.clear();
+    dv.max_list_n = 0;
+    for (uint32_t c : hi.list_n) dv.max_list_n = std::max(dv.max_list_n, c);
+    dv.blocks = b->d_blocks;
+    dv.ids = b->d_ids;
+    dv.ex = b->d_ex;
+    dv.f_add_ex = b->d_fae;
+    dv.f_rescale_ex = b->d_fre;
+    dv.list_owner = hi.shard_count > 1 ? b->d_owner : nullptr;
+    int rc;
+    if ((rc = prepare_coarse_tc(h))) return rc;
+    if ((rc = prepare_coarse_sample(h))) return rc;
+    if ((rc = prepare_ex_lanes(h))) return rc;
+    void* stp = nullptr;
+    RBQ_CUDA(cudaMalloc(&stp, sizeof(DevStats) + 64));
+    RBQ_CUDA(cudaMemset(stp, 0, sizeof(DevStats) + 64));
+    h->allocations.push_back(stp);
+    h->d_stats = reinterpret_cast<DevStats*>(stp);
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    *out = h;
+    b->h = nullptr;
+    delete b;
     return RBQ_OK;
 }

@@ -648,42 +648,82 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_exact_kernel(DevInde
     }
 }
 
-// Filter mode, step 2: the rank-th best of a query's sample scores = the filter threshold.  One CTA of 128 threads per query,
-// the sample (<= 4096 scores) in registers, bisection on the 32-bit order key.
-constexpr int kThrThreads = 128, kThrVpt = 32;
-__global__ void __launch_bounds__(kThrThreads) sample_threshold_kernel(const float* __restrict__ ss, uint32_t samp_n, uint32_t rank, int desc,
-                                                                      float* __restrict__ thr) {
-    __shared__ uint32_t s_cnt[2][kThrThreads / 32];
+// Filter mode, step 2: the rank-th best of a query's sample scores = the filter threshold.  16 keys per thread (WARPS warps per
+// query: 512 sample scores -> one warp, no block barrier), bisection on the order key between the sample's min and max.
+constexpr int kThrVpt = 16;
+template <int WARPS>
+__global__ void __launch_bounds__(128) sample_threshold_kernel(const float* __restrict__ ss, uint32_t nq, uint32_t samp_n, uint32_t rank, int desc,
+                                                              float* __restrict__ thr) {
+    constexpr int QPB = 4 / WARPS;  // queries per 128-thread block
+    __shared__ uint32_t s_red[3][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* row = ss + (size_t)blockIdx.x * samp_n;
+    const uint32_t q = blockIdx.x * QPB + (WARPS == 1 ? warp : WARPS == 2 ? (warp >> 1) : 0);
+    const int sub = WARPS == 1 ? 0 : WARPS == 2 ? (warp & 1) : warp;  // this warp's part of the query's sample
+    const bool live = q < nq;
+    const float* row = ss + (size_t)(live ? q : 0) * samp_n;
     uint32_t key[kThrVpt];
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
     for (int j = 0; j < kThrVpt; ++j) {
-        const uint32_t c = (uint32_t)tid + kThrThreads * j;
-        key[j] = c < samp_n ? order_key(row[c], desc != 0) : 0xffffffffu;
+        const uint32_t c = (uint32_t)(sub * 32 + lane) + 32u * WARPS * j;
+        key[j] = 0xffffffffu;
+        if (c < samp_n) {
+            key[j] = order_key(row[c], desc != 0);
+            kmin = min(kmin, key[j]);
+            kmax = max(kmax, key[j]);
+        }
     }
-    uint32_t lo = 0u, hi = 0xffffffffu;  // smallest K with #(key <= K) >= rank lies in [lo, hi]
-    for (int it = 0; it < 32; ++it) {
+    // reduce (min, max) and later the counts over the query's warps
+    auto all_min = [&](uint32_t v) { return __reduce_min_sync(0xffffffffu, v); };
+    auto all_max = [&](uint32_t v) { return __reduce_max_sync(0xffffffffu, v); };
+    kmin = all_min(kmin);
+    kmax = all_max(kmax);
+    if (WARPS > 1) {
+        if (lane == 0) {
+            s_red[0][warp] = kmin;
+            s_red[1][warp] = kmax;
+        }
+        __syncthreads();
+        const int w0 = WARPS == 2 ? (warp & ~1) : 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            kmin = min(kmin, s_red[0][w0 + w]);
+            kmax = max(kmax, s_red[1][w0 + w]);
+        }
+    }
+    uint32_t lo = kmin, hi = kmax;  // smallest K with #(key <= K) >= rank lies in [lo, hi] (rank <= samp_n)
+    for (int it = 0; it < 32 && (WARPS > 1 || lo < hi); ++it) {  // multi-warp: fixed trip count keeps the barriers uniform
         const uint32_t mid = lo + ((hi - lo) >> 1);
         uint32_t c = 0;
 #pragma unroll
         for (int j = 0; j < kThrVpt; ++j) c += key[j] <= mid;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (WARPS > 1) {
+            if (lane == 0) s_red[2][warp] = c;
+            __syncthreads();
+            const int w0 = WARPS == 2 ? (warp & ~1) : 0;
+            c = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) s_cnt[it & 1][warp] = c;
-        __syncthreads();
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w = 0; w < kThrThreads / 32; ++w) tot += s_cnt[it & 1][w];
-        if (tot >= rank) hi = mid;
-        else lo = mid + 1u;
+            for (int w = 0; w < WARPS; ++w) c += s_red[2][w0 + w];
+            __syncthreads();
+        }
+        if (lo < hi) {
+            if (c >= rank) hi = mid;
+            else lo = mid + 1u;
+        }
     }
-    if (tid == 0) thr[blockIdx.x] = key_to_float(hi, desc != 0);
+    if (live && sub == 0 && lane == 0) thr[q] = key_to_float(hi, desc != 0);
 }
 int launch_sample_threshold(const float* d_samp_scores, size_t nq, uint32_t samp_n, uint32_t rank, int metric, float* d_thr, cudaStream_t st) {
     if (nq == 0) return RBQ_OK;
-    if (samp_n > (uint32_t)(kThrThreads * kThrVpt) || rank == 0 || rank > samp_n) return fail(RBQ_INVALID_CONFIG, "sample threshold: bad sample size or rank");
-    sample_threshold_kernel<<<(unsigned)nq, kThrThreads, 0, st>>>(d_samp_scores, samp_n, rank, metric == RBQ_METRIC_INNER_PRODUCT, d_thr);
+    if (samp_n > 128u * kThrVpt || rank == 0 || rank > samp_n) return fail(RBQ_INVALID_CONFIG, "sample threshold: bad sample size or rank");
+    const int desc = metric == RBQ_METRIC_INNER_PRODUCT;
+    if (samp_n <= 32u * kThrVpt)
+        sample_threshold_kernel<1><<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
+    else if (samp_n <= 64u * kThrVpt)
+        sample_threshold_kernel<2><<<(unsigned)((nq + 1) / 2), 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
+    else
+        sample_threshold_kernel<4><<<(unsigned)nq, 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

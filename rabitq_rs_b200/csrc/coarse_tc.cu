@@ -32,6 +32,8 @@ constexpr int THREADS = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, 
 constexpr int ACC_BUFS = 2;           // accumulator buffers in tensor memory: the epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int TMEM_COLS = ACC_BUFS * BN;  // 512 = the whole tensor memory of the SM (one CTA per SM: 193 KB of shared memory)
 constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int HIT_SLOTS = 16;         // filter drain: hits of one row in one tile staged in shared memory (slot-major: no bank conflicts)
+constexpr size_t SMEM_HITS = (size_t)HIT_SLOTS * BM * 8;
 }  // namespace tc
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) accumulator buffer full, [2S+2..2S+4) accumulator buffer drained; then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_BUFS);
+    uint2* hits = reinterpret_cast<uint2*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES) + 256);  // kGemmFilter only: [HIT_SLOTS][BM]
     const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull0 = s_u32(bars + 2 * STAGES),
                    tempty0 = s_u32(bars + 2 * STAGES + ACC_BUFS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,6 +226,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 best_m = m_blk;
                 best = ~0ull;
             }
+            uint32_t nhit = 0;  // kGemmFilter: centroids of this tile that beat the row's threshold
+            const int erow = quarter * 32 + lane;
             bar_wait(tfull0 + 8 * buf, (ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ncols_tile = min(BN, e.ncols - n_blk * BN);  // columns of this tile that exist
@@ -287,8 +292,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                             if (MODE == kGemmFilter) {
                                 const bool pass = (l2 ? sc <= thr : sc >= thr) && (j + u < lim);
                                 if (pass) {
-                                    const uint32_t slot = atomicAdd(e.cand_cnt + row, 1u);
-                                    if (slot < e.cap) e.cand[(size_t)row * e.cap + slot] = CandRec{sc, (uint32_t)(n0 + j + u)};
+                                    // staged, so that the row's global counter is bumped once per tile (an atomic that returns
+                                    // a value is a round trip to L2: one per hit stalled the whole drain)
+                                    if (nhit < (uint32_t)HIT_SLOTS) {
+                                        hits[nhit * BM + erow] = make_uint2(__float_as_uint(sc), (uint32_t)(n0 + j + u));
+                                    } else {
+                                        const uint32_t slot = atomicAdd(e.cand_cnt + row, 1u);
+                                        if (slot < e.cap) e.cand[(size_t)row * e.cap + slot] = CandRec{sc, (uint32_t)(n0 + j + u)};
+                                    }
+                                    ++nhit;
                                 }
                             } else {  // arg-min over max(score, 0), ties to the lower column (reference src/kmeans.rs:505-516)
                                 const unsigned long long key =
@@ -303,6 +315,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty0 + 8 * buf);
+            if (MODE == kGemmFilter) {
+                const uint32_t ns = min(nhit, (uint32_t)HIT_SLOTS);
+                if (ns) {
+                    const uint32_t base = atomicAdd(e.cand_cnt + row, ns);
+                    for (uint32_t k = 0; k < ns; ++k)
+                        if (base + k < e.cap) {
+                            const uint2 hv = hits[k * BM + erow];
+                            e.cand[(size_t)row * e.cap + base + k] = CandRec{__uint_as_float(hv.x), hv.y};
+                        }
+                }
+            }
         }
         if (MODE == kGemmArgmin) flush_best();
     }
@@ -316,15 +339,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 // ---- operand preparation ------------------------------------------------------------------------------
 // rows x D fp32 -> rows x 3D bf16 in the order the GEMM wants, plus |x|^2 per row.
 // query side: [hi | hi | lo]; centroid side: [hi | lo | hi]
-__global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int D, int centroid_side,
+__global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int in_dim, int D, int centroid_side,
                                   __nv_bfloat16* __restrict__ out, float* __restrict__ n2) {
     const int row = blockIdx.x;
     if (row >= rows) return;
-    const float* xr = x + (size_t)row * D;
+    const float* xr = x + (size_t)row * in_dim;
     __nv_bfloat16* o = out + (size_t)row * 3 * D;
     float acc = 0.0f;
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        const float v = xr[i];
+        const float v = i < in_dim ? xr[i] : 0.0f;  // columns in_dim..D are zero padding (k-means in the original space)
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         o[i] = hi;
@@ -343,11 +366,14 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int D, 
     }
 }
 
-int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st) {
+int launch_split_bf16_pad(const float* d_x, size_t rows, int in_dim, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st) {
     if (rows == 0) return RBQ_OK;
-    split_bf16_kernel<<<(unsigned)rows, 128, 0, st>>>(d_x, (int)rows, D, centroid_side, reinterpret_cast<__nv_bfloat16*>(d_out), d_n2);
+    split_bf16_kernel<<<(unsigned)rows, 128, 0, st>>>(d_x, (int)rows, in_dim, D, centroid_side, reinterpret_cast<__nv_bfloat16*>(d_out), d_n2);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
+}
+int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st) {
+    return launch_split_bf16_pad(d_x, rows, D, D, centroid_side, d_out, d_n2, st);
 }
 
 // rows idx[0..n) of a row-major byte matrix -> dst (16-byte granules); builds the centroid sample of the filter mode
@@ -403,10 +429,11 @@ static int gemm_sms() {
 
 template <int MODE>
 static int launch_gemm_mode(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, int num_kb, int mtiles, int ntiles, cudaStream_t st) {
-    RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+    const size_t smem = tc::SMEM + (MODE == kGemmFilter ? tc::SMEM_HITS : 0);
+    RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (long long)mtiles * ntiles;
     const int grid = (int)std::min<long long>(total, gemm_sms());
-    coarse_gemm_kernel<MODE><<<grid, tc::THREADS, tc::SMEM, st>>>(ma, mb, epi, num_kb, mtiles, ntiles);
+    coarse_gemm_kernel<MODE><<<grid, tc::THREADS, smem, st>>>(ma, mb, epi, num_kb, mtiles, ntiles);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

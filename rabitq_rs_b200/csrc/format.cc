@@ -97,6 +97,40 @@ struct Reader {
 };
 }  // namespace
 
+// From list_n_all + (shard_rank, shard_count): the owner of every list (size-balanced over the bytes a list occupies on the
+// device) and this shard's geometry (list_n, blk_off, vec_off).  Shared by the loader and the streaming builder, so that a
+// shard built in place equals the same shard loaded from the complete file.
+int shard_layout(HostIndex& ix) {
+    const uint64_t ncl = ix.nlist;
+    const size_t stride = ix.block_stride(), exs = ix.ex_stride();
+    std::vector<uint64_t> bytes(ncl);
+    for (uint64_t c = 0; c < ncl; ++c) {
+        uint64_t nv = ix.list_n_all[c];
+        bytes[c] = (nv + kBatch - 1) / kBatch * stride + nv * (exs + 16);
+    }
+    std::vector<int> owner;
+    assign_shards(bytes, ix.shard_count, owner);
+    ix.list_owner.resize(ncl);
+    for (uint64_t c = 0; c < ncl; ++c) ix.list_owner[c] = (uint8_t)owner[c];
+    ix.list_n.assign(ncl, 0);
+    ix.blk_off.assign(ncl + 1, 0);
+    ix.vec_off.assign(ncl + 1, 0);
+    uint64_t own_vec = 0, own_blk = 0;
+    for (uint64_t c = 0; c < ncl; ++c) {
+        ix.blk_off[c] = (uint32_t)own_blk;
+        ix.vec_off[c] = own_vec;
+        if (owner[c] == ix.shard_rank) {
+            ix.list_n[c] = ix.list_n_all[c];
+            own_vec += ix.list_n_all[c];
+            own_blk += (ix.list_n_all[c] + kBatch - 1) / kBatch;
+        }
+    }
+    ix.blk_off[ncl] = (uint32_t)own_blk;
+    ix.vec_off[ncl] = own_vec;
+    if (own_blk > 0xFFFFFFFFull) return fail(RBQ_INVALID_CONFIG, "shard holds more than 2^32 blocks");
+    return RBQ_OK;
+}
+
 // Two passes over the stream: (1) walk it to learn every list's size (needed for the shard map)
 // and validate structure; (2) copy the lists this shard owns.  The CRC covers the whole stream.
 int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, HostIndex& ix) {
@@ -193,35 +227,11 @@ int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, Host
     ix.nvec_total = nvec;
     (void)lists_begin;
 
-    // shard map
-    std::vector<uint64_t> bytes(ncl);
-    for (uint64_t c = 0; c < ncl; ++c) {
-        uint64_t nv = ix.list_n_all[c];
-        bytes[c] = (nv + kBatch - 1) / kBatch * stride + nv * (exs + 16);
-    }
-    std::vector<int> owner;
-    assign_shards(bytes, shard_count, owner);
-    ix.list_owner.resize(ncl);
-    for (uint64_t c = 0; c < ncl; ++c) ix.list_owner[c] = (uint8_t)owner[c];
-
-    // pass 2
+    int rc_layout = shard_layout(ix);
+    if (rc_layout) return rc_layout;
+    std::vector<int> owner(ix.list_owner.begin(), ix.list_owner.end());
+    const uint64_t own_vec = ix.vec_off[ncl], own_blk = ix.blk_off[ncl];
     ix.centroids.resize(ncl * (size_t)D);
-    ix.list_n.assign(ncl, 0);
-    ix.blk_off.assign(ncl + 1, 0);
-    ix.vec_off.assign(ncl + 1, 0);
-    uint64_t own_vec = 0, own_blk = 0;
-    for (uint64_t c = 0; c < ncl; ++c) {
-        ix.blk_off[c] = (uint32_t)own_blk;
-        ix.vec_off[c] = own_vec;
-        if (owner[c] == shard_rank) {
-            ix.list_n[c] = ix.list_n_all[c];
-            own_vec += ix.list_n_all[c];
-            own_blk += (ix.list_n_all[c] + kBatch - 1) / kBatch;
-        }
-    }
-    ix.blk_off[ncl] = (uint32_t)own_blk;
-    ix.vec_off[ncl] = own_vec;
-    if (own_blk > 0xFFFFFFFFull) return fail(RBQ_INVALID_CONFIG, "shard holds more than 2^32 blocks");
     ix.blocks.resize(own_blk * stride);
     ix.ids.resize(own_vec);
     ix.ex.resize(own_vec * exs);

@@ -54,6 +54,7 @@ uint32_t crc32_ieee(uint32_t crc, const uint8_t* p, size_t n);
 int parse_rbq1(const uint8_t* p, size_t n, int shard_rank, int shard_count, HostIndex& out);
 void write_rbq1(const HostIndex& ix, std::vector<uint8_t>& out);
 void assign_shards(const std::vector<uint64_t>& list_bytes, int shard_count, std::vector<int>& owner);
+int shard_layout(HostIndex& ix);  // list_owner / list_n / blk_off / vec_off from list_n_all and the shard coordinates
 
 // ---- device view passed by value to kernels ---------------------------------------------------
 struct DevIndex {
@@ -221,6 +222,7 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
                            size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st,
                            bool need_ip = true);
 int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
+int launch_split_bf16_pad(const float* d_x, size_t rows, int in_dim, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
 int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st, int terms = 3);
 // coarse_tc.cu: the persistent tcgen05 GEMM behind every dense contraction of the engine.  A: rows x (3D bf16, pitch 3D), B: cols x
 // (3D bf16); terms = 3 uses the whole split (fp32-class dot products), terms = 1 only the leading hi x hi block (bf16-class).
@@ -272,8 +274,8 @@ struct BuildOut {  // device arrays, one entry per vector in list-concatenated o
 };
 int launch_build_quantize(const DevIndex& ix, const float* d_rot, const uint32_t* d_list_of, size_t n,
                           const float* d_cents, float t_const, const double* d_t_per_vec, BuildOut out,
-                          cudaStream_t st);
-int launch_rotate_only(const DevIndex& ix, const float* d_in, size_t n, float* d_out, cudaStream_t st);
+                          cudaStream_t st, const unsigned long long* d_dst_pos = nullptr);
+int launch_rotate_only(const DevIndex& ix, const float* d_in, size_t n, float* d_out, cudaStream_t st, const uint32_t* d_src = nullptr);
 double best_rescale_factor_host(const float* o_abs, size_t dim, int ex_bits);
 float const_scaling_factor_host(size_t D, int ex_bits, uint64_t seed);
 

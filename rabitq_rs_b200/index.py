@@ -163,6 +163,15 @@ class IvfRabitqIndex:
         _check(_ffi.lib().rbq_index_save_mem(self._need(), _ptr(buf), buf.size, C.byref(n)))
         return buf.tobytes()
 
+    def save_lists_to_bytes(self, keep):
+        """RBQ1 stream holding only the lists flagged in keep[cluster_count] (the others empty): see rbq_index_save_lists_mem."""
+        keep = np.ascontiguousarray(keep, np.uint8)
+        n = C.c_size_t()
+        _check(_ffi.lib().rbq_index_save_lists_mem(self._need(), _ptr(keep), keep.size, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _check(_ffi.lib().rbq_index_save_lists_mem(self._need(), _ptr(keep), keep.size, _ptr(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
+
     # ---- build (train_with_clusters / train) ----------------------------------------------------
     def fit_with_clusters(self, data, centroids, assignments, total_bits=7, rotator_type="random", seed=42,
                           faster_config=True, rotator_state=None):
@@ -380,6 +389,49 @@ class IvfRabitqIndex:
         _check(_ffi.lib().rbq_debug_scan_list(self._need(), _ptr(q), q.size, int(cluster), _ptr(accu), _ptr(ip),
                                               _ptr(est), _ptr(lb), max(slots, 1)))
         return accu[:slots], ip[:slots], est[:slots], lb[:slots]
+
+
+class IndexBuilder:
+    """Streaming train_with_clusters on device-resident data (include/rbq.h: rbq_builder_*): announce the list sizes, add
+    chunks of (vectors, assignments) CUDA tensors in ascending id order, finish() -> IvfRabitqIndex.  With shard_count > 1
+    only the lists of shard_rank are kept (the shard rbq_index_load would keep from the complete file)."""
+
+    def __init__(self, dim, centroids, list_sizes, total_bits=7, metric="euclidean", rotator_type="random", seed=42, device=0,
+                 shard_rank=0, shard_count=1, max_chunk=1 << 20, rotator_state=None):
+        cents = np.ascontiguousarray(centroids, np.float32)
+        sizes = np.ascontiguousarray(list_sizes, np.uint32)
+        if cents.ndim != 2 or cents.shape[1] != dim or sizes.shape != (cents.shape[0],):
+            raise ValueError("centroids must be [nlist, dim] and list_sizes [nlist]")
+        rs = None if rotator_state is None else np.ascontiguousarray(rotator_state, np.uint8)
+        self.device, self.metric = int(device), _metric_from_str(metric)
+        self._b = C.c_void_p()
+        _check(_ffi.lib().rbq_builder_create(int(dim), _ptr(cents), cents.shape[0], _ptr(sizes), int(total_bits), int(self.metric),
+                                             int(_rotator_from_str(rotator_type)), int(seed), _ptr(rs), self.device, int(shard_rank),
+                                             int(shard_count), int(max_chunk), C.byref(self._b)))
+
+    def add(self, x, assign, id_base, stream=None):
+        """x: [m, dim] float32 CUDA tensor, assign: [m] int32/uint32 CUDA tensor of list ids; vector i gets id id_base + i."""
+        import torch
+
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and assign.is_cuda and assign.is_contiguous() and assign.numel() == x.shape[0]
+        st = C.c_void_p(stream) if stream else C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _check(_ffi.lib().rbq_builder_add_device(self._b, C.c_void_p(x.data_ptr()), C.c_void_p(assign.data_ptr()), x.shape[0], int(id_base), st))
+
+    def finish(self):
+        h = C.c_void_p()
+        b, self._b = self._b, None
+        _check(_ffi.lib().rbq_builder_finish(b, C.byref(h)))
+        ix = IvfRabitqIndex(device=self.device)
+        ix._adopt(h)
+        return ix
+
+    def __del__(self):
+        try:
+            if getattr(self, "_b", None):
+                _ffi.lib().rbq_builder_free(self._b)
+                self._b = None
+        except Exception:
+            pass
 
 
 def shard_assignment(blob, shard_count):

@@ -1,42 +1,65 @@
-"""Coarse clustering for `fit` (plumbing around the build path, torch on the GPU).
+"""k-means for `fit` on the GPU: thin wrappers over librbq's rbq_kmeans_device / rbq_kmeans_assign_device
+(csrc/kmeans.cu -- the reference's src/kmeans.rs pipeline with the assignment on the engine's tcgen05 GEMM, arg-min fused
+into the epilogue, and a deterministic centroid update).  torch only holds the device buffers."""
+import ctypes as C
 
-The reference's k-means (src/kmeans.rs: Faiss-style Lloyd, <=256 sampled points per centroid, 30
-iterations, sgemm assignment) is outside the drop-in scope: any clustering produces a valid index
-and search parity never depends on it, because both engines read the same index file."""
 import numpy as np
 
+from . import _ffi
+from .index import _check
 
-def kmeans_gpu(data, k, iters=10, seed=42, device=0, max_points_per_centroid=256, chunk=1 << 16):
+
+def _stream(dev):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def kmeans_device(x, k, iters=10, seed=42, max_points_per_centroid=256):
+    """x: [n, dim] float32 CUDA tensor -> centroids [k, dim] CUDA tensor (Lloyd on a training subset, like the reference)."""
+    import torch
+
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    n, dim = x.shape
+    cents = torch.empty((k, dim), dtype=torch.float32, device=x.device)
+    _check(_ffi.lib().rbq_kmeans_device(C.c_void_p(x.data_ptr()), n, dim, int(k), int(iters), int(seed), int(max_points_per_centroid),
+                                        C.c_void_p(cents.data_ptr()), x.device.index or 0, _stream(x.device)))
+    return cents
+
+
+def assign_device(x, cents, out=None):
+    """Nearest centroid of every row of x (CUDA tensors) -> int32 CUDA tensor (values are u32 cluster ids)."""
+    import torch
+
+    assert x.is_cuda and cents.is_cuda and x.is_contiguous() and cents.is_contiguous()
+    n, dim = x.shape
+    out = out if out is not None else torch.empty(n, dtype=torch.int32, device=x.device)
+    _check(_ffi.lib().rbq_kmeans_assign_device(C.c_void_p(x.data_ptr()), n, dim, C.c_void_p(cents.data_ptr()), cents.shape[0],
+                                               C.c_void_p(out.data_ptr()), x.device.index or 0, _stream(x.device)))
+    return out
+
+
+def kmeans_gpu(base, k, iters=10, seed=42, device=0, max_points_per_centroid=256):
+    """base: [n, dim] float32 numpy array (host).  Returns (centroids [k, dim] float32, assignments [n] uint32), both numpy.
+    The data is uploaded in slices; only the training subset and one slice are resident at a time."""
     import torch
 
     dev = torch.device("cuda", device)
-    n, dim = data.shape
-    g = torch.Generator(device="cpu").manual_seed(int(seed) & 0x7FFFFFFF)
-    x_all = torch.from_numpy(np.ascontiguousarray(data, np.float32))
-    n_train = min(n, k * max_points_per_centroid)
-    sel = torch.randperm(n, generator=g)[:n_train] if n_train < n else torch.arange(n)
-    xt = x_all[sel].to(dev)
-    cents = xt[torch.randperm(n_train, generator=g)[:k].to(dev)].clone()
-
-    def assign(x, c):
-        out = torch.empty(x.shape[0], dtype=torch.int64, device=dev)
-        cn = (c * c).sum(1)
-        for s in range(0, x.shape[0], chunk):
-            xc = x[s:s + chunk]
-            out[s:s + chunk] = (cn[None, :] - 2.0 * (xc @ c.T)).argmin(1)
-        return out
-
-    for _ in range(iters):
-        a = assign(xt, cents)
-        sums = torch.zeros_like(cents).index_add_(0, a, xt)
-        cnt = torch.bincount(a, minlength=k).to(torch.float32)
-        new = sums / cnt.clamp(min=1.0)[:, None]
-        empty = cnt == 0
-        if empty.any():  # re-seed empty clusters on random training points
-            idx = torch.randint(0, n_train, (int(empty.sum()),), generator=g).to(dev)
-            new[empty] = xt[idx]
-        cents = new
-    final = torch.empty(n, dtype=torch.int64)
-    for s in range(0, n, 1 << 20):
-        final[s:s + (1 << 20)] = assign(x_all[s:s + (1 << 20)].to(dev), cents).cpu()
-    return cents.cpu().numpy().astype(np.float32), final.numpy().astype(np.uint32)
+    base = np.ascontiguousarray(base, np.float32)
+    n, dim = base.shape
+    nt = min(n, k * max_points_per_centroid)
+    with torch.cuda.device(dev):
+        if nt < n:  # the training subset is drawn on the host side of the wrapper so that the whole set never has to be resident
+            rng = np.random.default_rng(seed)
+            sel = np.sort(rng.choice(n, nt, replace=False))
+            xt = torch.from_numpy(base[sel]).to(dev)
+        else:
+            xt = torch.from_numpy(base).to(dev)
+        cents = kmeans_device(xt, k, iters, seed, max_points_per_centroid=max(max_points_per_centroid, (nt + k - 1) // k))
+        assign = np.empty(n, np.uint32)
+        step = max(1, (1 << 30) // (dim * 4))
+        for s in range(0, n, step):
+            xs = xt[s:s + step] if nt == n else torch.from_numpy(base[s:s + step]).to(dev)
+            assign[s:s + step] = assign_device(xs, cents).cpu().numpy().view(np.uint32)
+        out = cents.cpu().numpy()
+    return out, assign
