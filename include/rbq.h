@@ -195,6 +195,8 @@ typedef struct rbq_search_stats {
     float ms_tail_kernel;       /* the tail FastScan kernel alone (events around that one launch; 0 in sequential mode) */
     uint32_t coarse_mode_used;  /* coarse stage the call ran: 0 exact, 1 dense tensor-core scores, 2 filtered in the GEMM epilogue */
     uint32_t front_chunk;       /* queries per front-end chunk */
+    uint64_t fallback_queries;  /* queries the list-major head pass handed to the sequential kernel (nearest list longer than the
+                                   dense head buffer, or fewer than top_k candidates in it) */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */

@@ -388,9 +388,46 @@ __attribute__((target("avx2"))) static void accumulate_block_avx2(const uint8_t*
 }
 #endif
 
-static bool g_have_avx2 = false;
+#if defined(__x86_64__)
+// AVX-512BW form of the same formulation (the reference dispatches to accumulate_batch_avx512 on such hosts,
+// src/simd.rs:972-1016): 64 code bytes = 4 codebooks per step, vpshufb per 128-bit lane.
+__attribute__((target("avx512f,avx512bw"))) static void accumulate_block_avx512(const uint8_t* codes, const uint8_t* lut, size_t D,
+                                                                               uint16_t* res) {
+    const __m512i m4 = _mm512_set1_epi8(0x0f), m8 = _mm512_set1_epi16(0x00ff);
+    __m512i lo_e = _mm512_setzero_si512(), lo_o = lo_e, hi_e = lo_e, hi_o = lo_e;
+    const size_t len = D * 4;
+    for (size_t i = 0; i < len; i += 64) {
+        const __m512i c = _mm512_loadu_si512((const void*)(codes + i));
+        const __m512i t = _mm512_loadu_si512((const void*)(lut + i));
+        const __m512i rl = _mm512_shuffle_epi8(t, _mm512_and_si512(c, m4));
+        const __m512i rh = _mm512_shuffle_epi8(t, _mm512_and_si512(_mm512_srli_epi16(c, 4), m4));
+        lo_e = _mm512_add_epi16(lo_e, _mm512_and_si512(rl, m8));
+        lo_o = _mm512_add_epi16(lo_o, _mm512_srli_epi16(rl, 8));
+        hi_e = _mm512_add_epi16(hi_e, _mm512_and_si512(rh, m8));
+        hi_o = _mm512_add_epi16(hi_o, _mm512_srli_epi16(rh, 8));
+    }
+    alignas(64) uint16_t le[32], lo[32], he[32], ho[32];
+    _mm512_store_si512((void*)le, lo_e);
+    _mm512_store_si512((void*)lo, lo_o);
+    _mm512_store_si512((void*)he, hi_e);
+    _mm512_store_si512((void*)ho, hi_o);
+    for (int w = 0; w < 8; ++w) {
+        const int je = 2 * w, jo = 2 * w + 1;
+        res[KPERM0[je]] = (uint16_t)(le[w] + le[w + 8] + le[w + 16] + le[w + 24]);
+        res[KPERM0[jo]] = (uint16_t)(lo[w] + lo[w + 8] + lo[w + 16] + lo[w + 24]);
+        res[KPERM0[je] + 16] = (uint16_t)(he[w] + he[w + 8] + he[w + 16] + he[w + 24]);
+        res[KPERM0[jo] + 16] = (uint16_t)(ho[w] + ho[w + 8] + ho[w + 16] + ho[w + 24]);
+    }
+}
+#endif
+
+static bool g_have_avx2 = false, g_have_avx512 = false;
 static void accumulate_block(const uint8_t* codes, const uint8_t* lut, size_t D, uint16_t* res) {
 #if defined(__x86_64__)
+    if (g_have_avx512 && D % 16 == 0) {
+        accumulate_block_avx512(codes, lut, D, res);
+        return;
+    }
     if (g_have_avx2 && D % 8 == 0) {
         accumulate_block_avx2(codes, lut, D, res);
         return;
@@ -1386,6 +1423,7 @@ static struct Init {
 #if defined(__x86_64__)
         g_have_avx2 = __builtin_cpu_supports("avx2");
         g_have_fma = g_have_avx2 && __builtin_cpu_supports("fma");
+        g_have_avx512 = g_have_avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
 #endif
     }
 } g_init;
@@ -1403,6 +1441,7 @@ void orc_set_simd(int on) {
 #if defined(__x86_64__)
     g_have_avx2 = on && __builtin_cpu_supports("avx2");
     g_have_fma = on && g_have_avx2 && __builtin_cpu_supports("fma");
+    g_have_avx512 = on >= 1 && on != 2 && g_have_avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");  // on == 2: AVX2 only
 #endif
 }
 int orc_num_threads() {
@@ -1412,6 +1451,16 @@ int orc_num_threads() {
     return 1;
 #endif
 }
+// The batch search runs one query per OpenMP thread (= batch_search's rayon par_iter).  Launchers such as torchrun export
+// OMP_NUM_THREADS=1 to their children; the benchmark sets the count explicitly so the CPU arm uses all the host's cores.
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int orc_simd_level() { return g_have_avx512 ? 512 : g_have_avx2 ? 256 : 0; }
 
 // --- primitives ---
 float orc_dot(const float* a, const float* b, size_t n) { return dot(a, b, n); }

@@ -14,10 +14,32 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
+def _cpu_stamp():
+    """The library is built -march=native: one built on another host (it travels with the repo snapshot) must be rebuilt."""
+    try:
+        import hashlib
+
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+        return hashlib.sha1(flags.encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
     src = os.path.join(_HERE, "oracle.cc")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CXX": ""})
+    stamp_path = os.path.join(_HERE, ".build_stamp")
+    stamp = _cpu_stamp()
+    try:
+        have = open(stamp_path).read().strip()
+    except OSError:
+        have = ""
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src) or \
+        os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "Makefile"))
+    if force or stale or have != stamp:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"], env={**os.environ, "CXX": ""})
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
     return _LIB_PATH
 
 
@@ -71,6 +93,16 @@ def set_simd(on):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the batch search (one query per thread).  Call with os.cpu_count() when the process was started
+    by a launcher that exports OMP_NUM_THREADS=1 (torchrun)."""
+    lib().orc_set_num_threads(int(n))
+
+
+def simd_level():
+    return lib().orc_simd_level()
 
 
 def dot(a, b):

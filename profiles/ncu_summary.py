@@ -22,6 +22,10 @@ for w in want:
     for i, h in enumerate(hdr):
         if h == w:
             print(f"{h} [{units[i]}] = {vals[i]}")
+# tensor pipe / tensor memory activity (tcgen05 kernels): every exported metric that names them
+for i, h in enumerate(hdr):
+    if any(t in h for t in ('pipe_tensor', 'tmem', 'pipe_uniform', 'lts__t_bytes.sum', 'lts__throughput', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'sm__inst_executed_pipe_tma')):
+        print(f"{h} [{units[i]}] = {vals[i]}")
 for i, h in enumerate(hdr):
     if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio'):
         try:
@@ -41,7 +45,7 @@ tot_i = sum(int(r[ci['Instructions Executed']]) for r in data)
 print(f"SASS lines {len(data)}, warp-instructions {tot_i}, samples {tot_s}")
 ops, ops_s = collections.Counter(), collections.Counter()
 for r in data:
-    m = re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ci['Source']])
+    m = re.match(r'\s*(@!?U?PT?\d*\s+)?([A-Z][A-Z0-9_.]+)', r[ci['Source']])
     op = m.group(2).split('.')[0] if m else '?'
     ops[op] += int(r[ci['Instructions Executed']])
     ops_s[op] += int(r[ci['# Samples']])

@@ -16,7 +16,7 @@ class SearchStats(C.Structure):
                 ("ms_select", C.c_float), ("ms_scan", C.c_float),
                 ("tail_blocks", C.c_uint64), ("tail_bytes", C.c_uint64), ("tail_pairs", C.c_uint64),
                 ("survivors", C.c_uint64), ("overflow_queries", C.c_uint64),
-                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32)]
+                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32), ("fallback_queries", C.c_uint64)]
 
 
 _lib = None

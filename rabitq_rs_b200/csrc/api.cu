@@ -154,7 +154,9 @@ int rbq::prepare_coarse_sample(rbq_index* h) {
     d.samp_n = 0;
     const size_t nl = d.nlist, D = d.D;
     if (nl < 2048) return RBQ_OK;
-    size_t S = std::min<size_t>(4096, std::max<size_t>(512, (nl / 16 + 255) / 256 * 256));
+    // 512 scores per query for tables up to 8192 lists, 1024 beyond: one warp ranks them in registers; a sparser sample
+    // only loosens the threshold (more candidates per query), never the guarantee
+    size_t S = std::min<size_t>(1024, std::max<size_t>(512, (nl / 16 + 255) / 256 * 256));
     const size_t stride = nl / S;
     std::vector<uint32_t> idx(S);
     uint64_t st = 0x9e3779b97f4a7c15ull ^ (uint64_t)nl;
@@ -234,6 +236,7 @@ Plan make_plan(const rbq_index* h, size_t nq, size_t nprobe) {
     if (p.coarse < 0 || p.coarse == 2) {
         p.rank = filter_sample_rank(ix.nlist, ix.samp_n, nprobe, p.terms);
         p.cap = filter_cand_cap(ix.nlist, ix.samp_n, nprobe, p.terms);
+        // auto: the filter whenever the index has a centroid sample (>= 2048 lists) and nprobe leaves it selective
         const bool ok = p.rank != 0 && p.cap != 0;
         p.coarse = ok ? 2 : 1;
     }
@@ -347,6 +350,7 @@ int run_front(const rbq_index* h, const WsLayout& L, const Plan& pl, const float
     GemmEpi e;
     e.nq = (int)m;
     e.metric = ix.metric;
+    e.shifted = 1;  // sample scores, filter threshold and candidate scores all live in the shifted domain (|c|^2 - 2 q.c)
     e.qn2 = L.d_qn2 + c0;
     e.ncols = (int)ix.samp_n;
     e.cn2 = ix.samp_n2;
@@ -395,6 +399,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
     const WsLayout L = carve_ws(h, ws_base, pl, nprobe, top_k);
     const TailWs& tw = L.tw;
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};  // [6]: the tail FastScan kernel alone
+    bool any_list_major = false;
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
         int rc;
@@ -403,6 +408,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         // head pass (the first owned list, sequential, fills the heap) -> tail kernel (all remaining pairs grouped by list)
         // -> replay pass (survivors in reference order).  Both are exact.
         const bool list_major = h->scan_mode == 2 || (h->scan_mode == 0 && nprobe >= 4 && n * nprobe >= 8 * (size_t)ix.nlist);
+        any_list_major |= list_major;
         if (list_major)  // surv_cnt | list_cnt | list_fill | counters
             RBQ_CUDA(cudaMemsetAsync(tw.surv_cnt, 0, (qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4, st));
         // Front end (rotate + LUT, coarse scores, probe selection) and the head pass are independent per query: they run chunk
@@ -413,28 +419,35 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         int head_launch = 0, ci = 0;
         for (size_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
             const size_t m = std::min(chunk, n - c0);
-            const bool last = c0 + chunk >= n;
             if (feed) {
                 if ((rc = feed->issue(q0 + c0, m, c0, ci))) return rc;
                 RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[ci % HostFeed::kEvents], 0));
             }
+            // profiled calls time every chunk's stages with its own events (read back after the tile)
+            cudaEvent_t* ce = nullptr;
+            if (h->profiling && ci < 32) {
+                ce = h->ev_chunk[ci];
+                for (int i = 0; i < 5; ++i)
+                    if (!ce[i]) RBQ_CUDA(cudaEventCreate(&ce[i]));
+                cudaEventRecord(ce[0], st);
+            }
             const float* dq = feed ? feed->d_q + c0 * ix.dim : d_queries + (q0 + c0) * ix.dim;
-            if ((rc = run_front(h, L, pl, dq, c0, m, nprobe, st, launches, true, h->profiling && last ? h->ev[1] : nullptr,
-                                h->profiling && last ? h->ev[2] : nullptr)))
-                return rc;
-            if (h->profiling && last) cudaEventRecord(h->ev[3], st);
+            if ((rc = run_front(h, L, pl, dq, c0, m, nprobe, st, launches, true, ce ? ce[1] : nullptr, ce ? ce[2] : nullptr))) return rc;
+            if (ce) cudaEventRecord(ce[3], st);
             // head: FastScan of every query's first owned list + the reference's sequential loop over it
             if (list_major && (rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                                 d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, c0, m, &head_launch)))
                 return rc;
+            if (ce) cudaEventRecord(ce[4], st);
         }
+        const int timed_chunks = std::min(ci, 32);
         if (!list_major) {
+            if (h->profiling) cudaEventRecord(h->ev[4], st);
             if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
                                   d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFull, nullptr, st)))
                 return rc;
             *launches += 1;
-            if (h->profiling) {
-                cudaEventRecord(h->ev[4], st);
+            if (h->profiling) {  // sequential schedule: the whole scan is reported as the head stage (ms[3] += ev4 -> ev5)
                 cudaEventRecord(h->ev[5], st);
                 cudaEventRecord(h->ev[6], st);
             }
@@ -457,24 +470,27 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         }
         if (h->profiling) {
             RBQ_CUDA(cudaEventSynchronize(h->ev[6]));
-            // with several front-end chunks the stage events bracket the LAST chunk only: prep/coarse/select then cover that
-            // chunk, and everything before it is charged to the prep stage (ev[0] -> ev[1])
-            for (int i = 0; i < 6; ++i) {
+            auto el = [&](cudaEvent_t a, cudaEvent_t b) {
                 float t = 0;
-                cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
-                ms[i] += t;
+                return cudaEventElapsedTime(&t, a, b) == cudaSuccess ? t : 0.0f;
+            };
+            for (int c = 0; c < timed_chunks; ++c) {  // prep | coarse | select | head of every chunk
+                cudaEvent_t* ce = h->ev_chunk[c];
+                for (int i = 0; i < 4; ++i) ms[i] += el(ce[i], ce[i + 1]);
             }
-            if (list_major) {
-                float t = 0;
-                cudaEventElapsedTime(&t, h->ev[7], h->ev[8]);
-                ms[6] += t;
-            }
+            ms[4] += el(h->ev[4], h->ev[5]);
+            ms[5] += el(h->ev[5], h->ev[6]);
+            if (list_major) ms[6] += el(h->ev[7], h->ev[8]);
         }
     }
     if (h->profiling) {
         h->last_stats.ms_prep = ms[0];
         h->last_stats.ms_coarse = ms[1];
         h->last_stats.ms_select = ms[2];
+        if (!any_list_major) {  // sequential schedule: everything sits in the "tail" slot of the events
+            ms[3] += ms[4];
+            ms[4] = 0.0f;
+        }
         h->last_stats.ms_scan = ms[3] + ms[4] + ms[5];
         h->last_stats.ms_scan_head = ms[3];
         h->last_stats.ms_scan_tail = ms[4];
@@ -568,6 +584,9 @@ void rbq_index_free(rbq_index* h) {
             if (e) cudaEventDestroy(e);
         for (auto& e : h->feed_ev)
             if (e) cudaEventDestroy(e);
+        for (auto& row : h->ev_chunk)
+            for (auto& e : row)
+                if (e) cudaEventDestroy(e);
         if (h->busy_ev) cudaEventDestroy(h->busy_ev);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
@@ -724,6 +743,21 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     std::lock_guard<std::mutex> lk(h->mu);
     DevStats ds;
     if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));  // asynchronous entry points may still be running
+    if (h->dist_phase == 3) {  // stage times of a profiled phased search (the events were recorded by the three rbq_dist_* calls)
+        h->dist_phase = 0;
+        auto el = [&](int a, int b) {
+            float t = 0;
+            return cudaEventElapsedTime(&t, h->ev[a], h->ev[b]) == cudaSuccess ? t : 0.0f;
+        };
+        h->last_stats.ms_prep = el(0, 1);
+        h->last_stats.ms_coarse = el(1, 2);  // coarse scores + probe selection + export of this rank's query slice
+        h->last_stats.ms_select = 0.0f;
+        h->last_stats.ms_scan_head = el(3, 4);
+        h->last_stats.ms_scan_tail = el(5, 9);
+        h->last_stats.ms_scan_replay = el(9, 6);
+        h->last_stats.ms_tail_kernel = el(7, 8);
+        h->last_stats.ms_scan = h->last_stats.ms_scan_head + h->last_stats.ms_scan_tail + h->last_stats.ms_scan_replay;
+    }
     RBQ_CUDA(cudaMemcpy(&ds, h->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
     h->last_stats.blocks_scanned = ds.blocks;
     h->last_stats.bytes_scanned = ds.blocks * (uint64_t)h->dev.block_stride;
@@ -735,6 +769,7 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     h->last_stats.tail_pairs = ds.tail_pairs;
     h->last_stats.survivors = ds.survivors;
     h->last_stats.overflow_queries = ds.overflow_queries;
+    h->last_stats.fallback_queries = ds.fallback_queries;
     unsigned int fb = 0;
     RBQ_CUDA(cudaMemcpy(&fb, h->fallback_counter(), sizeof(fb), cudaMemcpyDeviceToHost));
     h->last_stats.coarse_fallbacks = fb;
@@ -888,6 +923,7 @@ int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Serial serial(h, st);
     h->last_stats = rbq_search_stats{};
+    h->dist_phase = 0;
     h->last_stats.queries = nq;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
@@ -958,12 +994,14 @@ int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, co
     if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, st, &launches,
                           h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
         return rc;
+    if (h->profiling) cudaEventRecord(h->ev[9], st);
     if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, nq, nprobe, top_k, d_ids, d_scores, d_counts, h->d_stats, L.tw, st, &launches)))
         return rc;
     if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats,
                           h->work_counter(), kScanFallback, &L.tw, st)))
         return rc;
     if (h->profiling) cudaEventRecord(h->ev[6], st);
+    h->dist_phase = h->profiling ? 3 : 0;
     h->last_stats.kernel_launches = launches + 2;
     return RBQ_OK;
 }

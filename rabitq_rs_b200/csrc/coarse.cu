@@ -648,24 +648,20 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_exact_kernel(DevInde
     }
 }
 
-// Filter mode, step 2: the rank-th best of a query's sample scores = the filter threshold.  16 keys per thread (WARPS warps per
-// query: 512 sample scores -> one warp, no block barrier), bisection on the order key between the sample's min and max.
-constexpr int kThrVpt = 16;
-template <int WARPS>
+// Filter mode, step 2: the rank-th best of a query's sample scores = the filter threshold.  One warp per query, the sample
+// (<= 1024 scores) in registers, bisection on the order key between the sample's min and max (no block barrier).
+template <int VPT>
 __global__ void __launch_bounds__(128) sample_threshold_kernel(const float* __restrict__ ss, uint32_t nq, uint32_t samp_n, uint32_t rank, int desc,
                                                               float* __restrict__ thr) {
-    constexpr int QPB = 4 / WARPS;  // queries per 128-thread block
-    __shared__ uint32_t s_red[3][4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t q = blockIdx.x * QPB + (WARPS == 1 ? warp : WARPS == 2 ? (warp >> 1) : 0);
-    const int sub = WARPS == 1 ? 0 : WARPS == 2 ? (warp & 1) : warp;  // this warp's part of the query's sample
-    const bool live = q < nq;
-    const float* row = ss + (size_t)(live ? q : 0) * samp_n;
-    uint32_t key[kThrVpt];
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float* row = ss + (size_t)q * samp_n;
+    uint32_t key[VPT];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-    for (int j = 0; j < kThrVpt; ++j) {
-        const uint32_t c = (uint32_t)(sub * 32 + lane) + 32u * WARPS * j;
+    for (int j = 0; j < VPT; ++j) {
+        const uint32_t c = (uint32_t)lane + 32u * j;
         key[j] = 0xffffffffu;
         if (c < samp_n) {
             key[j] = order_key(row[c], desc != 0);
@@ -673,57 +669,25 @@ __global__ void __launch_bounds__(128) sample_threshold_kernel(const float* __re
             kmax = max(kmax, key[j]);
         }
     }
-    // reduce (min, max) and later the counts over the query's warps
-    auto all_min = [&](uint32_t v) { return __reduce_min_sync(0xffffffffu, v); };
-    auto all_max = [&](uint32_t v) { return __reduce_max_sync(0xffffffffu, v); };
-    kmin = all_min(kmin);
-    kmax = all_max(kmax);
-    if (WARPS > 1) {
-        if (lane == 0) {
-            s_red[0][warp] = kmin;
-            s_red[1][warp] = kmax;
-        }
-        __syncthreads();
-        const int w0 = WARPS == 2 ? (warp & ~1) : 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            kmin = min(kmin, s_red[0][w0 + w]);
-            kmax = max(kmax, s_red[1][w0 + w]);
-        }
-    }
-    uint32_t lo = kmin, hi = kmax;  // smallest K with #(key <= K) >= rank lies in [lo, hi] (rank <= samp_n)
-    for (int it = 0; it < 32 && (WARPS > 1 || lo < hi); ++it) {  // multi-warp: fixed trip count keeps the barriers uniform
+    uint32_t lo = __reduce_min_sync(0xffffffffu, kmin), hi = __reduce_max_sync(0xffffffffu, kmax);
+    while (lo < hi) {  // smallest K with #(key <= K) >= rank (rank <= samp_n, so K <= max key)
         const uint32_t mid = lo + ((hi - lo) >> 1);
         uint32_t c = 0;
 #pragma unroll
-        for (int j = 0; j < kThrVpt; ++j) c += key[j] <= mid;
+        for (int j = 0; j < VPT; ++j) c += key[j] <= mid;
         c = __reduce_add_sync(0xffffffffu, c);
-        if (WARPS > 1) {
-            if (lane == 0) s_red[2][warp] = c;
-            __syncthreads();
-            const int w0 = WARPS == 2 ? (warp & ~1) : 0;
-            c = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) c += s_red[2][w0 + w];
-            __syncthreads();
-        }
-        if (lo < hi) {
-            if (c >= rank) hi = mid;
-            else lo = mid + 1u;
-        }
+        if (c >= rank) hi = mid;
+        else lo = mid + 1u;
     }
-    if (live && sub == 0 && lane == 0) thr[q] = key_to_float(hi, desc != 0);
+    if (lane == 0) thr[q] = key_to_float(hi, desc != 0);
 }
 int launch_sample_threshold(const float* d_samp_scores, size_t nq, uint32_t samp_n, uint32_t rank, int metric, float* d_thr, cudaStream_t st) {
     if (nq == 0) return RBQ_OK;
-    if (samp_n > 128u * kThrVpt || rank == 0 || rank > samp_n) return fail(RBQ_INVALID_CONFIG, "sample threshold: bad sample size or rank");
+    if (samp_n > 1024u || rank == 0 || rank > samp_n) return fail(RBQ_INVALID_CONFIG, "sample threshold: bad sample size or rank");
     const int desc = metric == RBQ_METRIC_INNER_PRODUCT;
-    if (samp_n <= 32u * kThrVpt)
-        sample_threshold_kernel<1><<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
-    else if (samp_n <= 64u * kThrVpt)
-        sample_threshold_kernel<2><<<(unsigned)((nq + 1) / 2), 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
-    else
-        sample_threshold_kernel<4><<<(unsigned)nq, 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
+    const unsigned grid = (unsigned)((nq + 3) / 4);
+    if (samp_n <= 512u) sample_threshold_kernel<16><<<grid, 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
+    else sample_threshold_kernel<32><<<grid, 128, 0, st>>>(d_samp_scores, (uint32_t)nq, samp_n, rank, desc, d_thr);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
@@ -774,7 +738,9 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
     if (nq == 0) return RBQ_OK;
     if (nprobe > (size_t)kMaxNprobe)
         return fail(RBQ_INVALID_CONFIG, "nprobe exceeds the device probe-selection limit (4096)");
-    const int sort_n = sort_size(std::min<size_t>(nprobe + 48, (size_t)kMaxNprobe));
+    // room for the re-score band around the nprobe-th score: a handful of centroids with fp32-class scores, up to ~nprobe more
+    // with bf16-class scores (1-term GEMM)
+    const int sort_n = sort_size(std::min<size_t>(eps_g > 1e-3f ? 2 * nprobe + 64 : nprobe + 48, (size_t)kMaxNprobe));
     if (ix.nlist <= 16u * kSelThreads && sort_n <= 256) {
         const size_t smem_f = (size_t)sort_n * 20 + (size_t)ix.D * 4;
         const bool ipn = need_ip || ix.metric == RBQ_METRIC_INNER_PRODUCT;

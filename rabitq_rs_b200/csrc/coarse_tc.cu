@@ -28,12 +28,17 @@ constexpr int UK = 16;       // UMMA K for 16-bit inputs
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
-constexpr int THREADS = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+// Epilogue warps: several per scheduler (a lone epilogue warp per scheduler ran at ~0.13 IPC: dependent-issue latency).  Warp w
+// drains lane quarter w % 4 of column part (w - 2) / 4.  The score-matrix drain is bound by its scattered stores and runs best
+// with 8 warps, the filter / arg-min drains are instruction-latency bound and take 16 (measured: DESIGN.md).
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == kGemmScores ? 8 : 16; }
+__host__ __device__ constexpr int threads(int mode) { return (2 + epi_warps(mode)) * 32; }  // warp 0: TMA, warp 1: MMA + TMEM alloc, the rest: epilogue
 constexpr int ACC_BUFS = 2;           // accumulator buffers in tensor memory: the epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int TMEM_COLS = ACC_BUFS * BN;  // 512 = the whole tensor memory of the SM (one CTA per SM: 193 KB of shared memory)
 constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int HIT_SLOTS = 16;         // filter drain: hits of one row in one tile staged in shared memory (slot-major: no bank conflicts)
-constexpr size_t SMEM_HITS = (size_t)HIT_SLOTS * BM * 8;
+// filter drain: hits of one (row, column part) staged in shared memory (slot-major: no bank conflicts), flushed with ONE counter
+// bump per tile (or when the next HIT_SLOTS columns might not fit): 32 / PARTS slots of (float score, u8 column) per thread
+constexpr size_t SMEM_HITS = (size_t)32 * BM * 5;
 }  // namespace tc
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +86,27 @@ __device__ __forceinline__ uint32_t tc_order_key(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// 32 accumulator columns of this warp's TMEM lane quarter -> registers (asynchronous: valid after tmem_ld_wait on the same array)
+__device__ __forceinline__ void tmem_ld32(uint32_t (&r)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// waits for every tcgen05.ld of this thread; the array is an in/out operand so that no use of it can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+
 // Persistent GEMM: every CTA walks a sequence of 128 x 256 output tiles.  Three roles: one thread feeds the 4-stage
 // shared-memory ring with TMA, one thread issues tcgen05.mma into one of the two 256-column accumulator buffers, four warps
 // drain the other buffer.  MODE picks what the drain does with a score:
@@ -88,10 +114,11 @@ __device__ __forceinline__ uint32_t tc_order_key(float f) {
 //   kGemmFilter  compare with the row's threshold and append the few that pass to the row's candidate list
 //   kGemmArgmin  keep the row's best (k-means assignment); tiles of one row block are consecutive so it lives in registers
 template <int MODE>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__global__ void __launch_bounds__(tc::threads(MODE), 1)
     coarse_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmEpi e, int num_kb,
                        int mtiles, int ntiles) {
     using namespace tc;
+    constexpr int EPI_WARPS = epi_warps(MODE), PARTS = EPI_WARPS / 4, PART_COLS = BN / PARTS, HIT_SLOTS = 32 / PARTS;
     extern __shared__ unsigned char gsm_raw[];
     unsigned char* gsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = gsm;
@@ -99,7 +126,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) accumulator buffer full, [2S+2..2S+4) accumulator buffer drained; then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_BUFS);
-    uint2* hits = reinterpret_cast<uint2*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES) + 256);  // kGemmFilter only: [HIT_SLOTS][BM]
+    float* hit_score = reinterpret_cast<float*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES) + 256);  // kGemmFilter only: [HIT_SLOTS][PARTS * BM]
+    uint8_t* hit_col = reinterpret_cast<uint8_t*>(hit_score + HIT_SLOTS * BM * PARTS);                 //                  [HIT_SLOTS][PARTS * BM]
     const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull0 = s_u32(bars + 2 * STAGES),
                    tempty0 = s_u32(bars + 2 * STAGES + ACC_BUFS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,7 +165,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         }
         for (int b = 0; b < ACC_BUFS; ++b) {
             bar_init(tfull0 + 8 * b, 1);
-            bar_init(tempty0 + 8 * b, 4);  // one arrival per epilogue warp
+            bar_init(tempty0 + 8 * b, EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,6 +232,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     } else {
         // ===== epilogue: TMEM -> registers -> (scores | candidate lists | running arg-min) =====
         const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int half = (warp - 2) >> 2;  // its part of the tile's 256 columns
         const bool l2 = e.metric == RBQ_METRIC_L2;
         uint32_t ti = 0;
         int best_m = -1;  // kGemmArgmin: row block the running best belongs to
@@ -218,7 +247,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             const uint32_t buf = ti & 1u;
             const int row = m_blk * BM + quarter * 32 + lane;
             const bool row_ok = row < e.nq;
-            const float qq = (row_ok && l2) ? __ldg(e.qn2 + row) : 0.0f;
+            const float qq = (row_ok && l2 && !e.shifted) ? __ldg(e.qn2 + row) : 0.0f;
             float thr = 0.0f;
             if (MODE == kGemmFilter) thr = row_ok ? __ldg(e.thr + row) : (l2 ? -INFINITY : INFINITY);
             if (MODE == kGemmArgmin && m_blk != best_m) {
@@ -226,24 +255,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 best_m = m_blk;
                 best = ~0ull;
             }
-            uint32_t nhit = 0;  // kGemmFilter: centroids of this tile that beat the row's threshold
-            const int erow = quarter * 32 + lane;
+            uint32_t nhit = 0;  // kGemmFilter: staged centroids of this tile that beat the row's threshold
+            const int erow = half * BM + quarter * 32 + lane;  // staging column of this thread
+            // staged hits -> the row's candidate list: one bump of its global counter, then plain stores
+            auto flush_hits = [&]() {
+                if (nhit) {
+                    const uint32_t base = atomicAdd(e.cand_cnt + row, nhit);
+                    for (uint32_t k = 0; k < nhit; ++k)
+                        if (base + k < e.cap)
+                            e.cand[(size_t)row * e.cap + base + k] =
+                                CandRec{hit_score[k * PARTS * BM + erow], (uint32_t)(n_blk * BN) + hit_col[k * PARTS * BM + erow]};
+                    nhit = 0;
+                }
+            };
             bar_wait(tfull0 + 8 * buf, (ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ncols_tile = min(BN, e.ncols - n_blk * BN);  // columns of this tile that exist
-            for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // one 32-column group of the tile: r = its accumulators
+            auto process = [&](const uint32_t (&r)[32], const int c0) {
                 const int n0 = n_blk * BN + c0;
                 const bool full32 = n0 + 32 <= e.ncols && (e.ncols & 3) == 0;
                 if (MODE == kGemmScores) {
@@ -260,7 +289,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const float g = __uint_as_float(r[j + u]);
-                                    pv[u] = l2 ? (qq + pc[u]) - 2.0f * g : g;
+                                    pv[u] = !l2 ? g : e.shifted ? __fmaf_rn(-2.0f, g, pc[u]) : (qq + pc[u]) - 2.0f * g;
                                 }
                                 *reinterpret_cast<float4*>(out + j) = v;
                             }
@@ -268,12 +297,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                             for (int j = 0; j < 32; ++j)
                                 if (n0 + j < e.ncols) {
                                     const float g = __uint_as_float(r[j]);
-                                    out[j] = l2 ? (qq + e.cn2[n0 + j]) - 2.0f * g : g;
+                                    out[j] = !l2 ? g : e.shifted ? __fmaf_rn(-2.0f, g, e.cn2[n0 + j]) : (qq + e.cn2[n0 + j]) - 2.0f * g;
                                 }
                         }
                     }
                 } else {
                     const int lim = min(32, e.ncols - n0);
+                    // scores of the 32 columns (independent: no branches between them)
+                    float sc[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,25 +319,66 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float g = __uint_as_float(r[j + u]);
-                            const float sc = l2 ? (qq + pc[u]) - 2.0f * g : g;
-                            if (MODE == kGemmFilter) {
-                                const bool pass = (l2 ? sc <= thr : sc >= thr) && (j + u < lim);
-                                if (pass) {
-                                    // staged, so that the row's global counter is bumped once per tile (an atomic that returns
-                                    // a value is a round trip to L2: one per hit stalled the whole drain)
-                                    if (nhit < (uint32_t)HIT_SLOTS) {
-                                        hits[nhit * BM + erow] = make_uint2(__float_as_uint(sc), (uint32_t)(n0 + j + u));
-                                    } else {
-                                        const uint32_t slot = atomicAdd(e.cand_cnt + row, 1u);
-                                        if (slot < e.cap) e.cand[(size_t)row * e.cap + slot] = CandRec{sc, (uint32_t)(n0 + j + u)};
-                                    }
-                                    ++nhit;
+                            sc[j + u] = !l2 ? g : e.shifted ? __fmaf_rn(-2.0f, g, pc[u]) : (qq + pc[u]) - 2.0f * g;
+                        }
+                    }
+                    if (MODE == kGemmFilter) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (uint32_t)(l2 ? sc[j] <= thr : sc[j] >= thr) << j;
+                        if (lim < 32) mask &= (1u << lim) - 1u;
+                        if (mask) {  // rare per thread on large centroid tables: a few hundred hits per row over the whole table
+#pragma unroll
+                            for (int hh = 0; hh < 32 / HIT_SLOTS; ++hh) {  // HIT_SLOTS columns at a time: always fit the staging after a flush
+                                const uint32_t mh = (mask >> (HIT_SLOTS * hh)) & ((1u << HIT_SLOTS) - 1u);
+                                if (mh) {
+                                    if (nhit + (uint32_t)__popc(mh) > (uint32_t)HIT_SLOTS) flush_hits();
+#pragma unroll
+                                    for (int j = 0; j < HIT_SLOTS; ++j)
+                                        if ((mh >> j) & 1u) {
+                                            hit_score[nhit * PARTS * BM + erow] = sc[HIT_SLOTS * hh + j];
+                                            hit_col[nhit * PARTS * BM + erow] = (uint8_t)(c0 + HIT_SLOTS * hh + j);
+                                            ++nhit;
+                                        }
                                 }
-                            } else {  // arg-min over max(score, 0), ties to the lower column (reference src/kmeans.rs:505-516)
-                                const unsigned long long key =
-                                    ((unsigned long long)tc_order_key(fmaxf(sc, 0.0f)) << 32) | (uint32_t)(n0 + j + u);
-                                if (j + u < lim && key < best) best = key;
                             }
+                        }
+                    } else {  // arg-min over max(score, 0), ties to the lower column (reference src/kmeans.rs:505-516)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const unsigned long long key = ((unsigned long long)tc_order_key(fmaxf(sc[j], 0.0f)) << 32) | (uint32_t)(n0 + j);
+                            if (j < lim && key < best) best = key;
+                        }
+                    }
+                }
+            };
+            {
+                const int cbeg = half * PART_COLS;  // this warp's columns of the tile: [cbeg, cbeg + PART_COLS)
+                const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)cbeg;
+                const int ngroups = max(0, min(PART_COLS, ncols_tile - cbeg) + 31) / 32;
+                if (PARTS >= 4) {
+                    // many warps per scheduler hide the TMEM latency: one buffer keeps the register count low enough for 18 warps
+                    uint32_t ra[32];
+                    for (int g = 0; g < ngroups; ++g) {
+                        tmem_ld32(ra, tbase + 32u * (uint32_t)g);
+                        tmem_ld_wait(ra);
+                        process(ra, cbeg + 32 * g);
+                    }
+                } else {
+                    // software pipeline over the groups: the TMEM load of group g+1 is in flight while group g is processed
+                    uint32_t ra[32], rb[32];
+                    if (ngroups > 0) {
+                        tmem_ld32(ra, tbase);
+                        tmem_ld_wait(ra);
+                    }
+                    for (int g = 0; g < ngroups; g += 2) {
+                        if (g + 1 < ngroups) tmem_ld32(rb, tbase + 32u * (uint32_t)(g + 1));
+                        process(ra, cbeg + 32 * g);
+                        if (g + 1 < ngroups) {
+                            tmem_ld_wait(rb);
+                            if (g + 2 < ngroups) tmem_ld32(ra, tbase + 32u * (uint32_t)(g + 2));
+                            process(rb, cbeg + 32 * (g + 1));
+                            if (g + 2 < ngroups) tmem_ld_wait(ra);
                         }
                     }
                 }
@@ -315,17 +387,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty0 + 8 * buf);
-            if (MODE == kGemmFilter) {
-                const uint32_t ns = min(nhit, (uint32_t)HIT_SLOTS);
-                if (ns) {
-                    const uint32_t base = atomicAdd(e.cand_cnt + row, ns);
-                    for (uint32_t k = 0; k < ns; ++k)
-                        if (base + k < e.cap) {
-                            const uint2 hv = hits[k * BM + erow];
-                            e.cand[(size_t)row * e.cap + base + k] = CandRec{__uint_as_float(hv.x), hv.y};
-                        }
-                }
-            }
+            if (MODE == kGemmFilter) flush_hits();
         }
         if (MODE == kGemmArgmin) flush_best();
     }
@@ -433,7 +495,7 @@ static int launch_gemm_mode(const CUtensorMap& ma, const CUtensorMap& mb, const 
     RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (long long)mtiles * ntiles;
     const int grid = (int)std::min<long long>(total, gemm_sms());
-    coarse_gemm_kernel<MODE><<<grid, tc::THREADS, smem, st>>>(ma, mb, epi, num_kb, mtiles, ntiles);
+    coarse_gemm_kernel<MODE><<<grid, tc::threads(MODE), smem, st>>>(ma, mb, epi, num_kb, mtiles, ntiles);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

@@ -110,6 +110,7 @@ struct DevStats {
     unsigned long long tail_pairs;       // (query, list) pairs handed to the tail kernel
     unsigned long long survivors;        // tail candidates with lower bound < the query's head threshold
     unsigned long long overflow_queries; // queries whose survivor buffer overflowed (re-walked sequentially)
+    unsigned long long fallback_queries; // queries the head pass could not take (list longer than the dense buffer, heap not full after it)
 };
 // A tail candidate that may still enter the top-k: replayed in (rank, pos) order by the replay pass.
 struct Survivor {
@@ -233,7 +234,9 @@ struct CandRec {  // a centroid that passed the filter: its approximate score an
 };
 struct GemmEpi {
     int nq = 0, ncols = 0, metric = 0;
-    const float* qn2 = nullptr;      // |a|^2 per row (L2)
+    int shifted = 0;                 // L2 scores without the row's |a|^2: fma(-2, a.b, |b|^2) -- the filter mode's score domain (ordering per
+                                     // row is unchanged; one FFMA per score in the epilogue)
+    const float* qn2 = nullptr;      // |a|^2 per row (L2, unshifted)
     const float* cn2 = nullptr;      // |b|^2 per column (L2)
     float* scores = nullptr;         // kGemmScores: [nq][ncols]
     const float* thr = nullptr;      // kGemmFilter: per-row threshold (L2: keep score <= thr; IP: keep score >= thr)
@@ -295,7 +298,9 @@ struct rbq_index {
     unsigned int* work_counter() const { return reinterpret_cast<unsigned int*>(d_stats + 1); }
     unsigned int* fallback_counter() const { return work_counter() + 1; }
     mutable rbq_search_stats last_stats{};
-    mutable cudaEvent_t ev[9] = {};  // stage boundaries 0..6, then begin/end of the tail FastScan kernel alone
+    mutable cudaEvent_t ev[10] = {};  // stage boundaries 0..6, begin/end of the tail FastScan kernel alone, end of the tail stage (phased search)
+    mutable cudaEvent_t ev_chunk[32][5] = {};  // profiled calls: front-end / head boundaries of every chunk of a tile (created on first use)
+    mutable int dist_phase = 0;       // phased search: 3 after rbq_dist_tail (its stage times are read back lazily by rbq_last_search_stats)
     mutable cudaStream_t copy_stream = nullptr;  // H2D of host queries, overlapped with the front end (api.cu, HostFeed)
     mutable cudaStream_t compute_stream = nullptr;  // the host entry points' compute stream
     mutable cudaEvent_t feed_ev[16] = {};

@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
         }
         if (fallback) {
             if (lane == 0) {
+                if (a.stats) atomicAdd(&a.stats->fallback_queries, 1ull);
                 a.fb_list[atomicAdd(&a.counters[2], 1u)] = q;  // from scratch
                 a.tail_start[q] = a.nprobe;
                 a.tau[q] = INFINITY;

@@ -613,8 +613,8 @@ def test_coarse_filter_mode_matches_exact_coarse(rbq, oracle, case):
         gix.set_coarse_terms(3)
         for i in range(0, q.shape[0], 97):
             assert np.array_equal(c0[i], oix.search_dump(q[i], 1, nprobe)["probe"])
-    # end to end through the auto mode (= filter here), few fallbacks
-    gix.set_coarse_mode(-1)
+    # end to end in filter mode, few fallbacks
+    gix.set_coarse_mode(2)
     got = gix.batch_search(q, rbq.SearchParams(10, 16))
     st = gix.stats()
     assert st["coarse_mode_used"] == 2 and st["coarse_fallbacks"] <= q.shape[0] // 20, st
