@@ -134,6 +134,7 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     uint32_t* list_cnt;    // [nlist] pairs per list      } zeroed together with surv_cnt and the counters
     uint32_t* list_fill;   // [nlist] scatter cursors     }
     uint32_t* list_off;    // [nlist + 1]
+    void* plan_tot;        // [1024] per-CTA totals of the work planner (scan_tail.cu)
     uint32_t* pairs;       // [nq * nprobe] pair ids (q * nprobe + rank) grouped by list
     TailItem* items;       // [max_items]
     uint32_t* counters;    // [0] n_items, [1] item cursor
@@ -144,6 +145,8 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     uint32_t head_cap;     // slots per query (multiple of 32); longer lists send the query to the fallback path
     uint32_t head_rows;    // queries per head sub-chunk
     uint32_t* fb_list;     // [nq] queries left to the sequential fallback (counters[2] = how many)
+    uint32_t* qlist;       // [nq] phased search: queries whose head pass runs on this shard, compacted; qcount = how many
+    uint32_t* qcount;
 };
 constexpr uint32_t kFbResume = 0x80000000u;
 // counters[]: [0] tail items, [1] tail item cursor, [2] fallback queries, [3] head-resolve cursor, [4] refine cursor,

@@ -31,6 +31,8 @@ struct ResolveArgs {
     const Probe* probes;
     uint32_t nq, nprobe, top_k;
     const uint8_t* head_owner;  // phased multi-GPU search: 0 = another shard runs this query's head pass (nullptr: all ours)
+    const uint32_t* qlist;      // phased multi-GPU search: the queries whose head pass runs here, compacted (nullptr: identity);
+    const uint32_t* qcount;     //   their number.  q_begin / q_count then address SLOTS of qlist
     uint32_t q_begin, q_count, cursor;  // head stage: the queries [q_begin, q_begin + q_count) of this launch; cursor = its work counter slot
     const unsigned long long* filter;
     unsigned long long filter_nbits;
@@ -69,9 +71,13 @@ __device__ __forceinline__ uint32_t first_owned_rank(const Probe* __restrict__ p
 template <int NCB, bool WIDE>
 __global__ void __launch_bounds__(128, 3) head_scan_kernel(DevIndex ix, ResolveArgs a) {
     const int lane = threadIdx.x & 31;
-    const uint32_t q = a.q_begin + blockIdx.x * 4u + (threadIdx.x >> 5);
-    if (q >= a.q_begin + a.q_count) return;
-    if (a.head_owner != nullptr && !a.head_owner[q]) return;
+    const uint32_t slot = a.q_begin + blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (slot >= a.q_begin + a.q_count) return;
+    uint32_t q = slot;
+    if (a.qlist != nullptr) {
+        if (slot >= *a.qcount) return;
+        q = a.qlist[slot];
+    }
     const Probe* pr = a.probes + (size_t)q * a.nprobe;
     const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
     if (h >= a.nprobe) return;
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(128, 3) head_scan_kernel(DevIndex ix, ResolveA
     const bool l2 = ix.metric == RBQ_METRIC_L2;
     const uint32_t nb = (p.nv + kBatch - 1) / kBatch;
     const uint8_t* base = ix.blocks + (size_t)p.blk_off * ix.block_stride;
-    float2* out = a.head_buf + (size_t)(q - a.q_begin) * a.head_cap;
+    float2* out = a.head_buf + (size_t)(slot - a.q_begin) * a.head_cap;
     // the next block's codes and factors are in flight while the current block is looked up
     uint4 Cn[NCB];
     load_block_codes<NCB>(base, Cn, ncb, lane);
@@ -246,13 +252,10 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= a.q_count) break;
         q += a.q_begin;
-        if (a.head_owner != nullptr && !a.head_owner[q]) {  // another shard fills the heap first: all our pairs are tail pairs
-            if (lane == 0) {
-                a.out_counts[q] = 0u;
-                a.tail_start[q] = 0u;
-                a.tau[q] = INFINITY;
-            }
-            continue;
+        const uint32_t slot = q;  // row of the dense head buffer = slot - q_begin
+        if (a.qlist != nullptr) {
+            if (slot >= *a.qcount) break;
+            q = a.qlist[slot];
         }
         const Probe* pr = a.probes + (size_t)q * a.nprobe;
         const uint32_t h = first_owned_rank(pr, a.nprobe, 0, lane);
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
                 __syncwarp();
                 const uint32_t nv = p.nv, nb = (nv + kBatch - 1) / kBatch;
                 const unsigned long long vbase = p.vec_off;
-                const float2* hb = a.head_buf + (size_t)(q - a.q_begin) * a.head_cap;
+                const float2* hb = a.head_buf + (size_t)(slot - a.q_begin) * a.head_cap;
                 q_blocks = nb;
 
                 // candidate queue: slot i lives in lane i, in visit order
@@ -732,6 +735,24 @@ __global__ void probe_import_kernel(DevIndex ix, const rbq_probe_rec* __restrict
     probes[i] = p;
     if (i % nprobe == 0) head_owner[i / nprobe] = ix.list_owner == nullptr || ix.list_owner[r.cid] == (uint8_t)ix.shard_rank;
 }
+// Phased multi-GPU search: the queries whose nearest probed list this shard owns, compacted (any order), so that the head
+// kernels run on dense grids; every other query gets the "nothing done here" head state (all its pairs are tail pairs).
+__global__ void head_compact_kernel(const uint8_t* __restrict__ head_owner, uint32_t nq, uint32_t* __restrict__ qlist, uint32_t* __restrict__ qcount,
+                                    uint32_t* __restrict__ out_counts, uint32_t* __restrict__ tail_start, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = q < nq && head_owner[q] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(qcount, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) qlist[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = q;
+    else if (q < nq) {
+        out_counts[q] = 0u;
+        tail_start[q] = 0u;
+        tau[q] = INFINITY;
+    }
+}
+
 int launch_probe_export(const Probe* d_probes, size_t q_begin, size_t q_count, size_t nprobe, rbq_probe_rec* d_out, cudaStream_t st) {
     const size_t count = q_count * nprobe;
     if (count == 0) return RBQ_OK;
@@ -774,6 +795,8 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.q_count = (uint32_t)nq;
     a.cursor = 3;
     a.head_owner = nullptr;
+    a.qlist = nullptr;
+    a.qcount = nullptr;
     a.nprobe = (uint32_t)nprobe;
     a.top_k = (uint32_t)top_k;
     a.filter = reinterpret_cast<const unsigned long long*>(d_filter);
@@ -852,6 +875,15 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     ResolveArgs a;
     fill_args(a, ix, d_rot, d_lut, d_qs, d_probes, nq, nprobe, top_k, d_filter, filter_nbits, d_ids, d_scores, d_counts, d_stats, tw);
     a.head_owner = d_head_owner;
+    if (d_head_owner != nullptr) {  // compact the queries of this shard: slots [q_begin, q_begin + q_count) of tw.qlist
+        RBQ_CUDA(cudaMemsetAsync(tw.qcount, 0, 4, st));
+        head_compact_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_head_owner, (uint32_t)nq, tw.qlist, tw.qcount, d_counts, tw.tail_start,
+                                                                       tw.tau);
+        RBQ_CUDA(cudaGetLastError());
+        a.qlist = tw.qlist;
+        a.qcount = tw.qcount;
+        if (launches) *launches += 1;
+    }
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0, a.stage_bufs);
     const size_t smem = (size_t)w.total * kResWarps;

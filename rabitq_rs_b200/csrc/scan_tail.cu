@@ -42,82 +42,114 @@ __global__ void tail_count_kernel(const Probe* __restrict__ probes, const uint32
     if (p.nv != 0) atomicAdd(&list_cnt[p.cid], 1u);
 }
 
-// One CTA: exclusive scan of the per-list pair counts and of the per-list item counts; writes the work items.  Items of long
-// lists (more than one accumulator group of `big_blocks` blocks) come first: they take two or more passes over the K dimension
-// in the tensor-core kernel, and starting them early shortens the under-filled end of the persistent grid.
-__global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_n,
-                                                         uint32_t nlist, uint32_t per_item, uint32_t big_blocks,
-                                                         uint32_t* __restrict__ list_off, TailItem* __restrict__ items, uint32_t max_items,
-                                                         uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_pairs[64], s_items[64], s_big[64];  // [0,32): warp totals, [32,64): their inclusive scan
-    const uint32_t t = threadIdx.x, chunk = (nlist + 1023u) / 1024u;
-    const uint32_t c0 = min(t * chunk, nlist), c1 = min(c0 + chunk, nlist);
-    auto is_big = [&](uint32_t c) { return (list_n[c] + kBatch - 1) / kBatch > big_blocks; };
-    uint32_t np = 0, ni = 0, nbig = 0;
-    for (uint32_t c = c0; c < c1; ++c) {
-        const uint32_t n = list_cnt[c], k = (n + per_item - 1) / per_item;
-        np += n;
-        ni += k;
-        if (is_big(c)) nbig += k;
-    }
-    // inclusive scan over the 1024 threads: shuffles inside a warp, then the 32 warp totals
-    const uint32_t lane = t & 31u, wid = t >> 5;
-    uint32_t xp = np, xi = ni, xb = nbig;
+// Work planning: exclusive scans of the per-list pair counts and item counts, then the work items.  Items of long lists (more
+// than one accumulator group of `big_blocks` blocks) come first: they take two or more passes over the K dimension in the
+// tensor-core kernel, and starting them early shortens the under-filled end of the persistent grid.
+// Two launches of 1024-thread CTAs, one list per thread: (1) per-CTA scans + CTA totals, (2) every CTA re-scans the (<= 1024)
+// CTA totals for its own base and writes its lists' offsets and items.  (The first version walked all lists in ONE CTA:
+// 0.36 ms at 65536 lists, a cost every shard of a multi-GPU search paid in full.)
+struct PlanRec {
+    uint32_t pairs, items, big;
+};
+__device__ __forceinline__ PlanRec plan_block_scan(PlanRec v, PlanRec* s_warp, PlanRec& total) {
+    // inclusive scan of (pairs, items, big) over the 1024 threads of the CTA; returns the inclusive value, total = CTA sum
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 #pragma unroll
     for (uint32_t o = 1; o < 32; o <<= 1) {
-        const uint32_t ap = __shfl_up_sync(0xffffffffu, xp, o), ai = __shfl_up_sync(0xffffffffu, xi, o), ab = __shfl_up_sync(0xffffffffu, xb, o);
+        const uint32_t ap = __shfl_up_sync(0xffffffffu, v.pairs, o), ai = __shfl_up_sync(0xffffffffu, v.items, o),
+                       ab = __shfl_up_sync(0xffffffffu, v.big, o);
         if (lane >= o) {
-            xp += ap;
-            xi += ai;
-            xb += ab;
+            v.pairs += ap;
+            v.items += ai;
+            v.big += ab;
         }
     }
-    if (lane == 31) {
-        s_pairs[wid] = xp;
-        s_items[wid] = xi;
-        s_big[wid] = xb;
-    }
+    if (lane == 31) s_warp[wid] = v;
     __syncthreads();
     if (wid == 0) {
-        uint32_t yp = s_pairs[lane], yi = s_items[lane], yb = s_big[lane];
+        PlanRec w = s_warp[lane];
 #pragma unroll
         for (uint32_t o = 1; o < 32; o <<= 1) {
-            const uint32_t ap = __shfl_up_sync(0xffffffffu, yp, o), ai = __shfl_up_sync(0xffffffffu, yi, o), ab = __shfl_up_sync(0xffffffffu, yb, o);
+            const uint32_t ap = __shfl_up_sync(0xffffffffu, w.pairs, o), ai = __shfl_up_sync(0xffffffffu, w.items, o),
+                           ab = __shfl_up_sync(0xffffffffu, w.big, o);
             if (lane >= o) {
-                yp += ap;
-                yi += ai;
-                yb += ab;
+                w.pairs += ap;
+                w.items += ai;
+                w.big += ab;
             }
         }
-        s_pairs[32 + lane] = yp;  // inclusive totals of warps 0..lane
-        s_items[32 + lane] = yi;
-        s_big[32 + lane] = yb;
+        s_warp[32 + lane] = w;  // inclusive totals of warps 0..lane
     }
     __syncthreads();
-    const uint32_t bp = wid ? s_pairs[32 + wid - 1] : 0u, bi = wid ? s_items[32 + wid - 1] : 0u, bb = wid ? s_big[32 + wid - 1] : 0u;
-    const uint32_t inc_pairs = bp + xp, inc_items = bi + xi, inc_big = bb + xb;  // inclusive prefix of this thread
-    const uint32_t tot_pairs = s_pairs[63], tot_items = s_items[63];
-    const uint32_t total_big = s_big[63];
-    uint32_t po = inc_pairs - np;
-    uint32_t ib = inc_big - nbig;                                    // next slot among the big items
-    uint32_t is = total_big + (inc_items - ni) - (inc_big - nbig);  // next slot among the others
-    for (uint32_t c = c0; c < c1; ++c) {
-        const uint32_t n = list_cnt[c];
+    if (wid) {
+        const PlanRec b = s_warp[32 + wid - 1];
+        v.pairs += b.pairs;
+        v.items += b.items;
+        v.big += b.big;
+    }
+    total = s_warp[63];
+    __syncthreads();
+    return v;
+}
+__global__ void __launch_bounds__(1024) tail_plan_local_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_n,
+                                                              uint32_t nlist, uint32_t per_item, uint32_t big_blocks, PlanRec* __restrict__ cta_tot) {
+    __shared__ PlanRec s_warp[64];
+    const uint32_t c = blockIdx.x * 1024u + threadIdx.x;
+    PlanRec v{0u, 0u, 0u};
+    if (c < nlist) {
+        const uint32_t n = list_cnt[c], k = (n + per_item - 1) / per_item;
+        v.pairs = n;
+        v.items = k;
+        v.big = (list_n[c] + kBatch - 1) / kBatch > big_blocks ? k : 0u;
+    }
+    PlanRec total;
+    plan_block_scan(v, s_warp, total);
+    if (threadIdx.x == 0) cta_tot[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) tail_plan_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_n,
+                                                         uint32_t nlist, uint32_t per_item, uint32_t big_blocks, const PlanRec* __restrict__ cta_tot,
+                                                         uint32_t* __restrict__ list_off, TailItem* __restrict__ items, uint32_t max_items,
+                                                         uint32_t* __restrict__ counters) {
+    __shared__ PlanRec s_warp[64];
+    __shared__ PlanRec s_base, s_all;
+    const uint32_t t = threadIdx.x, nctas = gridDim.x;
+    // base of this CTA = sum of the totals of the CTAs before it; grand totals = sum of all (nctas <= 1024)
+    PlanRec mine{0u, 0u, 0u};
+    if (t < nctas) mine = cta_tot[t];
+    PlanRec all;
+    const PlanRec inc = plan_block_scan(mine, s_warp, all);
+    if (t == blockIdx.x) s_base = PlanRec{inc.pairs - mine.pairs, inc.items - mine.items, inc.big - mine.big};
+    if (t == 0) s_all = all;
+    __syncthreads();
+    const PlanRec base = s_base, grand = s_all;
+    const uint32_t c = blockIdx.x * 1024u + t;
+    PlanRec v{0u, 0u, 0u};
+    uint32_t n = 0;
+    bool big = false;
+    if (c < nlist) {
+        n = list_cnt[c];
+        const uint32_t k = (n + per_item - 1) / per_item;
+        big = (list_n[c] + kBatch - 1) / kBatch > big_blocks;
+        v = PlanRec{n, k, big ? k : 0u};
+    }
+    PlanRec total;
+    const PlanRec loc = plan_block_scan(v, s_warp, total);
+    if (c < nlist) {
+        const uint32_t po = base.pairs + loc.pairs - v.pairs;                       // first pair slot of the list
+        const uint32_t before_items = base.items + loc.items - v.items, before_big = base.big + loc.big - v.big;
+        uint32_t io = big ? before_big : grand.big + (before_items - before_big);  // next slot among the big / the other items
         list_off[c] = po;
         if (n) {
             const uint32_t chunks = (n + per_item - 1) / per_item, sz = (n + chunks - 1) / chunks;  // balanced chunks
-            uint32_t& io = is_big(c) ? ib : is;
-            for (uint32_t j = 0; j < chunks; ++j) {
+            for (uint32_t j = 0; j < chunks; ++j, ++io) {
                 const uint32_t b = j * sz, e = min(n, b + sz);
                 if (io < max_items && b < e) items[io] = TailItem{c, po + b, e - b, 0u};
-                ++io;
             }
         }
-        po += n;
     }
-    if (t == 1023) {
-        list_off[nlist] = tot_pairs;
-        counters[0] = min(tot_items, max_items);
+    if (blockIdx.x == 0 && t == 0) {
+        list_off[nlist] = grand.pairs;
+        counters[0] = min(grand.items, max_items);
         counters[1] = 0u;
     }
 }
@@ -326,8 +358,8 @@ static uint32_t g_surv_cap_override = 0;  // test knob: forces survivor-buffer o
 void tail_debug_set_survivor_cap(uint32_t cap) { g_surv_cap_override = cap; }
 static uint32_t tail_surv_cap(size_t top_k) {
     if (g_surv_cap_override) return g_surv_cap_override;
-    size_t c = (256 + 4 * top_k + 31) / 32 * 32;
-    return (uint32_t)std::min<size_t>(std::max<size_t>(c, 512), 1024);
+    (void)top_k;
+    return 1024;  // the largest the replay's sort keys address (10-bit slot): an overflowing query costs a sequential re-walk of its tail
 }
 
 // dense head buffer: room for the longest list of the shard (lists beyond 64Ki vectors send their queries to the sequential
@@ -348,11 +380,13 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     n += nq * 4 + 256;                               // tau
     n += (nq + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4 + 256;  // surv_cnt | list_cnt | list_fill | counters (zeroed together)
     n += ((size_t)ix.nlist + 1) * 4 + 256;           // list_off
+    n += 1024 * 12 + 256;                            // plan_tot
     n += nq * nprobe * 4 + 256;                      // pairs
     n += max_items * sizeof(TailItem) + 256;
     n += nq * cap * sizeof(Survivor) + 256;
     n += (size_t)tail_head_rows(ix, nq) * tail_head_cap(ix) * 8 + 256;  // head_buf
     n += nq * 4 + 256;                                   // fb_list
+    n += nq * 4 + 512;                                   // qlist + qcount
     return n;
 }
 
@@ -375,6 +409,7 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.list_fill = tw.list_cnt + ix.nlist;
     tw.counters = tw.list_fill + ix.nlist;
     tw.list_off = reinterpret_cast<uint32_t*>(take(((size_t)ix.nlist + 1) * 4));
+    tw.plan_tot = take(1024 * 12);
     tw.pairs = reinterpret_cast<uint32_t*>(take(nq * nprobe * 4));
     tw.items = reinterpret_cast<TailItem*>(take((size_t)tw.max_items * sizeof(TailItem)));
     tw.surv = reinterpret_cast<Survivor*>(take(nq * (size_t)tw.surv_cap * sizeof(Survivor)));
@@ -382,6 +417,8 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.head_rows = tail_head_rows(ix, nq);
     tw.head_buf = reinterpret_cast<float2*>(take((size_t)tw.head_rows * tw.head_cap * 8));
     tw.fb_list = reinterpret_cast<uint32_t*>(take(nq * 4));
+    tw.qlist = reinterpret_cast<uint32_t*>(take(nq * 4));
+    tw.qcount = reinterpret_cast<uint32_t*>(take(16));
 }
 
 template <int NCB, bool WIDE>
@@ -426,8 +463,12 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
     const size_t npairs = nq * nprobe;
     const unsigned tb = 256, gb = (unsigned)((npairs + tb - 1) / tb);
     tail_count_kernel<<<gb, tb, 0, st>>>(d_probes, tw.tail_start, (uint32_t)nq, (uint32_t)nprobe, tw.list_cnt);
-    tail_plan_kernel<<<1, 1024, 0, st>>>(tw.list_cnt, ix.list_n, ix.nlist, tw.pairs_per_item, 8u, tw.list_off, tw.items, tw.max_items,
-                                         tw.counters);
+    const unsigned plan_ctas = (ix.nlist + 1023u) / 1024u;
+    if (plan_ctas > 1024u) return fail(RBQ_INVALID_CONFIG, "more than 2^20 inverted lists are not supported by the tail planner");
+    PlanRec* plan_tot = reinterpret_cast<PlanRec*>(tw.plan_tot);
+    tail_plan_local_kernel<<<plan_ctas, 1024, 0, st>>>(tw.list_cnt, ix.list_n, ix.nlist, tw.pairs_per_item, 8u, plan_tot);
+    tail_plan_kernel<<<plan_ctas, 1024, 0, st>>>(tw.list_cnt, ix.list_n, ix.nlist, tw.pairs_per_item, 8u, plan_tot, tw.list_off, tw.items,
+                                                 tw.max_items, tw.counters);
     tail_scatter_kernel<<<gb, tb, 0, st>>>(d_probes, tw.tail_start, (uint32_t)nq, (uint32_t)nprobe, tw.list_off, tw.list_fill,
                                            tw.pairs);
     RBQ_CUDA(cudaGetLastError());
@@ -448,7 +489,7 @@ int launch_tail(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_
     a.stats = d_stats;
     a.seg_blocks = 1;
     a.has_ex = ix.ex_bits != 0;
-    if (launches) *launches += 4;
+    if (launches) *launches += 5;
     if (ev_begin) cudaEventRecord(ev_begin, st);
     rc = launch_tail_fastscan(ix, a, st);
     if (ev_end) cudaEventRecord(ev_end, st);
