@@ -399,6 +399,8 @@ def main():
         from rabitq_rs_b200.distributed import ShardedSearcher
 
         searcher = ShardedSearcher(ix, rank, world)
+        if os.environ.get("RBQ_BENCH_PY_COLLECTIVES") is None:  # A/B knob: the three-call form with torch.distributed collectives
+            searcher.init_comm()                                # default: librbq's own NCCL communicator, one C call per batch
     stream = torch.cuda.current_stream(dev)
 
     def search_device(npb):

@@ -161,6 +161,25 @@ int rbq_dist_head(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, c
 int rbq_dist_tail(const rbq_index* ix, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids,
                   float* d_scores, uint32_t* d_counts, void* stream);
 
+/* ---- multi-GPU search as ONE call (librbq owns the NCCL communicator; NCCL is dlopen'ed when these are first used) ----
+ * What a Rust caller of batch_search (src/ivf.rs:1743) uses to spread one index over the GPUs of a box: one process (or
+ * thread) per GPU, each with its shard handle (rbq_index_load / rbq_builder_* with shard_rank, shard_count).
+ *  rbq_comm_unique_id: rank 0 creates the 128-byte rendezvous id and ships it to the other ranks (any transport).
+ *  rbq_comm_init:      collective; rank / world must equal the handle's shard coordinates.
+ *  rbq_search_batch_sharded_device: the three phases above with their exchanges (all-gather of the probe slices, MIN
+ *      all-reduce of the thresholds, all-gather of the packed local top-k) and the merge, all enqueued on `stream`; every
+ *      rank passes the whole batch (device) and receives the merged result (device).  Same answers as the three-call form.
+ *  rbq_search_batch_sharded: host buffers; every rank passes the same batch, uploads only its 1/world slice over its own
+ *      host link (the slices are all-gathered over NVLink) and receives the merged result.  Synchronous. */
+#define RBQ_COMM_ID_BYTES 128
+int rbq_comm_unique_id(uint8_t* id_out);
+int rbq_comm_init(rbq_index* ix, const uint8_t* id, int rank, int world);
+int rbq_comm_destroy(rbq_index* ix);
+int rbq_search_batch_sharded_device(const rbq_index* ix, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
+                                    uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream);
+int rbq_search_batch_sharded(const rbq_index* ix, const float* queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, uint64_t* ids,
+                             float* scores, uint32_t* counts);
+
 /* The same merge over ONE all-gathered buffer: shard s occupies bytes [s*chunk_bytes, (s+1)*chunk_bytes) holding
  * ids[nq*top_k] (u64) | scores[nq*top_k] (f32) | counts[nq] (u32); chunk_bytes is a multiple of 8.  One collective
  * instead of three. */
@@ -235,6 +254,17 @@ int rbq_debug_probe(const rbq_index* ix, const float* queries, size_t nq, size_t
  * (simd::accumulate_batch_avx2 src/simd.rs:972, compute_batch_distances_u16 :1932). */
 int rbq_debug_scan_list(const rbq_index* ix, const float* query, size_t dim, size_t cluster,
                         uint32_t* accu, float* ip, float* est, float* lb, size_t cap_vectors);
+
+/* Stage probes through the PRODUCT kernels of the list-major schedule (host buffers; nq*cap output arrays).
+ * which = 0: head_scan_kernel -- for every query the dense rows of its nearest non-empty probed list: out_a = lower bound (after
+ *   the non-finite fallback, src/ivf.rs:2031-2042), out_b = ip_x0_qr (ex_bits > 0) or the estimate, out_n[q] = list length;
+ * which = 1: the tail FastScan kernel (tcgen05 one-hot GEMM) over ALL probed lists with the pruning threshold at +inf: one
+ *   record per vector (out_r = probe rank, out_p = position, out_a, out_b as above) in arbitrary order, out_n[q] records. */
+int rbq_debug_stage(const rbq_index* ix, int which, const float* queries, size_t nq, size_t dim, size_t nprobe, size_t cap,
+                    float* out_a, float* out_b, uint32_t* out_r, uint32_t* out_p, uint32_t* out_n);
+/* K10 (ip_packed_ex2_f32 / ip_packed_ex6_f32 / generic, src/simd.rs:1722-1825) through the product's refine path: the ex-code
+ * dot of the first n vectors of `cluster` against the rotated query. */
+int rbq_debug_ex_dot(const rbq_index* ix, const float* query, size_t dim, size_t cluster, size_t n, float* out);
 
 /* Test knob (process-wide): capacity of the per-query survivor buffer of the list-major scan; 0 restores the
  * default (derived from top_k).  A query that overflows it has its tail re-walked sequentially (still exact). */

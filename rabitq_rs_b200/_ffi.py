@@ -63,6 +63,11 @@ def lib():
     L.rbq_dist_front.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, vp, vp]
     L.rbq_dist_head.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp, vp]
     L.rbq_dist_tail.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp]
+    L.rbq_comm_unique_id.argtypes = [vp]
+    L.rbq_comm_init.argtypes = [vp, vp, i32, i32]
+    L.rbq_comm_destroy.argtypes = [vp]
+    L.rbq_search_batch_sharded_device.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp, vp, vp]
+    L.rbq_search_batch_sharded.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp, vp]
     L.rbq_shard_assignment.argtypes = [vp, sz, i32, vp, vp, sz, C.POINTER(sz)]
     L.rbq_last_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.rbq_set_profiling.argtypes = [vp, i32]
@@ -73,6 +78,8 @@ def lib():
     L.rbq_debug_query_prep.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.rbq_debug_probe.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.rbq_debug_scan_list.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, sz]
+    L.rbq_debug_stage.argtypes = [vp, i32, vp, sz, sz, sz, sz, vp, vp, vp, vp, vp]
+    L.rbq_debug_ex_dot.argtypes = [vp, vp, sz, sz, sz, vp]
     _lib = L
     return L
 

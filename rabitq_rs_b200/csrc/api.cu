@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "nccl_loader.h"
 #include "rbq_internal.h"
 
 using namespace rbq;
@@ -587,6 +588,8 @@ void rbq_index_free(rbq_index* h) {
         for (auto& row : h->ev_chunk)
             for (auto& e : row)
                 if (e) cudaEventDestroy(e);
+        if (h->comm) nccl_api().comm_destroy(h->comm);
+        if (h->dist_ws) cudaFree(h->dist_ws);
         if (h->busy_ev) cudaEventDestroy(h->busy_ev);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
@@ -910,18 +913,11 @@ int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, s
     if (*nprobe < 2) return fail(RBQ_INVALID_CONFIG, "phased search needs nprobe >= 2");
     return RBQ_OK;
 }
-}  // namespace
 
-int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, size_t q_begin,
-                   size_t q_count, rbq_probe_rec* d_probes, void* stream) {
-    Plan pl;
-    int rc = dist_args(h, nq, dim, top_k, &nprobe, &pl);
-    if (rc) return rc;
-    if (q_begin > nq || q_count > nq - q_begin) return fail(RBQ_INVALID_CONFIG, "query slice out of range");
-    DeviceGuard g(h->device);
-    std::lock_guard<std::mutex> lk(h->mu);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Serial serial(h, st);
+// The three phases without locking / argument checks (the public entry points and the one-call sharded search share them).
+int dist_front_impl(const rbq_index* h, const Plan& pl, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, size_t q_begin,
+                    size_t q_count, rbq_probe_rec* d_probes, cudaStream_t st) {
+    int rc;
     h->last_stats = rbq_search_stats{};
     h->dist_phase = 0;
     h->last_stats.queries = nq;
@@ -950,15 +946,9 @@ int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t
     return RBQ_OK;
 }
 
-int rbq_dist_head(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes, float* d_tau,
-                  uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream) {
-    Plan pl;
-    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
-    if (rc) return rc;
-    DeviceGuard g(h->device);
-    std::lock_guard<std::mutex> lk(h->mu);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Serial serial(h, st);
+int dist_head_impl(const rbq_index* h, const Plan& pl, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes, float* d_tau,
+                   uint64_t* d_ids, float* d_scores, uint32_t* d_counts, cudaStream_t st) {
+    int rc;
     if (h->ws_bytes < ws_need(h, pl, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
     const DevIndex& ix = h->dev;
     const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
@@ -976,15 +966,9 @@ int rbq_dist_head(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, co
     return RBQ_OK;
 }
 
-int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids, float* d_scores,
-                  uint32_t* d_counts, void* stream) {
-    Plan pl;
-    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
-    if (rc) return rc;
-    DeviceGuard g(h->device);
-    std::lock_guard<std::mutex> lk(h->mu);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Serial serial(h, st);
+int dist_tail_impl(const rbq_index* h, const Plan& pl, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids, float* d_scores,
+                   uint32_t* d_counts, cudaStream_t st) {
+    int rc;
     if (h->ws_bytes < ws_need(h, pl, nprobe, top_k, h->dev.dim, false, 0)) return fail(RBQ_INVALID_CONFIG, "rbq_dist_front must run first");
     const DevIndex& ix = h->dev;
     const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
@@ -1003,6 +987,199 @@ int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, co
     if (h->profiling) cudaEventRecord(h->ev[6], st);
     h->dist_phase = h->profiling ? 3 : 0;
     h->last_stats.kernel_launches = launches + 2;
+    return RBQ_OK;
+}
+}  // namespace
+
+int rbq_dist_front(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, size_t q_begin,
+                   size_t q_count, rbq_probe_rec* d_probes, void* stream) {
+    Plan pl;
+    int rc = dist_args(h, nq, dim, top_k, &nprobe, &pl);
+    if (rc) return rc;
+    if (q_begin > nq || q_count > nq - q_begin) return fail(RBQ_INVALID_CONFIG, "query slice out of range");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
+    return dist_front_impl(h, pl, d_queries, nq, dim, top_k, nprobe, q_begin, q_count, d_probes, st);
+}
+
+int rbq_dist_head(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const rbq_probe_rec* d_probes, float* d_tau,
+                  uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream) {
+    Plan pl;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
+    return dist_head_impl(h, pl, nq, top_k, nprobe, d_probes, d_tau, d_ids, d_scores, d_counts, st);
+}
+
+int rbq_dist_tail(const rbq_index* h, size_t nq, size_t top_k, size_t nprobe, const float* d_tau, uint64_t* d_ids, float* d_scores,
+                  uint32_t* d_counts, void* stream) {
+    Plan pl;
+    int rc = dist_args(h, nq, 0, top_k, &nprobe, &pl);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
+    return dist_tail_impl(h, pl, nq, top_k, nprobe, d_tau, d_ids, d_scores, d_counts, st);
+}
+
+// ---- multi-GPU search as ONE call: the three phases with their NCCL exchanges enqueued on one stream ---------------------
+// No reference counterpart (src/ivf.rs is single-process).  librbq owns the communicator: rank 0 creates an id
+// (rbq_comm_unique_id), the caller ships its 128 bytes to the other ranks by whatever means it has, every rank calls
+// rbq_comm_init on its shard handle.  NCCL is loaded at run time (dlopen libnccl.so.2): single-GPU users do not need it.
+namespace {
+int nccl_check(int r, const char* what) {
+    if (r == 0) return RBQ_OK;
+    return fail(RBQ_CUDA_ERROR, std::string("NCCL error in ") + what + ": " + nccl_api().get_error_string(r));
+}
+size_t dist_slice(size_t nq, int world) { return (((nq + world - 1) / world) + 127) / 128 * 128; }  // padded slice length (GEMM row tile)
+}  // namespace
+
+int rbq_comm_unique_id(uint8_t* id_out) {
+    if (!id_out) return fail(RBQ_INVALID_CONFIG, "null argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    return nccl_check(nccl_api().get_unique_id(id_out), "ncclGetUniqueId");
+}
+
+int rbq_comm_init(rbq_index* h, const uint8_t* id, int rank, int world) {
+    if (!h || !id) return fail(RBQ_INVALID_CONFIG, "null argument");
+    if (rank != h->host.shard_rank || world != h->host.shard_count)
+        return fail(RBQ_INVALID_CONFIG, "communicator rank/size must equal the handle's shard_rank/shard_count");
+    int rc = nccl_load();
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->comm) return fail(RBQ_INVALID_CONFIG, "the handle already has a communicator");
+    return nccl_check(nccl_api().comm_init_rank(&h->comm, world, id, rank), "ncclCommInitRank");
+}
+
+int rbq_comm_destroy(rbq_index* h) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->busy_ev) cudaEventSynchronize(h->busy_ev);
+    if (h->comm) {
+        nccl_api().comm_destroy(h->comm);
+        h->comm = nullptr;
+    }
+    if (h->dist_ws) cudaFree(h->dist_ws);
+    h->dist_ws = nullptr;
+    h->dist_ws_bytes = 0;
+    return RBQ_OK;
+}
+
+namespace {
+// the caller holds the handle's lock and has validated the arguments; extra_bytes of the exchange workspace are reserved in front
+// (host entry: staging of the queries and of the merged result)
+int sharded_search_impl(const rbq_index* h, const Plan& pl, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
+                        uint64_t* d_ids, float* d_scores, uint32_t* d_counts, cudaStream_t st, size_t extra_bytes, char** extra_out) {
+    int rc;
+    const int world = h->host.shard_count, rank = h->host.shard_rank;
+    // exchange buffers: probe records of all (padded) slices | thresholds | every shard's packed local top-k
+    const size_t per = dist_slice(nq, world);
+    const size_t chunk = (nq * top_k * 12 + nq * 4 + 15) / 16 * 16;
+    const size_t need = extra_bytes + 256 + per * world * nprobe * sizeof(rbq_probe_rec) + 256 + nq * 4 + 256 + chunk * world + 256;
+    if (h->dist_ws_bytes < need) {
+        if (h->dist_ws) {
+            RBQ_CUDA(cudaDeviceSynchronize());
+            cudaFree(h->dist_ws);
+        }
+        h->dist_ws = nullptr;
+        h->dist_ws_bytes = 0;
+        RBQ_CUDA(cudaMalloc(&h->dist_ws, need));
+        h->dist_ws_bytes = need;
+    }
+    Carver cv{(char*)h->dist_ws};
+    char* extra = cv.take<char>(extra_bytes);
+    if (extra_out) *extra_out = extra;
+    if (d_queries == nullptr) return RBQ_OK;  // sizing / staging pass of the host entry
+    rbq_probe_rec* d_rec = cv.take<rbq_probe_rec>(per * world * nprobe);
+    float* d_tau = cv.take<float>(nq);
+    char* d_gath = cv.take<char>(chunk * world);
+    char* mine = d_gath + (size_t)rank * chunk;
+    uint64_t* l_ids = reinterpret_cast<uint64_t*>(mine);
+    float* l_sc = reinterpret_cast<float*>(mine + nq * top_k * 8);
+    uint32_t* l_cn = reinterpret_cast<uint32_t*>(mine + nq * top_k * 12);
+    const NcclApi& nc = nccl_api();
+    const size_t q_begin = std::min((size_t)rank * per, nq), q_count = std::min((size_t)(rank + 1) * per, nq) - q_begin;
+    // 1. front end for this rank's slice; the slices (16 B per probe) are all-gathered in place
+    if ((rc = dist_front_impl(h, pl, d_queries, nq, dim, top_k, nprobe, q_begin, q_count, d_rec, st))) return rc;
+    const size_t slice_bytes = per * nprobe * sizeof(rbq_probe_rec);
+    if ((rc = nccl_check(nc.all_gather((const char*)d_rec + (size_t)rank * slice_bytes, d_rec, slice_bytes, /*ncclChar*/ 0, h->comm, st), "ncclAllGather")))
+        return rc;
+    // 2. head pass where this shard owns the query's nearest list; thresholds MIN-reduced
+    if ((rc = dist_head_impl(h, pl, nq, top_k, nprobe, d_rec, d_tau, l_ids, l_sc, l_cn, st))) return rc;
+    if ((rc = nccl_check(nc.all_reduce(d_tau, d_tau, nq, /*ncclFloat32*/ 7, /*ncclMin*/ 3, h->comm, st), "ncclAllReduce"))) return rc;
+    // 3. tail + replay on this shard's lists; the packed local top-k (one chunk per rank) all-gathered in place and merged
+    if ((rc = dist_tail_impl(h, pl, nq, top_k, nprobe, d_tau, l_ids, l_sc, l_cn, st))) return rc;
+    if ((rc = nccl_check(nc.all_gather(mine, d_gath, chunk, /*ncclChar*/ 0, h->comm, st), "ncclAllGather"))) return rc;
+    rc = launch_merge(h->host.metric, world, nq, top_k, reinterpret_cast<const uint64_t*>(d_gath), reinterpret_cast<const float*>(d_gath + nq * top_k * 8),
+                      reinterpret_cast<const uint32_t*>(d_gath + nq * top_k * 12), d_ids, d_scores, d_counts, st, chunk / 8, chunk / 4, chunk / 4);
+    h->last_stats.kernel_launches += 1;
+    return rc;
+}
+}  // namespace
+
+
+int rbq_search_batch_sharded_device(const rbq_index* h, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
+                                    uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (!h->comm) return fail(RBQ_INVALID_CONFIG, "rbq_comm_init must be called on the shard handle first");
+    if (!d_queries) return fail(RBQ_INVALID_CONFIG, "null buffer");
+    Plan pl;
+    int rc = dist_args(h, nq, dim, top_k, &nprobe, &pl);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Serial serial(h, st);
+    return sharded_search_impl(h, pl, d_queries, nq, dim, top_k, nprobe, d_ids, d_scores, d_counts, st, 0, nullptr);
+}
+
+// Host buffers: every rank passes the SAME batch; each uploads only its 1/world slice over its own host link and the slices
+// are all-gathered over NVLink, the merged result comes back to every rank's host buffers.  Synchronous.
+int rbq_search_batch_sharded(const rbq_index* h, const float* queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, uint64_t* ids,
+                             float* scores, uint32_t* counts) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    if (!h->comm) return fail(RBQ_INVALID_CONFIG, "rbq_comm_init must be called on the shard handle first");
+    if (!queries || !ids || !scores || !counts) return fail(RBQ_INVALID_CONFIG, "null buffer");
+    Plan pl;
+    int rc = dist_args(h, nq, dim, top_k, &nprobe, &pl);
+    if (rc) return rc;
+    const int world = h->host.shard_count, rank = h->host.shard_rank;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->compute_stream) {
+        RBQ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        RBQ_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+        for (auto& e : h->feed_ev) RBQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t st = h->compute_stream;
+    Serial serial(h, st);
+    const size_t per = (nq + world - 1) / world;
+    const size_t q_bytes = per * world * dim * 4, out_bytes = nq * top_k * 12 + nq * 4 + 64;
+    char* extra = nullptr;
+    if ((rc = sharded_search_impl(h, pl, nullptr, nq, dim, top_k, nprobe, nullptr, nullptr, nullptr, st, q_bytes + 256 + out_bytes, &extra))) return rc;
+    float* d_q = reinterpret_cast<float*>(extra);
+    char* d_out = extra + ((q_bytes + 255) & ~(size_t)255);
+    uint64_t* d_ids = reinterpret_cast<uint64_t*>(d_out);
+    float* d_sc = reinterpret_cast<float*>(d_out + nq * top_k * 8);
+    uint32_t* d_cn = reinterpret_cast<uint32_t*>(d_out + nq * top_k * 12);
+    const size_t lo = std::min((size_t)rank * per, nq), hi = std::min((size_t)(rank + 1) * per, nq);
+    if (hi > lo) RBQ_CUDA(cudaMemcpyAsync(d_q + lo * dim, queries + lo * dim, (hi - lo) * dim * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = nccl_check(nccl_api().all_gather(d_q + (size_t)rank * per * dim, d_q, per * dim * 4, /*ncclChar*/ 0, h->comm, st), "ncclAllGather")))
+        return rc;
+    if ((rc = sharded_search_impl(h, pl, d_q, nq, dim, top_k, nprobe, d_ids, d_sc, d_cn, st, q_bytes + 256 + out_bytes, nullptr))) return rc;
+    RBQ_CUDA(cudaMemcpyAsync(ids, d_ids, nq * top_k * 8, cudaMemcpyDeviceToHost, st));
+    RBQ_CUDA(cudaMemcpyAsync(scores, d_sc, nq * top_k * 4, cudaMemcpyDeviceToHost, st));
+    RBQ_CUDA(cudaMemcpyAsync(counts, d_cn, nq * 4, cudaMemcpyDeviceToHost, st));
+    RBQ_CUDA(cudaStreamSynchronize(st));
     return RBQ_OK;
 }
 
@@ -1116,6 +1293,120 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
     h->last_stats.queries = nq;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
+    return RBQ_OK;
+}
+
+// Stage probes through the PRODUCT kernels of the list-major schedule (the kernels a search launches, not a debug twin).
+// which == 0: head_scan_kernel -- the dense (lower bound, ip | estimate) rows of every query's nearest list:
+//             out_a[q*cap + i] = lower bound, out_b[q*cap + i] = ip (ex_bits > 0) or estimate, out_n[q] = list length.
+// which == 1: the tail FastScan kernel (tail_tc_kernel) over ALL probed lists with the threshold at +inf, so every vector
+//             survives: records (rank, position, lower bound, ip | estimate) in arbitrary order, out_n[q] of them per query
+//             (cap must hold them; <= 1024).  out_a / out_b / out_r / out_p are nq*cap arrays.
+int rbq_debug_stage(const rbq_index* h, int which, const float* queries, size_t nq, size_t dim, size_t nprobe, size_t cap, float* out_a,
+                    float* out_b, uint32_t* out_r, uint32_t* out_p, uint32_t* out_n) {
+    int rc = check_search_args(h, dim, 1, &nprobe);
+    if (rc) return rc;
+    if (nq == 0) return RBQ_OK;
+    if (which != 0 && which != 1) return fail(RBQ_INVALID_CONFIG, "stage must be 0 (head scan) or 1 (tail scan)");
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));
+    const size_t top_k = 1;
+    const Plan pl = make_plan(h, nq, nprobe);
+    if (pl.qt < nq) return fail(RBQ_INVALID_CONFIG, "too many queries for a stage probe");
+    const size_t base = ws_need(h, pl, nprobe, top_k, dim, false, 0);
+    if ((rc = ensure_ws(h, base + nq * dim * 4 + nq * 16 + 4096))) return rc;
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
+    const DevIndex& ix = h->dev;
+    Carver cv{(char*)h->ws};
+    cv.off = base;
+    float* d_q = cv.take<float>(nq * dim);
+    uint64_t* d_ids = cv.take<uint64_t>(nq);
+    float* d_sc = cv.take<float>(nq);
+    uint32_t* d_cn = cv.take<uint32_t>(nq);
+    RBQ_CUDA(cudaMemcpy(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice));
+    uint64_t launches = 0;
+    for (size_t c0 = 0; c0 < nq; c0 += pl.cq) {
+        const size_t m = std::min(pl.cq, nq - c0);
+        if ((rc = run_front(h, L, pl, d_q + c0 * dim, c0, m, nprobe, nullptr, &launches, true, nullptr, nullptr, true))) return rc;
+    }
+    RBQ_CUDA(cudaMemset(L.tw.surv_cnt, 0, (pl.qt + 2 * (size_t)ix.nlist + kTailCounters + kHeadCursors) * 4));
+    std::vector<Probe> pr(nq * nprobe);
+    RBQ_CUDA(cudaMemcpy(pr.data(), L.d_pr, pr.size() * sizeof(Probe), cudaMemcpyDeviceToHost));
+    if (which == 0) {
+        if (nq > L.tw.head_rows) return fail(RBQ_INVALID_CONFIG, "too many queries for one head sub-chunk");
+        int hl = 0;
+        if ((rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_sc, d_cn, h->d_stats, L.tw, nullptr, &launches, 0,
+                              nq, &hl)))
+            return rc;
+        std::vector<float2> row(L.tw.head_cap);
+        for (size_t q = 0; q < nq; ++q) {
+            uint32_t nv = 0;
+            for (size_t r = 0; r < nprobe; ++r)
+                if (pr[q * nprobe + r].nv) {
+                    nv = pr[q * nprobe + r].nv;
+                    break;
+                }
+            out_n[q] = nv;
+            if (nv > cap || nv > L.tw.head_cap) return fail(RBQ_INVALID_CONFIG, "output buffers too small for the head list");
+            RBQ_CUDA(cudaMemcpy(row.data(), L.tw.head_buf + q * (size_t)L.tw.head_cap, (size_t)nv * 8, cudaMemcpyDeviceToHost));
+            for (uint32_t i = 0; i < nv; ++i) {
+                out_a[q * cap + i] = row[i].x;
+                out_b[q * cap + i] = row[i].y;
+            }
+        }
+        return RBQ_OK;
+    }
+    // tail over every pair, threshold +inf
+    if (cap > L.tw.surv_cap) return fail(RBQ_INVALID_CONFIG, "cap exceeds the survivor buffer (1024)");
+    if ((rc = launch_fill_u32(L.tw.tail_start, nq, 0u, nullptr))) return rc;
+    if ((rc = launch_fill_u32(reinterpret_cast<uint32_t*>(L.tw.tau), nq, 0x7f800000u, nullptr))) return rc;
+    if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, nullptr, &launches))) return rc;
+    std::vector<uint32_t> cnt(nq);
+    RBQ_CUDA(cudaMemcpy(cnt.data(), L.tw.surv_cnt, nq * 4, cudaMemcpyDeviceToHost));
+    std::vector<Survivor> sv(L.tw.surv_cap);
+    for (size_t q = 0; q < nq; ++q) {
+        out_n[q] = cnt[q];
+        if (cnt[q] > cap) return fail(RBQ_INVALID_CONFIG, "more survivors than the output buffers hold");
+        RBQ_CUDA(cudaMemcpy(sv.data(), L.tw.surv + q * (size_t)L.tw.surv_cap, (size_t)cnt[q] * sizeof(Survivor), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < cnt[q]; ++i) {
+            out_r[q * cap + i] = sv[i].rank;
+            out_p[q * cap + i] = sv[i].pos;
+            out_a[q * cap + i] = sv[i].lower;
+            out_b[q * cap + i] = sv[i].x;
+        }
+    }
+    return RBQ_OK;
+}
+
+// Stage probe for K10 (ip_packed_ex2_f32 / ip_packed_ex6_f32, src/simd.rs:1722-1825): the ex-code dot of the first n vectors of
+// `cluster` against one query, through the product's refine path.
+int rbq_debug_ex_dot(const rbq_index* h, const float* query, size_t dim, size_t cluster, size_t n, float* out) {
+    size_t np = 1;
+    int rc = check_search_args(h, dim, 1, &np);
+    if (rc) return rc;
+    if (cluster >= h->host.nlist || n > h->host.list_n[cluster]) return fail(RBQ_INVALID_CONFIG, "cluster / count out of range");
+    if (n == 0 || h->dev.ex_bits == 0) return RBQ_OK;
+    DeviceGuard g(h->device);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->busy_ev) RBQ_CUDA(cudaEventSynchronize(h->busy_ev));
+    const size_t D = h->dev.D;
+    if ((rc = ensure_ws(h, dim * 4 + D * 8 + 64 + n * 12 + 16384))) return rc;
+    Carver cv{(char*)h->ws};
+    float* d_q = cv.take<float>(dim);
+    float* d_rot = cv.take<float>(D);
+    uint8_t* d_lut = cv.take<uint8_t>(D * 4);
+    QueryScalars* d_qs = cv.take<QueryScalars>(1);
+    unsigned long long* d_gv = cv.take<unsigned long long>(n);
+    float* d_out = cv.take<float>(n);
+    std::vector<unsigned long long> gv(n);
+    for (size_t i = 0; i < n; ++i) gv[i] = h->host.vec_off[cluster] + i;
+    RBQ_CUDA(cudaMemcpy(d_q, query, dim * 4, cudaMemcpyHostToDevice));
+    RBQ_CUDA(cudaMemcpy(d_gv, gv.data(), n * 8, cudaMemcpyHostToDevice));
+    if ((rc = launch_query_prep(h->dev, d_q, 1, d_rot, d_lut, d_qs, nullptr))) return rc;
+    TailWs tw{};
+    if ((rc = launch_ex_dot_debug(h->dev, d_rot, d_gv, (int)n, d_out, tw, nullptr))) return rc;
+    RBQ_CUDA(cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost));
     return RBQ_OK;
 }
 

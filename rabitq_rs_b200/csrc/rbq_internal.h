@@ -214,6 +214,8 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
                          size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
                          const TailWs& tw, cudaStream_t st, uint64_t* launches);
 void tail_debug_set_survivor_cap(uint32_t cap);  // 0 = default
+int launch_fill_u32(uint32_t* d_p, size_t n, uint32_t v, cudaStream_t st);
+int launch_ex_dot_debug(const DevIndex& ix, const float* d_rot, const unsigned long long* d_gv, int n, float* d_out, const TailWs& tw, cudaStream_t st);
 size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k);
 void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, char* base, TailWs& tw);
 int launch_scan_debug(const DevIndex& ix, const uint8_t* d_lut, const QueryScalars* d_qs, uint32_t cluster,
@@ -313,5 +315,8 @@ struct rbq_index {
                                // 1: dense tensor-core scores + exact re-score, 2: tensor-core scores filtered in the GEMM epilogue
     int coarse_terms = 3;      // bf16 split terms multiplied by the coarse GEMM: 3 (fp32-class scores) or 1 (bf16-class, wider re-score band)
     float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|) with 3 terms
+    void* comm = nullptr;                   // ncclComm_t of the one-call sharded search (rbq_comm_init); NCCL is dlopen'ed
+    mutable void* dist_ws = nullptr;        // its exchange buffers
+    mutable size_t dist_ws_bytes = 0;
     mutable cudaEvent_t busy_ev = nullptr;  // recorded after the last kernel of every call: the next call's stream waits on it
 };

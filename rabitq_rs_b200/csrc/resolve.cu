@@ -688,6 +688,34 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     }
 }
 
+// Stage probe for K10: the ex-code dot of `n` stored vectors (global positions gv[i]) against one rotated query, through the
+// product's own refine path (load_rql + refine_batch: lane-major rows, 8 FMA chains, AVX2-order horizontal sum).
+__global__ void __launch_bounds__(32) ex_dot_debug_kernel(DevIndex ix, ResolveArgs a, const unsigned long long* __restrict__ gv, int n,
+                                                         float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    const int lane = threadIdx.x;
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs);
+    load_rql(res_smem + L.rq, a.rql_row, a.rot, ix.D, ix.exl_lane, lane);
+    __syncwarp();
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        const int m = min(32, n - b0);
+        const unsigned long long g = lane < m ? gv[b0 + lane] : 0ull;
+        const float d = refine_batch(ix, a, g, m, smem_u32(res_smem + L.stage), smem_u32(res_smem + L.rq), lane);
+        if (lane < m) out[b0 + lane] = d;
+        __syncwarp();
+    }
+}
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+int launch_fill_u32(uint32_t* d_p, size_t n, uint32_t v, cudaStream_t st) {
+    if (n == 0) return RBQ_OK;
+    fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_p, n, v);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
+}
+
 int prepare_ex_lanes(rbq_index* h) {
     DevIndex& d = h->dev;
     d.exl = nullptr;
@@ -951,6 +979,19 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     const unsigned grid = res_grid(nq, smem);
     RBQ_RES_LAUNCH(resolve_replay_kernel, smem, grid);
     if (launches) *launches += 1;
+    return RBQ_OK;
+}
+
+int launch_ex_dot_debug(const DevIndex& ix, const float* d_rot, const unsigned long long* d_gv, int n, float* d_out, const TailWs& tw, cudaStream_t st) {
+    if (n == 0 || ix.ex_bits == 0) return RBQ_OK;
+    int rc = res_limits();
+    if (rc) return rc;
+    ResolveArgs a;
+    fill_args(a, ix, d_rot, nullptr, nullptr, nullptr, 1, 1, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr, tw);
+    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs);
+    RBQ_CUDA(cudaFuncSetAttribute(ex_dot_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.total));
+    ex_dot_debug_kernel<<<1, 32, w.total, st>>>(ix, a, d_gv, n, d_out);
+    RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
 

@@ -79,6 +79,31 @@ class ShardedSearcher:
     def __init__(self, ix, rank, world, group=None):
         self.ix, self.rank, self.world, self.group = ix, rank, world, group
         self._key = None
+        self.native = False
+
+    def init_comm(self):
+        """Give librbq its own NCCL communicator (rbq_comm_init): search()/search_host() then run as ONE C call per batch
+        (rbq_search_batch_sharded[_device]: kernels and collectives enqueued back to back on one stream) instead of three
+        C calls interleaved with torch.distributed collectives.  The 128-byte rendezvous id travels over torch.distributed."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _ffi
+        from .index import _check
+
+        dev = self.ix_device() if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _check(_ffi.lib().rbq_comm_unique_id(buf))
+            idt.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        dist.broadcast(idt, 0, group=self.group)
+        raw = (C.c_uint8 * 128)(*idt.cpu().tolist())
+        _check(_ffi.lib().rbq_comm_init(self.ix.handle, raw, self.rank, self.world))
+        self.native = True
+        return self
 
     def _buffers(self, nq, k, nprobe, dev):
         import torch
@@ -111,6 +136,19 @@ class ShardedSearcher:
         # the exchange buffers with the same number
         nprobe = min(max(int(nprobe), 1), self.ix.cluster_count())
         b = self._buffers(nq, k, nprobe, dq.device)
+        if self.native:
+            import ctypes as C
+
+            import torch
+
+            from . import _ffi
+            from .index import _check
+
+            _check(_ffi.lib().rbq_search_batch_sharded_device(self.ix.handle, C.c_void_p(dq.data_ptr()), nq, dq.shape[1], int(k), nprobe,
+                                                              C.c_void_p(b.m_ids.data_ptr()), C.c_void_p(b.m_sc.data_ptr()),
+                                                              C.c_void_p(b.m_cn.data_ptr()),
+                                                              C.c_void_p(torch.cuda.current_stream(dq.device).cuda_stream)))
+            return b.m_ids, b.m_sc, b.m_cn
         q0, qc = b.slices[self.rank]
         self.ix.dist_front(dq, k, nprobe, q0, qc, b.probes)
         mine = b.probes[self.rank * b.per:(self.rank + 1) * b.per]
@@ -130,6 +168,19 @@ class ShardedSearcher:
         import torch.distributed as dist
 
         nq, dim = hq.shape
+        if self.native:  # one synchronous C call: H2D of this rank's slice, NVLink all-gather, phased search, D2H of the merged result
+            import ctypes as C
+
+            from . import _ffi
+            from .index import _check
+
+            if getattr(self, "_hout", None) is None or self._hout[0].shape != (nq, k):
+                self._hout = (torch.empty((nq, k), dtype=torch.int64).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                              torch.empty(nq, dtype=torch.int32).pin_memory())
+            a, b_, c = self._hout
+            _check(_ffi.lib().rbq_search_batch_sharded(self.ix.handle, C.c_void_p(hq.data_ptr()), nq, dim, int(k), int(nprobe),
+                                                       C.c_void_p(a.data_ptr()), C.c_void_p(b_.data_ptr()), C.c_void_p(c.data_ptr())))
+            return a, b_, c
         per = (nq + self.world - 1) // self.world
         if getattr(self, "_dq", None) is None or self._dq.shape != (per * self.world, dim):
             self._dq = torch.empty((per * self.world, dim), dtype=torch.float32, device=self.ix_device())

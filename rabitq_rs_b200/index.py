@@ -381,6 +381,25 @@ class IvfRabitqIndex:
         _check(_ffi.lib().rbq_debug_probe(self._need(), _ptr(q), nq, dim, npb, _ptr(cids), _ptr(consts)))
         return cids, consts
 
+    def debug_stage(self, which, queries, nprobe, cap):
+        """Product-kernel stage probe (rbq_debug_stage): which=0 head scan rows, which=1 tail survivors with threshold +inf.
+        Returns (a, b, rank, pos, n) with [nq, cap] arrays (rank/pos only meaningful for which=1)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        nq, dim = q.shape
+        a = np.zeros((nq, cap), np.float32)
+        b = np.zeros((nq, cap), np.float32)
+        r = np.zeros((nq, cap), np.uint32)
+        p = np.zeros((nq, cap), np.uint32)
+        n = np.zeros(nq, np.uint32)
+        _check(_ffi.lib().rbq_debug_stage(self._need(), int(which), _ptr(q), nq, dim, int(nprobe), int(cap), _ptr(a), _ptr(b), _ptr(r), _ptr(p), _ptr(n)))
+        return a, b, r, p, n
+
+    def debug_ex_dot(self, query, cluster, n):
+        q = np.ascontiguousarray(query, np.float32)
+        out = np.zeros(max(int(n), 1), np.float32)
+        _check(_ffi.lib().rbq_debug_ex_dot(self._need(), _ptr(q), q.size, int(cluster), int(n), _ptr(out)))
+        return out[:n]
+
     def debug_scan_list(self, query, cluster, list_len):
         q = np.ascontiguousarray(query, np.float32)
         slots = (list_len + 31) // 32 * 32

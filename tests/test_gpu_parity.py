@@ -634,3 +634,163 @@ def test_empty_filter_admits_nothing(rbq, oracle):
     assert gix.search_filtered(data[3], rbq.SearchParams(10, 8), []) == []
     ids, sc, cnt = gix.batch_search(data[:300], rbq.SearchParams(10, 8), np.zeros(0, np.uint64))
     assert (cnt == 0).all()
+
+
+def test_one_call_sharded_search_world_of_one(rbq, oracle):
+    """rbq_search_batch_sharded[_device] (librbq's own NCCL communicator, the three phases + exchanges in one call) on a
+    one-rank communicator: every code path of the multi-GPU call, same answers as the plain search and the oracle."""
+    import ctypes as C
+
+    import torch
+    from rabitq_rs_b200 import _ffi
+
+    data, oix, blob = oracle_index(6000, 96, 48, 7, 0, kind="clustered")
+    gix = _load(rbq, blob)
+    L = _ffi.lib()
+    uid = (C.c_uint8 * 128)()
+    assert L.rbq_comm_unique_id(uid) == 0, _ffi.last_error()
+    assert L.rbq_comm_init(gix.handle, uid, 0, 1) == 0, _ffi.last_error()
+    assert L.rbq_comm_init(gix.handle, uid, 0, 1) != 0          # second communicator on the same handle is refused
+    q = _queries(data, 700, 5)
+    nq, k, nprobe = q.shape[0], 10, 12
+    dq = torch.from_numpy(q).cuda()
+    ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    cn = torch.empty(nq, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        rc = L.rbq_search_batch_sharded_device(gix.handle, C.c_void_p(dq.data_ptr()), nq, q.shape[1], k, nprobe, C.c_void_p(ids.data_ptr()),
+                                               C.c_void_p(sc.data_ptr()), C.c_void_p(cn.data_ptr()), st)
+        assert rc == 0, _ffi.last_error()
+    torch.cuda.synchronize()
+    got = (ids.cpu().numpy().astype(np.uint64), sc.cpu().numpy(), cn.cpu().numpy().astype(np.uint32))
+    assert assert_results_match(got, oix.search_batch(q, k, nprobe)) == nq
+    h_ids = np.zeros((nq, k), np.uint64)
+    h_sc = np.zeros((nq, k), np.float32)
+    h_cn = np.zeros(nq, np.uint32)
+    rc = L.rbq_search_batch_sharded(gix.handle, q.ctypes.data_as(C.c_void_p), nq, q.shape[1], k, nprobe, h_ids.ctypes.data_as(C.c_void_p),
+                                    h_sc.ctypes.data_as(C.c_void_p), h_cn.ctypes.data_as(C.c_void_p))
+    assert rc == 0, _ffi.last_error()
+    assert np.array_equal(h_ids, got[0]) and np.array_equal(h_sc, got[1]) and np.array_equal(h_cn, got[2])
+    assert L.rbq_comm_destroy(gix.handle) == 0
+    rc = L.rbq_search_batch_sharded_device(gix.handle, C.c_void_p(dq.data_ptr()), nq, q.shape[1], k, nprobe, C.c_void_p(ids.data_ptr()),
+                                           C.c_void_p(sc.data_ptr()), C.c_void_p(cn.data_ptr()), st)
+    assert rc == 2 and "rbq_comm_init" in _ffi.last_error()
+
+
+# ---- stage probes through the PRODUCT kernels of the list-major schedule ---------------------------------------------
+def _oracle_list_rows(oracle, oix, d, rank, metric, has_ex):
+    """(lower bound after the non-finite fallback, ip | estimate) of every vector of the rank-th probed list (oracle)."""
+    D = oix.padded_dim
+    c = int(d["probe"][rank])
+    nv = oix.list_len(c)
+    blocks = oix.list_blocks(c).reshape(-1, 4 * D + 384)
+    g_add, g_err, dot_qc = (d["probe_f"][rank, i] for i in range(3))
+    lows, xs = [], []
+    for b in range(blocks.shape[0]):
+        ea = oracle.accumulate_block(blocks[b, :4 * D], d["lut"], D)
+        fac = blocks[b, 4 * D:].view(np.float32)
+        ip, est, lb = oracle.batch_distances(ea, d["delta"], d["sum_vl"], fac[:32], fac[32:64], fac[64:], g_add, g_err, d["k1x"])
+        lb = lb.copy()
+        bad = ~np.isfinite(lb)
+        lb[bad] = np.float32(0.0) if metric == 0 else np.float32(-(np.float32(dot_qc) + np.float32(d["qnorm"])))
+        lows.append(lb)
+        xs.append(ip if has_ex else est)
+    if not lows:
+        return np.zeros(0, np.float32), np.zeros(0, np.float32)
+    return np.concatenate(lows)[:nv], np.concatenate(xs)[:nv]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_product_head_and_tail_kernels_bit_exact(rbq, oracle, geom):
+    """The kernels a list-major search launches -- head_scan_kernel (PRMT lookups) and the tail FastScan kernel (tcgen05 one-hot
+    GEMM) -- dumped directly: their lower bounds and ip / estimate values (hence the integer LUT sums behind them) equal the
+    oracle's for every vector of every probed list."""
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    q = _queries(data, 6, 13)
+    nprobe = min(4, nlist)
+    cap = 1024
+    ha, hb, _, _, hn = gix.debug_stage(0, q, nprobe, cap)
+    ta, tb, tr, tp, tn = gix.debug_stage(1, q, nprobe, cap)
+    for i in range(q.shape[0]):
+        d = oix.search_dump(q[i], 5, nprobe)
+        rows = [_oracle_list_rows(oracle, oix, d, r, metric, bits > 1) for r in range(nprobe)]
+        first = next(r for r in range(nprobe) if len(rows[r][0]))
+        lo, x = rows[first]
+        assert hn[i] == len(lo)
+        assert np.array_equal(ha[i, :hn[i]].view(np.uint32), lo.view(np.uint32)), "head scan lower bounds differ"
+        assert np.array_equal(hb[i, :hn[i]].view(np.uint32), x.view(np.uint32)), "head scan ip/estimate differs"
+        assert tn[i] == sum(len(r[0]) for r in rows), "tail kernel must report every vector when the threshold is +inf"
+        order = np.lexsort((tp[i, :tn[i]], tr[i, :tn[i]]))
+        exp_lo = np.concatenate([r[0] for r in rows])
+        exp_x = np.concatenate([r[1] for r in rows])
+        exp_rank = np.concatenate([np.full(len(r[0]), j, np.uint32) for j, r in enumerate(rows)])
+        assert np.array_equal(tr[i, :tn[i]][order], exp_rank)
+        assert np.array_equal(ta[i, :tn[i]][order].view(np.uint32), exp_lo.view(np.uint32)), "tail kernel lower bounds differ"
+        assert np.array_equal(tb[i, :tn[i]][order].view(np.uint32), exp_x.view(np.uint32)), "tail kernel ip/estimate differs"
+
+
+@pytest.mark.parametrize("geom", [(600, 128, 8, 7, 0, 1), (600, 960, 8, 3, 0, 1), (600, 768, 8, 7, 1, 1), (600, 768, 8, 5, 1, 1), (400, 32, 8, 3, 0, 0),
+                                  (600, 1536, 4, 7, 0, 1)])
+def test_product_ex_dot_bit_exact(rbq, oracle, geom):
+    """K10 through the product's refine path (lane-major rows, 8 FMA chains, AVX2-order horizontal sum) == the oracle's
+    ip_packed_ex (AVX2 lane order), bit for bit."""
+    n, dim, nlist, bits, metric, rot = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, rotator=rot, kind="uniform11")
+    gix = _load(rbq, blob)
+    ex_bits, D = bits - 1, oix.padded_dim
+    q = _queries(data, 1, 17)[0]
+    rq = oix.rotate(q)
+    from oracle.oracle import ex_bytes
+
+    for c in (0, nlist - 1):
+        nv = oix.list_len(c)
+        got = gix.debug_ex_dot(q, c, nv)
+        ex = oix.list_ex(c).reshape(nv, ex_bytes(D, ex_bits))
+        exp = np.array([oracle.ip_ex(rq, ex[v], ex_bits, fast=True) for v in range(nv)], np.float32)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), "ex-code dot differs"
+
+
+@pytest.mark.parametrize("bits", [7, 3])
+def test_full_size_gist1m_shape(rbq, oracle, bits):
+    """BASELINE config 3 at full size (1M x 960, nlist 4096, total_bits 7 and 3, 10k-query batch): the list-major schedule and
+    the sequential schedule agree on every query, the device entry equals the host entry, and 1 024 queries are checked
+    against the oracle on the same index bytes."""
+    import torch
+    from oracle import oracle as orc
+    from rabitq_rs_b200.kmeans import kmeans_gpu
+
+    n, dim, nlist, nq, k, nprobe = 1_000_000, 960, 4096, 10_000, 10, 16
+    g = torch.Generator(device="cuda").manual_seed(11)
+    centers = torch.randn(256, 32, generator=g, device="cuda")
+    proj = torch.randn(32, dim, generator=g, device="cuda") / 32 ** 0.5
+
+    def draw(m):
+        out = torch.empty((m, dim), dtype=torch.float32)
+        for s in range(0, m, 1 << 18):
+            mm = min(1 << 18, m - s)
+            z = centers[torch.randint(0, 256, (mm,), generator=g, device="cuda")] + 0.6 * torch.randn(mm, 32, generator=g, device="cuda")
+            out[s:s + mm] = (z @ proj + 0.05 * torch.randn(mm, dim, generator=g, device="cuda")).cpu()
+        return out.numpy()
+
+    base, q = draw(n), draw(nq)
+    cents, assign = kmeans_gpu(base, nlist, iters=4, seed=42, device=0)
+    ix = rbq.IvfRabitqIndex(dim, 0, device=0)
+    ix.fit_with_clusters(base, cents, assign, bits, "fht", seed=42, faster_config=True)
+    del base
+    p = rbq.SearchParams(k, nprobe)
+    ix.set_scan_mode(2)
+    a = ix.batch_search(q, p)
+    st = ix.stats()
+    assert st["tail_pairs"] > 0 and st["overflow_queries"] <= nq // 100, st
+    ix.set_scan_mode(1)
+    c = ix.batch_search(q, p)
+    assert all(np.array_equal(x, y) for x, y in zip(_canon_all(a), _canon_all(c))), "list-major != sequential schedule"
+    ids, sc, cnt = a
+    assert (cnt == k).all() and (ids < n).all() and (np.diff(sc, axis=1) >= 0).all()
+    ix.set_scan_mode(0)
+    oix = orc.Index.load_bytes(ix.save_to_bytes())
+    exp = oix.search_batch(q[:1024], k, nprobe)
+    assert assert_results_match((ids[:1024], sc[:1024], cnt[:1024]), exp, TOL, f"gist1m bits {bits}") == 1024
