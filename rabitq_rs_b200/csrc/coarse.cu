@@ -609,17 +609,64 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
 }
 
+// Exact fallback, cooperative form: a fallback query scored by ONE CTA costs ~1 us per 5 centroids x 1000 dims (2.5 ms at 16384
+// lists x 768 dims -- one such query stalled the whole batch).  Rounds of up to kFbRows queries: every (query, centroid slice)
+// gets its own CTA for the scoring, then one CTA per query selects.  fb_count[0] = number of fallback queries.
+constexpr int kFbRows = 64, kFbSlices = 64, kFbRounds = 2;
+__global__ void __launch_bounds__(kSelThreads) fallback_score_kernel(DevIndex ix, const float* __restrict__ rot, const uint32_t* __restrict__ fb_list,
+                                                                    const uint32_t* __restrict__ fb_count, uint32_t first, float* __restrict__ scratch) {
+    const uint32_t idx = first + blockIdx.y;
+    if (idx >= fb_count[0]) return;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    float* rq = reinterpret_cast<float*>(sel_smem);
+    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    const size_t q = fb_list[idx];
+    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+    __syncthreads();
+    const int per = (nl + kFbSlices - 1) / kFbSlices, c0 = (int)blockIdx.x * per, c1 = min(nl, c0 + per);
+    float* sc = scratch + (size_t)blockIdx.y * nl;
+    const int lane8 = tid & 7, grp = tid >> 3;
+    const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
+    for (int c = c0 + grp; c < c1; c += kSelThreads / 8) {
+        float l2, ip;
+        exact_pair(rq, ix.centroids + (size_t)c * D, D, lane8, gmask, &l2, &ip);
+        if (lane8 == 0) sc[c] = desc ? ip : l2;
+    }
+}
+__global__ void __launch_bounds__(kSelThreads) fallback_select_kernel(DevIndex ix, const float* __restrict__ rot, int nprobe, int sort_n,
+                                                                     Probe* __restrict__ probes, const uint32_t* __restrict__ fb_list,
+                                                                     const uint32_t* __restrict__ fb_count, uint32_t first, const float* __restrict__ scratch,
+                                                                     unsigned int* __restrict__ fallbacks) {
+    const uint32_t idx = first + blockIdx.x;
+    if (idx >= fb_count[0]) return;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
+    float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
+    __shared__ SelShared sh;
+    const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
+    const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
+    const size_t q = fb_list[idx];
+    if (tid == 0) atomicAdd(fallbacks, 1u);
+    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
+    __syncthreads();
+    gather_exact(scratch + (size_t)blockIdx.x * nl, nl, nprobe, desc, sh, sel);
+    sort_and_emit(ix, rq, sel, sort_n, nprobe, desc, probes + q * (size_t)nprobe);
+}
+
 // Exact fallback of the filter mode: the queries listed in fb_list get exact scores for every centroid (into a per-CTA scratch
 // row) and the exact selection, like the dense kernels' rare path.  Persistent: fb_count[0] = how many, fb_count[1] = cursor.
 __global__ void __launch_bounds__(kSelThreads) probe_select_exact_kernel(DevIndex ix, const float* __restrict__ rot, int nprobe, int sort_n,
                                                                         Probe* __restrict__ probes, const uint32_t* __restrict__ fb_list,
                                                                         uint32_t* __restrict__ fb_count, float* __restrict__ scratch,
-                                                                        unsigned int* __restrict__ fallbacks) {
+                                                                        unsigned int* __restrict__ fallbacks, uint32_t first) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(sel_smem);  // sort_n keys
     float* rq = reinterpret_cast<float*>(sel + sort_n);                         // D floats
     __shared__ SelShared sh;
     __shared__ uint32_t s_idx;
+    if (fb_count[0] <= first) return;  // the cooperative rounds took them all
     const int tid = threadIdx.x, nl = (int)ix.nlist, D = ix.D;
     const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
     float* sc = scratch + (size_t)blockIdx.x * nl;
@@ -628,7 +675,7 @@ __global__ void __launch_bounds__(kSelThreads) probe_select_exact_kernel(DevInde
     const uint32_t total = fb_count[0];
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_idx = atomicAdd(&fb_count[1], 1u);
+        if (tid == 0) s_idx = first + atomicAdd(&fb_count[1], 1u);
         __syncthreads();
         const uint32_t idx = s_idx;
         if (idx >= total) break;
@@ -804,10 +851,20 @@ int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const Query
     RBQ_CUDA(cudaGetLastError());
     const int sort_x = sort_size(nprobe);
     const size_t smem_x = (size_t)sort_x * 8 + (size_t)ix.D * 4;
-    if (smem_x > 48 * 1024)
+    if (smem_x > 48 * 1024) {
         RBQ_CUDA(cudaFuncSetAttribute(probe_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+        RBQ_CUDA(cudaFuncSetAttribute(fallback_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+    }
+    if (fw.fb_ctas < (uint32_t)kFbRows) return fail(RBQ_INVALID_CONFIG, "fallback scratch too small");
+    for (int r = 0; r < kFbRounds; ++r) {  // cooperative rounds: kFbRows queries each, every (query, centroid slice) on its own CTA
+        fallback_score_kernel<<<dim3(kFbSlices, kFbRows), kSelThreads, (size_t)ix.D * 4, st>>>(ix, d_rot, fw.fb_list, fw.fb_count, (uint32_t)(r * kFbRows),
+                                                                                               fw.fb_scratch);
+        fallback_select_kernel<<<kFbRows, kSelThreads, smem_x, st>>>(ix, d_rot, (int)nprobe, sort_x, d_probes, fw.fb_list, fw.fb_count,
+                                                                     (uint32_t)(r * kFbRows), fw.fb_scratch, d_fallbacks);
+    }
+    // whatever is left (more than kFbRounds * kFbRows fallback queries in one chunk): one CTA per query
     probe_select_exact_kernel<<<fw.fb_ctas, kSelThreads, smem_x, st>>>(ix, d_rot, (int)nprobe, sort_x, d_probes, fw.fb_list, fw.fb_count,
-                                                                       fw.fb_scratch, d_fallbacks);
+                                                                       fw.fb_scratch, d_fallbacks, (uint32_t)(kFbRounds * kFbRows));
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }
