@@ -193,6 +193,27 @@ int rbq_merge_topk_packed_device(const rbq_index* ix, int nshards, size_t nq, si
 int rbq_shard_assignment(const uint8_t* bytes, size_t len, int shard_count, int32_t* owner, uint32_t* list_sizes,
                          size_t cap_lists, size_t* nlist_out);
 
+/* ---- BruteForceRabitqIndex (src/brute_force.rs:203-650): no clustering, zero centroid, exhaustive scan ----
+ * rbq_bf_train        = train (:214-285; RabitqConfig::faster only on the device; MatrixRotator needs rotator_state)
+ * rbq_bf_load[_mem]   = load_from_path / load_from_reader (:388-523), "RBF1" v1, same validation and messages
+ * rbq_bf_save[_mem]   = save_to_path / save_to_writer (:298-385); out == NULL queries the size
+ * rbq_bf_search_batch = search / search_filtered (:526-650) for a batch of queries (host buffers): ids = positions in the
+ *                       training slice, L2: distance ascending, IP: score (= -distance) descending; the reference's
+ *                       sequential scalar float order is kept, so scores are bit-identical to it. */
+typedef struct rbq_bf_index rbq_bf_index;
+int rbq_bf_train(const float* data, size_t n, size_t dim, int total_bits, int metric, int rotator_type, uint64_t seed,
+                 int faster_config, const uint8_t* rotator_state, int device, rbq_bf_index** out);
+int rbq_bf_load(const char* path, int device, rbq_bf_index** out);
+int rbq_bf_load_mem(const uint8_t* bytes, size_t len, int device, rbq_bf_index** out);
+int rbq_bf_save(rbq_bf_index* ix, const char* path);
+int rbq_bf_save_mem(rbq_bf_index* ix, uint8_t* out, size_t cap, size_t* written);
+void rbq_bf_free(rbq_bf_index* ix);
+size_t rbq_bf_len(const rbq_bf_index* ix);
+size_t rbq_bf_dim(const rbq_bf_index* ix);
+size_t rbq_bf_padded_dim(const rbq_bf_index* ix);
+int rbq_bf_search_batch(rbq_bf_index* ix, const float* queries, size_t nq, size_t dim, size_t top_k, const uint64_t* filter_bits,
+                        size_t filter_nbits, uint64_t* ids, float* scores, uint32_t* counts);
+
 /* ---- diagnostics (SearchDiagnostics, src/ivf.rs:151-155, plus roofline accounting) ---- */
 typedef struct rbq_search_stats {
     uint64_t queries;           /* queries in the last search call on this handle */

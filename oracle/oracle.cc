@@ -709,6 +709,7 @@ static double best_rescale_factor(const float* o_abs, size_t dim, int ex_bits) {
 struct QVec {
     std::vector<uint8_t> bin_packed, ex_packed;
     float delta, vl, f_add, f_rescale, f_error, f_add_ex, f_rescale_ex;
+    float residual_norm = 0.0f;  // |r| (compute_one_bit_factors' fourth value; stored by the brute-force index file)
 };
 
 // src/quantizer.rs:140-262 quantize_with_centroid (+ :264-308, :310-335, :429-535)
@@ -752,6 +753,7 @@ static void quantize_with_centroid(const float* data, const float* cent, size_t 
     for (size_t i = 0; i < D; ++i) xu[i] = (float)bits[i] - 0.5f;
     float l2 = dot(r.data(), r.data(), D);
     float l2n = std::sqrt(l2);
+    out.residual_norm = l2n;
     float xun = dot(xu.data(), xu.data(), D);
     float ip_r = dot(r.data(), xu.data(), D);
     float ip_c = dot(cent, xu.data(), D);
@@ -1410,6 +1412,196 @@ static void kmeans(const float* x, size_t n, size_t dim, size_t k, int iters, ui
     }
 }
 
+// ---------------------------------------------------------------------------
+// brute_force.rs: BruteForceRabitqIndex (no clustering, zero centroid, exhaustive scan)
+// ---------------------------------------------------------------------------
+struct BfIndex {  // src/brute_force.rs:203-210
+    size_t dim = 0, D = 0;
+    int metric = 0, ex_bits = 0;
+    Rotator rot;
+    std::vector<QVec> vecs;
+};
+
+// src/brute_force.rs:214-285 train: rotate, quantise every vector against the zero centroid, in input order
+static int bf_train(BfIndex& ix, const float* data, size_t n, size_t dim, int total_bits, int metric, const Rotator& rot, float t_const) {
+    if (n == 0 || total_bits < 1 || total_bits > 16) return 2;
+    ix.dim = dim;
+    ix.rot = rot;
+    ix.D = rot.padded;
+    ix.metric = metric;
+    ix.ex_bits = total_bits - 1;
+    const size_t D = ix.D;
+    std::vector<float> zero(D, 0.0f);
+    ix.vecs.assign(n, QVec());
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long)n; ++i) {
+        std::vector<float> rd(D);
+        rotate(rot, data + (size_t)i * dim, rd.data());
+        quantize_with_centroid(rd.data(), zero.data(), D, ix.ex_bits, metric, t_const, ix.vecs[i]);
+    }
+    return 0;
+}
+
+// src/brute_force.rs:305-385 save_to_writer ("RBF1" v1: header, rotator bytes, per vector packed codes + 8 f32, CRC-32 trailer)
+static void bf_save(const BfIndex& ix, std::vector<uint8_t>& out) {
+    out.clear();
+    auto put = [&](const void* p, size_t n) { out.insert(out.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    auto u32 = [&](uint32_t v) { put(&v, 4); };
+    auto u64 = [&](uint64_t v) { put(&v, 8); };
+    auto u8 = [&](uint8_t v) { put(&v, 1); };
+    put("RBF1", 4);
+    u32(1);
+    u32((uint32_t)ix.dim);
+    u32((uint32_t)ix.D);
+    u8((uint8_t)ix.metric);
+    u8((uint8_t)ix.rot.type);
+    u8((uint8_t)ix.ex_bits);
+    u8((uint8_t)(ix.ex_bits + 1));
+    u64(ix.vecs.size());
+    if (ix.rot.type == 1) {
+        u64(ix.rot.flip.size());
+        put(ix.rot.flip.data(), ix.rot.flip.size());
+    } else {
+        u64(ix.rot.matrix.size() * 4);
+        put(ix.rot.matrix.data(), ix.rot.matrix.size() * 4);
+    }
+    for (const QVec& v : ix.vecs) {
+        put(v.bin_packed.data(), v.bin_packed.size());
+        put(v.ex_packed.data(), v.ex_packed.size());
+        const float meta[8] = {v.delta, v.vl, v.f_add, v.f_rescale, v.f_error, v.residual_norm, v.f_add_ex, v.f_rescale_ex};
+        put(meta, 32);
+    }
+    u32(crc_update(0, out.data() + 8, out.size() - 8));
+}
+
+// src/brute_force.rs:395-523 load_from_reader (same validation order and messages)
+static int bf_load(BfIndex& ix, const uint8_t* p, size_t n, std::string& err) {
+    size_t off = 0;
+    auto need = [&](size_t k) { return off + k <= n; };
+    auto fail_io = [&]() { err = "failed to fill whole buffer"; return 4; };
+    if (!need(4)) return fail_io();
+    if (std::memcmp(p, "RBF1", 4) != 0) { err = "unrecognized file header"; return 5; }
+    off = 4;
+    auto rd32 = [&](uint32_t& v) { if (!need(4)) return false; std::memcpy(&v, p + off, 4); off += 4; return true; };
+    auto rd64 = [&](uint64_t& v) { if (!need(8)) return false; std::memcpy(&v, p + off, 8); off += 8; return true; };
+    auto rd8 = [&](uint8_t& v) { if (!need(1)) return false; v = p[off++]; return true; };
+    uint32_t version, dim, D;
+    uint8_t metric, rt, exb, tb;
+    uint64_t cnt, rlen;
+    if (!rd32(version)) return fail_io();
+    if (version != 1) { err = "unsupported index format version"; return 5; }
+    if (!rd32(dim)) return fail_io();
+    if (dim == 0) { err = "dimension must be positive"; return 5; }
+    if (!rd32(D)) return fail_io();
+    if (D < dim) { err = "padded_dim must be >= dim"; return 5; }
+    if (!rd8(metric)) return fail_io();
+    if (metric > 1) { err = "unknown metric tag"; return 5; }
+    if (!rd8(rt)) return fail_io();
+    if (rt > 1) { err = "unknown rotator type tag"; return 5; }
+    if (!rd8(exb)) return fail_io();
+    if (exb > 16) { err = "ex_bits out of range"; return 5; }
+    if (!rd8(tb)) return fail_io();
+    if (tb == 0 || tb > 16) { err = "total_bits out of range"; return 5; }
+    if ((int)tb - 1 != (int)exb) { err = "total_bits does not match ex_bits"; return 5; }
+    if (!rd64(cnt) || !rd64(rlen)) return fail_io();
+    if (!need(rlen)) return fail_io();
+    ix = BfIndex();
+    ix.dim = dim;
+    ix.D = D;
+    ix.metric = metric;
+    ix.ex_bits = exb;
+    ix.rot.type = rt;
+    ix.rot.dim = dim;
+    ix.rot.padded = D;
+    if (rt == 1) {
+        if (rlen != 4 * (uint64_t)D / 8) { err = "FHT rotator flip bits length mismatch"; return 5; }
+        ix.rot.flip.assign(p + off, p + off + rlen);
+    } else {
+        if (rlen != (uint64_t)D * D * 4) { err = "rotator matrix length mismatch"; return 5; }
+        ix.rot.matrix.resize((size_t)D * D);
+        std::memcpy(ix.rot.matrix.data(), p + off, rlen);
+    }
+    off += rlen;
+    rotator_init_derived(ix.rot);
+    const size_t bsz = (D + 7) / 8, esz = exb > 0 ? ((size_t)D * exb + 7) / 8 : 0;
+    if (cnt > (n - off) / (bsz + esz + 32) + 1) return fail_io();
+    ix.vecs.assign(cnt, QVec());
+    for (uint64_t i = 0; i < cnt; ++i) {
+        if (!need(bsz + esz + 32)) return fail_io();
+        QVec& v = ix.vecs[i];
+        v.bin_packed.assign(p + off, p + off + bsz);
+        off += bsz;
+        v.ex_packed.assign(p + off, p + off + esz);
+        off += esz;
+        float meta[8];
+        std::memcpy(meta, p + off, 32);
+        off += 32;
+        v.delta = meta[0]; v.vl = meta[1]; v.f_add = meta[2]; v.f_rescale = meta[3];
+        v.f_error = meta[4]; v.residual_norm = meta[5]; v.f_add_ex = meta[6]; v.f_rescale_ex = meta[7];
+    }
+    const size_t crc_end = off;
+    uint32_t stored;
+    if (!rd32(stored)) return fail_io();
+    if (crc_update(0, p + 8, crc_end - 8) != stored) { err = "checksum mismatch"; return 5; }
+    return 0;
+}
+
+// src/brute_force.rs:545-650 search_internal: every vector, scalar loops in index order, BinaryHeap of the k smallest
+static int bf_search(const BfIndex& ix, const float* q, size_t top_k, const uint64_t* filter, size_t filter_nbits, uint64_t* ids, float* scores,
+                     uint32_t* count) {
+    *count = 0;
+    if (ix.vecs.empty()) return 3;
+    if (top_k == 0) return 0;
+    const size_t D = ix.D;
+    std::vector<float> rq(D);
+    rotate(ix.rot, q, rq.data());
+    float sum_q = 0.0f;
+    for (size_t i = 0; i < D; ++i) sum_q = sum_q + rq[i];
+    const float k1x = -0.5f * sum_q, cb = -((float)(1 << ix.ex_bits) - 0.5f), kbx = cb * sum_q, bscale = (float)(1 << ix.ex_bits);
+    const float g_add = 0.0f;
+    RustHeap heap;
+    std::vector<uint16_t> ex(D);
+    for (size_t vid = 0; vid < ix.vecs.size(); ++vid) {
+        if (filter && !((uint32_t)vid < filter_nbits && ((filter[(uint32_t)vid >> 6] >> (vid & 63)) & 1ull))) continue;
+        const QVec& v = ix.vecs[vid];
+        float bdot = 0.0f;
+        for (size_t i = 0; i < D; ++i) {
+            const float bit = (float)((v.bin_packed[i >> 3] >> (7 - (i & 7))) & 1);
+            const float pr = bit * rq[i];
+            bdot = bdot + pr;
+        }
+        const float bterm = bdot + k1x;
+        float t0 = v.f_add + g_add;
+        float t1 = v.f_rescale * bterm;
+        float dist = t0 + t1;
+        if (ix.ex_bits > 0) {
+            unpack_ex(v.ex_packed.data(), D, ix.ex_bits, ex.data());
+            float edot = 0.0f;
+            for (size_t i = 0; i < D; ++i) {
+                const float pr = (float)ex[i] * rq[i];
+                edot = edot + pr;
+            }
+            float tt = bscale * bdot;
+            tt = tt + edot;
+            tt = tt + kbx;
+            t0 = v.f_add_ex + g_add;
+            t1 = v.f_rescale_ex * tt;
+            dist = t0 + t1;
+        }
+        if (!std::isfinite(dist)) continue;
+        heap.push(HEnt{(uint64_t)vid, dist});
+        if (heap.d.size() > top_k) heap.pop();
+    }
+    heap.into_sorted();
+    std::stable_sort(heap.d.begin(), heap.d.end(), [](const HEnt& a, const HEnt& b) { return total_cmp(a.dist, b.dist) < 0; });
+    for (size_t i = 0; i < heap.d.size(); ++i) {
+        ids[i] = heap.d[i].id;
+        scores[i] = ix.metric == 0 ? heap.d[i].dist : -heap.d[i].dist;
+    }
+    *count = (uint32_t)heap.d.size();
+    return 0;
+}
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------
@@ -1673,5 +1865,49 @@ int orc_search_dump(void* h, const float* q, size_t top_k, size_t nprobe, uint64
         scores[i] = ix.metric == 0 ? res[i].dist : -res[i].dist;
     }
     return rc;
+}
+
+// --- brute-force index ---
+void* orc_bf_new() { return new BfIndex(); }
+void orc_bf_free(void* h) { delete (BfIndex*)h; }
+size_t orc_bf_len(void* h) { return ((BfIndex*)h)->vecs.size(); }
+size_t orc_bf_padded_dim(void* h) { return ((BfIndex*)h)->D; }
+int orc_bf_train(void* h, const float* data, size_t n, size_t dim, int total_bits, int metric, int rotator_type, const uint8_t* rotator_bytes,
+                 float t_const) {
+    Rotator r;
+    r.type = rotator_type;
+    r.dim = dim;
+    r.padded = padded_dim_for(rotator_type, dim);
+    if (rotator_type == 1) r.flip.assign(rotator_bytes, rotator_bytes + 4 * r.padded / 8);
+    else {
+        r.matrix.resize(r.padded * r.padded);
+        std::memcpy(r.matrix.data(), rotator_bytes, r.matrix.size() * 4);
+    }
+    rotator_init_derived(r);
+    return bf_train(*(BfIndex*)h, data, n, dim, total_bits, metric, r, t_const);
+}
+size_t orc_bf_save(void* h, uint8_t* out, size_t cap) {
+    std::vector<uint8_t> b;
+    bf_save(*(BfIndex*)h, b);
+    if (out && cap >= b.size()) std::memcpy(out, b.data(), b.size());
+    return b.size();
+}
+int orc_bf_load(void* h, const uint8_t* p, size_t n) {
+    std::string e;
+    int rc = bf_load(*(BfIndex*)h, p, n, e);
+    g_err = e;
+    return rc;
+}
+int orc_bf_search_batch(void* h, const float* queries, size_t nq, size_t dim, size_t top_k, const uint64_t* filter, size_t filter_nbits,
+                        uint64_t* ids, float* scores, uint32_t* counts) {
+    BfIndex& ix = *(BfIndex*)h;
+    if (dim != ix.dim) return 1;
+    int rc_all = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (long q = 0; q < (long)nq; ++q) {
+        int rc = bf_search(ix, queries + (size_t)q * dim, top_k, filter, filter_nbits, ids + (size_t)q * top_k, scores + (size_t)q * top_k, counts + q);
+        if (rc) rc_all = rc;
+    }
+    return rc_all;
 }
 }  // extern "C"

@@ -426,3 +426,78 @@ class Index:
             raise OracleError(rc, "search failed")
         return dict(ids=ids[:cnt.value], scores=scores[:cnt.value], rotated=rot, lut=lut, delta=sc[0],
                     sum_vl=sc[1], k1x=sc[2], kbx=sc[3], qnorm=sc[4], sum_q=sc[5], probe=probe, probe_f=pf)
+
+
+class BruteForceIndex:
+    """Oracle restatement of BruteForceRabitqIndex (src/brute_force.rs): train / save ("RBF1" v1) / load / search."""
+
+    def __init__(self):
+        L = lib()
+        L.orc_bf_new.restype = C.c_void_p
+        L.orc_bf_len.restype = C.c_size_t
+        L.orc_bf_padded_dim.restype = C.c_size_t
+        L.orc_bf_save.restype = C.c_size_t
+        self.h = C.c_void_p(L.orc_bf_new())
+
+    def __del__(self):
+        try:
+            lib().orc_bf_free(self.h)
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().orc_bf_len(self.h))
+
+    @property
+    def padded_dim(self):
+        return int(lib().orc_bf_padded_dim(self.h))
+
+    @classmethod
+    def train(cls, data, total_bits, metric, rotator_type=1, seed=42, faster_config=False, rotator_bytes=None):
+        data = _f32(data)
+        n, dim = data.shape
+        if rotator_bytes is None:
+            rotator_bytes = make_flip_bytes(dim, seed) if rotator_type == 1 else make_matrix_bytes(dim, seed)
+        rotator_bytes = np.ascontiguousarray(rotator_bytes, np.uint8)
+        t_const = -1.0
+        if faster_config and total_bits > 1:
+            t_const = const_scaling_factor(padded_dim(rotator_type, dim), total_bits - 1, seed)
+        self = cls()
+        rc = lib().orc_bf_train(self.h, _p(data), _sz(n), _sz(dim), int(total_bits), int(metric), int(rotator_type), _p(rotator_bytes),
+                                C.c_float(t_const))
+        if rc != 0:
+            raise OracleError(rc, "invalid configuration")
+        return self
+
+    def save_bytes(self):
+        n = lib().orc_bf_save(self.h, None, _sz(0))
+        buf = np.empty(n, np.uint8)
+        lib().orc_bf_save(self.h, _p(buf), _sz(n))
+        return buf.tobytes()
+
+    @classmethod
+    def load_bytes(cls, blob):
+        self = cls()
+        a = np.frombuffer(bytes(blob), np.uint8)
+        rc = lib().orc_bf_load(self.h, _p(a), _sz(a.size))
+        if rc != 0:
+            raise OracleError(rc, lib().orc_last_error().decode())
+        return self
+
+    def search_batch(self, queries, top_k, filter_bits=None):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, dim = q.shape
+        k = max(int(top_k), 1)
+        ids = np.zeros((nq, k), np.uint64)
+        scores = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        fb, fn = None, 0
+        if filter_bits is not None:
+            fb = np.ascontiguousarray(filter_bits, np.uint64)
+            fn = fb.size * 64
+        rc = lib().orc_bf_search_batch(self.h, _p(q), _sz(nq), _sz(dim), _sz(top_k), _p(fb), _sz(fn), _p(ids), _p(scores), _p(counts))
+        if rc != 0:
+            raise OracleError(rc, "search failed")
+        return ids[:, :top_k], scores[:, :top_k], counts

@@ -63,6 +63,17 @@ def lib():
     L.rbq_dist_front.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, vp, vp]
     L.rbq_dist_head.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp, vp]
     L.rbq_dist_tail.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp]
+    L.rbq_bf_train.argtypes = [vp, sz, sz, i32, i32, i32, u64, i32, vp, i32, C.POINTER(vp)]
+    L.rbq_bf_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.rbq_bf_load_mem.argtypes = [vp, sz, i32, C.POINTER(vp)]
+    L.rbq_bf_save.argtypes = [vp, C.c_char_p]
+    L.rbq_bf_save_mem.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.rbq_bf_free.argtypes = [vp]
+    L.rbq_bf_free.restype = None
+    for name in ("len", "dim", "padded_dim"):
+        f = getattr(L, "rbq_bf_" + name)
+        f.argtypes, f.restype = [vp], sz
+    L.rbq_bf_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, vp, vp]
     L.rbq_comm_unique_id.argtypes = [vp]
     L.rbq_comm_init.argtypes = [vp, vp, i32, i32]
     L.rbq_comm_destroy.argtypes = [vp]

@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kQWarps * 32) quantize_kernel(DevIndex ix, con
         out.f_rescale_ex[o] = f_rescale_ex;
         out.delta[o] = delta;
         out.vl[o] = vl;
+        if (out.rnorm) out.rnorm[o] = l2n;
     }
     // sign codes, MSB-first (simd.rs:141-150)
     uint8_t* brow = out.bin_rows + (size_t)o * (D / 8);

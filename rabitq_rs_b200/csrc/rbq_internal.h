@@ -279,6 +279,7 @@ struct BuildOut {  // device arrays, one entry per vector in list-concatenated o
     uint8_t* bin_rows;  // n * D/8, MSB-first row-major sign codes
     uint8_t* ex;        // n * ex_stride
     float *f_add, *f_rescale, *f_error, *f_add_ex, *f_rescale_ex, *delta, *vl;
+    float* rnorm = nullptr;  // |residual| (optional: stored by the brute-force index file only)
 };
 int launch_build_quantize(const DevIndex& ix, const float* d_rot, const uint32_t* d_list_of, size_t n,
                           const float* d_cents, float t_const, const double* d_t_per_vec, BuildOut out,

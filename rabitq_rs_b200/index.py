@@ -410,6 +410,108 @@ class IvfRabitqIndex:
         return accu[:slots], ip[:slots], est[:slots], lb[:slots]
 
 
+@dataclass(frozen=True)
+class BruteForceSearchParams:  # reference src/brute_force.rs:21-31
+    top_k: int
+
+
+class BruteForceRabitqIndex:
+    """Device-resident BruteForceRabitqIndex (src/brute_force.rs:203-650): train / save / load / search / search_filtered."""
+
+    def __init__(self, device=0):
+        self._h = None
+        self.device = int(device)
+
+    def close(self):
+        if self._h is not None:
+            _ffi.lib().rbq_bf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _need(self):
+        if self._h is None:
+            raise RuntimeError("Index not built yet. Call train() first.")
+        return self._h
+
+    @classmethod
+    def train(cls, data, total_bits, metric="euclidean", rotator_type="random", seed=42, use_faster_config=True, device=0, rotator_state=None):
+        data = np.ascontiguousarray(data, np.float32)
+        if data.ndim != 2:
+            raise ValueError("Data must be 2D array (N x D)")
+        self = cls(device)
+        rs = None if rotator_state is None else np.ascontiguousarray(rotator_state, np.uint8)
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_bf_train(_ptr(data), data.shape[0], data.shape[1], int(total_bits), int(_metric_from_str(metric)),
+                                       int(_rotator_from_str(rotator_type)), int(seed), int(bool(use_faster_config)), _ptr(rs), self.device,
+                                       C.byref(h)))
+        self._h = h
+        return self
+
+    @classmethod
+    def load_from_bytes(cls, blob, device=0):
+        self = cls(device)
+        buf = np.frombuffer(bytes(blob), np.uint8)
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_bf_load_mem(_ptr(buf), buf.size, self.device, C.byref(h)))
+        self._h = h
+        return self
+
+    @classmethod
+    def load_from_path(cls, path, device=0):
+        self = cls(device)
+        h = C.c_void_p()
+        _check(_ffi.lib().rbq_bf_load(str(path).encode(), self.device, C.byref(h)))
+        self._h = h
+        return self
+
+    def save_to_path(self, path):
+        _check(_ffi.lib().rbq_bf_save(self._need(), str(path).encode()))
+
+    def save_to_bytes(self):
+        n = C.c_size_t()
+        _check(_ffi.lib().rbq_bf_save_mem(self._need(), None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _check(_ffi.lib().rbq_bf_save_mem(self._need(), _ptr(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
+
+    def __len__(self):
+        return int(_ffi.lib().rbq_bf_len(self._need()))
+
+    def is_empty(self):
+        return len(self) == 0
+
+    def batch_search(self, queries, params, filter_bits=None):
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, dim = q.shape
+        k = int(params.top_k)
+        ids = np.full((nq, max(k, 1)), np.iinfo(np.uint64).max, np.uint64)
+        scores = np.zeros((nq, max(k, 1)), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        fb, nbits = None, 0
+        if filter_bits is not None:
+            fb = np.ascontiguousarray(filter_bits, np.uint64)
+            nbits = fb.size * 64
+            if fb.size == 0:
+                fb = np.zeros(1, np.uint64)
+        _check(_ffi.lib().rbq_bf_search_batch(self._need(), _ptr(q), nq, dim, k, _ptr(fb), nbits, _ptr(ids), _ptr(scores), _ptr(counts)))
+        return ids[:, :k], scores[:, :k], counts
+
+    def search(self, query, params):
+        ids, scores, counts = self.batch_search(np.asarray(query, np.float32)[None, :], params)
+        return [(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+    def search_filtered(self, query, params, allowed_ids):
+        ids, scores, counts = self.batch_search(np.asarray(query, np.float32)[None, :], params, ids_to_bitset(allowed_ids))
+        return [(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+
 class IndexBuilder:
     """Streaming train_with_clusters on device-resident data (include/rbq.h: rbq_builder_*): announce the list sizes, add
     chunks of (vectors, assignments) CUDA tensors in ascending id order, finish() -> IvfRabitqIndex.  With shard_count > 1

@@ -569,3 +569,33 @@ def test_oracle_reproduces_committed_fixtures(oracle, name):
     got = ix.search_batch(q, k, nprobe)
     assert np.array_equal(got[2], counts) and np.array_equal(got[0], ids)
     assert np.array_equal(got[1].view(np.uint32), scores.view(np.uint32))
+
+
+# ---- brute-force index restatement (src/brute_force.rs; src/tests.rs:912-1107) ----------------------------------------
+def test_bruteforce_oracle_reference_properties(oracle):
+    rng = np.random.default_rng(3)
+    data = (rng.random((300, 32), dtype=np.float32) * 2 - 1).astype(np.float32)
+    for metric in (0, 1):
+        ix = oracle.BruteForceIndex.train(data, 7, metric, faster_config=True)
+        ids, sc, cnt = ix.search_batch(data[:50], 1)
+        if metric == 0:
+            assert (ids[:, 0] == np.arange(50)).all()          # brute_force_search_recovers_identical_vectors
+        ids, sc, cnt = ix.search_batch(data[:10], 10)
+        d = np.diff(sc, axis=1)
+        assert (d >= 0).all() if metric == 0 else (d <= 0).all()  # results ordered (brute_force_*_search_is_consistent)
+        blob = ix.save_bytes()
+        assert blob[:4] == b"RBF1" and int.from_bytes(blob[4:8], "little") == 1
+        again = oracle.BruteForceIndex.load_bytes(blob)
+        assert again.save_bytes() == blob                       # brute_force_persistence_roundtrip
+        a, b = again.search_batch(data[:10], 5), ix.search_batch(data[:10], 5)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        bad = bytearray(blob)
+        bad[-1] ^= 1
+        with pytest.raises(oracle.OracleError, match="checksum mismatch"):
+            oracle.BruteForceIndex.load_bytes(bytes(bad))
+    # filtered search (brute_force_filtered_search_works)
+    words = np.zeros(5, np.uint64)
+    for i in (2, 40, 77):
+        words[i // 64] |= np.uint64(1) << np.uint64(i % 64)
+    ids, sc, cnt = ix.search_batch(data[:3], 5, filter_bits=words)
+    assert (cnt == 3).all() and all(set(ids[i, :3].tolist()) == {2, 40, 77} for i in range(3))
