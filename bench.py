@@ -311,6 +311,7 @@ def main():
     ap.add_argument("--save-ids", default="", help="write the (merged) result ids of the timed configuration to this .npy")
     ap.add_argument("--check-ids", default="", help="compare the (merged) result ids with this .npy (e.g. of a 1-GPU run of the same workload)")
     ap.add_argument("--oracle-sample", type=int, default=1024, help="queries checked against the CPU oracle on the same index bytes")
+    ap.add_argument("--no-exact-merge", action="store_true", help="multi-GPU: skip the extra exact-merge measurement")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -554,6 +555,32 @@ def main():
         for kk, vv in zip(sum_keys, tsum.tolist()):
             st[kk] = vv
 
+    # ---- multi-GPU: the exact-merge mode of the one-call sharded search (global replay at the home rank), timed beside the default
+    exact_info = None
+    if multi and searcher.native and not args.no_exact_merge:
+        ix.set_exact_merge(True)
+        nx = max(3, steps // 2)
+        ms_x, _ = timed(nprobe, nx, 2, False)
+        x_ids = search_device(nprobe)[0].cpu().numpy().astype(np.uint64)
+        sx = ix.stats()
+        ix.set_exact_merge(False)
+        tx = torch.tensor([float(sx["inexact_queries"]), float(sx["exchanged_records"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(tx, op=dist.ReduceOp.SUM)
+        exact_info = {"ms_per_step": ms_x / nx, "qps": nq * nx / (ms_x / 1000.0), "inexact_queries": int(tx[0].item()),
+                      "exchanged_records_per_step": int(tx[1].item()),
+                      "note": "rbq_set_exact_merge(1): survivors refined eagerly, records sent to the query's home rank, one global replay"}
+        if rank == 0 and ix_full is not None:  # rank 0 still holds the complete index: the single-GPU answer of the same batch
+            ix_full.batch_search_device(dq, k, nprobe, d_ids, d_sc, d_cn)
+            torch.cuda.synchronize(dev)
+            one = d_ids.cpu().numpy().astype(np.uint64)
+            exact_info["exact_ids_equal_single_gpu"] = float(np.mean(np.sort(one, 1) == np.sort(x_ids, 1)))
+            exact_info["phased_ids_equal_single_gpu"] = float(np.mean(np.sort(one, 1) == np.sort(final_ids, 1)))
+            exact_info["exact_queries_identical"] = int(np.sum(np.all(np.sort(one, 1) == np.sort(x_ids, 1), axis=1)))
+        if rank == 0 and args.check_ids and os.path.exists(args.check_ids):
+            ref_ids = np.load(args.check_ids)
+            exact_info["exact_ids_equal_reference_run"] = float(np.mean(np.sort(ref_ids, 1) == np.sort(x_ids, 1)))
+        log(f"exact merge: {exact_info}")
+
     # ---- optional recall-vs-QPS sweep (BASELINE config 3: "recall@10 vs QPS sweep") ----------------
     sweep = None
     if args.sweep:
@@ -693,6 +720,8 @@ def main():
         out["recall_qps_sweep"] = sweep
     if same_ids is not None:
         out["config"]["ids_equal_reference_run"] = round(same_ids, 6)
+    if exact_info is not None:
+        out["exact_merge"] = exact_info
     # ---- CPU baseline + parity of the timed configuration against the oracle ---------------------
     out["cpu_baseline"] = None
     if not args.no_cpu_baseline:

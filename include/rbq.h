@@ -179,6 +179,15 @@ int rbq_search_batch_sharded_device(const rbq_index* ix, const float* d_queries,
                                     uint64_t* d_ids, float* d_scores, uint32_t* d_counts, void* stream);
 int rbq_search_batch_sharded(const rbq_index* ix, const float* queries, size_t nq, size_t dim, size_t top_k, size_t nprobe, uint64_t* ids,
                              float* scores, uint32_t* counts);
+/* Exact merge (off by default).  The phased search lets every shard replay its own survivors against min(tau, local k-th
+ * distance); a shard may then admit a bound-violating candidate the single sequence of src/ivf.rs:2013-2127 skipped (about 4
+ * ids in 10 000 at GIST-1M).  With exact merge on, the one-call sharded search additionally refines every survivor, ships
+ * {visit key, lower bound, distance, id} records -- and the head pass' heap from the shard that ran it -- to the query's
+ * HOME rank (grouped ncclSend/ncclRecv), which replays the union in the reference's visit order against the live threshold:
+ * the single-GPU answer, bit for bit.  The home results are all-gathered over the phased answer.  The call synchronises
+ * with the host once (record counts).  Queries the exact path cannot take keep the phased answer and are counted in
+ * rbq_search_stats::inexact_queries.  Must be set identically on every rank. */
+int rbq_set_exact_merge(rbq_index* ix, int on);
 
 /* The same merge over ONE all-gathered buffer: shard s occupies bytes [s*chunk_bytes, (s+1)*chunk_bytes) holding
  * ids[nq*top_k] (u64) | scores[nq*top_k] (f32) | counts[nq] (u32); chunk_bytes is a multiple of 8.  One collective
@@ -237,6 +246,9 @@ typedef struct rbq_search_stats {
     uint32_t front_chunk;       /* queries per front-end chunk */
     uint64_t fallback_queries;  /* queries the list-major head pass handed to the sequential kernel (nearest list longer than the
                                    dense head buffer, or fewer than top_k candidates in it) */
+    uint64_t inexact_queries;   /* exact-merge sharded search: home queries of this rank that kept the phased answer (survivor
+                                   overflow on some shard, head pass that did not fill the heap, > 4096 candidate records) */
+    uint64_t exchanged_records; /* exact-merge sharded search: candidate records this rank received for its home queries */
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */

@@ -16,7 +16,8 @@ class SearchStats(C.Structure):
                 ("ms_select", C.c_float), ("ms_scan", C.c_float),
                 ("tail_blocks", C.c_uint64), ("tail_bytes", C.c_uint64), ("tail_pairs", C.c_uint64),
                 ("survivors", C.c_uint64), ("overflow_queries", C.c_uint64),
-                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32), ("fallback_queries", C.c_uint64)]
+                ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32), ("fallback_queries", C.c_uint64),
+                ("inexact_queries", C.c_uint64), ("exchanged_records", C.c_uint64)]
 
 
 _lib = None
@@ -79,6 +80,7 @@ def lib():
     L.rbq_comm_destroy.argtypes = [vp]
     L.rbq_search_batch_sharded_device.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp, vp, vp]
     L.rbq_search_batch_sharded.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp, vp]
+    L.rbq_set_exact_merge.argtypes = [vp, i32]
     L.rbq_shard_assignment.argtypes = [vp, sz, i32, vp, vp, sz, C.POINTER(sz)]
     L.rbq_last_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.rbq_set_profiling.argtypes = [vp, i32]

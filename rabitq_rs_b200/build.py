@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librbq.so")
-SOURCES = ["format.cc", "nccl_loader.cc", "query_prep.cu", "coarse.cu", "coarse_tc.cu", "scan.cu", "scan_tail.cu", "tail_tc.cu", "resolve.cu", "fetch.cu", "build.cu", "kmeans.cu", "bruteforce.cu", "api.cu"]
+SOURCES = ["format.cc", "nccl_loader.cc", "query_prep.cu", "coarse.cu", "coarse_tc.cu", "scan.cu", "scan_tail.cu", "tail_tc.cu", "resolve.cu", "fetch.cu", "build.cu", "kmeans.cu", "bruteforce.cu", "exact_merge.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-O2,-fno-fast-math",

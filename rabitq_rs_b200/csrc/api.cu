@@ -590,6 +590,9 @@ void rbq_index_free(rbq_index* h) {
                 if (e) cudaEventDestroy(e);
         if (h->comm) nccl_api().comm_destroy(h->comm);
         if (h->dist_ws) cudaFree(h->dist_ws);
+        if (h->xr_ws) cudaFree(h->xr_ws);
+        if (h->xr_recs) cudaFree(h->xr_recs);
+        if (h->xr_host) cudaFreeHost(h->xr_host);
         if (h->busy_ev) cudaEventDestroy(h->busy_ev);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
@@ -776,6 +779,7 @@ int rbq_last_search_stats(const rbq_index* h, rbq_search_stats* out) {
     unsigned int fb = 0;
     RBQ_CUDA(cudaMemcpy(&fb, h->fallback_counter(), sizeof(fb), cudaMemcpyDeviceToHost));
     h->last_stats.coarse_fallbacks = fb;
+    if (h->xr_inexact) RBQ_CUDA(cudaMemcpy(&h->last_stats.inexact_queries, h->xr_inexact, 8, cudaMemcpyDeviceToHost));
     *out = h->last_stats;
     return RBQ_OK;
 }
@@ -1059,6 +1063,13 @@ int rbq_comm_init(rbq_index* h, const uint8_t* id, int rank, int world) {
     return nccl_check(nccl_api().comm_init_rank(&h->comm, world, id, rank), "ncclCommInitRank");
 }
 
+int rbq_set_exact_merge(rbq_index* h, int on) {
+    if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->exact_merge = on != 0;
+    return RBQ_OK;
+}
+
 int rbq_comm_destroy(rbq_index* h) {
     if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
     DeviceGuard g(h->device);
@@ -1071,10 +1082,63 @@ int rbq_comm_destroy(rbq_index* h) {
     if (h->dist_ws) cudaFree(h->dist_ws);
     h->dist_ws = nullptr;
     h->dist_ws_bytes = 0;
+    if (h->xr_ws) cudaFree(h->xr_ws);
+    if (h->xr_recs) cudaFree(h->xr_recs);
+    if (h->xr_host) cudaFreeHost(h->xr_host);
+    h->xr_ws = h->xr_recs = nullptr;
+    h->xr_host = nullptr;
+    h->xr_inexact = nullptr;
+    h->xr_ws_bytes = h->xr_recs_bytes = 0;
     return RBQ_OK;
 }
 
 namespace {
+// exact merge: fixed-size part of its workspace (a pure function of nq, top_k, world)
+struct XrWs {
+    uint64_t* snap_ids;
+    float* snap_sc;
+    uint32_t* snap_cn;
+    uint32_t *all_cnt, *off, *cta_tot, *qoff, *flagged, *cursor;
+    unsigned long long *send_tot, *recv_tot, *rbase, *inexact;
+    char* gath2;
+    size_t chunk2;
+};
+int xr_carve(const rbq_index* h, size_t nq, size_t top_k, size_t per, int world, XrWs* X) {
+    X->chunk2 = (per * top_k * 12 + per * 4 + 15) / 16 * 16;
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver cv{pass ? (char*)h->xr_ws : nullptr};
+        X->snap_ids = cv.take<uint64_t>(nq * top_k);
+        X->snap_sc = cv.take<float>(nq * top_k);
+        X->snap_cn = cv.take<uint32_t>(nq);
+        X->all_cnt = cv.take<uint32_t>(nq * world);
+        X->off = cv.take<uint32_t>(nq + 1);
+        X->cta_tot = cv.take<uint32_t>((nq + 1023) / 1024 + 1);
+        X->qoff = cv.take<uint32_t>(per * world);
+        X->flagged = cv.take<uint32_t>(per + 1);
+        X->cursor = cv.take<uint32_t>(4);
+        X->send_tot = cv.take<unsigned long long>(world);
+        X->recv_tot = cv.take<unsigned long long>(world);
+        X->rbase = cv.take<unsigned long long>(world);
+        X->inexact = cv.take<unsigned long long>(2);
+        X->gath2 = cv.take<char>(X->chunk2 * world);
+        if (pass == 0) {
+            const size_t need = cv.off + 256;
+            if (h->xr_ws_bytes < need) {
+                if (h->xr_ws) {
+                    RBQ_CUDA(cudaDeviceSynchronize());
+                    cudaFree(h->xr_ws);
+                }
+                h->xr_ws = nullptr;
+                h->xr_ws_bytes = 0;
+                RBQ_CUDA(cudaMalloc(&h->xr_ws, need));
+                h->xr_ws_bytes = need;
+            }
+            if (!h->xr_host) RBQ_CUDA(cudaMallocHost((void**)&h->xr_host, (size_t)3 * kMaxShards * 8));
+        }
+    }
+    return RBQ_OK;
+}
+
 // the caller holds the handle's lock and has validated the arguments; extra_bytes of the exchange workspace are reserved in front
 // (host entry: staging of the queries and of the merged result)
 int sharded_search_impl(const rbq_index* h, const Plan& pl, const float* d_queries, size_t nq, size_t dim, size_t top_k, size_t nprobe,
@@ -1108,6 +1172,13 @@ int sharded_search_impl(const rbq_index* h, const Plan& pl, const float* d_queri
     uint32_t* l_cn = reinterpret_cast<uint32_t*>(mine + nq * top_k * 12);
     const NcclApi& nc = nccl_api();
     const size_t q_begin = std::min((size_t)rank * per, nq), q_count = std::min((size_t)(rank + 1) * per, nq) - q_begin;
+    const bool exact = h->exact_merge != 0;
+    XrWs X{};
+    h->xr_inexact = nullptr;
+    if (exact) {
+        if (nq >= ((size_t)1 << 31) / std::max<size_t>(top_k, 1)) return fail(RBQ_INVALID_CONFIG, "exact merge: batch too large");
+        if ((rc = xr_carve(h, nq, top_k, per, world, &X))) return rc;
+    }
     // 1. front end for this rank's slice; the slices (16 B per probe) are all-gathered in place
     if ((rc = dist_front_impl(h, pl, d_queries, nq, dim, top_k, nprobe, q_begin, q_count, d_rec, st))) return rc;
     const size_t slice_bytes = per * nprobe * sizeof(rbq_probe_rec);
@@ -1116,13 +1187,71 @@ int sharded_search_impl(const rbq_index* h, const Plan& pl, const float* d_queri
     // 2. head pass where this shard owns the query's nearest list; thresholds MIN-reduced
     if ((rc = dist_head_impl(h, pl, nq, top_k, nprobe, d_rec, d_tau, l_ids, l_sc, l_cn, st))) return rc;
     if ((rc = nccl_check(nc.all_reduce(d_tau, d_tau, nq, /*ncclFloat32*/ 7, /*ncclMin*/ 3, h->comm, st), "ncclAllReduce"))) return rc;
+    if (exact) {  // the heap after the head pass (the tail's replay overwrites it): travels to the home rank with the survivors
+        RBQ_CUDA(cudaMemcpyAsync(X.snap_ids, l_ids, nq * top_k * 8, cudaMemcpyDeviceToDevice, st));
+        RBQ_CUDA(cudaMemcpyAsync(X.snap_sc, l_sc, nq * top_k * 4, cudaMemcpyDeviceToDevice, st));
+        RBQ_CUDA(cudaMemcpyAsync(X.snap_cn, l_cn, nq * 4, cudaMemcpyDeviceToDevice, st));
+    }
     // 3. tail + replay on this shard's lists; the packed local top-k (one chunk per rank) all-gathered in place and merged
     if ((rc = dist_tail_impl(h, pl, nq, top_k, nprobe, d_tau, l_ids, l_sc, l_cn, st))) return rc;
     if ((rc = nccl_check(nc.all_gather(mine, d_gath, chunk, /*ncclChar*/ 0, h->comm, st), "ncclAllGather"))) return rc;
     rc = launch_merge(h->host.metric, world, nq, top_k, reinterpret_cast<const uint64_t*>(d_gath), reinterpret_cast<const float*>(d_gath + nq * top_k * 8),
                       reinterpret_cast<const uint32_t*>(d_gath + nq * top_k * 12), d_ids, d_scores, d_counts, st, chunk / 8, chunk / 4, chunk / 4);
     h->last_stats.kernel_launches += 1;
-    return rc;
+    if (rc || !exact) return rc;
+
+    // 4. exact merge (exact_merge.cu): every survivor refined, records shipped to the query's home rank, one global replay there
+    const WsLayout L = carve_ws(h, (char*)h->ws, pl, nprobe, top_k);
+    if ((rc = xr_launch_count_scan(L.tw, L.d_head_owner, X.snap_cn, nq, (uint32_t)per, (uint32_t)world, X.all_cnt + (size_t)rank * nq, X.off, X.cta_tot,
+                                   X.send_tot, st)))
+        return rc;
+    if ((rc = nccl_check(nc.all_gather(X.all_cnt + (size_t)rank * nq, X.all_cnt, nq * 4, /*ncclChar*/ 0, h->comm, st), "ncclAllGather"))) return rc;
+    if ((rc = xr_launch_plan(X.all_cnt, nq, q_begin, q_count, world, X.qoff, X.recv_tot, X.flagged, st))) return rc;
+    unsigned long long* hs = h->xr_host;  // [0, world): records to send per home rank, [world, 2 world): to receive per source, then bases
+    RBQ_CUDA(cudaMemcpyAsync(hs, X.send_tot, (size_t)world * 8, cudaMemcpyDeviceToHost, st));
+    RBQ_CUDA(cudaMemcpyAsync(hs + world, X.recv_tot, (size_t)world * 8, cudaMemcpyDeviceToHost, st));
+    RBQ_CUDA(cudaStreamSynchronize(st));  // the one host synchronisation of the call: message sizes
+    unsigned long long n_send = 0, n_recv = 0;
+    std::vector<unsigned long long> sbase(world);
+    for (int d = 0; d < world; ++d) {
+        sbase[d] = n_send;
+        n_send += hs[d];
+        hs[2 * world + d] = n_recv;
+        n_recv += hs[world + d];
+    }
+    const size_t rec_need = (size_t)(n_send + n_recv + 2) * sizeof(XrRec);
+    if (h->xr_recs_bytes < rec_need) {
+        if (h->xr_recs) cudaFree(h->xr_recs);
+        h->xr_recs = nullptr;
+        h->xr_recs_bytes = 0;
+        const size_t grow = rec_need + rec_need / 4;
+        RBQ_CUDA(cudaMalloc(&h->xr_recs, grow));
+        h->xr_recs_bytes = grow;
+    }
+    XrRec* d_send = reinterpret_cast<XrRec*>(h->xr_recs);
+    XrRec* d_recv = d_send + n_send + 1;
+    RBQ_CUDA(cudaMemcpyAsync(X.rbase, hs + 2 * world, (size_t)world * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = xr_launch_records(h->dev, L.d_rot, L.d_qs, L.d_pr, nq, nprobe, top_k, L.tw, L.d_head_owner, X.snap_ids, X.snap_sc, X.snap_cn,
+                                X.all_cnt + (size_t)rank * nq, X.off, d_send, X.cursor, st)))
+        return rc;
+    if ((rc = nccl_check(nc.group_start(), "ncclGroupStart"))) return rc;
+    for (int d = 0; d < world; ++d) {
+        if (hs[d]) nc.send(d_send + sbase[d], (size_t)hs[d] * sizeof(XrRec), /*ncclChar*/ 0, d, h->comm, st);
+        if (hs[world + d]) nc.recv(d_recv + hs[2 * world + d], (size_t)hs[world + d] * sizeof(XrRec), /*ncclChar*/ 0, d, h->comm, st);
+    }
+    if ((rc = nccl_check(nc.group_end(), "ncclGroupEnd"))) return rc;
+    RBQ_CUDA(cudaMemsetAsync(X.inexact, 0, 8, st));
+    char* home = X.gath2 + (size_t)rank * X.chunk2;
+    if ((rc = xr_launch_replay(d_recv, X.rbase, X.all_cnt, X.qoff, X.flagged, nq, q_begin, q_count, world, top_k, h->host.metric,
+                               reinterpret_cast<uint64_t*>(home), reinterpret_cast<float*>(home + per * top_k * 8),
+                               reinterpret_cast<uint32_t*>(home + per * top_k * 12), X.inexact, st)))
+        return rc;
+    if ((rc = nccl_check(nc.all_gather(home, X.gath2, X.chunk2, /*ncclChar*/ 0, h->comm, st), "ncclAllGather"))) return rc;
+    if ((rc = xr_launch_override(X.gath2, X.chunk2, per, nq, top_k, d_ids, d_scores, d_counts, st))) return rc;
+    h->xr_inexact = X.inexact;
+    h->last_stats.exchanged_records = n_recv;
+    h->last_stats.kernel_launches += 9;
+    return RBQ_OK;
 }
 }  // namespace
 

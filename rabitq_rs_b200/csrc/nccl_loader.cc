@@ -51,6 +51,10 @@ int nccl_load() {
     g_api.comm_destroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
     g_api.all_gather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(sym("ncclAllGather"));
     g_api.all_reduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclAllReduce"));
+    g_api.send = reinterpret_cast<int (*)(const void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclSend"));
+    g_api.recv = reinterpret_cast<int (*)(void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclRecv"));
+    g_api.group_start = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+    g_api.group_end = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
     g_api.get_error_string = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
     if (!g_why.empty()) {
         g_state = -1;

@@ -9,10 +9,13 @@
 namespace rbq {
 struct NcclApi {
     int (*get_unique_id)(void* id128) = nullptr;                                                    // ncclGetUniqueId
-    int (*comm_init_rank_raw)(void** comm, int nranks, const void* id_by_value, int rank) = nullptr;  // see nccl_loader.cc
     int (*comm_destroy)(void* comm) = nullptr;                                                      // ncclCommDestroy
     int (*all_gather)(const void* send, void* recv, size_t sendcount, int dtype, void* comm, cudaStream_t st) = nullptr;
     int (*all_reduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t st) = nullptr;
+    int (*send)(const void* buf, size_t count, int dtype, int peer, void* comm, cudaStream_t st) = nullptr;
+    int (*recv)(void* buf, size_t count, int dtype, int peer, void* comm, cudaStream_t st) = nullptr;
+    int (*group_start)() = nullptr;
+    int (*group_end)() = nullptr;
     const char* (*get_error_string)(int) = nullptr;
     int comm_init_rank(void** comm, int nranks, const uint8_t* id128, int rank) const;
 };

@@ -204,6 +204,24 @@ int launch_probe_import(const DevIndex& ix, const rbq_probe_rec* d_in, size_t nq
 // fetch.cu: fetch_embedding (position of an id; reconstruction of one stored vector)
 int launch_find_id(const DevIndex& ix, size_t nvec, uint64_t id, unsigned long long* d_pos, cudaStream_t st);
 int launch_fetch_embedding(const DevIndex& ix, uint32_t cid, uint32_t local, float delta, float vl, float* d_out, cudaStream_t st);
+// exact_merge.cu: global replay of the one-call sharded search (bit-identical multi-GPU results)
+struct XrRec {  // a candidate on its way to the query's home rank
+    unsigned long long key;  // visit order: head-state entry i -> i; survivor -> (probe rank + 1) << 32 | position
+    float lower;             // lower bound (head-state entries: -inf = admitted already)
+    float dist;              // refined distance (1-bit index: the estimate)
+    unsigned long long id;
+};
+int xr_launch_count_scan(const TailWs& tw, const uint8_t* d_head_owner, const uint32_t* d_head_cnt, size_t nq, uint32_t per, uint32_t world,
+                         uint32_t* d_cnt, uint32_t* d_off, uint32_t* d_cta_tot, unsigned long long* d_send_tot, cudaStream_t st);
+int xr_launch_records(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k,
+                      const TailWs& tw, const uint8_t* d_head_owner, const uint64_t* d_head_ids, const float* d_head_sc, const uint32_t* d_head_cnt,
+                      const uint32_t* d_cnt, const uint32_t* d_off, XrRec* d_recs, uint32_t* d_cursor, cudaStream_t st);
+int xr_launch_plan(const uint32_t* d_all_cnt, size_t nq, size_t q_begin, size_t q_count, int world, uint32_t* d_qoff, unsigned long long* d_recv_tot,
+                   uint32_t* d_flagged, cudaStream_t st);
+int xr_launch_replay(const XrRec* d_recv, const unsigned long long* d_rbase, const uint32_t* d_all_cnt, const uint32_t* d_qoff, const uint32_t* d_flagged,
+                     size_t nq, size_t q_begin, size_t q_count, int world, size_t top_k, int metric, uint64_t* d_out_ids, float* d_out_sc,
+                     uint32_t* d_out_cn, unsigned long long* d_inexact, cudaStream_t st);
+int xr_launch_override(const void* d_gath, size_t chunk, size_t per, size_t nq, size_t top_k, uint64_t* d_ids, float* d_sc, uint32_t* d_cn, cudaStream_t st);
 // resolve.cu: builds DevIndex::exl from the packed ex-codes already on the device (no-op for 1-bit indexes)
 int prepare_ex_lanes(rbq_index* h);
 int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs, const Probe* d_probes,
@@ -314,10 +332,18 @@ struct rbq_index {
     int scan_mode = 0;         // 0: auto, 1: sequential per-query walk, 2: list-major head/tail/replay
     int coarse_mode = -1;      // -1: auto (2 when the centroid table and nprobe allow it, else 1), 0: exact FP32 all-pairs,
                                // 1: dense tensor-core scores + exact re-score, 2: tensor-core scores filtered in the GEMM epilogue
+    int exact_merge = 0;       // one-call sharded search: 1 = global replay at the query's home rank (bit-identical to one GPU)
+    mutable unsigned long long last_inexact = 0;  // queries of the last exact-merge call that kept the phased answer
     int coarse_terms = 3;      // bf16 split terms multiplied by the coarse GEMM: 3 (fp32-class scores) or 1 (bf16-class, wider re-score band)
     float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|) with 3 terms
     void* comm = nullptr;                   // ncclComm_t of the one-call sharded search (rbq_comm_init); NCCL is dlopen'ed
     mutable void* dist_ws = nullptr;        // its exchange buffers
     mutable size_t dist_ws_bytes = 0;
+    mutable void* xr_ws = nullptr;          // exact merge: head-state snapshot, counts, offsets, home results (sized by nq, top_k)
+    mutable size_t xr_ws_bytes = 0;
+    mutable void* xr_recs = nullptr;        // exact merge: packed records to send | received records (sized per call)
+    mutable size_t xr_recs_bytes = 0;
+    mutable unsigned long long* xr_host = nullptr;  // pinned: per-peer record counts read back once per call
+    mutable unsigned long long* xr_inexact = nullptr;  // device counter behind last_stats.inexact_queries (inside xr_ws)
     mutable cudaEvent_t busy_ev = nullptr;  // recorded after the last kernel of every call: the next call's stream waits on it
 };

@@ -361,6 +361,10 @@ class IvfRabitqIndex:
     def set_coarse_terms(self, terms):
         _check(_ffi.lib().rbq_set_coarse_terms(self._need(), int(terms)))
 
+    def set_exact_merge(self, on):
+        """One-call sharded search: replay every query's candidates globally at its home rank (the single-GPU answer, bit for bit)."""
+        _check(_ffi.lib().rbq_set_exact_merge(self._need(), int(bool(on))))
+
     # ---- stage probes (tests) ---------------------------------------------------------------------
     def debug_query_prep(self, queries):
         q = np.ascontiguousarray(queries, np.float32)

@@ -672,6 +672,23 @@ def test_one_call_sharded_search_world_of_one(rbq, oracle):
                                     h_sc.ctypes.data_as(C.c_void_p), h_cn.ctypes.data_as(C.c_void_p))
     assert rc == 0, _ffi.last_error()
     assert np.array_equal(h_ids, got[0]) and np.array_equal(h_sc, got[1]) and np.array_equal(h_cn, got[2])
+    # exact merge on the one-rank communicator: eager refinement, record exchange (send/recv to self), global replay, override
+    plain = gix.batch_search(q, rbq.SearchParams(k, nprobe))
+    gix.set_exact_merge(True)
+    for kk, npb in ((k, nprobe), (40, 7), (3, 48)):
+        ids2 = torch.empty((nq, kk), dtype=torch.int64, device="cuda")
+        sc2 = torch.empty((nq, kk), dtype=torch.float32, device="cuda")
+        cn2 = torch.empty(nq, dtype=torch.int32, device="cuda")
+        rc = L.rbq_search_batch_sharded_device(gix.handle, C.c_void_p(dq.data_ptr()), nq, q.shape[1], kk, npb, C.c_void_p(ids2.data_ptr()),
+                                               C.c_void_p(sc2.data_ptr()), C.c_void_p(cn2.data_ptr()), st)
+        assert rc == 0, _ffi.last_error()
+        torch.cuda.synchronize()
+        got2 = (ids2.cpu().numpy().astype(np.uint64), sc2.cpu().numpy(), cn2.cpu().numpy().astype(np.uint32))
+        assert assert_results_match(got2, oix.search_batch(q, kk, npb)) == nq
+        stx = gix.stats()
+        assert stx["exchanged_records"] > 0 and stx["inexact_queries"] < nq // 4, stx
+    gix.set_exact_merge(False)
+    assert np.array_equal(plain[0], got[0])
     assert L.rbq_comm_destroy(gix.handle) == 0
     rc = L.rbq_search_batch_sharded_device(gix.handle, C.c_void_p(dq.data_ptr()), nq, q.shape[1], k, nprobe, C.c_void_p(ids.data_ptr()),
                                            C.c_void_p(sc.data_ptr()), C.c_void_p(cn.data_ptr()), st)
