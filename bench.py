@@ -556,7 +556,7 @@ def main():
             st[kk] = vv
 
     # ---- multi-GPU: the exact-merge mode of the one-call sharded search (global replay at the home rank), timed beside the default
-    exact_info = None
+    exact_info = x_ids = None
     if multi and searcher.native and not args.no_exact_merge:
         ix.set_exact_merge(True)
         nx = max(3, steps // 2)
@@ -739,10 +739,11 @@ def main():
         if src is not None:
             qps, cores, sample, res, _ = oracle_baseline(src[0], src[1], k, nprobe, log=log, max_sample=src[3])
             same = float(np.mean(res[0][:, :k] == final_ids[:sample, :k]))
+            same_x = f" (exact-merge mode: {float(np.mean(res[0][:, :k] == x_ids[:sample, :k])):.4f})" if x_ids is not None else ""
             out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                    "sample": f"first {sample} of the {nq} queries, same index bytes"
                                              + (f" (the {src[2]} lists those queries probe)" if src[2] != wl["nlist"] else "")
-                                             + f", nprobe={nprobe}; ids identical to the GPU result: {same:.4f}"}
+                                             + f", nprobe={nprobe}; ids identical to the GPU result: {same:.4f}{same_x}"}
     emit(out)
     if multi:
         dist.destroy_process_group()

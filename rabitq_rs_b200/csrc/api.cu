@@ -914,7 +914,6 @@ int dist_args(const rbq_index* h, size_t nq, size_t dim_or_zero, size_t top_k, s
     if (top_k == 0 || nq == 0) return fail(RBQ_INVALID_CONFIG, "phased search needs nq > 0 and top_k > 0");
     *pl = make_plan(h, nq, *nprobe);
     if (pl->qt < nq) return fail(RBQ_INVALID_CONFIG, "phased search handles one tile of queries per batch (131072 queries, 2^26 probes): split the batch");
-    if (*nprobe < 2) return fail(RBQ_INVALID_CONFIG, "phased search needs nprobe >= 2");
     return RBQ_OK;
 }
 

@@ -455,8 +455,8 @@ def test_full_size_properties_sift1m_shape(rbq, oracle):
     assert assert_results_match((ids[:256], sc[:256], cnt[:256]), exp, TOL, "sift1m sample") == 256
 
 
-@pytest.mark.parametrize("metric,bits", [(0, 7), (1, 3), (0, 1)])
-def test_phased_sharded_search_matches_single_shard(rbq, oracle, metric, bits):
+@pytest.mark.parametrize("metric,bits,nprobe", [(0, 7, 16), (1, 3, 16), (0, 1, 16), (0, 7, 1), (1, 3, 2), (0, 7, 64)])
+def test_phased_sharded_search_matches_single_shard(rbq, oracle, metric, bits, nprobe):
     """The three-phase multi-GPU search (rbq_dist_front / _head / _tail) with 3 list shards emulated on one device:
     the exchanges (all-gather of the probe slices, MIN all-reduce of tau, all-gather of the local top-k) are done
     with torch ops.  The merged result must equal the single-shard search except where a lower bound is violated
@@ -466,7 +466,7 @@ def test_phased_sharded_search_matches_single_shard(rbq, oracle, metric, bits):
 
     data, oix, blob = oracle_index(20000, 128, 64, bits, metric, kind="clustered")
     q = _queries(data, 2000, 17)
-    nq, k, nprobe, world = q.shape[0], 10, 16, 3
+    nq, k, world = q.shape[0], 10, 3
     full = _load(rbq, blob)
     want = full.batch_search(q, rbq.SearchParams(k, nprobe))
     shards = [_load(rbq, blob, shard_rank=r, shard_count=world) for r in range(world)]
@@ -675,7 +675,7 @@ def test_one_call_sharded_search_world_of_one(rbq, oracle):
     # exact merge on the one-rank communicator: eager refinement, record exchange (send/recv to self), global replay, override
     plain = gix.batch_search(q, rbq.SearchParams(k, nprobe))
     gix.set_exact_merge(True)
-    for kk, npb in ((k, nprobe), (40, 7), (3, 48)):
+    for kk, npb in ((k, nprobe), (40, 7), (3, 48), (k, 1), (k, 2)):
         ids2 = torch.empty((nq, kk), dtype=torch.int64, device="cuda")
         sc2 = torch.empty((nq, kk), dtype=torch.float32, device="cuda")
         cn2 = torch.empty(nq, dtype=torch.int32, device="cuda")
