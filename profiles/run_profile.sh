@@ -9,7 +9,7 @@ WL=${2:-gist1m}
 shift; shift
 mkdir -p gpurun_out
 export RBQ_CUDA_PROFILER=1
-KREGEX='regex:query_prep|coarse_|probe_select|sample_threshold|scan_kernel|tail_|merge_kernel|split_bf16|head_scan|resolve_|refine_'
+KREGEX='regex:query_prep|coarse_|probe_|sample_threshold|scan_kernel|tail_|merge_kernel|split_bf16|head_scan|head_compact|resolve_|refine_|fallback_|xr_|empty_rank|fill_u'
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k "$KREGEX" -c 200 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --workload $WL --nprobe 16 --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/launches_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off -k "$KREGEX" -c 40 -f -o gpurun_out/step_${TAG} \

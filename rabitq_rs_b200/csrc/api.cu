@@ -870,14 +870,12 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         // 4 chunks per tile: the H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks
         // hide more of the copy but run the per-query kernels on grids too small to fill the GPU and cost 6 launches each
         // (measured at GIST/10k, same box: 4 chunks 3.26M QPS, 8: 2.87M, 16: 2.23M); RBQ_FEED_CHUNKS overrides (1 = no overlap)
-        static const long forced = [] {
-            const char* e = getenv("RBQ_FEED_CHUNKS");
-            return e ? std::min(16L, std::max(1L, atol(e))) : 4L;
-        }();
+        const char* fe = getenv("RBQ_FEED_CHUNKS");  // read per call: tuning scripts sweep it inside one process
+        const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : 4L;
         feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
         if (n < 2048) feed.chunk = n;
         // search_device copies queries [q0, q0+n) itself (feed) and indexes outputs from the tile start
-        static const bool trace = getenv("RBQ_TRACE") != nullptr;
+        const bool trace = getenv("RBQ_TRACE") != nullptr;
         timespec t0, t1, t2;
         if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
         rc = search_device(h, nullptr, n, top_k, nprobe, d_f, filter_nbits, d_ids, d_sc, d_cn, (char*)h->ws, pl, st, &launches, &feed);

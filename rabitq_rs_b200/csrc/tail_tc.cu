@@ -23,6 +23,7 @@
 //     beats the query's head threshold -- the same survivors as the PRMT kernel, appended in any order (the replay
 //     sorts them).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "scan_common.cuh"
@@ -43,7 +44,9 @@ constexpr int PD_MAX = 6;                    // largest prefetch distance in chu
 // tensor core lag the producers by at most STAGES chunks).  The raw packed-code ring (4 bytes per producer thread and chunk,
 // read by the producers only) has PD + 2 slots.
 constexpr int PRODUCER_WARPS = 4 * MT_MAX;   // one block of the group per warp
-constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;  // + the MMA issuer warp
+constexpr int ISSUER_WARPS = MT_MAX;         // one MMA issuer warp per 128-vector tile: the tiles accumulate independently, and one thread
+                                             // needs ~190 clk to issue one of these small MMAs (descriptor moves through the uniform datapath)
+constexpr int THREADS = (PRODUCER_WARPS + ISSUER_WARPS) * 32;
 constexpr int A_COLS = KCH / 4;              // TMEM columns of one tile's K-chunk (4 one-hot bytes per 32-bit column)
 constexpr int B_STAGE = NQ * KCH;            // 8 KB
 constexpr int SURV_CAP = 256;                // survivors staged in shared memory between flushes
@@ -95,15 +98,52 @@ __device__ __forceinline__ uint32_t onehot32(uint32_t pos) {
     return d;
 }
 
+// one leader lane of the (converged) warp; unlike `lane == 0` the compiler keeps the guarded code on the uniform path
+__device__ __forceinline__ bool tt_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tt_bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // barrier among the 8 producer warps only (the issuer warp never joins it)
 __device__ __forceinline__ void tt_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(tt::PRODUCER_WARPS * 32) : "memory"); }
 
+#ifdef RBQ_TT_PROBE
+// dev-only phase clocks of producer warp 0 lane 0 of every CTA (build with -DRBQ_TT_PROBE; printed by launch_tail_tc):
+// [0] item set-up, [1] wait empty, [2] cp.async wait, [3] build row, [4] st + wait::st, [5] fences + arrive, [6] wait accd,
+// [7] epilogue, [8] chunks, [9] items, [10] total
+__device__ unsigned long long g_tt_probe[16];
+__device__ int g_tt_variant;  // timing experiments (results become wrong): bit 0 no proxy fence, bit 1 no raw-code copies, bit 2 no B copies
+#define TT_VARIANT(bit) ((g_tt_variant >> (bit)) & 1)
+#define TT_CLK(i)                                            \
+    do {                                                     \
+        if (tid == 0) {                                      \
+            const long long t_ = clock64();                  \
+            pr_[i] += (unsigned long long)(t_ - t_last_);    \
+            t_last_ = t_;                                    \
+        }                                                    \
+    } while (0)
+#else
+#define TT_CLK(i) do { } while (0)
+#define TT_VARIANT(bit) 0
+#endif
+
 template <bool WIDE, int PD>
 __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(DevIndex ix, TailArgs a) {
     using namespace tt;
+#ifdef RBQ_TT_PROBE
+    unsigned long long pr_[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last_ = clock64();
+    const long long t_begin_ = t_last_;
+#endif
     constexpr int BSTAGES = PD + STAGES, RSTAGES = PD + 2;
     extern __shared__ unsigned char tt_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tt_raw) + 1023) & ~(uintptr_t)1023);
@@ -115,16 +155,16 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
     const uint32_t nkc = ((uint32_t)ncb + 7u) / 8u;  // K-chunks of 8 codebooks
     const bool l2 = ix.metric == RBQ_METRIC_L2;
     const uint32_t sB_u32 = smem_u32(sB);
-    // barriers: full[stage] (256 producer arrivals), empty[stage] (tcgen05.commit), accumulators done (tcgen05.commit)
+    // barriers: full[stage] (256 producer arrivals), empty[stage] (one tcgen05.commit per issuer warp), accumulators done (ditto)
     const uint32_t full0 = smem_u32(&mi->bars[0]), empty0 = smem_u32(&mi->bars[STAGES]), accd = smem_u32(&mi->bars[2 * STAGES]);
-    const bool issuer = warp == PRODUCER_WARPS;
+    const bool issuer = warp >= PRODUCER_WARPS;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, PRODUCER_WARPS * 32);  // every producer thread arrives (measured faster than syncwarp + one lane)
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, ISSUER_WARPS);
         }
-        mbar_init(accd, 1);
+        mbar_init(accd, ISSUER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mi->surv_n = 0;
     }
@@ -174,6 +214,9 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
         __syncthreads();
         const uint32_t item = mi->item;
         if (item >= a.counters[0]) break;
+#ifdef RBQ_TT_PROBE
+        if (tid == 0) pr_[9] += 1;
+#endif
         // the staged survivors go out when the buffer is half full (everyone reads the same count here: nobody appends
         // between the barriers above and the first epilogue of the item)
         if (!issuer && mi->surv_n > (uint32_t)SURV_CAP / 2) flush_survivors();
@@ -184,17 +227,28 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
         const uint32_t idesc = tt_idesc(min((uint32_t)NQ, (P + 15u) & ~15u));
 
         if (issuer) {
-            // ===== MMA issuer: waits for a produced stage, issues its MMAs, commits the stage back =====
-            for (uint32_t b0 = 0; b0 < nb; b0 += 4 * MT_MAX) {
-                const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb - b0), mt_cnt = (nbg + 3) / 4;
-                for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
+            // ===== MMA issuer of tile `mt`: waits for a produced stage, issues the tile's MMAs, commits the stage back =====
+            // Every operand of tcgen05.mma travels through the uniform datapath.  Values the compiler cannot prove warp-uniform
+            // (anything loaded from memory or derived from threadIdx) cost an ELECT + six R2UR moves per instruction -- ~190 clk
+            // per MMA for one thread, which made the issuer the bottleneck of these small MMAs.  A warp-wide OR of identical
+            // values (REDUX) is uniform by construction, and elect.sync instead of `lane == 0` keeps the branch uniform: the MMAs
+            // then issue back to back from uniform registers.
+            const uint32_t mt = __reduce_or_sync(0xffffffffu, (uint32_t)(warp - PRODUCER_WARPS));
+            const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+            const uint32_t nb_u = __reduce_or_sync(0xffffffffu, nb), idesc_u = __reduce_or_sync(0xffffffffu, idesc);
+            const uint32_t nkc_u = __reduce_or_sync(0xffffffffu, nkc);
+            const uint32_t d_tm = tmem_u + mt * (uint32_t)NQ;
+            for (uint32_t b0 = 0; b0 < nb_u; b0 += 4 * MT_MAX) {
+                const uint32_t nbg = min((uint32_t)(4 * MT_MAX), nb_u - b0), mt_cnt = (nbg + 3) / 4;
+                const bool have_tile = mt < mt_cnt;
+                for (uint32_t kc = 0; kc < nkc_u; ++kc, ++chunk_seq) {
                     const uint32_t s = chunk_seq % STAGES;
                     tt_bar_wait(full0 + 8 * s, (chunk_seq / STAGES) & 1u);
-                    if (lane == 0) {
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t db = tt_desc(sB_u32 + (chunk_seq % BSTAGES) * B_STAGE);
-                        for (uint32_t mt = 0; mt < mt_cnt; ++mt) {
-                            const uint32_t ta = tmem + (uint32_t)ACC_COLS + (s * MT_MAX + mt) * (uint32_t)A_COLS;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tt_elect_one()) {
+                        if (have_tile) {
+                            const uint64_t db = tt_desc(sB_u32 + (chunk_seq % BSTAGES) * B_STAGE);
+                            const uint32_t ta = tmem_u + (uint32_t)ACC_COLS + (s * MT_MAX + mt) * (uint32_t)A_COLS;
 #pragma unroll
                             for (int k = 0; k < KCH / 32; ++k) {
                                 const uint32_t acc = (kc | (uint32_t)k) ? 1u : 0u;
@@ -203,16 +257,20 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
                                     ".reg .pred p;\n"
                                     "setp.ne.b32 p, %4, 0;\n"
                                     "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
-                                    "}" ::"r"(tmem + mt * NQ),
-                                    "r"(ta + (uint32_t)(8 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(acc)
+                                    "}" ::"r"(d_tm),
+                                    "r"(ta + (uint32_t)(8 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc_u), "r"(acc)
                                     : "memory");
                             }
-                        }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
-                                     : "memory");
-                        if (kc + 1 == nkc)
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accd)
+                            // the commits track this thread's MMAs only: every issuer arrives once per stage / group
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
                                          : "memory");
+                            if (kc + 1 == nkc_u)
+                                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accd)
+                                             : "memory");
+                        } else {  // the group has no such tile: plain arrivals keep the barrier counts
+                            tt_bar_arrive(empty0 + 8 * s);
+                            if (kc + 1 == nkc_u) tt_bar_arrive(accd);
+                        }
                     }
                     __syncwarp();
                 }
@@ -273,8 +331,8 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
                     const uint32_t koff = kc * KCH, bst = (seq % BSTAGES) * B_STAGE;
 #pragma unroll
                     for (int i = 0; i < NQ * 8 / (PRODUCER_WARPS * 32); ++i)
-                        if (koff < blim[i]) cp_async16(bdst[i] + bst, bsrc[i] + koff);
-                    if (kc < rlim)
+                        if (koff < blim[i] && !TT_VARIANT(2)) cp_async16(bdst[i] + bst, bsrc[i] + koff);
+                    if (kc < rlim && !TT_VARIANT(1))
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rdst + (seq % RSTAGES) * (uint32_t)(PRODUCER_WARPS * 32 * 4)),
                                      "l"(rsrc + koff)
                                      : "memory");
@@ -284,14 +342,22 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
             // every earlier MMA has completed (accumulator barrier), so all stages are free
 #pragma unroll
             for (int d = 0; d < PD; ++d) prefetch((uint32_t)d, chunk_seq + d);
+            TT_CLK(0);
             for (uint32_t kc = 0; kc < nkc; ++kc, ++chunk_seq) {
                 const uint32_t s = chunk_seq % STAGES, use = chunk_seq / STAGES;
+#ifdef RBQ_TT_PROBE
+                if (tid == 0) pr_[8] += 1;
+#endif
                 // chunk_seq - 2 was the last reader of A stage s.  (Building the row before this wait was measured slower:
                 // 0.65 vs 0.61 ms at GIST/10k -- the row would stay live in 32 registers across the wait.)
                 if (use > 0) tt_bar_wait(empty0 + 8 * s, (use - 1) & 1u);
+                TT_CLK(1);
                 prefetch(kc + PD, chunk_seq + PD);  // the operands of chunk kc + PD start travelling
+                TT_CLK(11);
                 asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");  // this thread's pieces of chunk kc have landed
+                TT_CLK(2);
                 __syncwarp();  // the other lanes' pieces of the warp's raw words have landed too
+                TT_CLK(12);
                 // the one-hot row of this thread's vector for codebooks 8*kc .. 8*kc+7, built in registers
                 uint32_t r[32];
                 if ((uint32_t)warp < nbg) {
@@ -311,6 +377,12 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
                         r[4 * c + 3] = onehot32(pos - 96u);
                     }
                 }
+#ifdef RBQ_TT_PROBE
+                if (tid == 0) {  // keep the row's last word live up to here so that the build is timed, not sunk below the clock read
+                    asm volatile("" ::"r"(r[31]), "r"(r[0]));
+                }
+#endif
+                TT_CLK(3);
                 if ((uint32_t)warp < nbg) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)ACC_COLS + (s * MT_MAX + (uint32_t)(warp >> 2)) * (uint32_t)A_COLS;
@@ -325,12 +397,15 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
                         : "memory");
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
+                TT_CLK(4);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                fence_proxy_async();  // its B pieces (generic-proxy writes) -> visible to the tensor core's async-proxy reads
+                if (!TT_VARIANT(0)) fence_proxy_async();  // its B pieces (generic-proxy writes) -> visible to the tensor core's async-proxy reads
                 tt_bar_arrive(full0 + 8 * s);
+                TT_CLK(5);
             }
             // ---- epilogue: sums -> K8 -> survivors ----
             tt_bar_wait(accd, groups & 1u);
+            TT_CLK(6);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (uint32_t mt = (uint32_t)(warp >> 2); mt < mt_cnt; mt += PRODUCER_WARPS / 4) {
                 const uint32_t bg = mt * 4u + (uint32_t)lq;  // this warp's block of the tile; TMEM lane = 32*lq + vector
@@ -398,8 +473,15 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
             // TMEM reads done before this thread's next arrival on a `full` barrier lets the issuer overwrite the accumulators
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             groups += 1;
+            TT_CLK(7);
         }
     }
+#ifdef RBQ_TT_PROBE
+    if (tid == 0) {
+        pr_[10] = (unsigned long long)(clock64() - t_begin_);
+        for (int i = 0; i < 13; ++i) atomicAdd(&g_tt_probe[i], pr_[i]);
+    }
+#endif
     if (!issuer) flush_survivors();
     __syncthreads();
     if (warp == 0) {
@@ -420,8 +502,22 @@ template <bool WIDE, int PD>
 static int launch_tail_tc_ex(const DevIndex& ix, const TailArgs& a, int sms, cudaStream_t st) {
     const size_t smem = tt::smem_bytes(PD);
     RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<WIDE, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef RBQ_TT_PROBE
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tt_probe, z, sizeof(z));
+    const int variant = getenv("RBQ_TT_VARIANT") ? atoi(getenv("RBQ_TT_VARIANT")) : 0;
+    cudaMemcpyToSymbol(g_tt_variant, &variant, sizeof(variant));
+#endif
     tail_tc_kernel<WIDE, PD><<<tt::CTAS_PER_SM * sms, tt::THREADS, smem, st>>>(ix, a);
     RBQ_CUDA(cudaGetLastError());
+#ifdef RBQ_TT_PROBE
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(z, g_tt_probe, sizeof(z));
+    const double nc = (double)(tt::CTAS_PER_SM * sms);
+    fprintf(stderr, "[tt probe] per CTA: setup %.0f wait_empty %.0f cpasync %.0f build %.0f st %.0f arrive %.0f wait_acc %.0f epilogue %.0f | chunks %.0f items %.1f total %.0f clk\n",
+            z[0] / nc, z[1] / nc, z[2] / nc, z[3] / nc, z[4] / nc, z[5] / nc, z[6] / nc, z[7] / nc, z[8] / nc, z[9] / nc, z[10] / nc);
+    fprintf(stderr, "[tt probe]   prefetch issue %.0f, syncwarp %.0f\n", z[11] / nc, z[12] / nc);
+#endif
     return RBQ_OK;
 }
 
