@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-mode", type=int, default=int(os.environ.get("RBQ_SCAN_MODE", "0")), help="0 auto, 1 sequential, 2 list-major")
     ap.add_argument("--coarse-mode", type=int, default=int(os.environ.get("RBQ_COARSE_MODE", "-1")), help="-1 auto, 0 exact, 1 dense TC, 2 filtered TC")
-    ap.add_argument("--coarse-terms", type=int, default=int(os.environ.get("RBQ_COARSE_TERMS", "3")), help="bf16 terms of the coarse GEMM (3 or 1)")
+    ap.add_argument("--coarse-terms", type=int, default=int(os.environ.get("RBQ_COARSE_TERMS", "0")), help="bf16 terms of the coarse GEMM (3, 1, 0 = auto)")
     ap.add_argument("--save-ids", default="", help="write the (merged) result ids of the timed configuration to this .npy")
     ap.add_argument("--check-ids", default="", help="compare the (merged) result ids with this .npy (e.g. of a 1-GPU run of the same workload)")
     ap.add_argument("--oracle-sample", type=int, default=1024, help="queries checked against the CPU oracle on the same index bytes")
@@ -693,7 +693,8 @@ def main():
                               "bytes_per_step": scan_bytes / steps, "ms_per_step": scan_ms / steps,
                               "kernels": "head_scan + resolve_head + tail_* + resolve_lazy/replay (+ fallback scan); "
                                          + ("per-rank time = max over ranks, bytes = sum over ranks" if multi else "1 GPU")}
-    coarse_flops = 2.0 * nq * wl["nlist"] * D * (3 if args.coarse_terms == 3 else 1)
+    terms_used = int(st.get("coarse_terms_used", 0)) // max(steps, 1) or args.coarse_terms
+    coarse_flops = 2.0 * nq * wl["nlist"] * D * terms_used
     out = {"metric": metric_name, "value": value, "unit": "queries/s", "n_gpus": world,
            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "u8 LUT sums + f32", "data": "synthetic", "config": config,
@@ -701,7 +702,7 @@ def main():
                    "d2h_bytes_per_step": int(nq * k * 12 + nq * 4)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
            "stage_ms_per_step": {n_: float(st[kk]) / steps for n_, kk in zip(("prep", "coarse", "select", "scan"), stage_keys[:4])},
-           "coarse": {"mode": int(st.get("coarse_mode_used", 0)) // max(steps, 1), "terms": args.coarse_terms,
+           "coarse": {"mode": int(st.get("coarse_mode_used", 0)) // max(steps, 1), "terms": terms_used,
                       "front_chunk": int(st.get("front_chunk", 0)) // max(steps, 1),
                       "gemm_tflops_executed": coarse_flops / 1e12 / (st["ms_coarse"] / steps / 1000.0) if st["ms_coarse"] > 0 and not multi else None},
            "scan_split": {"schedule": "list-major (head/tail/replay)" if list_major else "sequential",

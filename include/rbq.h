@@ -249,6 +249,8 @@ typedef struct rbq_search_stats {
     uint64_t inexact_queries;   /* exact-merge sharded search: home queries of this rank that kept the phased answer (survivor
                                    overflow on some shard, head pass that did not fill the heap, > 4096 candidate records) */
     uint64_t exchanged_records; /* exact-merge sharded search: candidate records this rank received for its home queries */
+    uint32_t coarse_terms_used; /* bf16 terms the coarse GEMM multiplied (3 or 1) */
+    uint32_t reserved_;
 } rbq_search_stats;
 int rbq_last_search_stats(const rbq_index* ix, rbq_search_stats* out);
 /* When on, search calls time each stage with CUDA events (adds host syncs; off by default). */
@@ -269,8 +271,9 @@ int rbq_set_scan_mode(rbq_index* ix, int mode);
  * -1 = auto (default): 2 when available, else 1.
  * All of them produce the reference's probe list bit for bit. */
 int rbq_set_coarse_mode(rbq_index* ix, int mode);
-/* bf16 terms of the coarse GEMM: 3 (default; operands split hi+lo, fp32-class scores, a handful of re-scored centroids)
- * or 1 (a third of the tensor work, bf16-class scores, a wider band of centroids re-scored exactly).  Exact either way. */
+/* bf16 terms of the coarse GEMM: 3 (operands split hi+lo, fp32-class scores, a handful of re-scored centroids), 1 (a third
+ * of the tensor work, bf16-class scores, a wider band of centroids re-scored exactly) or 0 = auto (default): 1 when the GEMM
+ * is the larger part of the front end (padded_dim >= 512), else 3.  Exact either way. */
 int rbq_set_coarse_terms(rbq_index* ix, int terms);
 
 /* ---- stage probes (parity tests call each device stage in isolation; host buffers) ----

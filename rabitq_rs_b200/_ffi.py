@@ -17,7 +17,8 @@ class SearchStats(C.Structure):
                 ("tail_blocks", C.c_uint64), ("tail_bytes", C.c_uint64), ("tail_pairs", C.c_uint64),
                 ("survivors", C.c_uint64), ("overflow_queries", C.c_uint64),
                 ("ms_scan_head", C.c_float), ("ms_scan_tail", C.c_float), ("ms_scan_replay", C.c_float), ("ms_tail_kernel", C.c_float), ("coarse_mode_used", C.c_uint32), ("front_chunk", C.c_uint32), ("fallback_queries", C.c_uint64),
-                ("inexact_queries", C.c_uint64), ("exchanged_records", C.c_uint64)]
+                ("inexact_queries", C.c_uint64), ("exchanged_records", C.c_uint64),
+                ("coarse_terms_used", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 _lib = None

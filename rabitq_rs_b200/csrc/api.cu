@@ -231,7 +231,7 @@ Plan make_plan(const rbq_index* h, size_t nq, size_t nprobe) {
     Plan p;
     const size_t pair_cap = std::max<size_t>(1, ((size_t)1 << 26) / std::max<size_t>(nprobe, 1));
     p.qt = std::min<size_t>({nq, (size_t)131072, pair_cap});
-    p.terms = h->coarse_terms == 1 ? 1 : 3;
+    p.terms = h->coarse_terms == 1 ? 1 : h->coarse_terms == 3 ? 3 : (ix.D >= 512 ? 1 : 3);  // 0 = auto
     p.eps = p.terms == 1 ? 4.39453125e-3f /* 2^-8 + 2^-11: bf16 rounding of both operands */ : h->coarse_eps;
     p.coarse = h->coarse_mode;
     if (p.coarse < 0 || p.coarse == 2) {
@@ -724,7 +724,7 @@ int rbq_set_coarse_mode(rbq_index* h, int mode) {
 }
 int rbq_set_coarse_terms(rbq_index* h, int terms) {
     if (!h) return fail(RBQ_INVALID_CONFIG, "null index handle");
-    if (terms != 1 && terms != 3) return fail(RBQ_INVALID_CONFIG, "coarse terms must be 1 or 3");
+    if (terms != 0 && terms != 1 && terms != 3) return fail(RBQ_INVALID_CONFIG, "coarse terms must be 0 (auto), 1 or 3");
     std::lock_guard<std::mutex> lk(h->mu);
     h->coarse_terms = terms;
     return RBQ_OK;
@@ -808,6 +808,7 @@ int rbq_search_batch_device(const rbq_index* h, const float* d_queries, size_t n
                        (char*)h->ws, pl, st, &launches);
     h->last_stats.kernel_launches = launches;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.coarse_terms_used = (uint32_t)pl.terms;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
     return rc;
 }
@@ -867,11 +868,12 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     if (feed.copy != st) RBQ_CUDA(cudaStreamWaitEvent(feed.copy, h->busy_ev, 0));
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
-        // 4 chunks per tile: the H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks
-        // hide more of the copy but run the per-query kernels on grids too small to fill the GPU and cost 6 launches each
-        // (measured at GIST/10k, same box: 4 chunks 3.26M QPS, 8: 2.87M, 16: 2.23M); RBQ_FEED_CHUNKS overrides (1 = no overlap)
+        // The H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks hide more of the copy but run
+        // the per-query kernels on partial waves (a front end + head pass of 1 280 queries costs 2.5x its share of a 10 000-query
+        // one) -- measured at GIST/10k with profiles/e2e_probe.py: 1 chunk 2.52 ms, 2: 2.41, 3: 2.41, 4: 2.60, 8: 3.27.  Default:
+        // chunks of ~3 400 queries, at most 4 per tile; RBQ_FEED_CHUNKS overrides (1 = no overlap).
         const char* fe = getenv("RBQ_FEED_CHUNKS");  // read per call: tuning scripts sweep it inside one process
-        const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : 4L;
+        const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : std::min(4L, std::max(1L, (long)((n + 1700) / 3400)));
         feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
         if (n < 2048) feed.chunk = n;
         // search_device copies queries [q0, q0+n) itself (feed) and indexes outputs from the tile start
@@ -895,6 +897,7 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     }
     h->last_stats.kernel_launches = launches;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.coarse_terms_used = (uint32_t)pl.terms;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
     return RBQ_OK;
 }
@@ -923,6 +926,7 @@ int dist_front_impl(const rbq_index* h, const Plan& pl, const float* d_queries, 
     h->dist_phase = 0;
     h->last_stats.queries = nq;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.coarse_terms_used = (uint32_t)pl.terms;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
     if ((rc = ensure_ws(h, ws_need(h, pl, nprobe, top_k, dim, false, 0)))) return rc;
     RBQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats) + 16, st));
@@ -1418,6 +1422,7 @@ int rbq_debug_probe(const rbq_index* h, const float* queries, size_t nq, size_t 
     h->last_stats = rbq_search_stats{};
     h->last_stats.queries = nq;
     h->last_stats.coarse_mode_used = (uint32_t)pl.coarse;
+    h->last_stats.coarse_terms_used = (uint32_t)pl.terms;
     h->last_stats.front_chunk = (uint32_t)pl.cq;
     return RBQ_OK;
 }

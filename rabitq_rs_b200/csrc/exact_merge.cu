@@ -124,38 +124,11 @@ struct XrArgs {
     uint32_t* cursor;
 };
 
-// Declared in resolve.cu (same translation-unit-local helpers are not visible here): the refine path is re-stated through the
-// shared header pieces (ex_dot_chain / hsum8) with its own staging -- one candidate per 8-lane group, rows copied by cp.async.
-__device__ __forceinline__ float xr_refine32(const DevIndex& ix, unsigned long long gv, int nb, uint32_t stage_u32, uint32_t rql_u32, uint32_t exl_row,
-                                             uint32_t rql_row, int lane) {
-    const int g = lane >> 3, j = lane & 7;
-    const uint32_t LB = ix.exl_lane;
-    const uint32_t my_row = (uint32_t)lane * exl_row;
-    const uint32_t qrow = rql_u32 + (uint32_t)j * rql_row;
-    float exdot = 0.0f;
-    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
-        const int c = r0 + g;
-        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
-        if (c < nb) {
-            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
-            for (uint32_t p = 0; p < LB; p += 16) cp_async16(stage_u32 + my_row + p, src + p);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        float part = 0.0f;
-        if (c < nb) part = ex_dot_chain(stage_u32 + my_row, qrow, LB);
-        part = hsum8(part);
-        const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
-        if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
-    }
-    return exdot;
-}
-
 __global__ void __launch_bounds__(128) xr_records_kernel(DevIndex ix, XrArgs a) {
     extern __shared__ __align__(16) unsigned char xr_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const uint32_t per_warp = 32u * a.exl_row + 8u * a.rql_row;
+    const uint32_t per_warp = 32u * a.exl_row + 4u * a.rql_row;
     unsigned char* wbase = xr_smem + (size_t)warp * per_warp;
     const uint32_t stage_u32 = smem_u32(wbase), rql_u32 = smem_u32(wbase + 32u * a.exl_row);
     unsigned char* rql = wbase + 32u * a.exl_row;
@@ -184,10 +157,7 @@ __global__ void __launch_bounds__(128) xr_records_kernel(DevIndex ix, XrArgs a) 
         if (a.has_ex) {
             s = a.qs[q];
             __syncwarp();
-            for (int i = lane; i < 8 * (int)ix.exl_lane; i += 32) {  // rotated query in chain order (resolve.cu::load_rql)
-                const int j = i & 7, t = i >> 3;
-                reinterpret_cast<float*>(rql + (size_t)j * a.rql_row)[t] = i < D ? __ldg(a.rot + (size_t)q * D + i) : 0.0f;
-            }
+            load_rql2(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);  // rotated query in paired chain order
             __syncwarp();
         }
         for (uint32_t b0 = 0; b0 < ns; b0 += 32) {
@@ -204,7 +174,7 @@ __global__ void __launch_bounds__(128) xr_records_kernel(DevIndex ix, XrArgs a) 
             }
             float dist = rec.x;  // 1-bit index: the estimate is the distance
             if (a.has_ex) {
-                const float exdot = xr_refine32(ix, gv, m, stage_u32, rql_u32, a.exl_row, a.rql_row, lane);
+                const float exdot = refine_batch2(ix, gv, m, stage_u32, rql_u32, a.exl_row, a.rql_row, 1u, lane);
                 if (i < ns) {
                     // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
                     const float fae = __ldg(ix.f_add_ex + gv), fre = __ldg(ix.f_rescale_ex + gv);
@@ -431,13 +401,13 @@ int xr_launch_records(const DevIndex& ix, const float* d_rot, const QueryScalars
     a.head_sc = d_head_sc;
     a.head_cnt = d_head_cnt;
     a.recs = d_recs;
-    a.exl_row = exl_row_stride((uint32_t)ix.D);
-    a.rql_row = rql_row_stride((uint32_t)ix.D);
+    a.exl_row = exl2_lane_stride((uint32_t)ix.D);
+    a.rql_row = rql2_row_stride((uint32_t)ix.D);
     a.stage_bufs = 1;
     a.has_ex = ix.ex_bits != 0;
     a.cursor = d_cursor;
     RBQ_CUDA(cudaMemsetAsync(d_cursor, 0, 4, st));
-    const size_t smem = (size_t)4 * (32u * a.exl_row + 8u * a.rql_row);
+    const size_t smem = (size_t)4 * (32u * a.exl_row + 4u * a.rql_row);
     RBQ_CUDA(cudaFuncSetAttribute(xr_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     RBQ_CUDA(cudaGetDevice(&dev));

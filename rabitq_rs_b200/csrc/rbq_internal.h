@@ -334,7 +334,7 @@ struct rbq_index {
                                // 1: dense tensor-core scores + exact re-score, 2: tensor-core scores filtered in the GEMM epilogue
     int exact_merge = 0;       // one-call sharded search: 1 = global replay at the query's home rank (bit-identical to one GPU)
     mutable unsigned long long last_inexact = 0;  // queries of the last exact-merge call that kept the phased answer
-    int coarse_terms = 3;      // bf16 split terms multiplied by the coarse GEMM: 3 (fp32-class scores) or 1 (bf16-class, wider re-score band)
+    int coarse_terms = 0;      // bf16 split terms multiplied by the coarse GEMM: 3 (fp32-class scores), 1 (bf16-class, wider re-score band), 0 auto
     float coarse_eps = 4.8828125e-4f;  // 2^-11: assumed bound on |gemm(q.c) - q.c| / (|q||c|) with 3 terms
     void* comm = nullptr;                   // ncclComm_t of the one-call sharded search (rbq_comm_init); NCCL is dlopen'ed
     mutable void* dist_ws = nullptr;        // its exchange buffers

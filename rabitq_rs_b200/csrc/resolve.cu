@@ -49,8 +49,8 @@ struct ResolveArgs {
     Survivor* surv;
     const uint32_t* surv_cnt;
     uint32_t surv_cap;
-    uint32_t exl_row;   // shared-memory stride of a lane's staged code row (exl_row_stride)
-    uint32_t rql_row;   // shared-memory stride of a lane's query row (rql_row_stride)
+    uint32_t exl_row;   // shared-memory stride of a lane's two staged code rows (exl2_lane_stride)
+    uint32_t rql_row;   // shared-memory stride of a query pair-row (rql2_row_stride)
     uint32_t stage_bufs;  // 2: the rows of round r+1 travel while round r is multiplied; 1: one round at a time, less shared memory
     uint32_t has_ex;
     uint32_t flush_at;  // head resolve: refine as soon as this many candidates are queued
@@ -133,13 +133,13 @@ struct ResSmem {
     uint32_t stage, rq, si, sd, ord, slots, total;
 };
 __host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool topk, uint32_t surv_cap,
-                                                   uint32_t stage_bufs = 2) {
+                                                   uint32_t stage_bufs = 2, bool paired = false) {
     ResSmem w;
     uint32_t o = 0;
     w.stage = o;
-    o += refine ? stage_bufs * 32u * exl_row : 0;  // stage_bufs rounds of 4 candidates x 8 lane rows
+    o += refine ? stage_bufs * 32u * exl_row : 0;  // stage_bufs rounds of 32 lane regions (exl_row each): 4 candidates x 8 rows, or 8 x 4 x 2 rows (paired)
     w.rq = o;
-    o += refine ? 8u * rql_row : 0;
+    o += refine ? (paired ? 4u : 8u) * rql_row : 0;  // the query: 8 chain rows, or 4 pair-rows
     w.si = o;
     o += topk ? ((k * 8 + 15) / 16) * 16 : 0;
     w.sd = o;
@@ -158,59 +158,7 @@ __host__ __device__ inline ResSmem res_smem_layout(uint32_t exl_row, uint32_t rq
     return w;
 }
 
-// rotated query in chain order: row j (stride rql_row bytes), position t = q[8t + j]; positions past D/8 are zero
-__device__ __forceinline__ void load_rql(unsigned char* rql, uint32_t rql_row, const float* __restrict__ rot, int D, uint32_t lane_bytes,
-                                         int lane) {
-    for (int i = lane; i < 8 * (int)lane_bytes; i += 32) {
-        const int j = i & 7, t = i >> 3;
-        reinterpret_cast<float*>(rql + (size_t)j * rql_row)[t] = i < D ? __ldg(rot + i) : 0.0f;
-    }
-}
-
-// K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's
-// ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes): every lane
-// copies ITS chain's code row (DevIndex::exl) into its own shared-memory row with cp.async and multiplies it against
-// its query row -- no unpacking and no exchange between lanes.  With two staging buffers (a.stage_bufs == 2) the rows of
-// round r+1 travel while round r is multiplied; the default is one buffer (the candidates' rows were already pulled into
-// L2 when they were queued, and the smaller footprint lets more warps be resident, which measured faster).
-__device__ __forceinline__ float refine_batch(const DevIndex& ix, const ResolveArgs& a, unsigned long long gv, int nb, uint32_t stage_u32,
-                                              uint32_t rql_u32, int lane) {
-    const int g = lane >> 3, j = lane & 7;
-    const uint32_t LB = ix.exl_lane;
-    const uint32_t my_row = (uint32_t)lane * a.exl_row, buf_bytes = 32u * a.exl_row;
-    const uint32_t qrow = rql_u32 + (uint32_t)j * a.rql_row;
-    auto issue = [&](int r0, uint32_t buf) {
-        const int c = r0 + g;
-        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
-        if (c < nb) {
-            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
-            const uint32_t dst = stage_u32 + buf * buf_bytes + my_row;
-            for (uint32_t p = 0; p < LB; p += 16) cp_async16(dst + p, src + p);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const bool dbl = a.stage_bufs > 1u;
-    issue(0, 0u);
-    float exdot = 0.0f;
-    uint32_t buf = 0;
-    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
-        const int c = r0 + g;  // candidate served by this 8-lane group
-        if (dbl && r0 + kRefineSlots < nb) {
-            issue(r0 + kRefineSlots, buf ^ 1u);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        float part = 0.0f;
-        if (c < nb) part = ex_dot_chain(stage_u32 + buf * buf_bytes + my_row, qrow, LB);
-        part = hsum8(part);
-        const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
-        if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
-        if (dbl) buf ^= 1u;
-        else if (r0 + kRefineSlots < nb) issue(r0 + kRefineSlots, 0u);  // the lane's own row is free again (only it reads it)
-    }
-    return exdot;
-}
+// load_rql2 / refine_batch2 (paired chains, 8 candidates per round): scan_common.cuh
 
 // ---- lane-major ex-codes (DevIndex::exl) ------------------------------------------------------------------------------
 // One thread per (vector, 16-dim chunk): decodes the chunk of the packed code (the reference's layouts, src/simd.rs:
@@ -237,7 +185,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, EXK != 0, true, 0, a.stage_bufs);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, EXK != 0, true, 0, a.stage_bufs, EXK == 2);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -269,7 +217,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
             if (p.nv > a.head_cap) {
                 fallback = true;
             } else {
-                if (EXK != 0) load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
+                if (EXK != 0) load_rql_any<EXK == 2>(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
                 const QueryScalars s = a.qs[q];
                 __syncwarp();
                 const uint32_t nv = p.nv, nb = (nv + kBatch - 1) / kBatch;
@@ -293,7 +241,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 6) resolve_head_kernel(DevInde
                         fre = __ldg(ix.f_rescale_ex + q_gv);
                         q_vid = ix.ids[q_gv];
                     }
-                    const float exdot = refine_batch(ix, a, q_gv, qn, stage_u32, rql_u32, lane);
+                    const float exdot = refine_batch_any<EXK == 2>(ix, q_gv, qn, stage_u32, rql_u32, a.exl_row, a.rql_row, a.stage_bufs, lane);
                     q_ref += qn;
                     if (mine) {
                         // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
@@ -521,7 +469,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap, a.stage_bufs);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap, a.stage_bufs, EXK == 2);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -578,7 +526,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         }
         for (uint32_t i = lane; i < n_surv; i += 32) slots[i] = (uint16_t)((uint32_t)ord[i] & 1023u);
         __syncwarp();  // the keys are dead: their memory becomes the query rows and the refine staging
-        load_rql(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
+        load_rql_any<EXK == 2>(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);
         __syncwarp();
         // candidate queue: slot i lives in lane i, in visit order
         int qn = 0;
@@ -596,7 +544,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
                 fre = __ldg(ix.f_rescale_ex + q_gv);
                 q_vid = ix.ids[q_gv];
             }
-            const float exdot = refine_batch(ix, a, q_gv, qn, stage_u32, rql_u32, lane);
+            const float exdot = refine_batch_any<EXK == 2>(ix, q_gv, qn, stage_u32, rql_u32, a.exl_row, a.rql_row, a.stage_bufs, lane);
             q_ref += qn;
             if (mine) {
                 // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
@@ -689,18 +637,19 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
 }
 
 // Stage probe for K10: the ex-code dot of `n` stored vectors (global positions gv[i]) against one rotated query, through the
-// product's own refine path (load_rql + refine_batch: lane-major rows, 8 FMA chains, AVX2-order horizontal sum).
+// product's own refine path (the form the resolve kernels use for this padded_dim: lane-major rows, 8 FMA chains, AVX2-order sum).
+template <bool PAIRED>
 __global__ void __launch_bounds__(32) ex_dot_debug_kernel(DevIndex ix, ResolveArgs a, const unsigned long long* __restrict__ gv, int n,
                                                          float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs);
-    load_rql(res_smem + L.rq, a.rql_row, a.rot, ix.D, ix.exl_lane, lane);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs, PAIRED);
+    load_rql_any<PAIRED>(res_smem + L.rq, a.rql_row, a.rot, ix.D, ix.exl_lane, lane);
     __syncwarp();
     for (int b0 = 0; b0 < n; b0 += 32) {
         const int m = min(32, n - b0);
         const unsigned long long g = lane < m ? gv[b0 + lane] : 0ull;
-        const float d = refine_batch(ix, a, g, m, smem_u32(res_smem + L.stage), smem_u32(res_smem + L.rq), lane);
+        const float d = refine_batch_any<PAIRED>(ix, g, m, smem_u32(res_smem + L.stage), smem_u32(res_smem + L.rq), a.exl_row, a.rql_row, a.stage_bufs, lane);
         if (lane < m) out[b0 + lane] = d;
         __syncwarp();
     }
@@ -811,6 +760,15 @@ static int res_limits() {
     return RBQ_OK;
 }
 
+// which refine form the resolve kernels use for this index (RBQ_REFINE_PAIRED=0/1 overrides the padded_dim rule)
+static bool refine_paired(const DevIndex& ix) {
+    static const int forced = [] {
+        const char* e = getenv("RBQ_REFINE_PAIRED");
+        return e ? atoi(e) : -1;
+    }();
+    return forced >= 0 ? forced != 0 : refine_paired_for((uint32_t)ix.D);
+}
+
 static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, const QueryScalars* d_qs,
                       const Probe* d_probes, size_t nq, size_t nprobe, size_t top_k, const uint64_t* d_filter, size_t filter_nbits,
                       uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats, const TailWs& tw) {
@@ -842,8 +800,9 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.surv = tw.surv;
     a.surv_cnt = tw.surv_cnt;
     a.surv_cap = tw.surv_cap;
-    a.exl_row = exl_row_stride((uint32_t)ix.D);
-    a.rql_row = rql_row_stride((uint32_t)ix.D);
+    const bool paired = refine_paired(ix);
+    a.exl_row = paired ? exl2_lane_stride((uint32_t)ix.D) : exl_row_stride((uint32_t)ix.D);
+    a.rql_row = paired ? rql2_row_stride((uint32_t)ix.D) : rql_row_stride((uint32_t)ix.D);
     static const uint32_t stage_bufs = [] {
         const char* e = getenv("RBQ_STAGE_BUFS");
         return (uint32_t)(e && atoi(e) == 2 ? 2 : 1);
@@ -852,14 +811,14 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.has_ex = ix.ex_bits != 0;
     static const uint32_t flush_at = [] {
         const char* e = getenv("RBQ_FLUSH_AT");
-        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : kRefineSlots));  // one refine round per flush (measured best)
+        return (uint32_t)std::min(32, std::max(0, e ? atoi(e) : 0));  // 0: one refine round per flush (measured best)
     }();
-    a.flush_at = flush_at;
+    a.flush_at = flush_at ? flush_at : (paired ? kRefineSlots2 : kRefineSlots);
     static const uint32_t lazy_flush_at = [] {
         const char* e = getenv("RBQ_LAZY_FLUSH");
-        return (uint32_t)std::min(32, std::max(1, e ? atoi(e) : kRefineSlots));
+        return (uint32_t)std::min(32, std::max(0, e ? atoi(e) : 0));
     }();
-    a.lazy_flush_at = lazy_flush_at;
+    a.lazy_flush_at = lazy_flush_at ? lazy_flush_at : (paired ? kRefineSlots2 : kRefineSlots);
 }
 
 template <int NCB, bool WIDE>
@@ -875,17 +834,15 @@ static unsigned res_grid(size_t nq, size_t smem) {
     return (unsigned)std::min<size_t>((nq + kResWarps - 1) / kResWarps, (size_t)g_res_sms * per_sm);
 }
 
+// kernel instances: <0> 1-bit index (nothing to refine), <1> eight-lane refine, <2> paired refine
 #define RBQ_RES_LAUNCH(KERNEL, smem, grid)                                                                               \
     do {                                                                                                                  \
         if (ix.ex_bits == 0) {                                                                                            \
             RBQ_CUDA(cudaFuncSetAttribute(KERNEL<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
             KERNEL<0><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
-        } else if (ix.ex_bits == 2) {                                                                                     \
+        } else if (refine_paired(ix)) {                                                                                   \
             RBQ_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
             KERNEL<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
-        } else if (ix.ex_bits == 6) {                                                                                     \
-            RBQ_CUDA(cudaFuncSetAttribute(KERNEL<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
-            KERNEL<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
         } else {                                                                                                          \
             RBQ_CUDA(cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));           \
             KERNEL<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);                                                         \
@@ -913,7 +870,7 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
         if (launches) *launches += 1;
     }
     const int ncb_lane = (ix.D / 4 + 31) / 32;
-    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0, a.stage_bufs);
+    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, true, 0, a.stage_bufs, refine_paired(ix));
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "resolve kernel shared memory exceeds the device limit");
     // the dense head buffer holds tw.head_rows queries: the slice is walked in sub-chunks that reuse it (same stream)
@@ -955,16 +912,13 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     fill_args(a, ix, d_rot, nullptr, d_qs, d_probes, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, d_stats, tw);
     if (ix.ex_bits != 0) {
         // sorted survivors, refinement on demand against the live threshold (one kernel)
-        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap, a.stage_bufs);
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap, a.stage_bufs, refine_paired(ix));
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
         const unsigned grid = res_grid(nq, smem);
-        if (ix.ex_bits == 2) {
+        if (refine_paired(ix)) {
             RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             resolve_lazy_kernel<2><<<grid, kResWarps * 32, smem, st>>>(ix, a);
-        } else if (ix.ex_bits == 6) {
-            RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            resolve_lazy_kernel<6><<<grid, kResWarps * 32, smem, st>>>(ix, a);
         } else {
             RBQ_CUDA(cudaFuncSetAttribute(resolve_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             resolve_lazy_kernel<1><<<grid, kResWarps * 32, smem, st>>>(ix, a);
@@ -988,9 +942,14 @@ int launch_ex_dot_debug(const DevIndex& ix, const float* d_rot, const unsigned l
     if (rc) return rc;
     ResolveArgs a;
     fill_args(a, ix, d_rot, nullptr, nullptr, nullptr, 1, 1, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr, tw);
-    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs);
-    RBQ_CUDA(cudaFuncSetAttribute(ex_dot_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.total));
-    ex_dot_debug_kernel<<<1, 32, w.total, st>>>(ix, a, d_gv, n, d_out);
+    const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, 1, true, false, 0, a.stage_bufs, refine_paired(ix));
+    if (refine_paired(ix)) {
+        RBQ_CUDA(cudaFuncSetAttribute(ex_dot_debug_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.total));
+        ex_dot_debug_kernel<true><<<1, 32, w.total, st>>>(ix, a, d_gv, n, d_out);
+    } else {
+        RBQ_CUDA(cudaFuncSetAttribute(ex_dot_debug_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.total));
+        ex_dot_debug_kernel<false><<<1, 32, w.total, st>>>(ix, a, d_gv, n, d_out);
+    }
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
 }

@@ -287,6 +287,190 @@ __device__ __forceinline__ float hsum8(float a) {
     return a;
 }
 
+// ---- eight-lane refine (one chain per lane, 4 candidates per round): used where the paired form's larger staging would cost
+// resident warps (padded_dim > 640)
+// rotated query in chain order: row j (stride rql_row bytes), position t = q[8t + j]; positions past D/8 are zero
+__device__ __forceinline__ void load_rql(unsigned char* rql, uint32_t rql_row, const float* __restrict__ rot, int D, uint32_t lane_bytes,
+                                         int lane) {
+    for (int i = lane; i < 8 * (int)lane_bytes; i += 32) {
+        const int j = i & 7, t = i >> 3;
+        reinterpret_cast<float*>(rql + (size_t)j * rql_row)[t] = i < D ? __ldg(rot + i) : 0.0f;
+    }
+}
+
+// K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's
+// ex-code dot in lane i.  Candidates are served 4 at a time by the four 8-lane groups (= the 8 AVX lanes): every lane
+// copies ITS chain's code row (DevIndex::exl) into its own shared-memory row with cp.async and multiplies it against
+// its query row -- no unpacking and no exchange between lanes.  With two staging buffers (stage_bufs == 2) the rows of
+// round r+1 travel while round r is multiplied; the default is one buffer (the candidates' rows were already pulled into
+// L2 when they were queued, and the smaller footprint lets more warps be resident, which measured faster).
+__device__ __forceinline__ float refine_batch(const DevIndex& ix, unsigned long long gv, int nb, uint32_t stage_u32, uint32_t rql_u32,
+                                              uint32_t exl_row, uint32_t rql_row, uint32_t stage_bufs, int lane) {
+    const int g = lane >> 3, j = lane & 7;
+    const uint32_t LB = ix.exl_lane;
+    const uint32_t my_row = (uint32_t)lane * exl_row, buf_bytes = 32u * exl_row;
+    const uint32_t qrow = rql_u32 + (uint32_t)j * rql_row;
+    auto issue = [&](int r0, uint32_t buf) {
+        const int c = r0 + g;
+        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
+        if (c < nb) {
+            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
+            const uint32_t dst = stage_u32 + buf * buf_bytes + my_row;
+            for (uint32_t p = 0; p < LB; p += 16) cp_async16(dst + p, src + p);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const bool dbl = stage_bufs > 1u;
+    issue(0, 0u);
+    float exdot = 0.0f;
+    uint32_t buf = 0;
+    for (int r0 = 0; r0 < nb; r0 += kRefineSlots) {
+        const int c = r0 + g;  // candidate served by this 8-lane group
+        if (dbl && r0 + kRefineSlots < nb) {
+            issue(r0 + kRefineSlots, buf ^ 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        float part = 0.0f;
+        if (c < nb) part = ex_dot_chain(stage_u32 + buf * buf_bytes + my_row, qrow, LB);
+        part = hsum8(part);
+        const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
+        if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
+        if (dbl) buf ^= 1u;
+        else if (r0 + kRefineSlots < nb) issue(r0 + kRefineSlots, 0u);  // the lane's own row is free again (only it reads it)
+    }
+    return exdot;
+}
+
+
+// ---- paired chains: one GPU lane runs TWO of the 8 AVX lanes (j and j + 4) with the packed FP32 instructions of sm_100
+// (add.rn.f32x2 / fma.rn.f32x2 = FADD2 / FFMA2: two IEEE operations per issue slot, each element rounded exactly like the scalar
+// instruction).  A candidate then needs 4 lanes instead of 8, a warp refines 8 candidates per round instead of 4, and the
+// byte->float subtraction and the fma cost one instruction per TWO codes: the refine loops are issue-bound, so this is where
+// their time goes.  The first step of the AVX2 horizontal sum (a_j + a_{j+4}) becomes an in-lane addition.
+constexpr int kRefineSlots2 = 8;  // candidates refined per round (8 x 4 lanes)
+// shared-memory strides (bytes): a lane's two staged code rows (row p at +0, row p + 4 at +exl_lane_bytes), and a pair-row of
+// the query (float2 (q[8t + p], q[8t + p + 4]) at index t); both 16 * odd, so 128-bit loads of consecutive lanes / the four
+// pair-rows fall on disjoint banks
+__host__ __device__ inline uint32_t exl2_lane_stride(uint32_t D) { return ((2u * exl_lane_bytes(D) / 16u) | 1u) * 16u; }
+__host__ __device__ inline uint32_t rql2_row_stride(uint32_t D) { return ((exl_lane_bytes(D) * 8u / 16u) | 1u) * 16u; }
+
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// rotated query in paired chain order: pair-row p (stride rql_row bytes), float2 t = (q[8t + p], q[8t + p + 4]); zero past D
+__device__ __forceinline__ void load_rql2(unsigned char* rql, uint32_t rql_row, const float* __restrict__ rot, int D, uint32_t lane_bytes,
+                                          int lane) {
+    for (int i = lane; i < 8 * (int)lane_bytes; i += 32) {
+        const int j = i & 7, t = i >> 3;
+        reinterpret_cast<float*>(rql + (size_t)(j & 3) * rql_row)[2 * t + (j >> 2)] = i < D ? __ldg(rot + i) : 0.0f;
+    }
+}
+// two chains: row0 / row1 = shared addresses of the code bytes of chains p and p + 4, qrow = the pair-row; returns a_p + a_{p+4}
+__device__ __forceinline__ float ex_dot_chain2(uint32_t row0, uint32_t row1, uint32_t qrow, uint32_t lane_bytes) {
+    unsigned long long acc = 0ull;  // (+0.0f, +0.0f)
+    const unsigned long long m23 = f32x2_pack(-8388608.0f, -8388608.0f);
+#pragma unroll 1
+    for (uint32_t t = 0; t < lane_bytes; t += 16) {
+        const uint4 w0 = lds128(row0 + t), w1 = lds128(row1 + t);
+        const uint32_t W0[4] = {w0.x, w0.y, w0.z, w0.w}, W1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 qa = lds128(qrow + 8u * t + 32u * (uint32_t)k), qb = lds128(qrow + 8u * t + 32u * (uint32_t)k + 16u);
+            // byte -> float without the conversion pipe: 0x4B0000xx is 2^23 + xx exactly, and the subtraction is exact
+            const unsigned long long c0 = f32x2_add(f32x2_pack(__uint_as_float(prmt(W0[k], 0x4B000000u, 0x7540u)), __uint_as_float(prmt(W1[k], 0x4B000000u, 0x7540u))), m23);
+            const unsigned long long c1 = f32x2_add(f32x2_pack(__uint_as_float(prmt(W0[k], 0x4B000000u, 0x7541u)), __uint_as_float(prmt(W1[k], 0x4B000000u, 0x7541u))), m23);
+            const unsigned long long c2 = f32x2_add(f32x2_pack(__uint_as_float(prmt(W0[k], 0x4B000000u, 0x7542u)), __uint_as_float(prmt(W1[k], 0x4B000000u, 0x7542u))), m23);
+            const unsigned long long c3 = f32x2_add(f32x2_pack(__uint_as_float(prmt(W0[k], 0x4B000000u, 0x7543u)), __uint_as_float(prmt(W1[k], 0x4B000000u, 0x7543u))), m23);
+            acc = f32x2_fma(c0, f32x2_pack(__uint_as_float(qa.x), __uint_as_float(qa.y)), acc);
+            acc = f32x2_fma(c1, f32x2_pack(__uint_as_float(qa.z), __uint_as_float(qa.w)), acc);
+            acc = f32x2_fma(c2, f32x2_pack(__uint_as_float(qb.x), __uint_as_float(qb.y)), acc);
+            acc = f32x2_fma(c3, f32x2_pack(__uint_as_float(qb.z), __uint_as_float(qb.w)), acc);
+        }
+    }
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+    return lo + hi;  // a_p + a_{p+4}: the first step of the AVX2 horizontal sum
+}
+// K10 for up to 32 candidates: lane i holds the global vector index of candidate i (i < nb); returns that candidate's ex-code
+// dot in lane i.  Candidates are served 8 at a time by the eight 4-lane groups: every lane copies ITS two chains' code rows
+// (DevIndex::exl rows p and p + 4) into its own shared-memory region with cp.async and multiplies them against its query
+// pair-row -- no unpacking and no exchange between lanes; the remaining two steps of the AVX2 horizontal sum
+// ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)) are two shuffles.  stage_bufs == 2: the rows of round r+1 travel while round r is multiplied.
+__device__ __forceinline__ float refine_batch2(const DevIndex& ix, unsigned long long gv, int nb, uint32_t stage_u32, uint32_t rql_u32,
+                                               uint32_t lane_stride, uint32_t rql_row, uint32_t stage_bufs, int lane) {
+    const int g = lane >> 2, p = lane & 3;
+    const uint32_t LB = ix.exl_lane;
+    const uint32_t my = (uint32_t)lane * lane_stride, buf_bytes = 32u * lane_stride;
+    const uint32_t qrow = rql_u32 + (uint32_t)p * rql_row;
+    auto issue = [&](int r0, uint32_t buf) {
+        const int c = r0 + g;
+        const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
+        if (c < nb) {
+            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)p * LB;
+            const uint32_t dst = stage_u32 + buf * buf_bytes + my;
+            for (uint32_t o = 0; o < LB; o += 16) {
+                cp_async16(dst + o, src + o);
+                cp_async16(dst + LB + o, src + 4u * LB + o);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const bool dbl = stage_bufs > 1u;
+    issue(0, 0u);
+    float exdot = 0.0f;
+    uint32_t buf = 0;
+    for (int r0 = 0; r0 < nb; r0 += kRefineSlots2) {
+        const int c = r0 + g;  // candidate served by this 4-lane group
+        if (dbl && r0 + kRefineSlots2 < nb) {
+            issue(r0 + kRefineSlots2, buf ^ 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        float part = 0.0f;
+        if (c < nb) {
+            const uint32_t row = stage_u32 + buf * buf_bytes + my;
+            part = ex_dot_chain2(row, row + LB, qrow, LB);
+        }
+        part = part + __shfl_xor_sync(0xffffffffu, part, 2);
+        part = part + __shfl_xor_sync(0xffffffffu, part, 1);
+        const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 7) * 4);
+        if (lane >= r0 && lane < r0 + kRefineSlots2) exdot = v;
+        if (dbl) buf ^= 1u;
+        else if (r0 + kRefineSlots2 < nb) issue(r0 + kRefineSlots2, 0u);  // the lane's own region is free again (only it reads it)
+    }
+    return exdot;
+}
+
+// PAIRED selects the form at compile time (the kernels are instantiated for both; the host picks by padded_dim)
+__host__ __device__ inline bool refine_paired_for(uint32_t D) { return D <= 640u; }
+template <bool PAIRED>
+__device__ __forceinline__ void load_rql_any(unsigned char* rql, uint32_t rql_row, const float* __restrict__ rot, int D, uint32_t lane_bytes, int lane) {
+    if (PAIRED) load_rql2(rql, rql_row, rot, D, lane_bytes, lane);
+    else load_rql(rql, rql_row, rot, D, lane_bytes, lane);
+}
+template <bool PAIRED>
+__device__ __forceinline__ float refine_batch_any(const DevIndex& ix, unsigned long long gv, int nb, uint32_t stage_u32, uint32_t rql_u32,
+                                                  uint32_t exl_row, uint32_t rql_row, uint32_t stage_bufs, int lane) {
+    if (PAIRED) return refine_batch2(ix, gv, nb, stage_u32, rql_u32, exl_row, rql_row, stage_bufs, lane);
+    return refine_batch(ix, gv, nb, stage_u32, rql_u32, exl_row, rql_row, stage_bufs, lane);
+}
+
+
 // ---- K11: warp-cooperative insertion into an ascending list of at most k (distance, id) pairs -----
 // Equal distances keep the earlier-visited entry first (and drop the newcomer at the boundary).
 __device__ __forceinline__ void topk_insert(float* sd, unsigned long long* si, int& cnt, int k, float d,

@@ -136,7 +136,9 @@ __device__ int g_tt_variant;  // timing experiments (results become wrong): bit 
 #define TT_VARIANT(bit) 0
 #endif
 
-template <bool WIDE, int PD>
+// FULLK: the codebook count is a multiple of 8 (padded_dim % 32 == 0), so no K-chunk is partial and the producers skip the
+// per-codebook "does it exist" selects
+template <bool WIDE, int PD, bool FULLK>
 __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(DevIndex ix, TailArgs a) {
     using namespace tt;
 #ifdef RBQ_TT_PROBE
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(tt::THREADS, tt::CTAS_PER_SM) tail_tc_kernel(D
                         // bit position of the 1 inside the codebook's 128-bit one-hot: 8 * nibble = (W ror (shift - 3)) & 0x78;
                         // past the last codebook: no bit at all
                         uint32_t pos = __funnelshift_r(W[c], W[c], nib_rot) & 0x78u;
-                        if ((uint32_t)c >= live) pos = 0xffffff00u;
+                        if (!FULLK && (uint32_t)c >= live) pos = 0xffffff00u;
                         r[4 * c + 0] = onehot32(pos);
                         r[4 * c + 1] = onehot32(pos - 32u);
                         r[4 * c + 2] = onehot32(pos - 64u);
@@ -498,17 +500,17 @@ bool tail_tc_supported(const DevIndex& ix) {
     return !off && ix.D % 16 == 0;
 }
 
-template <bool WIDE, int PD>
-static int launch_tail_tc_ex(const DevIndex& ix, const TailArgs& a, int sms, cudaStream_t st) {
+template <bool WIDE, int PD, bool FULLK>
+static int launch_tail_tc_k(const DevIndex& ix, const TailArgs& a, int sms, cudaStream_t st) {
     const size_t smem = tt::smem_bytes(PD);
-    RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<WIDE, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RBQ_CUDA(cudaFuncSetAttribute(tail_tc_kernel<WIDE, PD, FULLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifdef RBQ_TT_PROBE
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_tt_probe, z, sizeof(z));
     const int variant = getenv("RBQ_TT_VARIANT") ? atoi(getenv("RBQ_TT_VARIANT")) : 0;
     cudaMemcpyToSymbol(g_tt_variant, &variant, sizeof(variant));
 #endif
-    tail_tc_kernel<WIDE, PD><<<tt::CTAS_PER_SM * sms, tt::THREADS, smem, st>>>(ix, a);
+    tail_tc_kernel<WIDE, PD, FULLK><<<tt::CTAS_PER_SM * sms, tt::THREADS, smem, st>>>(ix, a);
     RBQ_CUDA(cudaGetLastError());
 #ifdef RBQ_TT_PROBE
     cudaStreamSynchronize(st);
@@ -519,6 +521,11 @@ static int launch_tail_tc_ex(const DevIndex& ix, const TailArgs& a, int sms, cud
     fprintf(stderr, "[tt probe]   prefetch issue %.0f, syncwarp %.0f\n", z[11] / nc, z[12] / nc);
 #endif
     return RBQ_OK;
+}
+
+template <bool WIDE, int PD>
+static int launch_tail_tc_ex(const DevIndex& ix, const TailArgs& a, int sms, cudaStream_t st) {
+    return ix.D % 32 == 0 ? launch_tail_tc_k<WIDE, PD, true>(ix, a, sms, st) : launch_tail_tc_k<WIDE, PD, false>(ix, a, sms, st);
 }
 
 int launch_tail_tc(const DevIndex& ix, const TailArgs& a, cudaStream_t st) {
