@@ -75,6 +75,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
+// one leader lane of the (converged) warp; unlike `lane == 0` the compiler keeps the guarded code on the uniform path
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
 // A,B K-major, N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
@@ -179,33 +191,41 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int t = t_begin; t < t_end; t += t_step) {
-                int m_blk, n_blk;
-                tile_mn(t, m_blk, n_blk);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES;
-                    bar_wait(empty0 + 8 * s, ((it / STAGES) & 1u) ^ 1u);
+        // ===== TMA producer: the warp walks the loop, one elected lane issues (operands stay in uniform registers) =====
+        uint32_t it = 0;
+        for (int t = t_begin; t < t_end; t += t_step) {
+            int m_blk, n_blk;
+            tile_mn(t, m_blk, n_blk);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % STAGES;
+                bar_wait(empty0 + 8 * s, ((it / STAGES) & 1u) ^ 1u);
+                if (elect_one()) {
                     bar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
                     tma_load_2d(s_u32(sA + (size_t)s * A_BYTES), &map_a, full0 + 8 * s, kb * BK, m_blk * BM);
                     tma_load_2d(s_u32(sB + (size_t)s * B_BYTES), &map_b, full0 + 8 * s, kb * BK, n_blk * BN);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer (one thread) =====
-            constexpr uint32_t idesc = umma_idesc(BM, BN);
-            uint32_t it = 0, ti = 0;
-            for (int t = t_begin; t < t_end; t += t_step, ++ti) {
-                const uint32_t buf = ti & 1u;
-                bar_wait(tempty0 + 8 * buf, ((ti >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer (free at first use)
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+        // tcgen05.mma takes its operands from uniform registers.  Behind `lane == 0`, with the TMEM base loaded from shared memory,
+        // the compiler wraps every MMA in an ELECT + R2UR sequence (~13 instructions, ~190 clk per MMA for one thread -- more than
+        // the 128 clk a 128x256x16 MMA occupies the tensor pipe).  A warp-wide OR of the (identical) base is uniform by construction
+        // and elect.sync keeps the branch on the uniform path: the MMAs of a k-block then issue back to back.
+        constexpr uint32_t idesc = umma_idesc(BM, BN);
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+        uint32_t it = 0, ti = 0;
+        for (int t = t_begin; t < t_end; t += t_step, ++ti) {
+            const uint32_t buf = ti & 1u;
+            bar_wait(tempty0 + 8 * buf, ((ti >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer (free at first use)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc_addr = tmem_u + buf * (uint32_t)BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % STAGES;
+                bar_wait(full0 + 8 * s, (it / STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc_addr = tmem + buf * (uint32_t)BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES;
-                    bar_wait(full0 + 8 * s, (it / STAGES) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
                     const uint64_t da = umma_desc(s_u32(sA + (size_t)s * A_BYTES));
                     const uint64_t db = umma_desc(s_u32(sB + (size_t)s * B_BYTES));
 #pragma unroll
@@ -224,9 +244,11 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
                     // frees the smem stage once the MMAs above have read it (implies fence::before_thread_sync)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s)
                                  : "memory");
+                    if (kb + 1 == num_kb)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull0 + 8 * buf)
+                                     : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull0 + 8 * buf)
-                             : "memory");
+                __syncwarp();
             }
         }
     } else {
