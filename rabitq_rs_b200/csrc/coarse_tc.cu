@@ -36,9 +36,6 @@ __host__ __device__ constexpr int threads(int mode) { return (2 + epi_warps(mode
 constexpr int ACC_BUFS = 2;           // accumulator buffers in tensor memory: the epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int TMEM_COLS = ACC_BUFS * BN;  // 512 = the whole tensor memory of the SM (one CTA per SM: 193 KB of shared memory)
 constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-// filter drain: hits of one (row, column part) staged in shared memory (slot-major: no bank conflicts), flushed with ONE counter
-// bump per tile (or when the next HIT_SLOTS columns might not fit): 32 / PARTS slots of (float score, u8 column) per thread
-constexpr size_t SMEM_HITS = (size_t)32 * BM * 5;
 }  // namespace tc
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,7 +127,7 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
     coarse_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmEpi e, int num_kb,
                        int mtiles, int ntiles) {
     using namespace tc;
-    constexpr int EPI_WARPS = epi_warps(MODE), PARTS = EPI_WARPS / 4, PART_COLS = BN / PARTS, HIT_SLOTS = 32 / PARTS;
+    constexpr int EPI_WARPS = epi_warps(MODE), PARTS = EPI_WARPS / 4, PART_COLS = BN / PARTS;
     extern __shared__ unsigned char gsm_raw[];
     unsigned char* gsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = gsm;
@@ -138,8 +135,6 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) accumulator buffer full, [2S+2..2S+4) accumulator buffer drained; then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_BUFS);
-    float* hit_score = reinterpret_cast<float*>(gsm + (size_t)STAGES * (A_BYTES + B_BYTES) + 256);  // kGemmFilter only: [HIT_SLOTS][PARTS * BM]
-    uint8_t* hit_col = reinterpret_cast<uint8_t*>(hit_score + HIT_SLOTS * BM * PARTS);                 //                  [HIT_SLOTS][PARTS * BM]
     const uint32_t full0 = s_u32(bars), empty0 = s_u32(bars + STAGES), tfull0 = s_u32(bars + 2 * STAGES),
                    tempty0 = s_u32(bars + 2 * STAGES + ACC_BUFS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,19 +272,6 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
                 best_m = m_blk;
                 best = ~0ull;
             }
-            uint32_t nhit = 0;  // kGemmFilter: staged centroids of this tile that beat the row's threshold
-            const int erow = half * BM + quarter * 32 + lane;  // staging column of this thread
-            // staged hits -> the row's candidate list: one bump of its global counter, then plain stores
-            auto flush_hits = [&]() {
-                if (nhit) {
-                    const uint32_t base = atomicAdd(e.cand_cnt + row, nhit);
-                    for (uint32_t k = 0; k < nhit; ++k)
-                        if (base + k < e.cap)
-                            e.cand[(size_t)row * e.cap + base + k] =
-                                CandRec{hit_score[k * PARTS * BM + erow], (uint32_t)(n_blk * BN) + hit_col[k * PARTS * BM + erow]};
-                    nhit = 0;
-                }
-            };
             bar_wait(tfull0 + 8 * buf, (ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ncols_tile = min(BN, e.ncols - n_blk * BN);  // columns of this tile that exist
@@ -349,19 +331,38 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) mask |= (uint32_t)(l2 ? sc[j] <= thr : sc[j] >= thr) << j;
                         if (lim < 32) mask &= (1u << lim) - 1u;
-                        if (mask) {  // rare per thread on large centroid tables: a few hundred hits per row over the whole table
+                        if (mask) {
+                            // One bump of the row's counter for all hits of the group, then straight-line predicated stores in
+                            // column order.  (The first version staged single hits in shared memory behind a branch per column:
+                            // with ~1 % of the scores passing, SOME lane of a warp has a hit in nearly every group, so every warp
+                            // walked all 32 branches -- 18 instructions per score, and the drain, not the tensor pipe, set the
+                            // kernel's time on the 16 384 / 65 536-list tables.  A two-pass variant -- masks first, one bump per
+                            // tile, scores re-read from tensor memory -- measured slower: more instructions.)
+                            const uint32_t n = (uint32_t)__popc(mask);
+                            const uint32_t base = atomicAdd(e.cand_cnt + row, n);
+                            if (base + n <= e.cap) {
+                                unsigned long long addr = reinterpret_cast<unsigned long long>(e.cand + (size_t)row * e.cap + base);
 #pragma unroll
-                            for (int hh = 0; hh < 32 / HIT_SLOTS; ++hh) {  // HIT_SLOTS columns at a time: always fit the staging after a flush
-                                const uint32_t mh = (mask >> (HIT_SLOTS * hh)) & ((1u << HIT_SLOTS) - 1u);
-                                if (mh) {
-                                    if (nhit + (uint32_t)__popc(mh) > (uint32_t)HIT_SLOTS) flush_hits();
-#pragma unroll
-                                    for (int j = 0; j < HIT_SLOTS; ++j)
-                                        if ((mh >> j) & 1u) {
-                                            hit_score[nhit * PARTS * BM + erow] = sc[HIT_SLOTS * hh + j];
-                                            hit_col[nhit * PARTS * BM + erow] = (uint8_t)(c0 + HIT_SLOTS * hh + j);
-                                            ++nhit;
-                                        }
+                                for (int j = 0; j < 32; ++j) {
+                                    const uint32_t hit = (mask >> j) & 1u;
+                                    asm volatile(
+                                        "{\n"
+                                        ".reg .pred p;\n"
+                                        "setp.ne.u32 p, %0, 0;\n"
+                                        "@p st.global.v2.b32 [%1], {%2, %3};\n"
+                                        "}" ::"r"(hit),
+                                        "l"(addr), "r"(__float_as_uint(sc[j])), "r"((uint32_t)(n0 + j))
+                                        : "memory");
+                                    addr += 8ull * hit;
+                                }
+                            } else {  // the list overflows (the query takes the exact fallback): keep what fits
+                                const uint32_t room = base < e.cap ? e.cap - base : 0u;
+                                CandRec* out = e.cand + (size_t)row * e.cap + base;
+                                uint32_t w = 0;
+                                for (int j = 0; j < 32; ++j) {
+                                    const bool hit = (mask >> j) & 1u;
+                                    if (hit && w < room) out[w] = CandRec{sc[j], (uint32_t)(n0 + j)};
+                                    w += hit ? 1u : 0u;
                                 }
                             }
                         }
@@ -409,7 +410,6 @@ __global__ void __launch_bounds__(tc::threads(MODE), 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty0 + 8 * buf);
-            if (MODE == kGemmFilter) flush_hits();
         }
         if (MODE == kGemmArgmin) flush_best();
     }
@@ -513,7 +513,7 @@ static int gemm_sms() {
 
 template <int MODE>
 static int launch_gemm_mode(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, int num_kb, int mtiles, int ntiles, cudaStream_t st) {
-    const size_t smem = tc::SMEM + (MODE == kGemmFilter ? tc::SMEM_HITS : 0);
+    const size_t smem = tc::SMEM;
     RBQ_CUDA(cudaFuncSetAttribute(coarse_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (long long)mtiles * ntiles;
     const int grid = (int)std::min<long long>(total, gemm_sms());
