@@ -740,7 +740,10 @@ def main():
         if src is not None:
             qps, cores, sample, res, _ = oracle_baseline(src[0], src[1], k, nprobe, log=log, max_sample=src[3])
             same = float(np.mean(res[0][:, :k] == final_ids[:sample, :k]))
-            same_x = f" (exact-merge mode: {float(np.mean(res[0][:, :k] == x_ids[:sample, :k])):.4f})" if x_ids is not None else ""
+            same_x = ""
+            if x_ids is not None:  # position-wise, and as per-query id sets (the order inside runs of bit-equal distances is class D1)
+                sets_eq = float(np.mean(np.sort(res[0][:, :k], 1) == np.sort(x_ids[:sample, :k], 1)))
+                same_x = f" (exact-merge mode: {float(np.mean(res[0][:, :k] == x_ids[:sample, :k])):.4f} position-wise, {sets_eq:.4f} as id sets)"
             out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                    "sample": f"first {sample} of the {nq} queries, same index bytes"
                                              + (f" (the {src[2]} lists those queries probe)" if src[2] != wl["nlist"] else "")

@@ -51,12 +51,12 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(kMbarSuspendHintNs)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -14,6 +14,10 @@ struct rbq_index;
 namespace rbq {
 
 constexpr int kBatch = 32;  // FASTSCAN_BATCH_SIZE (reference src/simd.rs:768)
+// suspend-time hint of mbarrier.try_wait (ns): the hardware may park the waiting thread until the phase completes or the hint
+// expires, so a waiting warp re-issues the instruction far less often.  Without a hint a spinning warp (the MMA issuers of the
+// tail kernel spend most of their time waiting) costs ~3 issue slots every ~60 clk: 19 % of that kernel's instructions.
+constexpr uint32_t kMbarSuspendHintNs = 0x989680u;
 constexpr int kMaxShards = 32;  // list_owner is one byte per list; the device merge walks one sorted list per lane
 
 // ---- error plumbing -------------------------------------------------------------------------

@@ -83,12 +83,12 @@ __device__ __forceinline__ void tt_bar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "TT_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra TT_DONE;\n"
         "bra TT_WAIT;\n"
         "TT_DONE:\n"
         "}" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(kMbarSuspendHintNs)
         : "memory");
 }
 // 1 << pos for pos in [0, 32), 0 otherwise (pos is taken as unsigned, so "negative" positions give 0)
