@@ -391,6 +391,27 @@ struct HostFeed {
     }
 };
 
+// The queries the head pass could not take (nearest list longer than the dense buffer, heap not full after it) are known once
+// the head kernels are enqueued; their sequential walk is one query's latency chain (~0.6 ms at 100M x 128) that nothing else
+// depends on, so it runs on a side stream beside the tail and replay kernels and is joined before the call's last kernel.
+int side_fork(const rbq_index* h, cudaStream_t st) {
+    if (!h->side_stream) {
+        int lo = 0, hi = 0;  // highest priority: its few CTAs must become resident before the persistent tail / replay grids fill the SMs
+        RBQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        RBQ_CUDA(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi));
+        RBQ_CUDA(cudaEventCreateWithFlags(&h->side_fork, cudaEventDisableTiming));
+        RBQ_CUDA(cudaEventCreateWithFlags(&h->side_join, cudaEventDisableTiming));
+    }
+    RBQ_CUDA(cudaEventRecord(h->side_fork, st));
+    RBQ_CUDA(cudaStreamWaitEvent(h->side_stream, h->side_fork, 0));
+    return RBQ_OK;
+}
+int side_join(const rbq_index* h, cudaStream_t st) {
+    RBQ_CUDA(cudaEventRecord(h->side_join, h->side_stream));
+    RBQ_CUDA(cudaStreamWaitEvent(st, h->side_join, 0));
+    return RBQ_OK;
+}
+
 // The pipeline on device buffers for one call (tiles internally).  d_filter may be null.
 int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t top_k, size_t nprobe,
                   const uint64_t* d_filter, size_t filter_nbits, uint64_t* d_ids, float* d_scores, uint32_t* d_counts,
@@ -454,19 +475,26 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
             }
         } else {
             if (h->profiling) cudaEventRecord(h->ev[4], st);
+            // the head pass' fallback queries: sequential walk on the side stream (normally an empty launch)
+            if ((rc = side_fork(h, st))) return rc;
+            if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallback, &tw, h->side_stream)))
+                return rc;
             // tail: all remaining (query, list) pairs grouped by list -> survivors
             if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, n, nprobe, d_filter, filter_nbits, h->d_stats, tw, st, launches,
                                   h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
                 return rc;
             if (h->profiling) cudaEventRecord(h->ev[5], st);
-            // ordered replay of the survivors with refinement on demand, then the (normally empty) sequential fallback
+            // ordered replay of the survivors with refinement on demand (+ the overflow tier), then the queries the replay tiers
+            // handed back (normally none), sequentially
             if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, n, nprobe, top_k, d_ids + q0 * top_k, d_scores + q0 * top_k,
                                            d_counts + q0, h->d_stats, tw, st, launches)))
                 return rc;
             if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallback, &tw, st)))
+                                  d_scores + q0 * top_k, d_counts + q0, h->d_stats, h->work_counter(), kScanFallbackResume, &tw, st)))
                 return rc;
-            *launches += 1;
+            if ((rc = side_join(h, st))) return rc;
+            *launches += 2;
             if (h->profiling) cudaEventRecord(h->ev[6], st);
         }
         if (h->profiling) {
@@ -593,6 +621,9 @@ void rbq_index_free(rbq_index* h) {
         if (h->xr_ws) cudaFree(h->xr_ws);
         if (h->xr_recs) cudaFree(h->xr_recs);
         if (h->xr_host) cudaFreeHost(h->xr_host);
+        if (h->side_stream) cudaStreamDestroy(h->side_stream);
+        if (h->side_fork) cudaEventDestroy(h->side_fork);
+        if (h->side_join) cudaEventDestroy(h->side_join);
         if (h->busy_ev) cudaEventDestroy(h->busy_ev);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
@@ -980,6 +1011,11 @@ int dist_tail_impl(const rbq_index* h, const Plan& pl, size_t nq, size_t top_k, 
     uint64_t launches = h->last_stats.kernel_launches;
     if (h->profiling) cudaEventRecord(h->ev[5], st);
     RBQ_CUDA(cudaMemcpyAsync(L.tw.tau, d_tau, nq * 4, cudaMemcpyDeviceToDevice, st));
+    // the head pass' fallback queries (this shard's): sequential walk on the side stream, beside the tail and replay kernels
+    if ((rc = side_fork(h, st))) return rc;
+    if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats,
+                          h->work_counter(), kScanFallback, &L.tw, h->side_stream)))
+        return rc;
     if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, st, &launches,
                           h->profiling ? h->ev[7] : nullptr, h->profiling ? h->ev[8] : nullptr)))
         return rc;
@@ -987,11 +1023,12 @@ int dist_tail_impl(const rbq_index* h, const Plan& pl, size_t nq, size_t top_k, 
     if ((rc = launch_refine_replay(ix, L.d_rot, L.d_qs, L.d_pr, nq, nprobe, top_k, d_ids, d_scores, d_counts, h->d_stats, L.tw, st, &launches)))
         return rc;
     if ((rc = launch_scan(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, h->d_stats,
-                          h->work_counter(), kScanFallback, &L.tw, st)))
+                          h->work_counter(), kScanFallbackResume, &L.tw, st)))
         return rc;
+    if ((rc = side_join(h, st))) return rc;
     if (h->profiling) cudaEventRecord(h->ev[6], st);
     h->dist_phase = h->profiling ? 3 : 0;
-    h->last_stats.kernel_launches = launches + 2;
+    h->last_stats.kernel_launches = launches + 3;
     return RBQ_OK;
 }
 }  // namespace
@@ -1489,7 +1526,7 @@ int rbq_debug_stage(const rbq_index* h, int which, const float* queries, size_t 
         return RBQ_OK;
     }
     // tail over every pair, threshold +inf
-    if (cap > L.tw.surv_cap) return fail(RBQ_INVALID_CONFIG, "cap exceeds the survivor buffer (1024)");
+    if (cap > L.tw.surv_cap) return fail(RBQ_INVALID_CONFIG, "cap exceeds the survivor buffer");
     if ((rc = launch_fill_u32(L.tw.tail_start, nq, 0u, nullptr))) return rc;
     if ((rc = launch_fill_u32(reinterpret_cast<uint32_t*>(L.tw.tau), nq, 0x7f800000u, nullptr))) return rc;
     if ((rc = launch_tail(ix, L.d_lut, L.d_qs, L.d_pr, nq, nprobe, nullptr, 0, h->d_stats, L.tw, nullptr, &launches))) return rc;

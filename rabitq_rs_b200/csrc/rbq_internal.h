@@ -106,7 +106,8 @@ struct Probe {  // one per (query, probe rank), written by the probe kernel (32 
     uint64_t vec_off;   // first vector of the list
 };
 // TailWs::counters: slots 0..7 belong to the tail / replay kernels, then one work cursor per head-stage launch of a call
-constexpr uint32_t kTailCounters = 8, kHeadCursors = 32;
+constexpr uint32_t kTailCounters = 12, kHeadCursors = 32;
+constexpr uint32_t kOvfCtas = 160;  // CTAs of the overflow tier (>= one per SM), each with 4096 x 24 B of record scratch
 struct DevStats {
     unsigned long long blocks, candidates, refined, admitted;
     // list-major tail stage (scan_tail.cu)
@@ -128,13 +129,19 @@ struct TailItem {  // work item of the tail kernel: a chunk of the (query, rank)
 };
 // kScanFallback: the queries listed in TailWs::fb_list (bit 31 clear: the whole probe sequence from scratch; bit 31 set:
 // resume from the head state at tail_start and walk the rest sequentially).
-enum ScanMode { kScanFull = 0, kScanHead = 1, kScanReplay = 2, kScanFallback = 3 };
+enum ScanMode { kScanFull = 0, kScanHead = 1, kScanReplay = 2, kScanFallback = 3, kScanFallbackResume = 4 };
+// kScanFallback walks TailWs::fb_list (queries the head pass could not take: from scratch; known after the head pass, so the
+// launch runs on a side stream beside the tail and replay kernels); kScanFallbackResume walks TailWs::fb2_list (queries the
+// replay tiers handed back: resume from the head state), after the replay.
 struct TailWs {  // device workspace of the head/tail/replay pipeline (per query tile)
     uint32_t* tail_start;  // [nq] first probe rank left to the tail stage (== nprobe: none)
     float* tau;            // [nq] k-th distance after the head stage (INF if the heap is not full)
     uint32_t* surv_cnt;    // [nq]
     Survivor* surv;        // [nq * surv_cap]
-    uint32_t surv_cap;
+    uint32_t surv_cap;     // slots per query (buffer stride)
+    uint32_t sort_cap;     // survivors the lazy replay sorts in shared memory; queries with sort_cap < n <= surv_cap take the overflow tier
+    uint32_t* ovf_list;    // [nq] queries of the overflow tier (counters[7] = how many, counters[8] = its work cursor)
+    void* ovf_recs;        // [kOvfCtas * 4096] XrRec: per-CTA record scratch of the overflow tier
     uint32_t* list_cnt;    // [nlist] pairs per list      } zeroed together with surv_cnt and the counters
     uint32_t* list_fill;   // [nlist] scatter cursors     }
     uint32_t* list_off;    // [nlist + 1]
@@ -148,13 +155,15 @@ struct TailWs {  // device workspace of the head/tail/replay pipeline (per query
     float2* head_buf;      // [head_rows * head_cap]: row (q - first query of the head sub-chunk)
     uint32_t head_cap;     // slots per query (multiple of 32); longer lists send the query to the fallback path
     uint32_t head_rows;    // queries per head sub-chunk
-    uint32_t* fb_list;     // [nq] queries left to the sequential fallback (counters[2] = how many)
+    uint32_t* fb_list;     // [nq] queries left to the sequential fallback by the head pass (counters[2] = how many, counters[6] = cursor)
+    uint32_t* fb2_list;    // [nq] queries handed back by the replay tiers, resume entries (counters[9] = how many, counters[10] = cursor)
     uint32_t* qlist;       // [nq] phased search: queries whose head pass runs on this shard, compacted; qcount = how many
     uint32_t* qcount;
 };
 constexpr uint32_t kFbResume = 0x80000000u;
 // counters[]: [0] tail items, [1] tail item cursor, [2] fallback queries, [3] head-resolve cursor, [4] refine cursor,
-// [5] replay cursor, [6] fallback cursor
+// [5] replay cursor, [6] fallback cursor, [7] overflow-tier queries, [8] overflow-tier cursor, [9] resume-fallback queries,
+// [10] resume-fallback cursor
 
 // arguments of the tail kernels (scan_tail.cu: PRMT lookups; tail_tc.cu: one-hot GEMM on the tensor cores)
 struct TailArgs {
@@ -349,5 +358,7 @@ struct rbq_index {
     mutable size_t xr_recs_bytes = 0;
     mutable unsigned long long* xr_host = nullptr;  // pinned: per-peer record counts read back once per call
     mutable unsigned long long* xr_inexact = nullptr;  // device counter behind last_stats.inexact_queries (inside xr_ws)
+    mutable cudaStream_t side_stream = nullptr;  // the head pass' sequential fallback runs here, beside the tail and replay kernels
+    mutable cudaEvent_t side_fork = nullptr, side_join = nullptr;
     mutable cudaEvent_t busy_ev = nullptr;  // recorded after the last kernel of every call: the next call's stream waits on it
 };

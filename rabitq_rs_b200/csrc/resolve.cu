@@ -45,10 +45,14 @@ struct ResolveArgs {
     uint32_t head_cap;
     uint32_t* tail_start;
     float* tau;
-    uint32_t* fb_list;
+    uint32_t* fb_list;   // head pass: queries it cannot take (from scratch)
+    uint32_t* fb2_list;  // replay tiers: queries handed back (resume entries)
     Survivor* surv;
     const uint32_t* surv_cnt;
-    uint32_t surv_cap;
+    uint32_t surv_cap;   // slots per query in the survivor buffer
+    uint32_t sort_cap;   // survivors the lazy replay sorts per query; sort_cap < n <= surv_cap: overflow tier
+    uint32_t* ovf_list;  // queries handed to the overflow tier (counters[7] entries)
+    XrRec* ovf_recs;     // overflow tier scratch: kOvfMaxRecs records per CTA
     uint32_t exl_row;   // shared-memory stride of a lane's two staged code rows (exl2_lane_stride)
     uint32_t rql_row;   // shared-memory stride of a query pair-row (rql2_row_stride)
     uint32_t stage_bufs;  // 2: the rows of round r+1 travel while round r is multiplied; 1: one round at a time, less shared memory
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(0, 0, k, false, true, a.surv_cap);
+    const ResSmem L = res_smem_layout(0, 0, k, false, true, a.sort_cap);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(wbase + L.si);
     float* sd = reinterpret_cast<float*>(wbase + L.sd);
@@ -384,8 +388,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
         if (q >= a.nq) break;
         const uint32_t start_pi = a.tail_start[q], n_surv = a.surv_cnt[q];
         if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
-        if (n_surv > a.surv_cap) {                           // survivor buffer overflowed: the sequential kernel re-walks the tail
-            if (lane == 0) a.fb_list[atomicAdd(&a.counters[2], 1u)] = q | kFbResume;
+        if (n_surv > a.sort_cap) {  // more than this kernel sorts: the overflow tier replays it; beyond the buffer: sequential re-walk of the tail
+            if (lane == 0) {
+                if (n_surv <= a.surv_cap) a.ovf_list[atomicAdd(&a.counters[7], 1u)] = q;
+                else a.fb2_list[atomicAdd(&a.counters[9], 1u)] = q | kFbResume;
+            }
             st_ovf += 1;
             continue;
         }
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;
-    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.surv_cap, a.stage_bufs, EXK == 2);
+    const ResSmem L = res_smem_layout(a.exl_row, a.rql_row, k, true, true, a.sort_cap, a.stage_bufs, EXK == 2);
     unsigned char* wbase = res_smem + (size_t)warp * L.total;
     const uint32_t stage_u32 = smem_u32(wbase + L.stage), rql_u32 = smem_u32(wbase + L.rq);
     unsigned char* rql = wbase + L.rq;
@@ -486,8 +493,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         if (q >= a.nq) break;
         const uint32_t start_pi = a.tail_start[q], n_surv = a.surv_cnt[q];
         if (start_pi >= a.nprobe || n_surv == 0) continue;  // the head result is already final
-        if (n_surv > a.surv_cap) {                           // survivor buffer overflowed: the sequential kernel re-walks the tail
-            if (lane == 0) a.fb_list[atomicAdd(&a.counters[2], 1u)] = q | kFbResume;
+        if (n_surv > a.sort_cap) {  // more than this kernel sorts: the overflow tier replays it; beyond the buffer: sequential re-walk of the tail
+            if (lane == 0) {
+                if (n_surv <= a.surv_cap) a.ovf_list[atomicAdd(&a.counters[7], 1u)] = q;
+                else a.fb2_list[atomicAdd(&a.counters[9], 1u)] = q | kFbResume;
+            }
             st_ovf += 1;
             continue;
         }
@@ -633,6 +643,189 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex i
         if (st_adm) atomicAdd(&a.stats->admitted, st_adm);
         if (st_ref) atomicAdd(&a.stats->refined, st_ref);
         if (st_ovf) atomicAdd(&a.stats->overflow_queries, st_ovf);
+    }
+}
+
+// ---- overflow tier: queries with more survivors than the lazy replay sorts (sort_cap < n <= surv_cap) -------------------
+// Such a query sits where the head threshold is loose (its nearest list is tiny, or -- phased multi-GPU search -- another
+// shard's): nearly every vector of its other lists survives.  The sequential kernel needs ~0.6 ms for one of them, a latency
+// chain that does not shrink with the number of GPUs.  Here one CTA takes the query: all survivors are refined EAGERLY by the
+// CTA's warps (independent, 8 or 4 candidates per warp and round), {visit key, lower bound, distance, id} records go to a
+// per-CTA scratch, the keys are bitonic-sorted in shared memory, and one warp replays the records in the reference's visit
+// order against the live threshold -- the same decisions as the lazy replay (src/ivf.rs:2044-2127), the distance of a
+// candidate does not depend on when it is computed.
+constexpr int kOvfWarps = 8;
+constexpr uint32_t kOvfMaxRecs = 4096;  // == the survivor buffer's slots per query at the default caps
+struct OvfSmem {
+    uint32_t keys, idx, warp0, warp_stride, si, sd, total;
+};
+__host__ __device__ inline OvfSmem ovf_smem_layout(uint32_t exl_row, uint32_t rql_row, uint32_t k, bool refine, bool paired, uint32_t stage_bufs) {
+    OvfSmem w;
+    uint32_t o = 0;
+    w.keys = o;
+    o += kOvfMaxRecs * 8u;
+    w.idx = o;
+    o += kOvfMaxRecs * 4u;
+    w.warp0 = o;
+    w.warp_stride = refine ? stage_bufs * 32u * exl_row + (paired ? 4u : 8u) * rql_row : 0u;
+    o += (uint32_t)kOvfWarps * w.warp_stride;
+    w.si = o;
+    o += ((k * 8 + 15) / 16) * 16;
+    w.sd = o;
+    o += ((k * 4 + 15) / 16) * 16;
+    w.total = o;
+    return w;
+}
+
+template <int EXK>
+__global__ void __launch_bounds__(kOvfWarps * 32) overflow_replay_kernel(DevIndex ix, ResolveArgs a) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    __shared__ uint32_t s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = ix.D, k = (int)a.top_k;
+    const OvfSmem L = ovf_smem_layout(a.exl_row, a.rql_row, a.top_k, EXK != 0, EXK == 2, a.stage_bufs);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(res_smem + L.keys);
+    uint32_t* ridx = reinterpret_cast<uint32_t*>(res_smem + L.idx);
+    unsigned char* wbase = res_smem + L.warp0 + (size_t)warp * L.warp_stride;
+    const uint32_t stage_u32 = smem_u32(wbase), rql_u32 = smem_u32(wbase + a.stage_bufs * 32u * a.exl_row);
+    unsigned char* rql = wbase + a.stage_bufs * 32u * a.exl_row;
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(res_smem + L.si);
+    float* sd = reinterpret_cast<float*>(res_smem + L.sd);
+    XrRec* recs = a.ovf_recs + (size_t)blockIdx.x * kOvfMaxRecs;
+    const bool l2 = ix.metric == RBQ_METRIC_L2;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(&a.counters[8], 1u);
+        __syncthreads();
+        const uint32_t slot = s_q;
+        if (slot >= a.counters[7]) break;
+        const uint32_t q = a.ovf_list[slot];
+        const uint32_t m = a.surv_cnt[q];  // sort_cap < m <= surv_cap (the lazy replay filed it)
+        if (m > kOvfMaxRecs) {             // cannot happen at the default caps; keep the exact path anyway
+            if (tid == 0) a.fb2_list[atomicAdd(&a.counters[9], 1u)] = q | kFbResume;
+            continue;
+        }
+        const Probe* pr = a.probes + (size_t)q * a.nprobe;
+        const Survivor* sv = a.surv + (size_t)q * a.surv_cap;
+        QueryScalars s{};
+        if (EXK != 0) {
+            s = a.qs[q];
+            load_rql_any<EXK == 2>(rql, a.rql_row, a.rot + (size_t)q * D, D, ix.exl_lane, lane);  // every warp stages its own copy
+            __syncwarp();
+        }
+        // 1. records: eager refinement, 32 survivors per warp and pass
+        for (uint32_t b0 = (uint32_t)warp * 32u; b0 < m; b0 += (uint32_t)kOvfWarps * 32u) {
+            const uint32_t i = b0 + (uint32_t)lane;
+            const int nb = (int)min(32u, m - b0);
+            Survivor rec = {0u, 0u, 0.0f, 0.0f};
+            unsigned long long gv = 0;
+            float g_add = 0.0f;
+            if (i < m) {
+                rec = sv[i];
+                const Probe* pp = pr + rec.rank;
+                gv = pp->vec_off + rec.pos;
+                g_add = pp->g_add;
+            }
+            float dist = rec.x;  // 1-bit index: the estimate is the distance
+            if (EXK != 0) {
+                const float exdot = refine_batch_any<EXK == 2>(ix, gv, nb, stage_u32, rql_u32, a.exl_row, a.rql_row, a.stage_bufs, lane);
+                if (i < m) {
+                    // distance = f_add_ex + g_add + f_rescale_ex * (binary_scale*ip + ex_dot + kbx)  (ivf.rs:2095-2099)
+                    const float fae = __ldg(ix.f_add_ex + gv), fre = __ldg(ix.f_rescale_ex + gv);
+                    float tt = s.bscale * rec.x;
+                    tt = tt + exdot;
+                    tt = tt + s.kbx;
+                    const float mm2 = fre * tt;
+                    const float aa = fae + g_add;
+                    dist = aa + mm2;
+                }
+            }
+            if (i < m) {
+                const unsigned long long key = ((unsigned long long)rec.rank << 32) | rec.pos;
+                recs[i] = XrRec{key, rec.lower, dist, ix.ids[gv]};
+                keys[i] = key;
+                ridx[i] = i;
+            }
+        }
+        uint32_t npad = 32;
+        while (npad < m) npad <<= 1;
+        for (uint32_t i = m + (uint32_t)tid; i < npad; i += (uint32_t)kOvfWarps * 32u) {
+            keys[i] = ~0ull;
+            ridx[i] = 0u;
+        }
+        __syncthreads();
+        // 2. visit order
+        for (uint32_t size = 2; size <= npad; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = (uint32_t)tid; t < npad / 2; t += (uint32_t)kOvfWarps * 32u) {
+                    const uint32_t i = 2 * t - (t & (stride - 1)), j2 = i + stride;
+                    const unsigned long long x = keys[i], y = keys[j2];
+                    if ((x > y) == ((i & size) == 0)) {
+                        keys[i] = y;
+                        keys[j2] = x;
+                        const uint32_t u = ridx[i];
+                        ridx[i] = ridx[j2];
+                        ridx[j2] = u;
+                    }
+                }
+                __syncthreads();
+            }
+        if (warp != 0) continue;
+        // 3. warp 0: the reference's loop over the candidates in visit order, resumed from the head pass' top-k
+        __threadfence_block();
+        const float tau_q = a.tau[q];
+        TopK tk;
+        tk.init(sd, si, k);
+        tk.cnt = (int)a.out_counts[q];
+        for (int i = lane; i < tk.cnt; i += 32) {
+            const float sc = a.out_scores[(size_t)q * k + i];
+            tk.set_at(i, l2 ? sc : -sc, a.out_ids[(size_t)q * k + i]);
+        }
+        // The threshold only moves when a candidate enters a full heap, and only a candidate whose distance beats the k-th
+        // distance AT THE START of the batch can do that (the k-th distance never rises).  So the batch is walked from one such
+        // candidate to the next; for the lanes in between the threshold is constant and "admitted" is a population count.  A
+        // query of this tier has thousands of candidates below a loose lower-bound threshold and a handful that change the heap.
+        unsigned long long q_adm = 0;
+        for (uint32_t b0 = 0; b0 < m; b0 += 32) {
+            const uint32_t i = b0 + (uint32_t)lane;
+            XrRec r{0ull, 0.0f, 0.0f, 0ull};
+            if (i < m) r = recs[ridx[i]];
+            const float kth0 = tk.theta();  // warp-collective for k <= 32: every lane calls it, outside any short-circuit
+            float theta = fminf(kth0, tau_q);
+            const bool below = i < m && r.lower < theta;  // stale threshold: superset of what the live one admits
+            const bool mover = below && isfinite(r.dist) && (tk.cnt < k || r.dist < kth0);
+            unsigned movers = __ballot_sync(0xffffffffu, mover);
+            int done = 0;  // lanes [0, done) are accounted for
+            while (movers) {
+                const int sl = __ffs(movers) - 1;
+                movers &= movers - 1;
+                // lanes [done, sl): admitted iff their lower bound beats the current threshold; none of them changes the heap
+                q_adm += (unsigned long long)__popc(__ballot_sync(0xffffffffu, lane >= done && lane < sl && below && r.lower < theta));
+                const float lb_s = __shfl_sync(0xffffffffu, r.lower, sl);
+                const float d_s = __shfl_sync(0xffffffffu, r.dist, sl);
+                const unsigned long long id_s = __shfl_sync(0xffffffffu, r.id, sl);
+                done = sl + 1;
+                if (lb_s >= theta) continue;  // skipped_by_lower_bound
+                q_adm += 1;
+                tk.insert(d_s, id_s, lane);   // finite by construction of `mover`
+                theta = fminf(tk.theta(), tau_q);
+            }
+            q_adm += (unsigned long long)__popc(__ballot_sync(0xffffffffu, lane >= done && below && r.lower < theta));
+        }
+        __syncwarp();
+        for (int i = lane; i < k; i += 32) {
+            const bool have = i < tk.cnt;
+            const float dv = tk.dist_at(i);
+            a.out_ids[(size_t)q * k + i] = have ? tk.id_at(i) : ~0ull;
+            a.out_scores[(size_t)q * k + i] = have ? (l2 ? dv : -dv) : 0.0f;
+        }
+        if (lane == 0) {
+            a.out_counts[q] = (uint32_t)tk.cnt;
+            if (a.stats) {
+                atomicAdd(&a.stats->admitted, q_adm);
+                if (EXK != 0) atomicAdd(&a.stats->refined, (unsigned long long)m);
+            }
+        }
     }
 }
 
@@ -797,9 +990,13 @@ static void fill_args(ResolveArgs& a, const DevIndex& ix, const float* d_rot, co
     a.tail_start = tw.tail_start;
     a.tau = tw.tau;
     a.fb_list = tw.fb_list;
+    a.fb2_list = tw.fb2_list;
     a.surv = tw.surv;
     a.surv_cnt = tw.surv_cnt;
     a.surv_cap = tw.surv_cap;
+    a.sort_cap = tw.sort_cap;
+    a.ovf_list = tw.ovf_list;
+    a.ovf_recs = reinterpret_cast<XrRec*>(tw.ovf_recs);
     const bool paired = refine_paired(ix);
     a.exl_row = paired ? exl2_lane_stride((uint32_t)ix.D) : exl_row_stride((uint32_t)ix.D);
     a.rql_row = paired ? rql2_row_stride((uint32_t)ix.D) : rql_row_stride((uint32_t)ix.D);
@@ -902,6 +1099,29 @@ int launch_head(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     return RBQ_OK;
 }
 
+// queries the lazy replay filed for the overflow tier (normally none: the kernel then exits at once)
+static int launch_overflow_tier(const DevIndex& ix, const ResolveArgs& a, cudaStream_t st, uint64_t* launches) {
+    static_assert(sizeof(XrRec) == 24, "overflow scratch is sized for 24-byte records");
+    const bool paired = refine_paired(ix);
+    const OvfSmem w = ovf_smem_layout(a.exl_row, a.rql_row, a.top_k, ix.ex_bits != 0, paired, a.stage_bufs);
+    const size_t smem = w.total;
+    if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "overflow-tier shared memory exceeds the device limit");
+    const unsigned grid = std::min<unsigned>((unsigned)g_res_sms, kOvfCtas);
+    if (ix.ex_bits == 0) {
+        RBQ_CUDA(cudaFuncSetAttribute(overflow_replay_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        overflow_replay_kernel<0><<<grid, kOvfWarps * 32, smem, st>>>(ix, a);
+    } else if (paired) {
+        RBQ_CUDA(cudaFuncSetAttribute(overflow_replay_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        overflow_replay_kernel<2><<<grid, kOvfWarps * 32, smem, st>>>(ix, a);
+    } else {
+        RBQ_CUDA(cudaFuncSetAttribute(overflow_replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        overflow_replay_kernel<1><<<grid, kOvfWarps * 32, smem, st>>>(ix, a);
+    }
+    RBQ_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return RBQ_OK;
+}
+
 int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScalars* d_qs, const Probe* d_probes, size_t nq,
                          size_t nprobe, size_t top_k, uint64_t* d_ids, float* d_scores, uint32_t* d_counts, DevStats* d_stats,
                          const TailWs& tw, cudaStream_t st, uint64_t* launches) {
@@ -912,7 +1132,7 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
     fill_args(a, ix, d_rot, nullptr, d_qs, d_probes, nq, nprobe, top_k, nullptr, 0, d_ids, d_scores, d_counts, d_stats, tw);
     if (ix.ex_bits != 0) {
         // sorted survivors, refinement on demand against the live threshold (one kernel)
-        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.surv_cap, a.stage_bufs, refine_paired(ix));
+        const ResSmem w = res_smem_layout(a.exl_row, a.rql_row, a.top_k, true, true, a.sort_cap, a.stage_bufs, refine_paired(ix));
         const size_t smem = (size_t)w.total * kResWarps;
         if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
         const unsigned grid = res_grid(nq, smem);
@@ -925,15 +1145,15 @@ int launch_refine_replay(const DevIndex& ix, const float* d_rot, const QueryScal
         }
         RBQ_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
-        return RBQ_OK;
+        return launch_overflow_tier(ix, a, st, launches);
     }
-    const ResSmem w = res_smem_layout(0, 0, a.top_k, false, true, a.surv_cap);
+    const ResSmem w = res_smem_layout(0, 0, a.top_k, false, true, a.sort_cap);
     const size_t smem = (size_t)w.total * kResWarps;
     if (smem > g_res_smem_optin) return fail(RBQ_INVALID_CONFIG, "replay kernel shared memory exceeds the device limit");
     const unsigned grid = res_grid(nq, smem);
     RBQ_RES_LAUNCH(resolve_replay_kernel, smem, grid);
     if (launches) *launches += 1;
-    return RBQ_OK;
+    return launch_overflow_tier(ix, a, st, launches);
 }
 
 int launch_ex_dot_debug(const DevIndex& ix, const float* d_rot, const unsigned long long* d_gv, int n, float* d_out, const TailWs& tw, cudaStream_t st) {

@@ -507,7 +507,7 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     if (mode != kScanFull && tw == nullptr) return fail(RBQ_INVALID_CONFIG, "head/replay scan needs the tail workspace");
     if (top_k > (size_t)kMaxTopK) return fail(RBQ_INVALID_CONFIG, "top_k exceeds the device limit (1024)");
     if (ix.D > 2048) return fail(RBQ_INVALID_CONFIG, "padded_dim > 2048 (high-accuracy LUT path) is not supported");
-    RBQ_CUDA(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned int), st));
+    if (mode != kScanFallback && mode != kScanFallbackResume) RBQ_CUDA(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned int), st));
     ScanArgs a;
     a.rot = d_rot;
     a.lut = d_lut;
@@ -534,6 +534,12 @@ int launch_scan(const DevIndex& ix, const float* d_rot, const uint8_t* d_lut, co
     a.fb_list = tw ? tw->fb_list : nullptr;
     a.fb_count = tw ? tw->counters + 2 : nullptr;
     if (mode == kScanFallback) a.work_counter = tw->counters + 6;
+    if (mode == kScanFallbackResume) {  // same kernel path, the replay tiers' list
+        a.mode = (uint32_t)kScanFallback;
+        a.fb_list = tw->fb2_list;
+        a.fb_count = tw->counters + 9;
+        a.work_counter = tw->counters + 10;
+    }
     const int ncb_lane = (ix.D / 4 + 31) / 32;
     if (ix.D > 1024) {
         if (ncb_lane <= 12) return launch_scan_ex<12, true>(ix, a, st);

@@ -356,11 +356,15 @@ static int tail_limits() {
 
 static uint32_t g_surv_cap_override = 0;  // test knob: forces survivor-buffer overflows
 void tail_debug_set_survivor_cap(uint32_t cap) { g_surv_cap_override = cap; }
-static uint32_t tail_surv_cap(size_t top_k) {
+// survivors per query the lazy replay sorts in shared memory (10-bit slot in its sort keys)
+static uint32_t tail_sort_cap(size_t top_k) {
     if (g_surv_cap_override) return g_surv_cap_override;
     (void)top_k;
-    return 1024;  // the largest the replay's sort keys address (10-bit slot): an overflowing query costs a sequential re-walk of its tail
+    return 1024;
 }
+// slots per query in the survivor buffer: queries between the two caps are replayed by the overflow tier (one CTA per query,
+// resolve.cu), queries beyond it by a sequential re-walk of their tail
+static uint32_t tail_surv_cap(size_t top_k) { return 4u * tail_sort_cap(top_k); }
 
 // dense head buffer: room for the longest list of the shard (lists beyond 64Ki vectors send their queries to the sequential
 // fallback), and as many query rows as fit 512 MiB -- the head pass runs over row-sized sub-chunks of the batch
@@ -385,7 +389,9 @@ size_t tail_ws_bytes(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k)
     n += max_items * sizeof(TailItem) + 256;
     n += nq * cap * sizeof(Survivor) + 256;
     n += (size_t)tail_head_rows(ix, nq) * tail_head_cap(ix) * 8 + 256;  // head_buf
-    n += nq * 4 + 256;                                   // fb_list
+    n += 2 * (nq * 4 + 256);                             // fb_list, fb2_list
+    n += nq * 4 + 256;                                   // ovf_list
+    n += (size_t)kOvfCtas * 4096 * 24 + 256;              // ovf_recs
     n += nq * 4 + 512;                                   // qlist + qcount
     return n;
 }
@@ -399,6 +405,7 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
         return r;
     };
     tw.surv_cap = tail_surv_cap(top_k);
+    tw.sort_cap = tail_sort_cap(top_k);
     tw.max_items = (uint32_t)(nq * nprobe / kPairsPerItem + ix.nlist + 1);
     tw.pairs_per_item = kPairsPerItem;
     tw.tail_start = reinterpret_cast<uint32_t*>(take(nq * 4));
@@ -417,6 +424,9 @@ void tail_ws_carve(const DevIndex& ix, size_t nq, size_t nprobe, size_t top_k, c
     tw.head_rows = tail_head_rows(ix, nq);
     tw.head_buf = reinterpret_cast<float2*>(take((size_t)tw.head_rows * tw.head_cap * 8));
     tw.fb_list = reinterpret_cast<uint32_t*>(take(nq * 4));
+    tw.fb2_list = reinterpret_cast<uint32_t*>(take(nq * 4));
+    tw.ovf_list = reinterpret_cast<uint32_t*>(take(nq * 4));
+    tw.ovf_recs = take((size_t)kOvfCtas * 4096 * 24);
     tw.qlist = reinterpret_cast<uint32_t*>(take(nq * 4));
     tw.qcount = reinterpret_cast<uint32_t*>(take(16));
 }

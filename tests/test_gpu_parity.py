@@ -352,23 +352,33 @@ def _canon_all(res):
     return out, sc, cnt
 
 
-def test_list_major_survivor_overflow_falls_back_exactly(rbq, oracle):
-    """With a 1-entry survivor buffer almost every query overflows; its tail is re-walked sequentially."""
+@pytest.mark.parametrize("geom", [(6000, 128, 64, 7, 0), (4000, 960, 32, 7, 0), (5000, 96, 48, 3, 1), (5000, 64, 48, 1, 0)])
+@pytest.mark.parametrize("cap", [1, 8, 48])
+def test_list_major_survivor_overflow_falls_back_exactly(rbq, oracle, geom, cap):
+    """Small survivor caps push queries off the lazy replay: with `cap` sorted entries the buffer holds 4 * cap, so a query
+    with cap < n <= 4 * cap survivors takes the overflow tier (one CTA: eager refinement, sort, replay) and one with more is
+    re-walked by the sequential kernel.  Every tier must reproduce the oracle, and the admitted count (the reference's
+    decisions) must not depend on the tier."""
     from rabitq_rs_b200 import _ffi
 
-    data, oix, blob = oracle_index(6000, 128, 64, 7, 0, kind="clustered")
+    n, dim, nlist, bits, metric = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, kind="clustered")
     gix = _load(rbq, blob)
     gix.set_scan_mode(2)
     q = _queries(data, 300, 21)
     exp = oix.search_batch(q, 20, 24)
-    assert _ffi.lib().rbq_debug_set_survivor_cap(1) == 0
+    got0 = gix.batch_search(q, rbq.SearchParams(20, 24))
+    st0 = gix.stats()
+    assert _ffi.lib().rbq_debug_set_survivor_cap(cap) == 0
     try:
         got = gix.batch_search(q, rbq.SearchParams(20, 24))
         st = gix.stats()
     finally:
         _ffi.lib().rbq_debug_set_survivor_cap(0)
     assert assert_results_match(got, exp, TOL, "overflow") == 300
+    assert assert_results_match(got0, exp, TOL, "default caps") == 300
     assert st["overflow_queries"] > 0
+    assert st["admitted"] == st0["admitted"], (st["admitted"], st0["admitted"])
 
 
 def test_list_major_filtered_edge_and_sharded(rbq, oracle):
