@@ -79,10 +79,14 @@ for ch in (1, 2, 4, 8):
     out[f"stages_chunks{ch}"] = {kk: round(float(vv), 4) for kk, vv in st.items() if kk.startswith("ms_")}
     log(f"stages, chunks {ch}: {out[f'stages_chunks{ch}']}")
 ix.set_profiling(False)
-for extra in sys.argv[3:]:  # KEY=VALUE environment knobs, each timed at the default chunk count
-    kk, vv = extra.split("=")
-    os.environ["RBQ_FEED_CHUNKS"] = "4"
-    os.environ[kk] = vv
+os.environ.pop("RBQ_FEED_CHUNKS", None)
+out["e2e_ms_default"] = wall(host_call)
+for extra in sys.argv[3:]:  # KEY=VALUE[,KEY=VALUE...] environment knobs, each combination timed (chunk count: the default unless given)
+    kv = [e.split("=") for e in extra.split(",")]
+    for kk, vv in kv:
+        os.environ[kk] = vv
     out[f"e2e_ms_{extra}"] = wall(host_call)
-    del os.environ[kk]
+    log(f"{extra}: {out[f'e2e_ms_{extra}']}")
+    for kk, _ in kv:
+        del os.environ[kk]
 print(json.dumps(out))

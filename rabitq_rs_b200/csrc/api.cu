@@ -224,7 +224,9 @@ struct Plan {
     int terms = 3;         // bf16 split terms of the GEMM (3: fp32-class, 1: bf16-class with a wider re-score band)
     float eps = 0.0f;      // bound on |gemm(q.c) - q.c| / (|q||c|)
     uint32_t rank = 0, cap = 0, fb_ctas = 0;  // filter mode: sample rank of the threshold, candidate capacity, fallback CTAs
+    int slots = 1;         // host entry: front-end scratch sets / streams the feed chunks alternate over (1: one stream)
 };
+constexpr int kMaxSlots = 4;
 
 Plan make_plan(const rbq_index* h, size_t nq, size_t nprobe) {
     const DevIndex& ix = h->dev;
@@ -261,7 +263,11 @@ struct WsLayout {
     uint8_t* d_head_owner;
     float* d_sc;   // coarse 0/1: [cq][nlist]
     FilterWs fw;   // coarse 2
+    float* d_scx[kMaxSlots - 1];   // the same scratch for slots 1.. (plan.slots > 1)
+    FilterWs fwx[kMaxSlots - 1];
     size_t end;
+    float* sc(int slot) const { return slot == 0 ? d_sc : d_scx[slot - 1]; }
+    const FilterWs& filter(int slot) const { return slot == 0 ? fw : fwx[slot - 1]; }
 };
 // One tile's device workspace.  The layout is a pure function of (plan, nprobe, top_k), so the phases of a multi-GPU search
 // find each other's data by carving again.  base == nullptr only measures.
@@ -280,20 +286,24 @@ WsLayout carve_ws(const rbq_index* h, char* ws_base, const Plan& pl, size_t npro
     char* tbase = cv.take<char>(tb);
     if (ws_base) tail_ws_carve(ix, qt, nprobe, top_k, tbase, L.tw);
     L.d_head_owner = cv.take<uint8_t>(qt);
-    L.d_sc = nullptr;
-    L.fw = FilterWs{};
-    if (pl.coarse == 2) {
-        L.fw.cap = pl.cap;
-        L.fw.fb_ctas = pl.fb_ctas;
-        L.fw.samp_scores = cv.take<float>(cq * ix.samp_n);
-        L.fw.thr = cv.take<float>(cq);
-        L.fw.cand = cv.take<CandRec>(cq * pl.cap);
-        L.fw.cand_cnt = cv.take<uint32_t>(cq + 2);
-        L.fw.fb_count = L.fw.cand_cnt + cq;
-        L.fw.fb_list = cv.take<uint32_t>(cq);
-        L.fw.fb_scratch = cv.take<float>((size_t)pl.fb_ctas * ix.nlist);
-    } else {
-        L.d_sc = cv.take<float>(cq * (size_t)ix.nlist);
+    for (int s = 0; s < std::max(1, std::min(pl.slots, kMaxSlots)); ++s) {  // slot 0 first: its offsets do not depend on plan.slots
+        float*& sc = s == 0 ? L.d_sc : L.d_scx[s - 1];
+        FilterWs& fw = s == 0 ? L.fw : L.fwx[s - 1];
+        sc = nullptr;
+        fw = FilterWs{};
+        if (pl.coarse == 2) {
+            fw.cap = pl.cap;
+            fw.fb_ctas = pl.fb_ctas;
+            fw.samp_scores = cv.take<float>(cq * ix.samp_n);
+            fw.thr = cv.take<float>(cq);
+            fw.cand = cv.take<CandRec>(cq * pl.cap);
+            fw.cand_cnt = cv.take<uint32_t>(cq + 2);
+            fw.fb_count = fw.cand_cnt + cq;
+            fw.fb_list = cv.take<uint32_t>(cq);
+            fw.fb_scratch = cv.take<float>((size_t)pl.fb_ctas * ix.nlist);
+        } else {
+            sc = cv.take<float>(cq * (size_t)ix.nlist);
+        }
     }
     L.end = cv.off + 4096;
     return L;
@@ -312,9 +322,10 @@ size_t ws_need(const rbq_index* h, const Plan& pl, size_t nprobe, size_t top_k, 
 // Front end for the queries [c0, c0 + m) of a tile (rows c0.. of the tile buffers): rotation + LUT (+ bf16 operand split),
 // centroid scores, probe selection with the per-list constants.  m <= plan.cq.
 int run_front(const rbq_index* h, const WsLayout& L, const Plan& pl, const float* dq, size_t c0, size_t m, size_t nprobe, cudaStream_t st,
-              uint64_t* launches, bool prep, cudaEvent_t ev_prep, cudaEvent_t ev_coarse, bool need_ip = false) {
+              uint64_t* launches, bool prep, cudaEvent_t ev_prep, cudaEvent_t ev_coarse, bool need_ip = false, int slot = 0) {
     const DevIndex& ix = h->dev;
     const size_t D = ix.D;
+    float* const d_sc = L.sc(slot);  // this slot's front-end scratch (chunks on different streams use different slots)
     int rc;
     const bool tc = pl.coarse != 0;
     bool split_done = false;
@@ -326,9 +337,9 @@ int run_front(const rbq_index* h, const WsLayout& L, const Plan& pl, const float
     }
     if (ev_prep) cudaEventRecord(ev_prep, st);
     if (pl.coarse == 0) {
-        if ((rc = launch_coarse_exact(ix, L.d_rot + c0 * D, m, L.d_sc, st))) return rc;
+        if ((rc = launch_coarse_exact(ix, L.d_rot + c0 * D, m, d_sc, st))) return rc;
         if (ev_coarse) cudaEventRecord(ev_coarse, st);
-        if ((rc = launch_probe_select(ix, L.d_rot + c0 * D, L.d_sc, m, nprobe, L.d_pr + c0 * nprobe, st))) return rc;
+        if ((rc = launch_probe_select(ix, L.d_rot + c0 * D, d_sc, m, nprobe, L.d_pr + c0 * nprobe, st))) return rc;
         *launches += 2;
         return RBQ_OK;
     }
@@ -337,16 +348,16 @@ int run_front(const rbq_index* h, const WsLayout& L, const Plan& pl, const float
         *launches += 1;
     }
     if (pl.coarse == 1) {
-        if ((rc = launch_coarse_tc(ix, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, m, L.d_sc, st, pl.terms))) return rc;
+        if ((rc = launch_coarse_tc(ix, L.d_qsplit + c0 * 3 * D, L.d_qn2 + c0, m, d_sc, st, pl.terms))) return rc;
         if (ev_coarse) cudaEventRecord(ev_coarse, st);
-        if ((rc = launch_probe_select_tc(ix, L.d_rot + c0 * D, L.d_sc, L.d_qs + c0, m, nprobe, pl.eps, L.d_pr + c0 * nprobe,
+        if ((rc = launch_probe_select_tc(ix, L.d_rot + c0 * D, d_sc, L.d_qs + c0, m, nprobe, pl.eps, L.d_pr + c0 * nprobe,
                                          h->fallback_counter(), st, need_ip)))
             return rc;
         *launches += 2;
         return RBQ_OK;
     }
     // filter mode: sample scores -> per-query threshold -> full GEMM keeping the centroids that beat it -> selection
-    const FilterWs& fw = L.fw;
+    const FilterWs& fw = L.filter(slot);
     RBQ_CUDA(cudaMemsetAsync(fw.cand_cnt, 0, (pl.cq + 2) * 4, st));  // candidate counters | fallback count | fallback cursor
     GemmEpi e;
     e.nq = (int)m;
@@ -382,6 +393,7 @@ struct HostFeed {
     const float* h_q = nullptr;   // host queries (whole call)
     float* d_q = nullptr;         // device staging for one tile
     size_t dim = 0, chunk = 0;
+    size_t first = 0;             // queries in the first chunk (0: same as the others): a short first copy starts the GPU earlier
     cudaStream_t copy = nullptr;
     cudaEvent_t* ev = nullptr;
     int issue(size_t q_abs, size_t m, size_t off_in_tile, int slot) {
@@ -438,12 +450,41 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         // that the H2D transfer of chunk c+1 overlaps the work on chunk c) and only the tail stage waits for the whole tile.
         size_t chunk = std::min(pl.cq, n);
         if (feed) chunk = std::max<size_t>(128, std::min(chunk, feed->chunk));
+        // Chunk slots (host entry, unprofiled): chunk ci runs on stream ci % nslots with that slot's front-end scratch and its own
+        // part of the dense head buffer.  A chunk of a few thousand queries fills the GPU only partly (0.6 waves of the prep kernel
+        // at 2 500 queries); on one stream that idle share is lost in every kernel (front end + head pass of a 10 000-query batch:
+        // 0.84 ms in one chunk, 1.12 in two, 1.47 in four), on alternating streams the next chunk's kernels take it.
+        int nslots = (feed && !h->profiling) ? std::max(1, std::min(pl.slots, kMaxSlots)) : 1;
+        const uint32_t slot_rows = tw.head_rows / (uint32_t)nslots;
+        if (chunk >= n || slot_rows < 128 || (n + chunk - 1) / chunk * ((chunk + slot_rows - 1) / std::max(slot_rows, 1u)) > kHeadCursors) nslots = 1;
+        cudaStream_t cs[kMaxSlots] = {st, nullptr, nullptr, nullptr};
+        TailWs tws[kMaxSlots] = {tw, tw, tw, tw};
+        if (nslots > 1) {
+            if (!h->slot_fork) {
+                RBQ_CUDA(cudaEventCreateWithFlags(&h->slot_fork, cudaEventDisableTiming));
+                for (int i = 0; i < kMaxSlots - 1; ++i) {
+                    RBQ_CUDA(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
+                    RBQ_CUDA(cudaEventCreateWithFlags(&h->slot_join[i], cudaEventDisableTiming));
+                }
+            }
+            RBQ_CUDA(cudaEventRecord(h->slot_fork, st));  // after the tile's memset (and whatever the call enqueued before)
+            for (int i = 1; i < nslots; ++i) {
+                cs[i] = h->slot_stream[i - 1];
+                RBQ_CUDA(cudaStreamWaitEvent(cs[i], h->slot_fork, 0));
+            }
+            for (int i = 0; i < nslots; ++i) {
+                tws[i].head_rows = slot_rows;
+                tws[i].head_buf = tw.head_buf + (size_t)i * slot_rows * tw.head_cap;
+            }
+        }
         int head_launch = 0, ci = 0;
-        for (size_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
-            const size_t m = std::min(chunk, n - c0);
+        for (size_t c0 = 0, m = 0; c0 < n; c0 += m, ++ci) {
+            m = std::min((feed && ci == 0 && feed->first) ? std::min(feed->first, chunk) : chunk, n - c0);
+            const int slot = ci % nslots;
+            cudaStream_t cst = cs[slot];
             if (feed) {
                 if ((rc = feed->issue(q0 + c0, m, c0, ci))) return rc;
-                RBQ_CUDA(cudaStreamWaitEvent(st, feed->ev[ci % HostFeed::kEvents], 0));
+                RBQ_CUDA(cudaStreamWaitEvent(cst, feed->ev[ci % HostFeed::kEvents], 0));
             }
             // profiled calls time every chunk's stages with its own events (read back after the tile)
             cudaEvent_t* ce = nullptr;
@@ -451,16 +492,20 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
                 ce = h->ev_chunk[ci];
                 for (int i = 0; i < 5; ++i)
                     if (!ce[i]) RBQ_CUDA(cudaEventCreate(&ce[i]));
-                cudaEventRecord(ce[0], st);
+                cudaEventRecord(ce[0], cst);
             }
             const float* dq = feed ? feed->d_q + c0 * ix.dim : d_queries + (q0 + c0) * ix.dim;
-            if ((rc = run_front(h, L, pl, dq, c0, m, nprobe, st, launches, true, ce ? ce[1] : nullptr, ce ? ce[2] : nullptr))) return rc;
-            if (ce) cudaEventRecord(ce[3], st);
+            if ((rc = run_front(h, L, pl, dq, c0, m, nprobe, cst, launches, true, ce ? ce[1] : nullptr, ce ? ce[2] : nullptr, false, slot))) return rc;
+            if (ce) cudaEventRecord(ce[3], cst);
             // head: FastScan of every query's first owned list + the reference's sequential loop over it
             if (list_major && (rc = launch_head(ix, L.d_rot, L.d_lut, L.d_qs, L.d_pr, n, nprobe, top_k, d_filter, filter_nbits, d_ids + q0 * top_k,
-                                                d_scores + q0 * top_k, d_counts + q0, h->d_stats, tw, st, launches, c0, m, &head_launch)))
+                                                d_scores + q0 * top_k, d_counts + q0, h->d_stats, tws[slot], cst, launches, c0, m, &head_launch)))
                 return rc;
-            if (ce) cudaEventRecord(ce[4], st);
+            if (ce) cudaEventRecord(ce[4], cst);
+        }
+        for (int i = 1; i < nslots; ++i) {  // the tail stage needs every chunk's probes and head state
+            RBQ_CUDA(cudaEventRecord(h->slot_join[i - 1], cs[i]));
+            RBQ_CUDA(cudaStreamWaitEvent(st, h->slot_join[i - 1], 0));
         }
         const int timed_chunks = std::min(ci, 32);
         if (!list_major) {
@@ -621,6 +666,11 @@ void rbq_index_free(rbq_index* h) {
         if (h->xr_ws) cudaFree(h->xr_ws);
         if (h->xr_recs) cudaFree(h->xr_recs);
         if (h->xr_host) cudaFreeHost(h->xr_host);
+        for (auto& x : h->slot_stream)
+            if (x) cudaStreamDestroy(x);
+        for (auto& x : h->slot_join)
+            if (x) cudaEventDestroy(x);
+        if (h->slot_fork) cudaEventDestroy(h->slot_fork);
         if (h->side_stream) cudaStreamDestroy(h->side_stream);
         if (h->side_fork) cudaEventDestroy(h->side_fork);
         if (h->side_join) cudaEventDestroy(h->side_join);
@@ -859,8 +909,14 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         std::memset(counts, 0, nq * 4);
         return RBQ_OK;
     }
-    const Plan pl = make_plan(h, nq, nprobe);
+    Plan pl = make_plan(h, nq, nprobe);
     const size_t qt = pl.qt;
+    {   // feed chunks alternate over `slots` streams, each with its own front-end scratch (search_device); RBQ_FEED_SLOTS overrides
+        const char* fs = getenv("RBQ_FEED_SLOTS");
+        pl.slots = fs ? (int)std::min<long>(kMaxSlots, std::max(1L, atol(fs))) : kMaxSlots;
+        // every slot carries a front-end scratch of plan.cq rows: no larger than a feed chunk can be (about a quarter of a tile)
+        if (pl.slots > 1) pl.cq = std::min(pl.cq, std::max<size_t>(5120, (qt / 4 + 255) / 128 * 128));
+    }
     // a filter that is present but empty (RoaringBitmap::new()) admits nothing (reference src/tests.rs
     // filtered_search_with_empty_filter): keep one zero word so the kernels see a non-null filter
     const size_t fwords = filter_bits ? std::max<size_t>((filter_nbits + 63) / 64, 1) : 0;
@@ -899,14 +955,26 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
     if (feed.copy != st) RBQ_CUDA(cudaStreamWaitEvent(feed.copy, h->busy_ev, 0));
     for (size_t q0 = 0; q0 < nq; q0 += qt) {
         const size_t n = std::min(qt, nq - q0);
-        // The H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks hide more of the copy but run
-        // the per-query kernels on partial waves (a front end + head pass of 1 280 queries costs 2.5x its share of a 10 000-query
-        // one) -- measured at GIST/10k with profiles/e2e_probe.py: 1 chunk 2.52 ms, 2: 2.41, 3: 2.41, 4: 2.60, 8: 3.27.  Default:
-        // chunks of ~3 400 queries, at most 4 per tile; RBQ_FEED_CHUNKS overrides (1 = no overlap).
+        // The H2D copy of chunk c+1 overlaps the front end and the head pass of chunk c.  More chunks hide more of the copy, but a
+        // chunk of a few thousand queries runs the per-query kernels on partial waves: on ONE stream the front end + head pass of
+        // a 10 000-query batch costs 0.84 ms in one chunk, 1.12 in two, 1.47 in four, 2.28 in eight.  The chunks therefore
+        // alternate over plan.slots streams (search_device), where the next chunk's kernels fill the idle share.  Measured at
+        // GIST-1M / 10k queries with profiles/e2e_probe.py (ms per call; H2D alone 0.72, device-resident step 1.53):
+        //   chunks      2     3     4     5     6     8    12
+        //   1 slot    2.15  2.14  2.27  2.41  2.56  2.89  3.61
+        //   2 slots   2.08  1.97  2.02  2.02  2.15  2.26  2.55
+        //   3 slots   2.16  1.98  1.96  1.96  2.05  2.13  2.33
+        //   4 slots   2.17  2.10  1.98  1.95  1.94  2.04  2.20
+        // Default: 4 slots, chunks of ~1 700 queries, at most 8 per tile; RBQ_FEED_CHUNKS / RBQ_FEED_SLOTS override (1 = off).
         const char* fe = getenv("RBQ_FEED_CHUNKS");  // read per call: tuning scripts sweep it inside one process
-        const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : std::min(4L, std::max(1L, (long)((n + 1700) / 3400)));
+        const long auto_chunks = pl.slots > 1 ? std::min(8L, std::max(1L, (long)((n + 800) / 1700))) : std::min(4L, std::max(1L, (long)((n + 1700) / 3400)));
+        const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : auto_chunks;
         feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
         if (n < 2048) feed.chunk = n;
+        const char* ff = getenv("RBQ_FEED_FIRST");  // tuning knob: queries in the first chunk
+        feed.first = ff ? (size_t)std::max(128L, atol(ff) / 128 * 128) : 0;
+        if (feed.first && feed.first < n && n >= 2048)  // the rest of the tile in `forced` equal chunks
+            feed.chunk = std::max<size_t>(feed.first, ((n - feed.first + forced - 1) / forced + 127) / 128 * 128);
         // search_device copies queries [q0, q0+n) itself (feed) and indexes outputs from the tile start
         const bool trace = getenv("RBQ_TRACE") != nullptr;
         timespec t0, t1, t2;

@@ -360,5 +360,9 @@ struct rbq_index {
     mutable unsigned long long* xr_inexact = nullptr;  // device counter behind last_stats.inexact_queries (inside xr_ws)
     mutable cudaStream_t side_stream = nullptr;  // the head pass' sequential fallback runs here, beside the tail and replay kernels
     mutable cudaEvent_t side_fork = nullptr, side_join = nullptr;
+    // host entry: the front end + head pass of consecutive feed chunks alternate over these streams (slot 0 = the compute stream), so
+    // that the partial waves of one chunk's kernels are filled by the next chunk's (api.cu, search_device)
+    mutable cudaStream_t slot_stream[3] = {};
+    mutable cudaEvent_t slot_fork = nullptr, slot_join[3] = {};
     mutable cudaEvent_t busy_ev = nullptr;  // recorded after the last kernel of every call: the next call's stream waits on it
 };

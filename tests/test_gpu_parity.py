@@ -279,6 +279,43 @@ def test_device_resident_entry_matches_host_entry(rbq, oracle):
     assert np.array_equal(sc.cpu().numpy(), host[1])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("slots,chunks,first", [(1, 4, 0), (2, 4, 0), (3, 5, 0), (4, 8, 0), (2, 3, 384), (4, 16, 128)])
+@pytest.mark.parametrize("geom", [(20000, 128, 256, 7, 0), (12000, 960, 64, 7, 0), (12000, 96, 128, 3, 1)])
+def test_host_feed_chunks_on_slot_streams(rbq, oracle, geom, slots, chunks, first, monkeypatch):
+    """Host entry: the feed chunks' front end + head pass alternate over `slots` streams (own front-end scratch, own part of
+    the dense head buffer).  Whatever the chunking, the answer is the device entry's (one chunk, one stream) and the oracle's,
+    in both scan schedules."""
+    import torch
+
+    n, dim, nlist, bits, metric = geom
+    data, oix, blob = oracle_index(n, dim, nlist, bits, metric, kind="clustered")
+    gix = _load(rbq, blob)
+    nq = 2600
+    q = _queries(data, nq, 33)
+    dq = torch.from_numpy(q).cuda()
+    ids = torch.empty((nq, 10), dtype=torch.int64, device="cuda")
+    sc = torch.empty((nq, 10), dtype=torch.float32, device="cuda")
+    cn = torch.empty(nq, dtype=torch.int32, device="cuda")
+    exp = oix.search_batch(q[:400], 10, 12)
+    monkeypatch.setenv("RBQ_FEED_SLOTS", str(slots))
+    monkeypatch.setenv("RBQ_FEED_CHUNKS", str(chunks))
+    if first:
+        monkeypatch.setenv("RBQ_FEED_FIRST", str(first))
+    for mode in (2, 1, 0):
+        gix.set_scan_mode(mode)
+        gix.batch_search_device(dq, 10, 12, ids, sc, cn)
+        torch.cuda.synchronize()
+        for rep in range(2):  # twice: the second call reuses the slot streams and the workspace
+            host = gix.batch_search(q, rbq.SearchParams(10, 12))
+            cnt = cn.cpu().numpy().astype(np.uint32)
+            assert np.array_equal(cnt, np.asarray(host[2]).astype(np.uint32)), (mode, rep)
+            live = np.arange(10)[None, :] < cnt[:, None]
+            assert np.array_equal(ids.cpu().numpy().astype(np.uint64)[live], host[0][live]), (mode, rep)
+            assert np.array_equal(sc.cpu().numpy()[live], host[1][live]), (mode, rep)
+        assert assert_results_match(tuple(a[:400] for a in host), exp, TOL, "slots") == 400
+
+
 COARSE_CASES = [  # (n, dim, nlist, metric, rotator, kind)
     (20000, 128, 512, 0, 1, "clustered"),
     (20000, 960, 300, 0, 1, "clustered"),     # nlist not a multiple of the GEMM tile, K' = 2880
