@@ -103,6 +103,10 @@ int launch_coarse_exact(const DevIndex& ix, const float* d_rot, size_t nq, float
 
 // ---- K5 + K6: exact top-nprobe and per-list constants -------------------------------------------
 constexpr int kSelThreads = 256;
+// launch_probe_select_cand, candidate capacity <= 512: CTA shape of the selection kernel.  Measured at GIST-1M / 10k queries / nprobe 16
+// (select stage, ms): 0 = 256 threads x 4 CTAs/SM, 16 centroid elements in flight per lane: 0.169; 1 = 32 in flight: 0.186;
+// 2 = 128 threads x 10 CTAs/SM: 0.164; 3 = 128 x 8, 32 in flight: 0.167; 4 = 256 x 5: 0.170; 5 = 128 threads x 12 CTAs/SM: 0.161.
+constexpr int kSelVariantDefault = 5;
 constexpr int kMaxNprobe = 4096;
 size_t probe_select_max_nprobe() { return kMaxNprobe; }
 
@@ -206,42 +210,34 @@ __device__ __forceinline__ void gather_exact(const float* __restrict__ sc, int n
 
 // l2_distance_sqr and dot of the query against one centroid, AVX2 lane order; all 8 lanes of the
 // group return both values.
-template <bool NEED_L2 = true, bool NEED_IP = true>
-__device__ __forceinline__ void exact_pair(const float* __restrict__ rq, const float* __restrict__ ce, int D, int lane8,
-                                           unsigned gmask, float* l2_out, float* ip_out) {
-    float al2 = 0.0f, aip = 0.0f;
-    // 16 centroid elements in flight per lane (the row comes from L2): the adds stay in index order
-    int i = lane8;
-    for (; i + 8 * 15 < D; i += 8 * 16) {
-        float b[16];
+template <int N, bool NEED_L2, bool NEED_IP>
+__device__ __forceinline__ void exact_batch(const float* __restrict__ rq, const float* __restrict__ ce, int i, float& al2, float& aip) {
+    float b[N];  // N centroid elements in flight per lane (the row comes from L2): the adds stay in index order
 #pragma unroll
-        for (int u = 0; u < 16; ++u) b[u] = __ldg(ce + i + 8 * u);
+    for (int u = 0; u < N; ++u) b[u] = __ldg(ce + i + 8 * u);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const float a = rq[i + 8 * u];
-            if (NEED_L2) {
-                const float d = a - b[u];
-                const float p = d * d;
-                al2 = al2 + p;
-            }
-            if (NEED_IP) {
-                const float m = a * b[u];
-                aip = aip + m;
-            }
-        }
-    }
-    for (; i < D; i += 8) {
-        const float a = rq[i], b = __ldg(ce + i);
+    for (int u = 0; u < N; ++u) {
+        const float a = rq[i + 8 * u];
         if (NEED_L2) {
-            const float d = a - b;
+            const float d = a - b[u];
             const float p = d * d;
             al2 = al2 + p;
         }
         if (NEED_IP) {
-            const float m = a * b;
+            const float m = a * b[u];
             aip = aip + m;
         }
     }
+}
+template <bool NEED_L2 = true, bool NEED_IP = true, int DEPTH = 16>
+__device__ __forceinline__ void exact_pair(const float* __restrict__ rq, const float* __restrict__ ce, int D, int lane8,
+                                           unsigned gmask, float* l2_out, float* ip_out) {
+    float al2 = 0.0f, aip = 0.0f;
+    int i = lane8;
+    for (; i + 8 * (DEPTH - 1) < D; i += 8 * DEPTH) exact_batch<DEPTH, NEED_L2, NEED_IP>(rq, ce, i, al2, aip);
+    if (DEPTH > 8)
+        for (; i + 8 * 7 < D; i += 8 * 8) exact_batch<8, NEED_L2, NEED_IP>(rq, ce, i, al2, aip);
+    for (; i < D; i += 8) exact_batch<1, NEED_L2, NEED_IP>(rq, ce, i, al2, aip);
     float l2 = 0.0f, ip = 0.0f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
@@ -396,8 +392,9 @@ struct SelList {
     uint32_t* fb_list;
     uint32_t* fb_count;
 };
-template <int KPT, bool NEED_IP, bool LIST>
-__global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
+// NT threads per CTA, MINB resident CTAs per SM asked of the compiler, DEPTH centroid elements in flight per lane of the exact re-score
+template <int KPT, bool NEED_IP, bool LIST, int NT = kSelThreads, int MINB = 4, int DEPTH = 16>
+__global__ void __launch_bounds__(NT, MINB) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
                                                                        float* __restrict__ scores,
                                                                        const QueryScalars* __restrict__ qs, int nprobe,
                                                                        int sort_n, float eps_g, Probe* __restrict__ probes,
@@ -409,7 +406,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     float* cl2 = reinterpret_cast<float*>(cand + sort_n);                       // sort_n exact l2
     float* cip = cl2 + sort_n;                                                  // sort_n exact ip
     __shared__ SelShared sh;
-    __shared__ uint32_t s_min[kSelThreads / 32], s_max[kSelThreads / 32];
+    static_assert(LIST || NT == kSelThreads, "the dense variant's rare path uses the kSelThreads-strided helpers");
+    __shared__ uint32_t s_min[NT / 32], s_max[NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, D = ix.D;
     const size_t q = blockIdx.x;
     const bool desc = ix.metric == RBQ_METRIC_INNER_PRODUCT;
@@ -427,13 +425,16 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     } else {
         sc = scores + q * (size_t)nl;
     }
-    for (int i = tid; i < D; i += kSelThreads) rq[i] = rot[q * D + i];
+    // scalars of the band test, loaded up front (their latency would otherwise sit between the select and the gather)
+    const float qn = qs[q].qnorm, cm = ix.cmax_norm;
+    const float fthr = LIST ? sl.fthr[q] : 0.0f;
+    for (int i = tid; i < D; i += NT) rq[i] = rot[q * D + i];
 
     uint32_t key[KPT], col[LIST ? KPT : 1];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-        const int c = tid + kSelThreads * j;
+        const int c = tid + NT * j;
         key[j] = 0u;
         if (LIST) col[j] = 0u;
         if (c < nl) {
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kSelThreads / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
         kmin = min(kmin, s_min[w]);
         kmax = max(kmax, s_max[w]);
     }
@@ -470,11 +471,11 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     while (hi > 0) {
         const int lo = hi > 8 ? hi - 8 : 0;
         const uint32_t dmask = (1u << (hi - lo)) - 1u;
-        sh.hist[tid] = 0;  // kSelThreads == 256 bins
+        for (int i = tid; i < 256; i += NT) sh.hist[i] = 0;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
-            const int c = tid + kSelThreads * j;
+            const int c = tid + NT * j;
             if (c < nl && (((unsigned long long)(key[j] ^ prefix)) >> hi) == 0ull) atomicAdd(&sh.hist[(key[j] >> lo) & dmask], 1u);
         }
         __syncthreads();
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
             __syncthreads();  // everyone has read the scan results; the histogram becomes the key list
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
-                const int c = tid + kSelThreads * j;
+                const int c = tid + NT * j;
                 if (c < nl && (((unsigned long long)(key[j] ^ prefix)) >> hi) == 0ull) sh.hist[atomicAdd(&sh.count, 1u)] = key[j];
             }
             __syncthreads();
@@ -533,7 +534,6 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
         }
     }
     const float T = key_to_float(prefix, desc);
-    const float qn = qs[q].qnorm, cm = ix.cmax_norm;
     const float round_terms = (1.2f * (float)D + 20.0f) * 5.9604645e-8f;
     float thr;
     if (!desc) {
@@ -544,12 +544,12 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     }
     const uint32_t thr_key = order_key(thr, desc);
     // LIST: the candidate list is complete only up to the filter threshold
-    const bool covered = !LIST || thr_key <= order_key(sl.fthr[q], desc);
+    const bool covered = !LIST || thr_key <= order_key(fthr, desc);
     if (tid == 0) sh.count = 0;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-        const int c = tid + kSelThreads * j;
+        const int c = tid + NT * j;
         if (c < nl && key[j] <= thr_key) {
             const unsigned int slot = atomicAdd(&sh.count, 1u);
             if (slot < (unsigned)sort_n) cand[slot] = LIST ? col[j] : (uint32_t)c;
@@ -560,10 +560,10 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     const int lane8 = tid & 7, grp = tid >> 3;
     const unsigned int gmask = 0xffu << ((tid & 31) & ~7);
     if (covered && m <= (unsigned)sort_n && m >= (unsigned)nprobe) {
-        for (unsigned int i = grp; i < m; i += kSelThreads / 8) {
+        for (unsigned int i = grp; i < m; i += NT / 8) {
             const uint32_t cid = cand[i];
             float l2, ip;  // L2 searches never read dot_query_centroid (src/ivf.rs:2031-2042 uses it for InnerProduct only)
-            exact_pair<true, NEED_IP>(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            exact_pair<true, NEED_IP, DEPTH>(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
             if (lane8 == 0) {
                 sel[i] = ((unsigned long long)order_key(desc ? ip : l2, desc) << 32) | cid;
                 cl2[i] = l2;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
         }
         __syncthreads();
         // exact keys are unique (cluster id in the low word): rank by counting, the nprobe smallest emit K6
-        for (unsigned int i = tid; i < m; i += kSelThreads) {
+        for (unsigned int i = tid; i < m; i += NT) {
             const unsigned long long mine = sel[i];
             unsigned int rank = 0;
             for (unsigned int j = 0; j < m; ++j) rank += sel[j] < mine;
@@ -598,8 +598,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) probe_select_fast_kernel(DevIn
     }
     // rare: exact scores for every centroid of this query, then the exact selection
     if (tid == 0) atomicAdd(fallbacks, 1u);
-    for (int i = tid; i < sort_n; i += kSelThreads) sel[i] = ~0ull;
-    for (int c = grp; c < nl; c += kSelThreads / 8) {
+    for (int i = tid; i < sort_n; i += NT) sel[i] = ~0ull;
+    for (int c = grp; c < nl; c += NT / 8) {
         float l2, ip;
         exact_pair(rq, ix.centroids + (size_t)c * D, D, lane8, gmask, &l2, &ip);
         if (lane8 == 0) sc[c] = desc ? ip : l2;
@@ -832,7 +832,42 @@ int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const Query
                                                                                           d_probes, d_fallbacks, sl);                \
     } while (0)
     const uint32_t kpt = (fw.cap + kSelThreads - 1) / kSelThreads;
-    if (kpt <= 2) {
+    // small candidate lists (cap <= 512): variants of the CTA shape / resident CTAs / re-score prefetch depth (RBQ_SEL_VARIANT, a
+    // tuning knob read per launch; default = the measured best)
+#define RBQ_SELV(KPT, IP, NTV, MINB, DEPTH)                                                                                            \
+    do {                                                                                                                              \
+        if (smem_f > 48 * 1024)                                                                                                       \
+            RBQ_CUDA(cudaFuncSetAttribute(probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));                                 \
+        probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH><<<(unsigned)nq, NTV, smem_f, st>>>(ix, d_rot, nullptr, d_qs, (int)nprobe, \
+                                                                                                    sort_n, eps_g, d_probes, d_fallbacks, sl); \
+    } while (0)
+    const char* ve = getenv("RBQ_SEL_VARIANT");
+    const int variant = ve ? atoi(ve) : kSelVariantDefault;
+    if (kpt <= 2 && variant > 0) {
+        switch (variant) {
+            case 1:
+                if (ipn) RBQ_SELV(2, true, 256, 4, 32);
+                else RBQ_SELV(2, false, 256, 4, 32);
+                break;
+            case 2:
+                if (ipn) RBQ_SELV(4, true, 128, 10, 16);
+                else RBQ_SELV(4, false, 128, 10, 16);
+                break;
+            case 3:
+                if (ipn) RBQ_SELV(4, true, 128, 8, 32);
+                else RBQ_SELV(4, false, 128, 8, 32);
+                break;
+            case 4:
+                if (ipn) RBQ_SELV(2, true, 256, 5, 16);
+                else RBQ_SELV(2, false, 256, 5, 16);
+                break;
+            default:
+                if (ipn) RBQ_SELV(4, true, 128, 12, 16);
+                else RBQ_SELV(4, false, 128, 12, 16);
+                break;
+        }
+    } else if (kpt <= 2) {
         if (ipn) RBQ_SELL(2, true);
         else RBQ_SELL(2, false);
     } else if (kpt <= 4) {
@@ -847,6 +882,7 @@ int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const Query
     } else {
         return fail(RBQ_INVALID_CONFIG, "candidate capacity exceeds the selection kernel's limit (4096)");
     }
+#undef RBQ_SELV
 #undef RBQ_SELL
     RBQ_CUDA(cudaGetLastError());
     const int sort_x = sort_size(nprobe);

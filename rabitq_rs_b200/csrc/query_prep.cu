@@ -9,6 +9,7 @@
 // independent, so running them in parallel does not change any rounding.  Division is IEEE
 // (-prec-div=true); roundf is round-half-away-from-zero like f32::round.
 #include <cfloat>
+#include <cstdlib>
 
 #include "rbq_internal.h"
 #include <cuda_bf16.h>
@@ -131,7 +132,12 @@ __global__ void __launch_bounds__(256) query_prep_kernel(DevIndex ix, const floa
 // bit-identical to fht() (reference src/rotation.rs:292-313).  x - y is evaluated as x + (-y) (same IEEE value).
 constexpr int kPrepWarps = 4;
 
-template <int E>
+// FASTQ: the LUT quantiser's `round((t - vl) / delta)` (an IEEE division + roundf per entry, ~20 instructions) is evaluated as
+// t' = (t - vl) * fl(1 / delta), whose distance from the reference's quotient is below 4.6e-5 for quotients in [0, 256)
+// (one rounding of the reciprocal, one of the product, half an ulp of the true quotient), and rounded with the 2^23 trick; an
+// entry whose t' lies within 1e-4 of a rounding boundary (or is not finite) takes the reference's expression instead, so the
+// byte is the reference's in every case.
+template <int E, bool FASTQ>
 __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevIndex ix, const float* __restrict__ queries, uint32_t nq,
                                                                          float* __restrict__ rot_out, uint8_t* __restrict__ lut_out,
                                                                          QueryScalars* __restrict__ qs_out,
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevInde
     const float vl = lmin, vr = lmax;
     const float delta = (vr - vl) / 255.0f;
     uint4* lut128 = reinterpret_cast<uint4*>(lut_out + (size_t)q * D * 4);
+    const float rinv = 1.0f / delta;
     for (int cb = lane; cb < ncb; cb += 32) {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (delta > 0.0f) {
@@ -278,9 +285,19 @@ __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevInde
             table(cb, t);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float x = roundf((t[j] - vl) / delta);
-                x = fminf(fmaxf(x, 0.0f), 255.0f);  // clamp(0,255); NaN -> 0 like `as u8`
-                w[j >> 2] |= (uint32_t)(x == x ? (int)x : 0) << (8 * (j & 3));
+                uint32_t byte;
+                const float a = t[j] - vl;
+                const float y = a * rinv + 8388608.0f;     // separate mul and add (-fmad=false); integer part in the low mantissa bits
+                const float d = a * rinv - (y - 8388608.0f);
+                if (FASTQ && fabsf(d) <= 0.4999f && y < 8388864.0f) {  // false for NaN / inf as well
+                    byte = __float_as_uint(y) & 0x1ffu;
+                    byte = byte > 255u ? 255u : byte;
+                } else {
+                    float x = roundf(a / delta);
+                    x = fminf(fmaxf(x, 0.0f), 255.0f);  // clamp(0,255); NaN -> 0 like `as u8`
+                    byte = (uint32_t)(x == x ? (int)x : 0);
+                }
+                w[j >> 2] |= byte << (8 * (j & 3));
             }
         }
         lut128[cb] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -302,17 +319,26 @@ __global__ void __launch_bounds__(kPrepWarps * 32) query_prep_fht_kernel(DevInde
     }
 }
 
-template <int E>
-static int launch_prep_fht(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut, QueryScalars* d_qs,
+template <int E, bool FASTQ>
+static int launch_prep_fht_q(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut, QueryScalars* d_qs,
                            cudaStream_t st, void* d_split, float* d_n2) {
     const size_t smem = (size_t)kPrepWarps * 2 * ix.D * sizeof(float);
     if (smem > 48 * 1024)
-        RBQ_CUDA(cudaFuncSetAttribute(query_prep_fht_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    query_prep_fht_kernel<E><<<(unsigned)((nq + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, smem, st>>>(ix, d_queries, (uint32_t)nq,
+        RBQ_CUDA(cudaFuncSetAttribute(query_prep_fht_kernel<E, FASTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    query_prep_fht_kernel<E, FASTQ><<<(unsigned)((nq + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, smem, st>>>(ix, d_queries, (uint32_t)nq,
                                                                                                             d_rot, d_lut, d_qs,
                                                                                                             reinterpret_cast<__nv_bfloat16*>(d_split), d_n2);
     RBQ_CUDA(cudaGetLastError());
     return RBQ_OK;
+}
+
+constexpr int kPrepFastQuantDefault = 1;
+template <int E>
+static int launch_prep_fht(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut, QueryScalars* d_qs,
+                           cudaStream_t st, void* d_split, float* d_n2) {
+    const char* e = getenv("RBQ_PREP_FASTQ");  // tuning knob, read per launch
+    if (e ? atoi(e) != 0 : kPrepFastQuantDefault != 0) return launch_prep_fht_q<E, true>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
+    return launch_prep_fht_q<E, false>(ix, d_queries, nq, d_rot, d_lut, d_qs, st, d_split, d_n2);
 }
 
 int launch_query_prep(const DevIndex& ix, const float* d_queries, size_t nq, float* d_rot, uint8_t* d_lut,
