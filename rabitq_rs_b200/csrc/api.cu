@@ -133,6 +133,14 @@ int rbq::prepare_coarse_tc(rbq_index* h) {
     h->allocations.push_back(n2);
     int rc = launch_split_bf16(d.centroids, nl, (int)D, 1, sp, n2, nullptr);
     if (rc) return rc;
+    d.cent_q4 = nullptr;
+    if (D % 32 == 0 && nl > 0) {  // lane-grouped copy for the exact re-score of the probe selection (coarse.cu)
+        float* q4 = nullptr;
+        RBQ_CUDA(cudaMalloc(&q4, nl * D * 4));
+        h->allocations.push_back(q4);
+        if ((rc = launch_centroid_q4(d.centroids, nl, (int)D, q4, nullptr))) return rc;
+        d.cent_q4 = q4;
+    }
     RBQ_CUDA(cudaDeviceSynchronize());
     double mx = 0.0;
     for (size_t c = 0; c < nl; ++c) {

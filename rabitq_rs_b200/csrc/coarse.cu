@@ -106,7 +106,8 @@ constexpr int kSelThreads = 256;
 // launch_probe_select_cand, candidate capacity <= 512: CTA shape of the selection kernel.  Measured at GIST-1M / 10k queries / nprobe 16
 // (select stage, ms): 0 = 256 threads x 4 CTAs/SM, 16 centroid elements in flight per lane: 0.169; 1 = 32 in flight: 0.186;
 // 2 = 128 threads x 10 CTAs/SM: 0.164; 3 = 128 x 8, 32 in flight: 0.167; 4 = 256 x 5: 0.170; 5 = 128 threads x 12 CTAs/SM: 0.161.
-constexpr int kSelVariantDefault = 5;
+// 6 = 5 with the lane-grouped centroid rows (exact_pair_q4): 0.109; 7 = 6 with 32 in flight: 0.119; 8 = 256 x 5 lane-grouped: 0.137.
+constexpr int kSelVariantDefault = 6;
 constexpr int kMaxNprobe = 4096;
 size_t probe_select_max_nprobe() { return kMaxNprobe; }
 
@@ -246,6 +247,71 @@ __device__ __forceinline__ void exact_pair(const float* __restrict__ rq, const f
     }
     *l2_out = l2;
     *ip_out = ip;
+}
+
+// The same two sums from the lane-grouped layouts (DevIndex::cent_q4, and the query staged the same way): "AVX lane" j reads its
+// elements j, j+8, j+16, ... four at a time as one float4, so a warp instruction of four 8-lane groups touches four 128-byte lines
+// instead of four 32-byte pieces per ELEMENT (the re-score was bound by those L1 wavefronts), and the query costs one LDS.128 per
+// four elements.  Same operations in the same order per lane: bit-identical to exact_pair.
+__host__ __device__ __forceinline__ int q4_index(int i) {  // position of element i in the lane-grouped row
+    const int j = i & 7, kk = i >> 3;
+    return (((kk >> 2) * 8 + j) << 2) + (kk & 3);
+}
+template <bool NEED_L2 = true, bool NEED_IP = true, int DEPTH4 = 4>
+__device__ __forceinline__ void exact_pair_q4(const float* __restrict__ rq4, const float* __restrict__ ce4, int D, int lane8,
+                                              unsigned gmask, float* l2_out, float* ip_out) {
+    float al2 = 0.0f, aip = 0.0f;
+    const float4* c4 = reinterpret_cast<const float4*>(ce4) + lane8;
+    const float4* r4 = reinterpret_cast<const float4*>(rq4) + lane8;
+    const int n4 = D >> 5;  // float4 per lane
+    for (int k = 0; k < n4; k += DEPTH4) {
+        float4 b[DEPTH4];
+#pragma unroll
+        for (int u = 0; u < DEPTH4; ++u)
+            if (k + u < n4) b[u] = __ldg(c4 + (k + u) * 8);
+#pragma unroll
+        for (int u = 0; u < DEPTH4; ++u) {
+            if (k + u < n4) {
+                const float4 a = r4[(k + u) * 8];
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (NEED_L2) {
+                        const float d = av[e] - bv[e];
+                        const float p = d * d;
+                        al2 = al2 + p;
+                    }
+                    if (NEED_IP) {
+                        const float m = av[e] * bv[e];
+                        aip = aip + m;
+                    }
+                }
+            }
+        }
+    }
+    float l2 = 0.0f, ip = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        if (NEED_L2) l2 = l2 + __shfl_sync(gmask, al2, l, 8);
+        if (NEED_IP) ip = ip + __shfl_sync(gmask, aip, l, 8);
+    }
+    *l2_out = l2;
+    *ip_out = ip;
+}
+__global__ void __launch_bounds__(256) centroid_q4_kernel(const float* __restrict__ in, size_t total, int D, float* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t row = idx / (size_t)D;
+    const int i = (int)(idx - row * (size_t)D);
+    out[row * (size_t)D + q4_index(i)] = in[idx];
+}
+int launch_centroid_q4(const float* d_in, size_t rows, int D, float* d_out, cudaStream_t st) {
+    const size_t total = rows * (size_t)D;
+    if (total == 0) return RBQ_OK;
+    if (D % 32 != 0) return fail(RBQ_INVALID_CONFIG, "lane-grouped centroids need padded_dim % 32 == 0");
+    centroid_q4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, total, D, d_out);
+    RBQ_CUDA(cudaGetLastError());
+    return RBQ_OK;
 }
 
 // bitonic sort of sel[0..sort_n) ascending, then K6 for the first nprobe entries
@@ -393,7 +459,8 @@ struct SelList {
     uint32_t* fb_count;
 };
 // NT threads per CTA, MINB resident CTAs per SM asked of the compiler, DEPTH centroid elements in flight per lane of the exact re-score
-template <int KPT, bool NEED_IP, bool LIST, int NT = kSelThreads, int MINB = 4, int DEPTH = 16>
+// Q4: the query is staged, and the centroid rows are read, in the lane-grouped layout (exact_pair_q4)
+template <int KPT, bool NEED_IP, bool LIST, int NT = kSelThreads, int MINB = 4, int DEPTH = 16, bool Q4 = false>
 __global__ void __launch_bounds__(NT, MINB) probe_select_fast_kernel(DevIndex ix, const float* __restrict__ rot,
                                                                        float* __restrict__ scores,
                                                                        const QueryScalars* __restrict__ qs, int nprobe,
@@ -407,6 +474,7 @@ __global__ void __launch_bounds__(NT, MINB) probe_select_fast_kernel(DevIndex ix
     float* cip = cl2 + sort_n;                                                  // sort_n exact ip
     __shared__ SelShared sh;
     static_assert(LIST || NT == kSelThreads, "the dense variant's rare path uses the kSelThreads-strided helpers");
+    static_assert(LIST || !Q4, "the dense variant's rare path reads the query in its natural order");
     __shared__ uint32_t s_min[NT / 32], s_max[NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, D = ix.D;
     const size_t q = blockIdx.x;
@@ -428,7 +496,7 @@ __global__ void __launch_bounds__(NT, MINB) probe_select_fast_kernel(DevIndex ix
     // scalars of the band test, loaded up front (their latency would otherwise sit between the select and the gather)
     const float qn = qs[q].qnorm, cm = ix.cmax_norm;
     const float fthr = LIST ? sl.fthr[q] : 0.0f;
-    for (int i = tid; i < D; i += NT) rq[i] = rot[q * D + i];
+    for (int i = tid; i < D; i += NT) rq[Q4 ? q4_index(i) : i] = rot[q * D + i];
 
     uint32_t key[KPT], col[LIST ? KPT : 1];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
@@ -563,7 +631,8 @@ __global__ void __launch_bounds__(NT, MINB) probe_select_fast_kernel(DevIndex ix
         for (unsigned int i = grp; i < m; i += NT / 8) {
             const uint32_t cid = cand[i];
             float l2, ip;  // L2 searches never read dot_query_centroid (src/ivf.rs:2031-2042 uses it for InnerProduct only)
-            exact_pair<true, NEED_IP, DEPTH>(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            if (Q4) exact_pair_q4<true, NEED_IP, (DEPTH + 3) / 4>(rq, ix.cent_q4 + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
+            else exact_pair<true, NEED_IP, DEPTH>(rq, ix.centroids + (size_t)cid * D, D, lane8, gmask, &l2, &ip);
             if (lane8 == 0) {
                 sel[i] = ((unsigned long long)order_key(desc ? ip : l2, desc) << 32) | cid;
                 cl2[i] = l2;
@@ -834,37 +903,50 @@ int launch_probe_select_cand(const DevIndex& ix, const float* d_rot, const Query
     const uint32_t kpt = (fw.cap + kSelThreads - 1) / kSelThreads;
     // small candidate lists (cap <= 512): variants of the CTA shape / resident CTAs / re-score prefetch depth (RBQ_SEL_VARIANT, a
     // tuning knob read per launch; default = the measured best)
-#define RBQ_SELV(KPT, IP, NTV, MINB, DEPTH)                                                                                            \
+#define RBQ_SELV(KPT, IP, NTV, MINB, DEPTH, Q4V)                                                                                            \
     do {                                                                                                                              \
         if (smem_f > 48 * 1024)                                                                                                       \
-            RBQ_CUDA(cudaFuncSetAttribute(probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH>,                                  \
+            RBQ_CUDA(cudaFuncSetAttribute(probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH, Q4V>,                                  \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));                                 \
-        probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH><<<(unsigned)nq, NTV, smem_f, st>>>(ix, d_rot, nullptr, d_qs, (int)nprobe, \
+        probe_select_fast_kernel<KPT, IP, true, NTV, MINB, DEPTH, Q4V><<<(unsigned)nq, NTV, smem_f, st>>>(ix, d_rot, nullptr, d_qs, (int)nprobe, \
                                                                                                     sort_n, eps_g, d_probes, d_fallbacks, sl); \
     } while (0)
     const char* ve = getenv("RBQ_SEL_VARIANT");
-    const int variant = ve ? atoi(ve) : kSelVariantDefault;
+    int variant = ve ? atoi(ve) : kSelVariantDefault;
+    if (variant >= 6 && ix.cent_q4 == nullptr) variant = 5;  // no lane-grouped centroids (padded_dim % 32 != 0)
     if (kpt <= 2 && variant > 0) {
         switch (variant) {
+            case 6:
+                if (ipn) RBQ_SELV(4, true, 128, 12, 16, true);
+                else RBQ_SELV(4, false, 128, 12, 16, true);
+                break;
+            case 7:
+                if (ipn) RBQ_SELV(4, true, 128, 10, 32, true);
+                else RBQ_SELV(4, false, 128, 10, 32, true);
+                break;
+            case 8:
+                if (ipn) RBQ_SELV(2, true, 256, 5, 16, true);
+                else RBQ_SELV(2, false, 256, 5, 16, true);
+                break;
             case 1:
-                if (ipn) RBQ_SELV(2, true, 256, 4, 32);
-                else RBQ_SELV(2, false, 256, 4, 32);
+                if (ipn) RBQ_SELV(2, true, 256, 4, 32, false);
+                else RBQ_SELV(2, false, 256, 4, 32, false);
                 break;
             case 2:
-                if (ipn) RBQ_SELV(4, true, 128, 10, 16);
-                else RBQ_SELV(4, false, 128, 10, 16);
+                if (ipn) RBQ_SELV(4, true, 128, 10, 16, false);
+                else RBQ_SELV(4, false, 128, 10, 16, false);
                 break;
             case 3:
-                if (ipn) RBQ_SELV(4, true, 128, 8, 32);
-                else RBQ_SELV(4, false, 128, 8, 32);
+                if (ipn) RBQ_SELV(4, true, 128, 8, 32, false);
+                else RBQ_SELV(4, false, 128, 8, 32, false);
                 break;
             case 4:
-                if (ipn) RBQ_SELV(2, true, 256, 5, 16);
-                else RBQ_SELV(2, false, 256, 5, 16);
+                if (ipn) RBQ_SELV(2, true, 256, 5, 16, false);
+                else RBQ_SELV(2, false, 256, 5, 16, false);
                 break;
             default:
-                if (ipn) RBQ_SELV(4, true, 128, 12, 16);
-                else RBQ_SELV(4, false, 128, 12, 16);
+                if (ipn) RBQ_SELV(4, true, 128, 12, 16, false);
+                else RBQ_SELV(4, false, 128, 12, 16, false);
                 break;
         }
     } else if (kpt <= 2) {

@@ -72,6 +72,8 @@ struct DevIndex {
     const uint8_t* flip;    // 4*D/8
     const float* matrix_t;  // Matrix rotator, TRANSPOSED (k-major) for coalesced reads
     const float* centroids; // nlist*D
+    const float* cent_q4;   // the centroids again with every row regrouped for 16-byte loads by the 8 "AVX lanes" of the exact
+                            // re-score: float4 (k4, j) at [(k4*8 + j)*4, +4) = elements 8*(4*k4 + e) + j, e = 0..3 (D % 32 == 0; else nullptr)
     const void* cent_split; // nlist*3D bf16: [hi | lo | hi] split of the centroids (tensor-core coarse stage)
     const float* cent_n2;   // |c|^2 per centroid
     float cmax_norm;        // max |c|
@@ -91,6 +93,7 @@ struct DevIndex {
     const uint8_t* exl;     // lane-major ex-codes (one byte per code, 8 rows of exl_lane bytes per vector; resolve.cu)
     uint32_t exl_lane;      // bytes per row: D/8 rounded up to 16
     uint32_t exl_stride;    // 8 * exl_lane
+    uint32_t exl_copy_coalesced;  // refine staging: 1 = a candidate's rows are copied in address order by its lane group (scan_common.cuh)
     const float* f_add_ex;
     const float* f_rescale_ex;
 };
@@ -259,6 +262,7 @@ int launch_probe_select_tc(const DevIndex& ix, const float* d_rot, float* d_scor
                            size_t nprobe, float eps_g, Probe* d_probes, unsigned int* d_fallbacks, cudaStream_t st,
                            bool need_ip = true);
 int launch_split_bf16(const float* d_x, size_t rows, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
+int launch_centroid_q4(const float* d_in, size_t rows, int D, float* d_out, cudaStream_t st);  // coarse.cu: DevIndex::cent_q4
 int launch_split_bf16_pad(const float* d_x, size_t rows, int in_dim, int D, int centroid_side, void* d_out, float* d_n2, cudaStream_t st);
 int launch_coarse_tc(const DevIndex& ix, const void* d_qsplit, const float* d_qn2, size_t nq, float* d_scores, cudaStream_t st, int terms = 3);
 // coarse_tc.cu: the persistent tcgen05 GEMM behind every dense contraction of the engine.  A: rows x (3D bf16, pitch 3D), B: cols x

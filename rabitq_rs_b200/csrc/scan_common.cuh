@@ -310,13 +310,32 @@ __device__ __forceinline__ float refine_batch(const DevIndex& ix, unsigned long 
     const uint32_t LB = ix.exl_lane;
     const uint32_t my_row = (uint32_t)lane * exl_row, buf_bytes = 32u * exl_row;
     const uint32_t qrow = rql_u32 + (uint32_t)j * rql_row;
+    const uint32_t npr = LB >> 4;  // 16-byte pieces per code row
     auto issue = [&](int r0, uint32_t buf) {
         const int c = r0 + g;
         const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
         if (c < nb) {
-            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
-            const uint32_t dst = stage_u32 + buf * buf_bytes + my_row;
-            for (uint32_t p = 0; p < LB; p += 16) cp_async16(dst + p, src + p);
+            if (ix.exl_copy_coalesced) {
+                // The candidate's 8 rows are one contiguous block of 8 * LB bytes: the group's 8 lanes copy it piece by piece in
+                // address order (lane j: pieces j, j + 8, ...), so one warp instruction reads 128 contiguous bytes per candidate --
+                // 4 lines instead of 32 half-used sectors (every lane walking its own row), which made the L1 the busiest unit of
+                // the refine kernels.  Piece f lands in row f / npr of the group's staging rows, where its chain's lane reads it.
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride;
+                const uint32_t dst = stage_u32 + buf * buf_bytes + (uint32_t)(g * 8) * exl_row;
+                uint32_t row = (uint32_t)j / npr, pc = (uint32_t)j - row * npr;
+                for (uint32_t f = (uint32_t)j; f < 8u * npr; f += 8u) {
+                    cp_async16(dst + row * exl_row + (pc << 4), src + ((size_t)f << 4));
+                    pc += 8u;
+                    while (pc >= npr) {
+                        pc -= npr;
+                        row += 1u;
+                    }
+                }
+            } else {
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)j * LB;
+                const uint32_t dst = stage_u32 + buf * buf_bytes + my_row;
+                for (uint32_t p = 0; p < LB; p += 16) cp_async16(dst + p, src + p);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -332,9 +351,10 @@ __device__ __forceinline__ float refine_batch(const DevIndex& ix, unsigned long 
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        if (ix.exl_copy_coalesced) __syncwarp();  // a lane's row was copied by the other lanes of its group
         float part = 0.0f;
         if (c < nb) part = ex_dot_chain(stage_u32 + buf * buf_bytes + my_row, qrow, LB);
-        part = hsum8(part);
+        part = hsum8(part);  // (full-mask shuffles: every lane is past its reads of the staging rows when the next copies are issued)
         const float v = __shfl_sync(0xffffffffu, part, ((lane - r0) & 3) * 8);
         if (lane >= r0 && lane < r0 + kRefineSlots) exdot = v;
         if (dbl) buf ^= 1u;
@@ -416,15 +436,32 @@ __device__ __forceinline__ float refine_batch2(const DevIndex& ix, unsigned long
     const uint32_t LB = ix.exl_lane;
     const uint32_t my = (uint32_t)lane * lane_stride, buf_bytes = 32u * lane_stride;
     const uint32_t qrow = rql_u32 + (uint32_t)p * rql_row;
+    const uint32_t npr = LB >> 4;  // 16-byte pieces per code row
     auto issue = [&](int r0, uint32_t buf) {
         const int c = r0 + g;
         const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
         if (c < nb) {
-            const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)p * LB;
-            const uint32_t dst = stage_u32 + buf * buf_bytes + my;
-            for (uint32_t o = 0; o < LB; o += 16) {
-                cp_async16(dst + o, src + o);
-                cp_async16(dst + LB + o, src + 4u * LB + o);
+            if (ix.exl_copy_coalesced) {
+                // the group's 4 lanes copy the candidate's contiguous 8 * LB bytes in address order (see refine_batch); row r of
+                // the block belongs to lane r & 3 of the group, first (r < 4) or second (r >= 4) staged row
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride;
+                const uint32_t dst = stage_u32 + buf * buf_bytes + (uint32_t)(g * 4) * lane_stride;
+                uint32_t row = (uint32_t)p / npr, pc = (uint32_t)p - row * npr;
+                for (uint32_t f = (uint32_t)p; f < 8u * npr; f += 4u) {
+                    cp_async16(dst + (row & 3u) * lane_stride + (row >> 2) * LB + (pc << 4), src + ((size_t)f << 4));
+                    pc += 4u;
+                    while (pc >= npr) {
+                        pc -= npr;
+                        row += 1u;
+                    }
+                }
+            } else {
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride + (size_t)p * LB;
+                const uint32_t dst = stage_u32 + buf * buf_bytes + my;
+                for (uint32_t o = 0; o < LB; o += 16) {
+                    cp_async16(dst + o, src + o);
+                    cp_async16(dst + LB + o, src + 4u * LB + o);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -441,6 +478,7 @@ __device__ __forceinline__ float refine_batch2(const DevIndex& ix, unsigned long
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        if (ix.exl_copy_coalesced) __syncwarp();  // a lane's rows were copied by the other lanes of its group
         float part = 0.0f;
         if (c < nb) {
             const uint32_t row = stage_u32 + buf * buf_bytes + my;
