@@ -472,7 +472,11 @@ __global__ void __launch_bounds__(kResWarps * 32) resolve_replay_kernel(DevIndex
 // the current (stale => looser => superset) threshold are queued, a full queue is refined in one batch and replayed
 // against the live threshold.  Same decisions as the reference, a fraction of the ex-code traffic and FMA chains.
 template <int EXK>
+#ifdef RBQ_EXL_COPY_REGULAR
+__global__ void __launch_bounds__(kResWarps * 32, 6) resolve_lazy_kernel(DevIndex ix, ResolveArgs a) {
+#else
 __global__ void __launch_bounds__(kResWarps * 32) resolve_lazy_kernel(DevIndex ix, ResolveArgs a) {
+#endif
     extern __shared__ __align__(16) unsigned char res_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = ix.D, k = (int)a.top_k;

@@ -316,19 +316,43 @@ __device__ __forceinline__ float refine_batch(const DevIndex& ix, unsigned long 
         const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
         if (c < nb) {
             if (ix.exl_copy_coalesced) {
-                // The candidate's 8 rows are one contiguous block of 8 * LB bytes: the group's 8 lanes copy it piece by piece in
-                // address order (lane j: pieces j, j + 8, ...), so one warp instruction reads 128 contiguous bytes per candidate --
-                // 4 lines instead of 32 half-used sectors (every lane walking its own row), which made the L1 the busiest unit of
-                // the refine kernels.  Piece f lands in row f / npr of the group's staging rows, where its chain's lane reads it.
-                const uint8_t* src = ix.exl + gv_c * ix.exl_stride;
+                // The candidate's 8 rows are one contiguous block of 8 * LB bytes: the group's 8 lanes copy it in address order,
+                // 128 contiguous bytes per warp instruction and candidate (4 lines instead of 32 half-used sectors when every lane
+                // walks its own row).  A piece lands in the staging row of the chain it belongs to, where that chain's lane reads it.
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride + 16u * (uint32_t)j;  // this lane's piece of stripe 0
                 const uint32_t dst = stage_u32 + buf * buf_bytes + (uint32_t)(g * 8) * exl_row;
-                uint32_t row = (uint32_t)j / npr, pc = (uint32_t)j - row * npr;
-                for (uint32_t f = (uint32_t)j; f < 8u * npr; f += 8u) {
-                    cp_async16(dst + row * exl_row + (pc << 4), src + ((size_t)f << 4));
-                    pc += 8u;
-                    while (pc >= npr) {
-                        pc -= npr;
-                        row += 1u;
+#ifdef RBQ_EXL_COPY_REGULAR  // cheaper address arithmetic for the regular row sizes.  Built with resolve_lazy_kernel capped at 80 registers (the extra
+                             // branches otherwise raise it to 118) it measured no better than the one loop below (GIST-1M head 0.401 vs 0.405 ms,
+                             // replay 0.235 vs 0.223), so it stays off; verified bit-exact (157 GPU tests) for the record.
+                if ((LB & 127u) == 0u) {  // every 128-byte stripe lies inside one row (padded_dim % 1024 == 0 or 960, ...)
+                    // (kept rolled: unrolling the 8 rows raised resolve_lazy_kernel from 80 to 121 registers and cost two resident CTAs per SM)
+                    uint32_t d = dst + 16u * (uint32_t)j;
+#pragma unroll 1
+                    for (int r = 0; r < 8; ++r) {
+#pragma unroll 1
+                        for (uint32_t o = 0; o < LB; o += 128u) cp_async16(d + o, src + o);
+                        d += exl_row;
+                        src += LB;
+                    }
+                } else if (LB == 64u || LB == 32u) {  // a stripe covers 2 or 4 whole rows
+                    const uint32_t sh = LB == 64u ? 2u : 1u;  // 16-byte pieces per row = 1 << sh
+                    uint32_t d = dst + ((uint32_t)j >> sh) * exl_row + (((uint32_t)j & ((1u << sh) - 1u)) << 4);
+                    const uint32_t dstep = (8u >> sh) * exl_row;
+                    for (uint32_t o = 0; o < 8u * LB; o += 128u) {
+                        cp_async16(d, src + o);
+                        d += dstep;
+                    }
+                } else
+#endif
+                {  // piece f = j, j + 8, ... sits in row f / npr (any row size)
+                    uint32_t row = (uint32_t)j / npr, pc = (uint32_t)j - row * npr;
+                    for (uint32_t f = (uint32_t)j; f < 8u * npr; f += 8u) {
+                        cp_async16(dst + row * exl_row + (pc << 4), src + ((size_t)(f - (uint32_t)j) << 4));
+                        pc += 8u;
+                        while (pc >= npr) {
+                            pc -= npr;
+                            row += 1u;
+                        }
                     }
                 }
             } else {
@@ -442,17 +466,37 @@ __device__ __forceinline__ float refine_batch2(const DevIndex& ix, unsigned long
         const unsigned long long gv_c = __shfl_sync(0xffffffffu, gv, c & 31);
         if (c < nb) {
             if (ix.exl_copy_coalesced) {
-                // the group's 4 lanes copy the candidate's contiguous 8 * LB bytes in address order (see refine_batch); row r of
-                // the block belongs to lane r & 3 of the group, first (r < 4) or second (r >= 4) staged row
-                const uint8_t* src = ix.exl + gv_c * ix.exl_stride;
+                // the group's 4 lanes copy the candidate's contiguous 8 * LB bytes in address order, 64 bytes per instruction (see
+                // refine_batch); row r of the block belongs to lane r & 3 of the group, first (r < 4) or second (r >= 4) staged row
+                const uint8_t* src = ix.exl + gv_c * ix.exl_stride + 16u * (uint32_t)p;  // this lane's piece of stripe 0
                 const uint32_t dst = stage_u32 + buf * buf_bytes + (uint32_t)(g * 4) * lane_stride;
-                uint32_t row = (uint32_t)p / npr, pc = (uint32_t)p - row * npr;
-                for (uint32_t f = (uint32_t)p; f < 8u * npr; f += 4u) {
-                    cp_async16(dst + (row & 3u) * lane_stride + (row >> 2) * LB + (pc << 4), src + ((size_t)f << 4));
-                    pc += 4u;
-                    while (pc >= npr) {
-                        pc -= npr;
-                        row += 1u;
+#ifdef RBQ_EXL_COPY_REGULAR
+                if ((LB & 63u) == 0u) {  // every 64-byte stripe lies inside one row
+#pragma unroll 1
+                    for (int r = 0; r < 8; ++r) {
+                        const uint32_t d = dst + (uint32_t)(r & 3) * lane_stride + (uint32_t)(r >> 2) * LB + 16u * (uint32_t)p;
+#pragma unroll 1
+                        for (uint32_t o = 0; o < LB; o += 64u) cp_async16(d + o, src + o);
+                        src += LB;
+                    }
+                } else if (LB == 32u) {  // a stripe covers two whole rows
+                    const uint32_t rl = (uint32_t)p >> 1, ol = ((uint32_t)p & 1u) << 4;
+#pragma unroll 1
+                    for (int st = 0; st < 4; ++st) {
+                        const uint32_t row = 2u * (uint32_t)st + rl;
+                        cp_async16(dst + (row & 3u) * lane_stride + (row >> 2) * LB + ol, src + 64u * (uint32_t)st);
+                    }
+                } else
+#endif
+                {  // piece f = p, p + 4, ... sits in row f / npr (any row size)
+                    uint32_t row = (uint32_t)p / npr, pc = (uint32_t)p - row * npr;
+                    for (uint32_t f = (uint32_t)p; f < 8u * npr; f += 4u) {
+                        cp_async16(dst + (row & 3u) * lane_stride + (row >> 2) * LB + (pc << 4), src + ((size_t)(f - (uint32_t)p) << 4));
+                        pc += 4u;
+                        while (pc >= npr) {
+                            pc -= npr;
+                            row += 1u;
+                        }
                     }
                 }
             } else {

@@ -122,6 +122,9 @@ SEARCH_CASES = [  # (n, dim, nlist, bits, metric, rot, kind, k, nprobe)
     (3000, 960, 32, 7, 0, 1, "clustered", 100, 8),
     (2000, 32, 16, 7, 0, 0, "uniform11", 5, 16),       # MatrixRotator
     (2000, 1280, 16, 3, 0, 1, "clustered", 10, 4),     # wide path
+    (3000, 256, 32, 7, 0, 1, "clustered", 10, 8),      # 32-byte code rows (paired refine, two rows per copy stripe)
+    (3000, 512, 32, 7, 1, 1, "clustered", 10, 8),      # 64-byte code rows
+    (3000, 640, 32, 3, 0, 1, "clustered", 20, 8),      # 80-byte code rows (irregular stripes)
     (3000, 768, 32, 5, 1, 1, "clustered", 10, 8),      # BASELINE config 4 geometry (768-d, inner product, total_bits 5:
                                                        # the reference panics on this width -- parity vs our oracle only)
 ]
@@ -797,7 +800,10 @@ def test_product_head_and_tail_kernels_bit_exact(rbq, oracle, geom):
 
 
 @pytest.mark.parametrize("geom", [(600, 128, 8, 7, 0, 1), (600, 960, 8, 3, 0, 1), (600, 768, 8, 7, 1, 1), (600, 768, 8, 5, 1, 1), (400, 32, 8, 3, 0, 0),
-                                  (600, 1536, 4, 7, 0, 1)])
+                                  (600, 1536, 4, 7, 0, 1),
+                                  # one geometry per shape of the staging copy (code rows of 32, 48, 64, 80 bytes: paired form; 128, 256: eight-lane)
+                                  (500, 256, 4, 7, 0, 1), (500, 384, 4, 3, 0, 1), (500, 512, 4, 7, 1, 1), (500, 640, 4, 7, 0, 1), (400, 1024, 4, 7, 0, 1),
+                                  (300, 2048, 4, 3, 0, 1)])
 def test_product_ex_dot_bit_exact(rbq, oracle, geom):
     """K10 through the product's refine path (lane-major rows, 8 FMA chains, AVX2-order horizontal sum) == the oracle's
     ip_packed_ex (AVX2 lane order), bit for bit."""
