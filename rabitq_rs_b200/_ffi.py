@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, os.environ.get("RBQ_LIB_NAME", "librbq.so"))  # RBQ_LIB_NAME: A/B builds of the same library (tuning only)
+LIB_PATH = os.path.join(_HERE, "librbq.so")
 
 OK, DIMENSION_MISMATCH, INVALID_CONFIG, EMPTY_INDEX, IO, INVALID_PERSISTENCE, CUDA_ERROR = range(7)
 
