@@ -402,6 +402,7 @@ struct HostFeed {
     float* d_q = nullptr;         // device staging for one tile
     size_t dim = 0, chunk = 0;
     size_t first = 0;             // queries in the first chunk (0: same as the others): a short first copy starts the GPU earlier
+    bool taper = false;           // the last chunks shrink (halving): the tail stage waits for the LAST chunk's front end + head pass
     cudaStream_t copy = nullptr;
     cudaEvent_t* ev = nullptr;
     int issue(size_t q_abs, size_t m, size_t off_in_tile, int slot) {
@@ -464,7 +465,7 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         // 0.84 ms in one chunk, 1.12 in two, 1.47 in four), on alternating streams the next chunk's kernels take it.
         int nslots = (feed && !h->profiling) ? std::max(1, std::min(pl.slots, kMaxSlots)) : 1;
         const uint32_t slot_rows = tw.head_rows / (uint32_t)nslots;
-        if (chunk >= n || slot_rows < 128 || (n + chunk - 1) / chunk * ((chunk + slot_rows - 1) / std::max(slot_rows, 1u)) > kHeadCursors) nslots = 1;
+        if (chunk >= n || slot_rows < 128 || ((n + chunk - 1) / chunk + 7) * ((chunk + slot_rows - 1) / std::max(slot_rows, 1u)) > kHeadCursors) nslots = 1;
         cudaStream_t cs[kMaxSlots] = {st, nullptr, nullptr, nullptr};
         TailWs tws[kMaxSlots] = {tw, tw, tw, tw};
         if (nslots > 1) {
@@ -488,6 +489,13 @@ int search_device(const rbq_index* h, const float* d_queries, size_t nq, size_t 
         int head_launch = 0, ci = 0;
         for (size_t c0 = 0, m = 0; c0 < n; c0 += m, ++ci) {
             m = std::min((feed && ci == 0 && feed->first) ? std::min(feed->first, chunk) : chunk, n - c0);
+            if (feed && feed->taper && nslots > 1 && n - c0 <= 2 * chunk) {
+                // Tapered end of the tile: everything after the last chunk's arrival is on the critical path (its front end and head
+                // pass, then the tail stage), and a chunk's kernels take time roughly in proportion to its size, so the final chunks
+                // halve down to a few hundred queries; the slot streams absorb the extra launches.
+                const size_t rem = n - c0;
+                m = rem <= 640 ? rem : std::min(chunk, std::max<size_t>(256, (rem / 2 + 127) / 128 * 128));
+            }
             const int slot = ci % nslots;
             cudaStream_t cst = cs[slot];
             if (feed) {
@@ -979,6 +987,11 @@ int rbq_search_batch_filtered(const rbq_index* h, const float* queries, size_t n
         const long forced = fe ? std::min(16L, std::max(1L, atol(fe))) : auto_chunks;
         feed.chunk = ((n + forced - 1) / forced + 127) / 128 * 128;
         if (n < 2048) feed.chunk = n;
+        // RBQ_FEED_TAPER=1: the last chunks of a tile halve down to a few hundred queries (a shorter critical path after the last
+        // copy, in theory).  Measured worse at GIST-1M / 10k queries (2.00 vs 1.95 ms per call, 4.31 vs 5.26 M QPS in the bench's
+        // L2-flushed timing: the small chunks' kernels cost their fixed latency each), so it is off.
+        const char* ft = getenv("RBQ_FEED_TAPER");
+        feed.taper = ft ? atoi(ft) != 0 : false;
         const char* ff = getenv("RBQ_FEED_FIRST");  // tuning knob: queries in the first chunk
         feed.first = ff ? (size_t)std::max(128L, atol(ff) / 128 * 128) : 0;
         if (feed.first && feed.first < n && n >= 2048)  // the rest of the tile in `forced` equal chunks

@@ -283,7 +283,7 @@ def test_device_resident_entry_matches_host_entry(rbq, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("slots,chunks,first", [(1, 4, 0), (2, 4, 0), (3, 5, 0), (4, 8, 0), (2, 3, 384), (4, 16, 128)])
+@pytest.mark.parametrize("slots,chunks,first", [(1, 4, 0), (2, 4, 0), (3, 5, 0), (4, 8, 0), (2, 3, 384), (4, 16, 128), (4, 3, -1)])
 @pytest.mark.parametrize("geom", [(20000, 128, 256, 7, 0), (12000, 960, 64, 7, 0), (12000, 96, 128, 3, 1)])
 def test_host_feed_chunks_on_slot_streams(rbq, oracle, geom, slots, chunks, first, monkeypatch):
     """Host entry: the feed chunks' front end + head pass alternate over `slots` streams (own front-end scratch, own part of
@@ -303,8 +303,10 @@ def test_host_feed_chunks_on_slot_streams(rbq, oracle, geom, slots, chunks, firs
     exp = oix.search_batch(q[:400], 10, 12)
     monkeypatch.setenv("RBQ_FEED_SLOTS", str(slots))
     monkeypatch.setenv("RBQ_FEED_CHUNKS", str(chunks))
-    if first:
+    if first > 0:
         monkeypatch.setenv("RBQ_FEED_FIRST", str(first))
+    if first < 0:  # optional tapered end of the tile (the last chunks halve)
+        monkeypatch.setenv("RBQ_FEED_TAPER", "1")
     for mode in (2, 1, 0):
         gix.set_scan_mode(mode)
         gix.batch_search_device(dq, 10, 12, ids, sc, cn)
